@@ -1,0 +1,151 @@
+/* znll.h -- C ABI of the B200-native unbinned-likelihood hot path (libznll.so).
+ *
+ * This is the drop-in boundary for zfit's UnbinnedNLL / ExtendedUnbinnedNLL value + gradient.
+ * The reference (zfit 0.28.0, pure Python on TensorFlow) has no FFI; its own plug-in slots for this
+ * path are the BaseLoss override hooks.  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  The Python host layer (zfit_b200/) binds
+ * these with ctypes and calls them from  _loss_func / _value_gradient.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures (streams are void*).
+ *   - every function returns 0 on success, non-zero on a programming / CUDA error
+ *     (text via znll_last_error()).  Numerical trouble (NaN/inf) is NEVER an error: it is
+ *     returned in the outputs so that LossEval's NaN strategy keeps working
+ *     (src/zfit/minimizers/evaluation.py:199-227).
+ *   - all arithmetic is fp64.
+ *
+ * Model trees
+ *   A channel's composite PDF is described as a pre-order array of znll_node.  The "slots" of a
+ *   tree are the scalar arguments its nodes take, concatenated in pre-order (a node's own slots
+ *   first, then its children's):
+ *       ZNLL_GAUSS  mu, sigma                 (src/zfit/models/dist_tfp.py:187-268)
+ *       ZNLL_EXP    lambda                    (src/zfit/models/basic.py:34-243)
+ *       ZNLL_CB     mu, sigma, alpha, n       (src/zfit/models/physics.py:31-45,83-142,233-336)
+ *       ZNLL_CHEB   c_0 .. c_degree           (src/zfit/models/polynomials.py:334-482)
+ *       ZNLL_SUM    frac_0 .. frac_{k-1}      (src/zfit/models/functor.py:74-313; ALL k fractions)
+ *       ZNLL_PROD   (none)                    (src/zfit/models/functor.py:331-483)
+ *   The library differentiates with respect to slots; the host applies d(slot)/d(theta)
+ *   (shared parameters, frac = yield/sum(yields), 1 - sum(fracs), user ComposedParameters).
+ */
+#ifndef ZNLL_H
+#define ZNLL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZNLL_ABI_VERSION 1
+#define ZNLL_MAX_COLS 8
+
+enum znll_kind {
+  ZNLL_GAUSS = 1,
+  ZNLL_EXP = 2,
+  ZNLL_CB = 3,
+  ZNLL_CHEB = 4,
+  ZNLL_SUM = 16,
+  ZNLL_PROD = 17
+};
+
+/* One node of a model tree, pre-order.  Leaf limits are fixed at plan time (they come from the
+ * PDF's Space / norm, src/zfit/core/space.py:1246-2239), only slots change per evaluation. */
+typedef struct znll_node {
+  int32_t kind;       /* enum znll_kind */
+  int32_t n_children; /* functors: number of direct children; leaves: 0 */
+  int32_t column;     /* leaves: index of the bound data column this leaf reads */
+  int32_t degree;     /* ZNLL_CHEB: polynomial degree d (slots c_0..c_d); else 0 */
+  double norm_lo;     /* leaves: normalisation integral limits (BasePDF.normalization, basepdf.py:198-251) */
+  double norm_hi;
+  double space_lo;    /* ZNLL_CHEB: rescale limits (rescale_minus_plus_one, polynomials.py:32-43) */
+  double space_hi;
+  double shift;       /* ZNLL_EXP: numerics data shift s (basic.py:128-154): centre of the norm, or 0
+                         inside a ProductPDF */
+} znll_node;
+
+/* flags for znll_eval / znll_launch */
+#define ZNLL_WANT_GRAD 1u /* also return the slot gradient (loss.value_gradient, core/loss.py:697-763) */
+#define ZNLL_KAHAN 2u     /* sumtype == "kahan" (core/loss.py:138-141); the kernels always use compensated
+                             fp64 accumulation, the flag is accepted for interface parity */
+
+typedef struct znll_plan znll_plan;
+
+int znll_abi_version(void);
+const char* znll_last_error(void);
+
+/* Number of CUDA devices visible (0 => the product path cannot run; there is no CPU fallback). */
+int znll_device_count(void);
+
+/* Create / destroy a plan of n_channels simultaneous channels on CUDA device `device`.
+ * Replaces: BaseLoss.__init__ holding model/data lists (core/loss.py:192-241). */
+int znll_plan_create(int device, int n_channels, znll_plan** out);
+void znll_plan_destroy(znll_plan* plan);
+
+/* Describe channel `ch`'s composite PDF.  Replaces the traced pdf() dispatch chain
+ * BasePDF.pdf -> _norm_pdf -> _call_pdf -> _fallback_pdf (core/basepdf.py:398-461).
+ * Selects the fused sm_100a kernel instantiated for this tree shape (ahead-of-time catalogue,
+ * else runtime instantiation of the same templates through NVRTC). */
+int znll_plan_set_model(znll_plan* plan, int ch, const znll_node* nodes, int n_nodes);
+
+/* Bind channel data that already lives in device memory (borrowed; the caller keeps it alive --
+ * Data owns the event tensors for the life of the loss, core/loss.py:226).  cols_dev[i] is a
+ * contiguous, 16-byte aligned fp64 column of n events (structure-of-arrays); w_dev may be NULL.
+ * Replaces: Data / LightDataset column access (core/data.py:876-982,1772-1937). */
+int znll_plan_bind_device(znll_plan* plan, int ch, int n_cols, const double* const* cols_dev,
+                          const double* w_dev, int64_t n_events);
+
+/* Same, from HOST buffers: the library allocates device columns, copies once, and owns them. */
+int znll_plan_bind_host(znll_plan* plan, int ch, int n_cols, const double* const* cols_host,
+                        const double* w_host, int64_t n_events);
+
+/* Sum of weights (or N) of the bound shard, computed on the device at bind time with the same
+ * deterministic reduction as the NLL.  Data.samplesize, core/data.py:268-275.  Multi-GPU: the
+ * host all-reduces it once and writes the global figure back with znll_plan_set_sumw. */
+int znll_plan_get_sumw(znll_plan* plan, int ch, double* sumw);
+int znll_plan_set_sumw(znll_plan* plan, int ch, double sumw);
+
+int znll_plan_n_slots(const znll_plan* plan, int ch);   /* slots of channel ch        */
+int znll_plan_n_acc(const znll_plan* plan, int ch);     /* accumulators of channel ch */
+int znll_plan_total_slots(const znll_plan* plan);       /* sum over channels          */
+int znll_plan_total_acc(const znll_plan* plan);
+/* name of the kernel instantiation chosen for channel ch, e.g. "Sum<CBall<0>,Expo<0>>" */
+const char* znll_plan_kernel_name(const znll_plan* plan, int ch);
+/* 1 if the instantiation came from the ahead-of-time catalogue, 2 if NVRTC built it */
+int znll_plan_kernel_origin(const znll_plan* plan, int ch);
+/* number of kernel launches issued through this plan so far (bench.py's gpu_launches) */
+int64_t znll_plan_launch_count(const znll_plan* plan);
+
+/* One evaluation of every channel: value_k = -sum_i (w_i*log(pdf_k(x_i)+1e-307) - log_offset)
+ * and, with ZNLL_WANT_GRAD, d value_k / d slot for every slot of every channel.
+ *   slots       [total_slots]   host, channel-major, pre-order
+ *   log_offset  per-event constant subtracted after the weight multiply (core/loss.py:134-137);
+ *               pass 0.0 for full=True
+ *   values      [n_channels]    host out
+ *   grad_slots  [total_slots]   host out (may be NULL without ZNLL_WANT_GRAD)
+ *   stream      cudaStream_t as void* (NULL = the plan's own stream)
+ * Synchronous with respect to its outputs.  Replaces _unbinned_nll_tf + _nll_calc_unbinned_tf
+ * (core/loss.py:73-142) and autodiff_value_gradient (z/math.py:236-261). */
+int znll_eval(znll_plan* plan, const double* slots, uint32_t flags, double log_offset,
+              double* values, double* grad_slots, void* stream);
+
+/* Split form for multi-GPU: launch leaves the raw accumulators of all channels in a device
+ * buffer (znll_plan_acc_device) so the caller can all-reduce (sum) them over ranks on the same
+ * stream; collect copies them back, synchronises, and applies the host epilogue. */
+int znll_launch(znll_plan* plan, const double* slots, uint32_t flags, double log_offset, void* stream);
+double* znll_plan_acc_device(znll_plan* plan);
+int znll_collect(znll_plan* plan, uint32_t flags, double* values, double* grad_slots, void* stream);
+
+/* Host-only helpers (no GPU needed): normalisation integral of one leaf and d I / d slot, exactly
+ * as the per-call prologue computes them.  Replaces the registered analytic integrals
+ * (dist_tfp.py:113-120, basic.py:211-229, physics.py:83-142, polynomials.py:443-478). */
+int znll_leaf_integral(const znll_node* leaf, const double* slots, double* integral, double* dintegral);
+
+/* Device micro-benchmark used for the roofline denominator: register-resident DFMA loop.
+ * Returns achieved FP64 TFLOP/s over `ms` milliseconds of work (approx.). */
+int znll_fp64_peak(int device, double ms, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZNLL_H */

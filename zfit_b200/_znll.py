@@ -1,0 +1,219 @@
+"""ctypes binding of ``libznll.so`` (C ABI declared in ``include/znll.h``).
+
+This is the only place the Python host layer touches native code.  There is no CPU fallback:
+if the library is missing or no CUDA device is visible, evaluating a loss raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libznll.so"
+
+GAUSS, EXP, CB, CHEB, SUM, PROD = 1, 2, 3, 4, 16, 17
+WANT_GRAD, KAHAN = 1, 2
+MAX_COLS = 8
+
+
+class Node(C.Structure):
+    """Mirror of ``znll_node`` (include/znll.h)."""
+
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("n_children", C.c_int32),
+        ("column", C.c_int32),
+        ("degree", C.c_int32),
+        ("norm_lo", C.c_double),
+        ("norm_hi", C.c_double),
+        ("space_lo", C.c_double),
+        ("space_hi", C.c_double),
+        ("shift", C.c_double),
+    ]
+
+
+class ZnllError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_DP = C.POINTER(C.c_double)
+
+# every symbol include/znll.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "znll_abi_version": (C.c_int, []),
+    "znll_last_error": (C.c_char_p, []),
+    "znll_device_count": (C.c_int, []),
+    "znll_plan_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "znll_plan_destroy": (None, [C.c_void_p]),
+    "znll_plan_set_model": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Node), C.c_int]),
+    "znll_plan_bind_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]),
+    "znll_plan_bind_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]),
+    "znll_plan_get_sumw": (C.c_int, [C.c_void_p, C.c_int, _DP]),
+    "znll_plan_set_sumw": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "znll_plan_n_slots": (C.c_int, [C.c_void_p, C.c_int]),
+    "znll_plan_n_acc": (C.c_int, [C.c_void_p, C.c_int]),
+    "znll_plan_total_slots": (C.c_int, [C.c_void_p]),
+    "znll_plan_total_acc": (C.c_int, [C.c_void_p]),
+    "znll_plan_kernel_name": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "znll_plan_kernel_origin": (C.c_int, [C.c_void_p, C.c_int]),
+    "znll_plan_launch_count": (C.c_int64, [C.c_void_p]),
+    "znll_eval": (C.c_int, [C.c_void_p, _DP, C.c_uint32, C.c_double, _DP, _DP, C.c_void_p]),
+    "znll_launch": (C.c_int, [C.c_void_p, _DP, C.c_uint32, C.c_double, C.c_void_p]),
+    "znll_plan_acc_device": (C.c_void_p, [C.c_void_p]),
+    "znll_collect": (C.c_int, [C.c_void_p, C.c_uint32, _DP, _DP, C.c_void_p]),
+    "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
+    "znll_fp64_peak": (C.c_int, [C.c_int, C.c_double, _DP]),
+}
+
+
+def lib():
+    """Load ``libznll.so`` (built in-tree by ``zfit_b200.build``).  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            msg = (
+                f"{LIB_PATH} is missing: build the CUDA extension with `python -m zfit_b200.build` "
+                "(there is no CPU fallback)."
+            )
+            raise ZnllError(msg)
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.znll_abi_version() != 1:
+            msg = "libznll.so ABI version mismatch; rebuild"
+            raise ZnllError(msg)
+        _lib = handle
+    return _lib
+
+
+def _check(rc):
+    if rc:
+        raise ZnllError(lib().znll_last_error().decode(errors="replace"))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_DP)
+
+
+def leaf_integral(node: Node, slots):
+    """Host-only: normalisation integral of a leaf and d I / d slot (no GPU needed)."""
+    slots = np.ascontiguousarray(slots, dtype=np.float64)
+    integral = np.zeros(1)
+    dint = np.zeros(32)
+    _check(lib().znll_leaf_integral(C.byref(node), _dptr(slots), _dptr(integral), _dptr(dint)))
+    return float(integral[0]), dint[: len(slots)].copy()
+
+
+class Plan:
+    """Owns a ``znll_plan``: per-channel model trees, bound device columns, launch + collect."""
+
+    def __init__(self, n_channels: int, device: int = 0):
+        self._h = C.c_void_p()
+        self._keep = []  # objects owning borrowed device memory
+        L = lib()
+        if L.znll_device_count() < 1:
+            msg = "no CUDA device visible: zfit_b200 evaluates losses only on the GPU (no CPU fallback)"
+            raise ZnllError(msg)
+        _check(L.znll_plan_create(device, n_channels, C.byref(self._h)))
+        self.n_channels = n_channels
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().znll_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_model(self, ch: int, nodes):
+        arr = (Node * len(nodes))(*nodes)
+        _check(lib().znll_plan_set_model(self._h, ch, arr, len(nodes)))
+        self._buffers()
+
+    def _buffers(self):
+        L = lib()
+        self.total_slots = L.znll_plan_total_slots(self._h)
+        self._values = np.zeros(self.n_channels)
+        self._grad = np.zeros(max(self.total_slots, 1))
+
+    def bind_device_ptrs(self, ch: int, col_ptrs, w_ptr, n: int, keepalive=None):
+        cols = (C.c_void_p * len(col_ptrs))(*col_ptrs)
+        _check(lib().znll_plan_bind_device(self._h, ch, len(col_ptrs), cols, C.c_void_p(w_ptr or 0), n))
+        self._keep.append(keepalive)
+
+    def bind_host(self, ch: int, cols, weights=None):
+        cols = [np.ascontiguousarray(c, dtype=np.float64) for c in cols]
+        n = len(cols[0])
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        _check(lib().znll_plan_bind_host(self._h, ch, len(cols), ptrs, C.c_void_p(w.ctypes.data if w is not None else 0), n))
+
+    def sumw(self, ch: int) -> float:
+        out = np.zeros(1)
+        _check(lib().znll_plan_get_sumw(self._h, ch, _dptr(out)))
+        return float(out[0])
+
+    def set_sumw(self, ch: int, v: float):
+        _check(lib().znll_plan_set_sumw(self._h, ch, float(v)))
+
+    def n_slots(self, ch: int) -> int:
+        return lib().znll_plan_n_slots(self._h, ch)
+
+    def n_acc(self, ch: int) -> int:
+        return lib().znll_plan_n_acc(self._h, ch)
+
+    def total_acc(self) -> int:
+        return lib().znll_plan_total_acc(self._h)
+
+    def kernel_name(self, ch: int) -> str:
+        return lib().znll_plan_kernel_name(self._h, ch).decode()
+
+    def kernel_origin(self, ch: int) -> int:
+        return lib().znll_plan_kernel_origin(self._h, ch)
+
+    def launch_count(self) -> int:
+        return int(lib().znll_plan_launch_count(self._h))
+
+    def eval(self, slots, *, grad=True, log_offset=0.0, kahan=False, stream=0):
+        """-> (values[n_channels], grad_slots[total_slots] | None); synchronous."""
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        if slots.size != self.total_slots:
+            msg = f"expected {self.total_slots} slots, got {slots.size}"
+            raise ValueError(msg)
+        flags = (WANT_GRAD if grad else 0) | (KAHAN if kahan else 0)
+        _check(
+            lib().znll_eval(
+                self._h, _dptr(slots), flags, float(log_offset), _dptr(self._values), _dptr(self._grad), C.c_void_p(stream)
+            )
+        )
+        return self._values.copy(), (self._grad[: self.total_slots].copy() if grad else None)
+
+    def launch(self, slots, *, grad=True, log_offset=0.0, stream=0):
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        flags = WANT_GRAD if grad else 0
+        _check(lib().znll_launch(self._h, _dptr(slots), flags, float(log_offset), C.c_void_p(stream)))
+
+    def acc_device_ptr(self) -> int:
+        return int(lib().znll_plan_acc_device(self._h) or 0)
+
+    def collect(self, *, grad=True, stream=0):
+        flags = WANT_GRAD if grad else 0
+        _check(lib().znll_collect(self._h, flags, _dptr(self._values), _dptr(self._grad), C.c_void_p(stream)))
+        return self._values.copy(), (self._grad[: self.total_slots].copy() if grad else None)
+
+
+def fp64_peak(device: int = 0, ms: float = 200.0) -> float:
+    out = np.zeros(1)
+    _check(lib().znll_fp64_peak(device, float(ms), _dptr(out)))
+    return float(out[0])

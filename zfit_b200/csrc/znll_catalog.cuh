@@ -1,0 +1,43 @@
+// znll_catalog.cuh -- helper to instantiate and register kernels ahead of time (nvcc, sm_100a).
+#pragma once
+#include "znll_device.cuh"
+#include "znll_internal.h"
+
+namespace znll {
+
+template <class M, bool W, bool G>
+cudaError_t launch_nll(const ZnllLaunchArgs& a, const double* consts, int grid, cudaStream_t stream) {
+  KArgs<M::NC> k;
+  for (int i = 0; i < ZNLL_MAXCOL; ++i) k.cols[i] = a.cols[i];
+  k.w = a.w;
+  k.n = a.n;
+  k.log_offset = a.log_offset;
+  k.partials = a.partials;
+  k.ticket = a.ticket;
+  k.out = a.out;
+  for (int i = 0; i < M::NC; ++i) k.c[i] = consts[i];
+  nll_kernel<M, W, G><<<grid, ZNLL_BLOCK, 0, stream>>>(k);
+  return cudaGetLastError();
+}
+
+template <class M>
+ZnllCatalogEntry make_entry(const char* name) {
+  ZnllCatalogEntry e;
+  e.name = name;
+  e.n_slots = M::NS;
+  e.n_consts = M::NC;
+  e.fn[0][0] = &launch_nll<M, false, false>;
+  e.fn[0][1] = &launch_nll<M, false, true>;
+  e.fn[1][0] = &launch_nll<M, true, false>;
+  e.fn[1][1] = &launch_nll<M, true, true>;
+  return e;
+}
+
+struct Registrar {
+  Registrar(const ZnllCatalogEntry* e, int n) { znll_catalog_register(e, n); }
+};
+
+}  // namespace znll
+
+// the stringified type must be the canonical name the host generates (no spaces)
+#define ZNLL_ENTRY(...) znll::make_entry<znll::__VA_ARGS__>(#__VA_ARGS__)

@@ -1,0 +1,891 @@
+// znll_host.cu -- C ABI (include/znll.h) of the B200-native unbinned-likelihood hot path.
+//
+// Host side of every evaluation:
+//   1. prologue   : walk the model tree, compute each leaf's analytic normalisation integral and
+//                   its slot derivatives in fp64 (libm), fill the kernel's constant block;
+//   2. launch     : one fused kernel per channel (ahead-of-time catalogue instantiation of the
+//                   templates in znll_device.cuh, or the same templates instantiated through NVRTC
+//                   for tree shapes outside the catalogue);
+//   3. epilogue   : fold the normalisation derivatives into the accumulated slot gradients.
+// There is no CPU evaluation path: without a CUDA device every compute entry point fails.
+#include <ctype.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/znll.h"
+#include "znll_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CUDA_OK(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e_));   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// catalogue registry
+// ------------------------------------------------------------------------------------------------
+static std::vector<ZnllCatalogEntry>& catalog() {
+  static std::vector<ZnllCatalogEntry> v;
+  return v;
+}
+void znll_catalog_register(const ZnllCatalogEntry* e, int n) {
+  for (int i = 0; i < n; ++i) catalog().push_back(e[i]);
+}
+const ZnllCatalogEntry* znll_catalog_find(const char* name) {
+  for (auto& e : catalog())
+    if (strcmp(e.name, name) == 0) return &e;
+  return nullptr;
+}
+int znll_catalog_size() { return (int)catalog().size(); }
+const ZnllCatalogEntry* znll_catalog_at(int i) { return &catalog()[i]; }
+
+// ------------------------------------------------------------------------------------------------
+// leaf integrals and their slot derivatives (host fp64)
+// ------------------------------------------------------------------------------------------------
+static const double kSqrt2 = 1.4142135623730951;
+static const double kSqrtHalf = 0.7071067811865476;
+static const double kInvSqrt2Pi = 0.3989422804014327;
+static const double kHalfLog2Pi = 0.9189385332046727;
+static const double kSqrtPiOver2 = 1.2533141373155001;
+
+// tfp.math.special.ndtr (Normal.cdf), reference call site src/zfit/models/dist_tfp.py:113-120
+static double ndtr(double x) {
+  const double w = x * kSqrtHalf, z = fabs(w);
+  double y;
+  if (z < kSqrtHalf)
+    y = 1.0 + erf(w);
+  else if (w > 0)
+    y = 2.0 - erfc(z);
+  else
+    y = erfc(z);
+  return 0.5 * y;
+}
+static double zphi(double z, int pow_z) {  // z^pow_z * phi(z), 0 at +-inf
+  if (isinf(z)) return 0.0;
+  const double p = kInvSqrt2Pi * exp(-0.5 * z * z);
+  return pow_z ? z * p : p;
+}
+
+static void gauss_integral(double mu, double sigma, double lo, double hi, double* I, double* dI) {
+  const double zh = (hi - mu) / sigma, zl = (lo - mu) / sigma;
+  *I = ndtr(zh) - ndtr(zl);
+  dI[0] = (zphi(zl, 0) - zphi(zh, 0)) / sigma;
+  dI[1] = (zphi(zl, 1) - zphi(zh, 1)) / sigma;
+}
+
+// src/zfit/models/basic.py:211-229 (shifted raw integral)
+static void exp_integral(double lam, double lo, double hi, double s, double* I, double* dI) {
+  const double eh = exp(lam * (hi - s)), el = exp(lam * (lo - s));
+  *I = eh / lam - el / lam;
+  dI[0] = ((hi - s) * eh - (lo - s) * el) / lam - (*I) / lam;
+}
+
+// src/zfit/models/polynomials.py:443-478
+static void cheb_T(double z, int maxdeg, double* T) {
+  T[0] = 1.0;
+  if (maxdeg >= 1) T[1] = z;
+  for (int k = 2; k <= maxdeg; ++k) T[k] = 2.0 * (z * T[k - 1]) - T[k - 2];
+}
+static void cheb_integral(const double* c, int deg, double lo, double hi, double slo, double shi, double* I,
+                          double* dI) {
+  const double zl = (2.0 * lo - slo - shi) / (shi - slo), zu = (2.0 * hi - slo - shi) / (shi - slo);
+  std::vector<double> Tu(deg + 3), Tl(deg + 3), J(deg + 1);
+  cheb_T(zu, deg + 1, Tu.data());
+  cheb_T(zl, deg + 1, Tl.data());
+  J[0] = zu - zl;
+  if (deg >= 1) J[1] = 0.5 * (zu * zu - zl * zl);
+  double integral = c[0] * J[0];
+  if (deg >= 1) integral += c[1] * J[1];
+  if (deg >= 2) {
+    double up = 0.0, low = 0.0;
+    for (int k = 2; k <= deg; ++k) {
+      const double nf = (double)k;
+      const double iu = nf * Tu[k + 1] / (nf * nf - 1.0) - zu * Tu[k] / (nf - 1.0);
+      const double il = nf * Tl[k + 1] / (nf * nf - 1.0) - zl * Tl[k] / (nf - 1.0);
+      J[k] = iu - il;
+      up += c[k] * iu;
+      low += c[k] * il;
+    }
+    integral += up - low;
+  }
+  const double scale = 0.5 * (shi - slo);
+  *I = integral * scale;
+  for (int k = 0; k <= deg; ++k) dI[k] = J[k] * scale;
+}
+
+// src/zfit/models/physics.py:83-142, plus the derivative of exactly those expressions
+static void cb_integral(double mu, double sigma, double alpha, double n, double lo, double hi, double* I,
+                        double* dI) {
+  const bool use_log = fabs(n - 1.0) < 1e-05;
+  const double s = fabs(sigma), a = fabs(alpha);
+  const double sgn_sigma = sigma < 0 ? -1.0 : 1.0, sgn_alpha = alpha < 0 ? -1.0 : 1.0;
+  double tmin = (lo - mu) / s, tmax = (hi - mu) / s;
+  if (alpha < 0) {
+    const double tm = tmin;
+    tmin = -tmax;
+    tmax = -tm;
+  }
+  const double A = pow(n / a, n) * exp(-0.5 * a * a);
+  const double B = n / a - a;
+  const double dA_dn = A * (log(n / a) + 1.0), dA_da = A * (-n / a - a);
+  const double dB_da = -n / (a * a) - 1.0, inva = 1.0 / a;
+  // integrand at a boundary t (the derivative of the reference's formula w.r.t. that boundary)
+  auto f_at = [&](double t) {
+    if (t < -a) {
+      const double u = B - t;
+      return use_log ? A / u : A * pow(u, -n);
+    }
+    return exp(-0.5 * t * t);
+  };
+  double Ival, dIa = 0.0, dIn = 0.0;
+  if (tmin >= -a) {
+    Ival = s * kSqrtPiOver2 * (erf(tmax / kSqrt2) - erf(tmin / kSqrt2));
+  } else {
+    const bool all_tail = tmax <= -a;
+    double u1 = B - tmin, u2 = all_tail ? B - tmax : n / a;
+    if (!(u1 > 0)) u1 = 1.0;  // safe_b_tmin_ones
+    if (all_tail && !(u2 > 0)) u2 = 1.0;
+    const double du1_da = dB_da, du2_da = all_tail ? dB_da : -n / (a * a);
+    double tailI, dT_dn, dT_da;
+    if (use_log) {
+      const double L = log(u1) - log(u2);
+      tailI = A * s * L;
+      dT_dn = s * (dA_dn * L + A * (1.0 / u1 - 1.0 / u2) * inva);
+      dT_da = s * (dA_da * L + A * (du1_da / u1 - du2_da / u2));
+    } else {
+      const double m = 1.0 - n;
+      const double p1 = 1.0 / pow(u1, n - 1.0), p2 = 1.0 / pow(u2, n - 1.0);
+      tailI = A * s / m * (p1 - p2);
+      dT_dn = s * ((dA_dn / m + A / (m * m)) * (p1 - p2) +
+                   A / m * (p1 * (-log(u1) + m * inva / u1) - p2 * (-log(u2) + m * inva / u2)));
+      dT_da = s * (dA_da / m * (p1 - p2) + A * (p1 / u1 * du1_da - p2 / u2 * du2_da));
+    }
+    double gaussI = 0.0, dG_da = 0.0;
+    if (!all_tail) {
+      gaussI = s * kSqrtPiOver2 * (erf(tmax / kSqrt2) - erf(-a / kSqrt2));
+      dG_da = s * exp(-0.5 * a * a);
+    }
+    Ival = all_tail ? tailI : tailI + gaussI;
+    dIa = dT_da + dG_da;
+    dIn = dT_dn;
+  }
+  const double fmax = f_at(tmax), fmin = f_at(tmin);
+  *I = Ival;
+  dI[0] = -sgn_alpha * (fmax - fmin);
+  dI[1] = sgn_sigma * (Ival / s - (tmax * fmax - tmin * fmin));
+  dI[2] = sgn_alpha * dIa;
+  dI[3] = dIn;
+}
+
+static int leaf_n_slots(const znll_node& nd) {
+  switch (nd.kind) {
+    case ZNLL_GAUSS: return 2;
+    case ZNLL_EXP: return 1;
+    case ZNLL_CB: return 4;
+    case ZNLL_CHEB: return nd.degree + 1;
+    default: return -1;
+  }
+}
+static int leaf_n_consts(const znll_node& nd) {
+  switch (nd.kind) {
+    case ZNLL_GAUSS: return 3;
+    case ZNLL_EXP: return 3;
+    case ZNLL_CB: return 13;
+    case ZNLL_CHEB: return 3 + nd.degree + 1;
+    default: return -1;
+  }
+}
+
+static int leaf_integral(const znll_node& nd, const double* s, double* I, double* dI) {
+  switch (nd.kind) {
+    case ZNLL_GAUSS: gauss_integral(s[0], s[1], nd.norm_lo, nd.norm_hi, I, dI); return 0;
+    case ZNLL_EXP: exp_integral(s[0], nd.norm_lo, nd.norm_hi, nd.shift, I, dI); return 0;
+    case ZNLL_CB: cb_integral(s[0], s[1], s[2], s[3], nd.norm_lo, nd.norm_hi, I, dI); return 0;
+    case ZNLL_CHEB: cheb_integral(s, nd.degree, nd.norm_lo, nd.norm_hi, nd.space_lo, nd.space_hi, I, dI); return 0;
+    default: return fail("znll_leaf_integral: node kind %d is not a leaf", nd.kind);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct NodeInfo {
+  znll_node nd;
+  int slot_off, const_off;  // this node's own slots / consts
+  int parent_sum_frac_slot; // nearest Sum ancestor's frac slot of the branch containing the node, or -1
+};
+
+struct Kernel {
+  std::string name;
+  int origin = 0;  // 1 catalogue, 2 nvrtc
+  const ZnllCatalogEntry* aot = nullptr;
+  void* cufunc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // CUfunction, NVRTC path
+};
+
+struct Channel {
+  std::vector<NodeInfo> nodes;
+  int n_slots = 0, n_consts = 0, n_acc = 0, acc_off = 0, slot_off = 0;
+  Kernel kernel;
+  bool bound = false;
+  const double* cols[ZNLL_MAX_COLS] = {nullptr};
+  const double* w = nullptr;
+  int n_cols = 0;
+  long long n = 0;
+  double sumw = 0.0;
+  std::vector<void*> owned;
+  double* d_partials = nullptr;
+  unsigned int* d_ticket = nullptr;
+  // per-call scratch
+  std::vector<double> consts, dlnI;  // dlnI: per slot, d ln I_leaf / d slot (0 for functor slots)
+  std::vector<double> slots;
+};
+
+struct znll_plan {
+  int device = 0, sm_count = 148;
+  std::vector<Channel> ch;
+  cudaStream_t stream = nullptr;
+  double* d_acc = nullptr;
+  double* h_acc = nullptr;  // pinned
+  int total_acc = 0, total_slots = 0;
+  long long launches = 0;
+  int max_grid = 0;
+};
+
+static void relayout(znll_plan* p) {
+  int a = 0, s = 0;
+  for (auto& c : p->ch) {
+    c.acc_off = a;
+    c.slot_off = s;
+    a += c.n_acc;
+    s += c.n_slots;
+  }
+  p->total_acc = a;
+  p->total_slots = s;
+}
+
+// recursive pre-order parse; returns index after the subtree
+static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int parent_frac_slot, std::string& name,
+                 int depth) {
+  if (i >= n_nodes) return -1;
+  if (depth > 16) return -1;
+  NodeInfo ni;
+  ni.nd = nodes[i];
+  ni.slot_off = c.n_slots;
+  ni.const_off = c.n_consts;
+  ni.parent_sum_frac_slot = parent_frac_slot;
+  const znll_node& nd = nodes[i];
+  char buf[64];
+  if (nd.kind == ZNLL_SUM || nd.kind == ZNLL_PROD) {
+    if (nd.n_children < 1 || nd.n_children > 16) return -1;
+    const bool is_sum = nd.kind == ZNLL_SUM;
+    if (is_sum) {
+      c.n_slots += nd.n_children;
+      c.n_consts += nd.n_children;
+    }
+    c.nodes.push_back(ni);
+    name += is_sum ? "Sum<" : "Prod<";
+    int j = i + 1;
+    for (int k = 0; k < nd.n_children; ++k) {
+      if (k) name += ",";
+      j = parse(c, nodes, n_nodes, j, is_sum ? ni.slot_off + k : parent_frac_slot, name, depth + 1);
+      if (j < 0) return -1;
+    }
+    name += ">";
+    return j;
+  }
+  const int ns = leaf_n_slots(nd), nc = leaf_n_consts(nd);
+  if (ns < 0 || nd.n_children != 0) return -1;
+  if (nd.column < 0 || nd.column >= ZNLL_MAX_COLS) return -1;
+  if (nd.kind == ZNLL_CHEB && (nd.degree < 0 || nd.degree > 16)) return -1;
+  c.n_slots += ns;
+  c.n_consts += nc;
+  c.nodes.push_back(ni);
+  switch (nd.kind) {
+    case ZNLL_GAUSS: snprintf(buf, sizeof buf, "Gauss<%d>", nd.column); break;
+    case ZNLL_EXP: snprintf(buf, sizeof buf, "Expo<%d>", nd.column); break;
+    case ZNLL_CB: snprintf(buf, sizeof buf, "CBall<%d>", nd.column); break;
+    default: snprintf(buf, sizeof buf, "Cheb<%d,%d>", nd.column, nd.degree); break;
+  }
+  name += buf;
+  return i + 1;
+}
+
+// prologue: slots -> consts (+ d ln I / d slot for the epilogue)
+static void fill_consts(Channel& c, const double* slots) {
+  c.consts.assign(c.n_consts, 0.0);
+  c.dlnI.assign(c.n_slots, 0.0);
+  for (auto& ni : c.nodes) {
+    const znll_node& nd = ni.nd;
+    const double* s = slots + ni.slot_off;
+    double* k = c.consts.data() + ni.const_off;
+    if (nd.kind == ZNLL_SUM) {
+      for (int i = 0; i < nd.n_children; ++i) k[i] = s[i];
+      continue;
+    }
+    if (nd.kind == ZNLL_PROD) continue;
+    double I = 0.0, dI[32];
+    leaf_integral(nd, s, &I, dI);
+    const int ns = leaf_n_slots(nd);
+    for (int i = 0; i < ns; ++i) c.dlnI[ni.slot_off + i] = dI[i] / I;
+    const double lnI = log(I);  // I <= 0 -> NaN, which must reach the caller (never an error)
+    switch (nd.kind) {
+      case ZNLL_GAUSS: {
+        const double mu = s[0], sigma = s[1];
+        k[0] = 1.0 / sigma;
+        k[1] = -(mu / sigma);
+        k[2] = -(kHalfLog2Pi + log(sigma)) - lnI;
+        break;
+      }
+      case ZNLL_EXP:
+        k[0] = s[0];
+        k[1] = nd.shift;
+        k[2] = -lnI;
+        break;
+      case ZNLL_CB: {
+        const double mu = s[0], sigma = s[1], alpha = s[2], n = s[3];
+        const double a = fabs(alpha), sg = alpha > 0 ? 1.0 : (alpha < 0 ? -1.0 : 0.0);
+        k[0] = mu;
+        k[1] = sg / sigma;
+        k[2] = 1.0 / sigma;
+        k[3] = a;
+        k[4] = n;
+        k[5] = n / a - a;
+        k[6] = n * log(n / a) - 0.5 * a * a - lnI;
+        k[7] = -lnI;
+        k[8] = log(n / a) + 1.0;
+        k[9] = 1.0 / a;
+        k[10] = -n / a - a;
+        k[11] = n / (a * a) + 1.0;
+        k[12] = sg;
+        break;
+      }
+      case ZNLL_CHEB: {
+        k[0] = 2.0 / (nd.space_hi - nd.space_lo);
+        k[1] = -(nd.space_lo + nd.space_hi) / (nd.space_hi - nd.space_lo);
+        k[2] = 1.0 / I;
+        for (int i = 0; i <= nd.degree; ++i) k[3 + i] = s[i] / I;
+        break;
+      }
+    }
+  }
+}
+
+// epilogue: raw accumulators -> channel NLL value and d value / d slot
+static void finish(const Channel& c, const double* acc, uint32_t flags, double* value, double* grad) {
+  const double S = acc[0] - acc[1];
+  *value = -S;
+  if (!(flags & ZNLL_WANT_GRAD) || !grad) return;
+  for (int j = 0; j < c.n_slots; ++j) grad[j] = acc[2 + j];
+  for (auto& ni : c.nodes) {
+    if (ni.nd.kind == ZNLL_SUM || ni.nd.kind == ZNLL_PROD) continue;
+    // K = sum_i w_i * d l_i / d(-ln I_leaf): the leaf's responsibility, read off the nearest Sum
+    // ancestor's fraction accumulator, or sum(w) when the leaf is only under products.
+    double K;
+    if (ni.parent_sum_frac_slot >= 0)
+      K = c.slots[ni.parent_sum_frac_slot] * acc[2 + ni.parent_sum_frac_slot];
+    else
+      K = c.sumw;
+    const int ns = leaf_n_slots(ni.nd);
+    for (int i = 0; i < ns; ++i) grad[ni.slot_off + i] -= K * c.dlnI[ni.slot_off + i];
+  }
+  for (int j = 0; j < c.n_slots; ++j) grad[j] = -grad[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// NVRTC path: same templates, instantiated at run time for tree shapes outside the catalogue
+// ------------------------------------------------------------------------------------------------
+extern "C" const char znll_device_src[];  // generated from znll_device.cuh at build time
+
+namespace rtc {
+typedef int (*nvrtcCreateProgram_t)(void**, const char*, const char*, int, const char* const*, const char* const*);
+typedef int (*nvrtcCompileProgram_t)(void*, int, const char* const*);
+typedef int (*nvrtcAddNameExpression_t)(void*, const char*);
+typedef int (*nvrtcGetLoweredName_t)(void*, const char*, const char**);
+typedef int (*nvrtcGetCUBINSize_t)(void*, size_t*);
+typedef int (*nvrtcGetCUBIN_t)(void*, char*);
+typedef int (*nvrtcGetProgramLogSize_t)(void*, size_t*);
+typedef int (*nvrtcGetProgramLog_t)(void*, char*);
+typedef int (*nvrtcDestroyProgram_t)(void**);
+typedef int (*cuModuleLoadData_t)(void**, const void*);
+typedef int (*cuModuleGetFunction_t)(void**, void*, const char*);
+typedef int (*cuLaunchKernel_t)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*,
+                                void**, void**);
+struct Api {
+  bool ok = false;
+  std::string why;
+  nvrtcCreateProgram_t create;
+  nvrtcCompileProgram_t compile;
+  nvrtcAddNameExpression_t addname;
+  nvrtcGetLoweredName_t lowered;
+  nvrtcGetCUBINSize_t cubinsize;
+  nvrtcGetCUBIN_t cubin;
+  nvrtcGetProgramLogSize_t logsize;
+  nvrtcGetProgramLog_t log;
+  nvrtcDestroyProgram_t destroy;
+  cuModuleLoadData_t modload;
+  cuModuleGetFunction_t getfn;
+  cuLaunchKernel_t launch;
+};
+static Api& api() {
+  static Api a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* hn = nullptr;
+    const char* nv[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+    for (auto n : nv)
+      if ((hn = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!hn || !hc) {
+      a.why = !hn ? "libnvrtc.so.12 not found" : "libcuda.so.1 not found";
+      return;
+    }
+#define L(h, field, sym)                                   \
+  a.field = (decltype(a.field))dlsym(h, sym);              \
+  if (!a.field) {                                          \
+    a.why = std::string("missing symbol ") + sym;          \
+    return;                                                \
+  }
+    L(hn, create, "nvrtcCreateProgram")
+    L(hn, compile, "nvrtcCompileProgram")
+    L(hn, addname, "nvrtcAddNameExpression")
+    L(hn, lowered, "nvrtcGetLoweredName")
+    L(hn, cubinsize, "nvrtcGetCUBINSize")
+    L(hn, cubin, "nvrtcGetCUBIN")
+    L(hn, logsize, "nvrtcGetProgramLogSize")
+    L(hn, log, "nvrtcGetProgramLog")
+    L(hn, destroy, "nvrtcDestroyProgram")
+    L(hc, modload, "cuModuleLoadData")
+    L(hc, getfn, "cuModuleGetFunction")
+    L(hc, launch, "cuLaunchKernel")
+#undef L
+    a.ok = true;
+  });
+  return a;
+}
+
+static std::mutex g_mu;
+static std::map<std::string, Kernel> g_cache;
+
+// compile nll_kernel<Model, W, G> for the four (W, G) variants
+static int build(const std::string& model, Kernel* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_cache.find(model);
+  if (it != g_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  Api& a = api();
+  if (!a.ok) return fail("model '%s' is not in the ahead-of-time catalogue and NVRTC is unavailable (%s)",
+                         model.c_str(), a.why.c_str());
+  std::string src = std::string(znll_device_src) + "\n";
+  void* prog = nullptr;
+  if (a.create(&prog, src.c_str(), "znll_rtc.cu", 0, nullptr, nullptr)) return fail("nvrtcCreateProgram failed");
+  std::string exprs[2][2];
+  // qualify nested names: insert "znll::" before every identifier that starts a template name
+  auto qualify = [](const std::string& m) {
+    std::string o;
+    size_t i = 0;
+    while (i < m.size()) {
+      if (isalpha((unsigned char)m[i])) {
+        size_t j = i;
+        while (j < m.size() && (isalnum((unsigned char)m[j]) || m[j] == '_')) ++j;
+        o += "znll::" + m.substr(i, j - i);
+        i = j;
+      } else {
+        o += m[i++];
+      }
+    }
+    return o;
+  };
+  const std::string q = qualify(model);
+  for (int w = 0; w < 2; ++w)
+    for (int g = 0; g < 2; ++g) {
+      exprs[w][g] = "znll::nll_kernel<" + q + "," + (w ? "true" : "false") + "," + (g ? "true" : "false") + ">";
+      a.addname(prog, exprs[w][g].c_str());
+    }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  const int rc = a.compile(prog, 3, opts);
+  if (rc) {
+    size_t n = 0;
+    a.logsize(prog, &n);
+    std::string log(n + 1, 0);
+    a.log(prog, &log[0]);
+    a.destroy(&prog);
+    return fail("NVRTC compile of '%s' failed: %.800s", model.c_str(), log.c_str());
+  }
+  size_t sz = 0;
+  a.cubinsize(prog, &sz);
+  std::vector<char> cubin(sz);
+  a.cubin(prog, cubin.data());
+  void* mod = nullptr;
+  cudaFree(0);  // make sure the primary context is current
+  if (a.modload(&mod, cubin.data())) {
+    a.destroy(&prog);
+    return fail("cuModuleLoadData failed for '%s'", model.c_str());
+  }
+  Kernel k;
+  k.name = model;
+  k.origin = 2;
+  for (int w = 0; w < 2; ++w)
+    for (int g = 0; g < 2; ++g) {
+      const char* low = nullptr;
+      a.lowered(prog, exprs[w][g].c_str(), &low);
+      if (!low || a.getfn(&k.cufunc[w][g], mod, low)) {
+        a.destroy(&prog);
+        return fail("cuModuleGetFunction failed for '%s'", exprs[w][g].c_str());
+      }
+    }
+  a.destroy(&prog);
+  g_cache[model] = k;
+  *out = k;
+  return 0;
+}
+
+static int launch(const Kernel& k, int w, int g, const ZnllLaunchArgs& la, const double* consts, int n_consts,
+                  int grid, cudaStream_t stream) {
+  // parameter block == znll::KArgs<NC>: the ZnllLaunchArgs prefix followed by NC doubles
+  std::vector<char> buf(sizeof(ZnllLaunchArgs) + sizeof(double) * (n_consts > 0 ? n_consts : 1));
+  memcpy(buf.data(), &la, sizeof(la));
+  memcpy(buf.data() + sizeof(la), consts, sizeof(double) * n_consts);
+  void* params[] = {buf.data()};
+  const int rc = api().launch(k.cufunc[w][g], grid, 1, 1, 256, 1, 1, 0, stream, params, nullptr);
+  if (rc) return fail("cuLaunchKernel failed with CUresult %d for '%s'", rc, k.name.c_str());
+  return 0;
+}
+}  // namespace rtc
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int znll_abi_version(void) { return ZNLL_ABI_VERSION; }
+const char* znll_last_error(void) { return g_err; }
+
+int znll_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int znll_plan_create(int device, int n_channels, znll_plan** out) {
+  if (!out || n_channels < 1) return fail("znll_plan_create: bad arguments");
+  if (znll_device_count() < 1)
+    return fail("znll_plan_create: no CUDA device visible; this library has no CPU fallback");
+  CUDA_OK(cudaSetDevice(device));
+  znll_plan* p = new znll_plan();
+  p->device = device;
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  p->sm_count = prop.multiProcessorCount;
+  p->max_grid = p->sm_count * 2;  // persistent: 2 resident CTAs of 256 threads per SM
+  p->ch.resize(n_channels);
+  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  *out = p;
+  return 0;
+}
+
+static void free_channel_data(Channel& c) {
+  for (void* q : c.owned) cudaFree(q);
+  c.owned.clear();
+  c.bound = false;
+}
+
+void znll_plan_destroy(znll_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (auto& c : p->ch) {
+    free_channel_data(c);
+    if (c.d_partials) cudaFree(c.d_partials);
+    if (c.d_ticket) cudaFree(c.d_ticket);
+  }
+  if (p->d_acc) cudaFree(p->d_acc);
+  if (p->h_acc) cudaFreeHost(p->h_acc);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int znll_plan_set_model(znll_plan* p, int ch, const znll_node* nodes, int n_nodes) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size() || !nodes || n_nodes < 1) return fail("znll_plan_set_model: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  Channel& c = p->ch[ch];
+  c.nodes.clear();
+  c.n_slots = c.n_consts = 0;
+  std::string name;
+  const int end = parse(c, nodes, n_nodes, 0, -1, name, 0);
+  if (end != n_nodes) return fail("znll_plan_set_model: malformed tree (parsed %d of %d nodes)", end, n_nodes);
+  c.n_acc = 2 + c.n_slots;
+  if (c.n_acc > 250) return fail("znll_plan_set_model: too many slots (%d)", c.n_slots);
+  Kernel k;
+  if (const ZnllCatalogEntry* e = znll_catalog_find(name.c_str())) {
+    if (e->n_slots != c.n_slots || e->n_consts != c.n_consts)
+      return fail("catalogue entry '%s' disagrees with the host layout (%d/%d vs %d/%d)", name.c_str(), e->n_slots,
+                  e->n_consts, c.n_slots, c.n_consts);
+    k.name = name;
+    k.origin = 1;
+    k.aot = e;
+  } else {
+    if (rtc::build(name, &k)) return 1;
+  }
+  c.kernel = k;
+  if (c.d_partials) cudaFree(c.d_partials), c.d_partials = nullptr;
+  if (!c.d_ticket) {
+    CUDA_OK(cudaMalloc(&c.d_ticket, sizeof(unsigned int)));
+    CUDA_OK(cudaMemset(c.d_ticket, 0, sizeof(unsigned int)));
+  }
+  CUDA_OK(cudaMalloc(&c.d_partials, sizeof(double) * (size_t)p->max_grid * c.n_acc));
+  relayout(p);
+  if (p->d_acc) cudaFree(p->d_acc), p->d_acc = nullptr;
+  if (p->h_acc) cudaFreeHost(p->h_acc), p->h_acc = nullptr;
+  CUDA_OK(cudaMalloc(&p->d_acc, sizeof(double) * p->total_acc));
+  CUDA_OK(cudaMemset(p->d_acc, 0, sizeof(double) * p->total_acc));
+  CUDA_OK(cudaMallocHost(&p->h_acc, sizeof(double) * p->total_acc));
+  return 0;
+}
+
+static int grid_for(const znll_plan* p, long long n) {
+  const long long nvec = (n + 1) / 2;  // two events per thread and iteration
+  long long g = (nvec + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > p->max_grid) g = p->max_grid;
+  return (int)g;
+}
+
+static int compute_sumw(znll_plan* p, Channel& c) {
+  if (!c.w) {
+    c.sumw = (double)c.n;
+    return 0;
+  }
+  if (c.n == 0) {
+    c.sumw = 0.0;
+    return 0;
+  }
+  double *d_part = nullptr, *d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_part, sizeof(double) * 2 * p->max_grid));
+  CUDA_OK(cudaMalloc(&d_out, sizeof(double) * 2));
+  const int grid = grid_for(p, c.n * 2);
+  cudaError_t e = znll_launch_sumw(c.w, c.n, d_part, c.d_ticket, d_out, grid, p->stream);
+  p->launches++;
+  double h[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  cudaFree(d_part);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail("sum of weights failed: %s", cudaGetErrorString(e));
+  c.sumw = h[0] - h[1];
+  return 0;
+}
+
+int znll_plan_bind_device(znll_plan* p, int ch, int n_cols, const double* const* cols_dev, const double* w_dev,
+                          int64_t n_events) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size() || n_cols < 1 || n_cols > ZNLL_MAX_COLS || !cols_dev || n_events < 0)
+    return fail("znll_plan_bind_device: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  Channel& c = p->ch[ch];
+  if (c.nodes.empty()) return fail("znll_plan_bind_device: set the model of channel %d first", ch);
+  for (auto& ni : c.nodes)
+    if (ni.nd.kind < ZNLL_SUM && ni.nd.column >= n_cols)
+      return fail("znll_plan_bind_device: model reads column %d but only %d bound", ni.nd.column, n_cols);
+  free_channel_data(c);
+  for (int i = 0; i < ZNLL_MAX_COLS; ++i) c.cols[i] = nullptr;
+  for (int i = 0; i < n_cols; ++i) {
+    if (n_events > 0 && (!cols_dev[i] || ((uintptr_t)cols_dev[i] & 15)))
+      return fail("znll_plan_bind_device: column %d is null or not 16-byte aligned", i);
+    c.cols[i] = cols_dev[i];
+  }
+  if (w_dev && ((uintptr_t)w_dev & 15)) return fail("znll_plan_bind_device: weights not 16-byte aligned");
+  c.w = w_dev;
+  c.n_cols = n_cols;
+  c.n = n_events;
+  c.bound = true;
+  return compute_sumw(p, c);
+}
+
+int znll_plan_bind_host(znll_plan* p, int ch, int n_cols, const double* const* cols_host, const double* w_host,
+                        int64_t n_events) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size() || n_cols < 1 || n_cols > ZNLL_MAX_COLS || !cols_host || n_events < 0)
+    return fail("znll_plan_bind_host: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  Channel& c = p->ch[ch];
+  free_channel_data(c);
+  std::vector<const double*> dev(n_cols);
+  std::vector<void*> owned;
+  const size_t bytes = sizeof(double) * (size_t)(n_events > 0 ? n_events : 1);
+  for (int i = 0; i <= n_cols; ++i) {
+    const double* src = i < n_cols ? cols_host[i] : w_host;
+    if (i == n_cols && !w_host) break;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e == cudaSuccess && n_events > 0) e = cudaMemcpy(d, src, sizeof(double) * (size_t)n_events, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      for (void* q : owned) cudaFree(q);
+      if (d) cudaFree(d);
+      return fail("znll_plan_bind_host: %s", cudaGetErrorString(e));
+    }
+    owned.push_back(d);
+    if (i < n_cols) dev[i] = (const double*)d;
+  }
+  const double* wd = w_host ? (const double*)owned.back() : nullptr;
+  const int rc = znll_plan_bind_device(p, ch, n_cols, dev.data(), wd, n_events);
+  if (rc) {
+    for (void* q : owned) cudaFree(q);
+    return rc;
+  }
+  p->ch[ch].owned = owned;
+  return 0;
+}
+
+int znll_plan_get_sumw(znll_plan* p, int ch, double* sumw) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size() || !sumw) return fail("znll_plan_get_sumw: bad arguments");
+  *sumw = p->ch[ch].sumw;
+  return 0;
+}
+int znll_plan_set_sumw(znll_plan* p, int ch, double sumw) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size()) return fail("znll_plan_set_sumw: bad arguments");
+  p->ch[ch].sumw = sumw;
+  return 0;
+}
+
+int znll_plan_n_slots(const znll_plan* p, int ch) { return (p && ch >= 0 && ch < (int)p->ch.size()) ? p->ch[ch].n_slots : -1; }
+int znll_plan_n_acc(const znll_plan* p, int ch) { return (p && ch >= 0 && ch < (int)p->ch.size()) ? p->ch[ch].n_acc : -1; }
+int znll_plan_total_slots(const znll_plan* p) { return p ? p->total_slots : -1; }
+int znll_plan_total_acc(const znll_plan* p) { return p ? p->total_acc : -1; }
+const char* znll_plan_kernel_name(const znll_plan* p, int ch) {
+  return (p && ch >= 0 && ch < (int)p->ch.size()) ? p->ch[ch].kernel.name.c_str() : "";
+}
+int znll_plan_kernel_origin(const znll_plan* p, int ch) {
+  return (p && ch >= 0 && ch < (int)p->ch.size()) ? p->ch[ch].kernel.origin : 0;
+}
+int64_t znll_plan_launch_count(const znll_plan* p) { return p ? p->launches : 0; }
+double* znll_plan_acc_device(znll_plan* p) { return p ? p->d_acc : nullptr; }
+
+int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_offset, void* stream) {
+  if (!p || !slots) return fail("znll_launch: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  const int g = (flags & ZNLL_WANT_GRAD) ? 1 : 0;
+  for (auto& c : p->ch) {
+    if (c.nodes.empty() || !c.bound) return fail("znll_launch: channel without model or data");
+    c.slots.assign(slots + c.slot_off, slots + c.slot_off + c.n_slots);
+    fill_consts(c, c.slots.data());
+    if (c.n == 0) {  // empty shard: contributes exact zeros
+      CUDA_OK(cudaMemsetAsync(p->d_acc + c.acc_off, 0, sizeof(double) * c.n_acc, st));
+      continue;
+    }
+    ZnllLaunchArgs la;
+    for (int i = 0; i < ZNLL_MAX_COLS; ++i) la.cols[i] = c.cols[i];
+    la.w = c.w;
+    la.n = c.n;
+    la.log_offset = log_offset;
+    la.partials = c.d_partials;
+    la.ticket = c.d_ticket;
+    la.out = p->d_acc + c.acc_off;
+    const int w = c.w ? 1 : 0;
+    const int grid = grid_for(p, c.n);
+    if (c.kernel.origin == 1) {
+      cudaError_t e = c.kernel.aot->fn[w][g](la, c.consts.data(), grid, st);
+      if (e != cudaSuccess) return fail("kernel launch failed (%s): %s", c.kernel.name.c_str(), cudaGetErrorString(e));
+    } else {
+      if (rtc::launch(c.kernel, w, g, la, c.consts.data(), c.n_consts, grid, st)) return 1;
+    }
+    p->launches++;
+  }
+  return 0;
+}
+
+int znll_collect(znll_plan* p, uint32_t flags, double* values, double* grad_slots, void* stream) {
+  if (!p || !values) return fail("znll_collect: bad arguments");
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  CUDA_OK(cudaMemcpyAsync(p->h_acc, p->d_acc, sizeof(double) * p->total_acc, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (size_t k = 0; k < p->ch.size(); ++k) {
+    const Channel& c = p->ch[k];
+    finish(c, p->h_acc + c.acc_off, flags, &values[k], grad_slots ? grad_slots + c.slot_off : nullptr);
+  }
+  return 0;
+}
+
+int znll_eval(znll_plan* p, const double* slots, uint32_t flags, double log_offset, double* values,
+              double* grad_slots, void* stream) {
+  if (znll_launch(p, slots, flags, log_offset, stream)) return 1;
+  return znll_collect(p, flags, values, grad_slots, stream);
+}
+
+int znll_leaf_integral(const znll_node* leaf, const double* slots, double* integral, double* dintegral) {
+  if (!leaf || !slots || !integral || !dintegral) return fail("znll_leaf_integral: bad arguments");
+  if (leaf_n_slots(*leaf) < 0) return fail("znll_leaf_integral: node kind %d is not a leaf", leaf->kind);
+  return leaf_integral(*leaf, slots, integral, dintegral);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// FP64 pipe micro-benchmark (roofline denominator)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) dfma_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3, x4 = x0 + 4e-3, x5 = x0 + 5e-3,
+         x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int znll_fp64_peak(int device, double ms, double* tflops) {
+  if (!tflops) return fail("znll_fp64_peak: bad arguments");
+  if (znll_device_count() < 1) return fail("znll_fp64_peak: no CUDA device");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount * 2 * 4, block = 256;
+  double* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, sizeof(double) * (size_t)grid * block));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int iters = 2000;
+  dfma_kernel<<<grid, block>>>(d, 200, 0.999999, 1e-7);  // warm-up
+  float t = 0.f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    dfma_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-7);
+    cudaEventRecord(e1);
+    CUDA_OK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&t, e0, e1);
+    if (t >= ms || rep == 5) break;
+    iters = (int)(iters * (ms / (t > 1e-3f ? t : 1e-3f)) * 1.05) + 1;
+  }
+  const double flops = 2.0 * 8 * 16 * (double)iters * (double)grid * block;
+  *tflops = flops / (t * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return 0;
+}

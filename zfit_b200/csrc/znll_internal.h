@@ -1,0 +1,31 @@
+// znll_internal.h -- shared between the host side (znll_host.cu) and the kernel catalogue TUs.
+#pragma once
+#include <cuda_runtime.h>
+
+struct ZnllLaunchArgs {
+  const double* cols[8];
+  const double* w;
+  long long n;
+  double log_offset;
+  double* partials;
+  unsigned int* ticket;
+  double* out;
+};
+
+// launches nll_kernel<M, WEIGHTED, GRAD> with `grid` blocks of 256 threads on `stream`
+typedef cudaError_t (*znll_launcher_t)(const ZnllLaunchArgs&, const double* consts, int grid, cudaStream_t stream);
+
+struct ZnllCatalogEntry {
+  const char* name;        // canonical type name, e.g. "Sum<CBall<0>,Expo<0>>"
+  int n_slots, n_consts;
+  znll_launcher_t fn[2][2];  // [weighted][grad]
+};
+
+// each catalogue TU registers its instantiations at static-init time
+void znll_catalog_register(const ZnllCatalogEntry* entries, int n);
+const ZnllCatalogEntry* znll_catalog_find(const char* name);
+int znll_catalog_size();
+const ZnllCatalogEntry* znll_catalog_at(int i);
+
+cudaError_t znll_launch_sumw(const double* w, long long n, double* partials, unsigned int* ticket, double* out,
+                             int grid, cudaStream_t stream);
