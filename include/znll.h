@@ -136,6 +136,10 @@ int znll_launch(znll_plan* plan, const double* slots, uint32_t flags, double log
 double* znll_plan_acc_device(znll_plan* plan);
 int znll_collect(znll_plan* plan, uint32_t flags, double* values, double* grad_slots, void* stream);
 
+/* Per-event normalised pdf values of channel ch on its bound events: out_host[n_events].
+ * Replaces BasePDF.pdf (core/basepdf.py:398-429) for plotting / diagnostics; not on the fit's hot path. */
+int znll_pdf(znll_plan* plan, int ch, const double* slots, double* out_host, void* stream);
+
 /* Host-only helpers (no GPU needed): normalisation integral of one leaf and d I / d slot, exactly
  * as the per-call prologue computes them.  Replaces the registered analytic integrals
  * (dist_tfp.py:113-120, basic.py:211-229, physics.py:83-142, polynomials.py:443-478). */

@@ -1,0 +1,131 @@
+"""Test double with the ``CudaEngine`` interface, backed by the CPU oracle (tests only).
+
+It lets the host layer (parameter ordering, chain rule through composed parameters, extended term,
+offsets, minimizer protocol) run on a CPU box, and gives the reference-side numbers for the GPU parity
+tests.  The lowered ``znll_node`` trees are translated back into oracle PDF trees whose parameters are
+the slots ``s0, s1, ...`` -- so the oracle differentiates with respect to exactly what the kernel does.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import nll as ON
+from oracle import pdfs as O
+from zfit_b200 import _znll as Z
+from zfit_b200 import distributed as D
+
+
+def _translate(nodes, obs, i, slot, in_prod):
+    nd = nodes[i]
+    if nd.kind == Z.SUM:
+        fr = [f"s{slot + k}" for k in range(nd.n_children)]
+        slot += nd.n_children
+        kids = []
+        j = i + 1
+        for _ in range(nd.n_children):
+            kid, j, slot = _translate(nodes, obs, j, slot, False)
+            kids.append(kid)
+        return _Sum(kids, fr), j, slot
+    if nd.kind == Z.PROD:
+        kids = []
+        j = i + 1
+        for _ in range(nd.n_children):
+            kid, j, slot = _translate(nodes, obs, j, slot, True)
+            kids.append(kid)
+        return O.ProductPDF(kids), j, slot
+    o = obs[nd.column]
+    lim = (nd.norm_lo, nd.norm_hi)
+    if nd.kind == Z.GAUSS:
+        return O.Gauss(f"s{slot}", f"s{slot + 1}", o, lim), i + 1, slot + 2
+    if nd.kind == Z.EXP:
+        return O.Exponential(f"s{slot}", o, lim), i + 1, slot + 1
+    if nd.kind == Z.CB:
+        return O.CrystalBall(f"s{slot}", f"s{slot + 1}", f"s{slot + 2}", f"s{slot + 3}", o, lim), i + 1, slot + 4
+    if nd.kind == Z.CHEB:
+        assert (nd.space_lo, nd.space_hi) == lim, "oracle translation needs norm == space for Chebyshev"
+        names = [f"s{slot + k}" for k in range(nd.degree + 1)]
+        return O.Chebyshev(names[1:], o, lim, coeff0=names[0]), i + 1, slot + nd.degree + 1
+    raise AssertionError(nd.kind)
+
+
+class _Sum:
+    def __init__(self, pdfs, fracs):
+        self.pdfs, self.fr = pdfs, fracs
+        self.limits = getattr(pdfs[0], "limits", None)
+
+    def pdf(self, B, x, P, norm=None):
+        tot = None
+        for p, f in zip(self.pdfs, self.fr):
+            t = p.pdf(B, x, P) * P[f]
+            tot = t if tot is None else tot + t
+        return tot
+
+    def integrate(self, B, P, limits, norm=False):  # fractions sum to one in the lowered cases
+        tot = None
+        for f in self.fr:
+            tot = P[f] if tot is None else tot + P[f]
+        return tot
+
+
+class OracleEngine:
+    def __init__(self, models, datas, fit_ranges):
+        self.slot_params = []
+        self.channels = []
+        for model, data, rng in zip(models, datas, fit_ranges):
+            nodes, slots = model._lower(data.obs, rng)
+            tree, end, ns = _translate(nodes, data.obs, 0, 0, False)
+            assert end == len(nodes) and ns == len(slots)
+            cols = {o: np.asarray(data.value(o)) for o in data.obs}
+            self.channels.append((tree, cols, data.weights, len(self.slot_params), ns))
+            self.slot_params.extend(slots)
+        self.n_local = [d.num_entries for d in datas]
+        self.samplesize = [d.samplesize for d in datas]
+        self.n_entries = list(self.n_local)
+        self.distributed = D.is_distributed()
+        if self.distributed:
+            import torch
+
+            t = torch.tensor(self.samplesize + [float(n) for n in self.n_local], dtype=torch.float64)
+            D.all_reduce_sum_(t, deterministic=True)
+            k = len(models)
+            self.samplesize = [float(v) for v in t[:k]]
+            self.n_entries = [int(round(float(v))) for v in t[k:]]
+        self.kernel_names = ["oracle"] * len(models)
+        self.ncalls = 0
+
+    def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
+        self.ncalls += 1
+        values, gs = [], np.zeros(len(self.slot_params))
+        for tree, cols, w, off, ns in self.channels:
+            names = [f"s{k}" for k in range(ns)]
+            theta = np.asarray(slots[off : off + ns], dtype=np.float64)
+            ww = None if w is None else [w]
+            if len(next(iter(cols.values()))) == 0:
+                values.append(0.0)
+                continue
+            if grad:
+                v, g = ON.value_and_gradient([tree], [cols], theta, names, weights=ww, log_offset=log_offset)
+                gs[off : off + ns] = g
+            else:
+                v = float(ON.unbinned_nll([tree], [cols], dict(zip(names, theta)), weights=ww, log_offset=log_offset))
+            values.append(v)
+        values = np.asarray(values, dtype=np.float64)
+        if self.distributed:
+            import torch
+
+            t = torch.from_numpy(np.concatenate([values, gs]))
+            D.all_reduce_sum_(t, deterministic=True)
+            values, gs = t[: len(values)].numpy().copy(), t[len(values) :].numpy().copy()
+        return values, (gs if grad else None)
+
+    def launch_count(self):
+        return 0
+
+    def close(self):
+        pass
+
+
+def use_oracle(loss):
+    loss._set_engine_factory(OracleEngine)
+    return loss

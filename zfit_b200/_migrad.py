@@ -1,0 +1,333 @@
+"""Native variable-metric minimizer with Minuit's conventions (stand-in driver when ``iminuit`` is absent).
+
+iminuit (C++ Minuit2) is what ``zfit.minimize.Minuit`` wraps (``src/zfit/minimizers/minimizer_minuit.py:175-319``);
+it is not installed in this image and cannot be.  This module implements the same *protocol* so that
+"Minuit fit wall time" is reportable and the loss is driven the way MIGRAD drives it:
+
+* parameter limits through Minuit's internal transformations (sin for two-sided, sqrt for one-sided),
+* a variable-metric (DFP with Minuit's rank-2 correction, ``DavidonErrorUpdator``) iteration with a
+  parabolic line search,
+* convergence on the estimated distance to minimum ``EDM = g^T V g / 2 < 0.002 * tol * errordef``
+  (with zfit's ``tol`` pre-divided by ``0.002 * errordef``, :313-315, that is ``EDM < zfit tol``),
+* a final HESSE (finite differences of the gradient) whose inverse is the covariance, with MIGRAD restarted
+  from it when the verified EDM is still above the goal (strategy 1 behaviour),
+* ``grad=None`` -> the driver's own finite-difference gradient of ``value`` (Minuit's default, :139-141).
+
+The driver only sees ``value(x)`` and ``gradient(x)`` callbacks of a ``LossEval``.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+class _Transform:
+    """Minuit2 ``SinParameterTransformation`` / ``SqrtLow/UpParameterTransformation``."""
+
+    def __init__(self, lower, upper):
+        self.lo = np.array([-np.inf if l is None else l for l in lower], dtype=np.float64)
+        self.up = np.array([np.inf if u is None else u for u in upper], dtype=np.float64)
+        self.both = np.isfinite(self.lo) & np.isfinite(self.up)
+        self.low_only = np.isfinite(self.lo) & ~np.isfinite(self.up)
+        self.up_only = ~np.isfinite(self.lo) & np.isfinite(self.up)
+
+    def to_internal(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        y = x.copy()
+        b = self.both
+        if b.any():
+            yy = 2.0 * (x[b] - self.lo[b]) / (self.up[b] - self.lo[b]) - 1.0
+            y[b] = np.arcsin(np.clip(yy, -1.0, 1.0))
+        m = self.low_only
+        if m.any():
+            y[m] = np.sqrt(np.maximum((x[m] - self.lo[m] + 1.0) ** 2 - 1.0, 0.0))
+        m = self.up_only
+        if m.any():
+            y[m] = np.sqrt(np.maximum((self.up[m] - x[m] + 1.0) ** 2 - 1.0, 0.0))
+        return y
+
+    def to_external(self, y):
+        y = np.asarray(y, dtype=np.float64)
+        x = y.copy()
+        b = self.both
+        if b.any():
+            x[b] = self.lo[b] + 0.5 * (self.up[b] - self.lo[b]) * (np.sin(y[b]) + 1.0)
+        m = self.low_only
+        if m.any():
+            x[m] = self.lo[m] - 1.0 + np.sqrt(y[m] ** 2 + 1.0)
+        m = self.up_only
+        if m.any():
+            x[m] = self.up[m] + 1.0 - np.sqrt(y[m] ** 2 + 1.0)
+        return x
+
+    def dext_dint(self, y):
+        y = np.asarray(y, dtype=np.float64)
+        d = np.ones_like(y)
+        b = self.both
+        if b.any():
+            d[b] = 0.5 * (self.up[b] - self.lo[b]) * np.cos(y[b])
+        m = self.low_only
+        if m.any():
+            d[m] = y[m] / np.sqrt(y[m] ** 2 + 1.0)
+        m = self.up_only
+        if m.any():
+            d[m] = -y[m] / np.sqrt(y[m] ** 2 + 1.0)
+        return d
+
+
+class MigradResult:
+    def __init__(self):
+        self.x = None
+        self.fval = None
+        self.edm = None
+        self.covariance = None
+        self.hessian = None
+        self.grad = None
+        self.valid = False
+        self.converged = False
+        self.nfcn = 0
+        self.ngrad = 0
+        self.message = ""
+        self.niter = 0
+
+
+def _num_grad(value, x, steps, fx):
+    g = np.zeros_like(x)
+    for i in range(x.size):
+        h = steps[i]
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h
+        xm[i] -= h
+        fp, fm = value(xp), value(xm)
+        g[i] = (fp - fm) / (2 * h)
+        # adapt the step like MnNumericalGradientCalculator: aim at |f''| h^2 ~ 8 eps^(2/3) |f| scale
+        g2 = (fp + fm - 2 * fx) / (h * h)
+        if np.isfinite(g2) and abs(g2) > 0:
+            hopt = math.sqrt(8.0 * 1e-11 * (abs(fx) + 1.0) / abs(g2))
+            steps[i] = min(max(hopt, 1e-9 * max(1.0, abs(x[i]))), 10 * h)
+    return g
+
+
+def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000, hesse=True, verbose=False):
+    """Variable-metric minimisation in Minuit's internal coordinates.
+
+    value(x_ext) -> float; gradient(x_ext) -> array or None (None: finite differences of value).
+    """
+    tr = _Transform(lower, upper)
+    res = MigradResult()
+    counter = {"f": 0, "g": 0}
+
+    def f_int(y):
+        counter["f"] += 1
+        return float(value(tr.to_external(y)))
+
+    num_steps = None
+
+    def g_int(y, fy=None):
+        if gradient is not None:
+            counter["g"] += 1
+            return np.asarray(gradient(tr.to_external(y)), dtype=np.float64) * tr.dext_dint(y)
+        if fy is None:
+            fy = f_int(y)
+        return _num_grad(f_int, y, num_steps, fy)
+
+    x0 = np.asarray(x0, dtype=np.float64)
+    y = tr.to_internal(x0)
+    n = y.size
+    d0 = np.abs(tr.dext_dint(y))
+    d0[d0 < 1e-8] = 1e-8
+    ysteps = np.abs(np.asarray(steps, dtype=np.float64)) / d0
+    ysteps = np.minimum(ysteps, 0.5)
+    num_steps = np.maximum(ysteps * 0.1, 1e-8)
+
+    f = f_int(y)
+    g = g_int(y, f)
+
+    def seed_metric(y, g):
+        """Diagonal seed from second derivatives along each axis (MnSeedGenerator)."""
+        V = np.zeros((n, n))
+        for i in range(n):
+            h = max(ysteps[i] * 0.05, 1e-7)
+            yp = y.copy()
+            yp[i] += h
+            if gradient is not None:
+                g2 = (g_int(yp)[i] - g[i]) / h
+            else:
+                ym = y.copy()
+                ym[i] -= h
+                g2 = (f_int(yp) + f_int(ym) - 2 * f) / (h * h)
+            if not np.isfinite(g2) or g2 <= 0:
+                g2 = 1.0 / max(ysteps[i] ** 2, 1e-16)
+            V[i, i] = 1.0 / g2
+        return V
+
+    def line_search(y, step, f0, gdel):
+        """Parabolic line search along `step` (MnLineSearch, simplified): returns (lambda, f) with f < f0 or (0, f0)."""
+        pts = []
+
+        def probe(lam):
+            fl = f_int(y + lam * step)
+            if np.isfinite(fl):
+                pts.append((lam, fl))
+            return fl
+
+        f1 = probe(1.0)
+        if np.isfinite(f1):
+            denom = 2.0 * (f1 - f0 - gdel)
+            lam2 = -gdel / denom if denom > 0 else 2.0
+            lam2 = min(max(lam2, 0.02), 8.0)
+        else:
+            lam2 = 0.1
+        if abs(lam2 - 1.0) > 0.02:
+            f2 = probe(lam2)
+            # one three-point refinement when both probes are finite and bracket something useful
+            if np.isfinite(f1) and np.isfinite(f2):
+                l1, l2 = 1.0, lam2
+                a = ((f1 - f0) / l1 - (f2 - f0) / l2) / (l1 - l2)
+                b = (f1 - f0) / l1 - a * l1
+                if a > 0:
+                    lam3 = min(max(-b / (2 * a), 0.01), 10.0)
+                    if min(abs(lam3 - l1), abs(lam3 - l2)) > 0.05 * lam3:
+                        probe(lam3)
+        best = min(pts, key=lambda t: t[1]) if pts else (0.0, f0)
+        lam = min([t[0] for t in pts], default=1.0)
+        tries = 0
+        while best[1] >= f0 and tries < 10:  # backtrack
+            tries += 1
+            lam *= 0.2
+            probe(lam)
+            best = min(pts, key=lambda t: t[1]) if pts else (0.0, f0)
+        if best[1] >= f0:
+            return 0.0, f0
+        return best
+
+    def verify(y, f, g, V):
+        """HESSE in internal coordinates; returns (converged, V, edm)."""
+        H = _hesse_internal(f_int, g_int, gradient is not None, y, f, g, V)
+        try:
+            w = np.linalg.eigvalsh(H)
+            if not np.all(w > 0):
+                return False, None, None
+            Vh = np.linalg.inv(H)
+        except np.linalg.LinAlgError:
+            return False, None, None
+        e = 0.5 * float(g @ Vh @ g)
+        return e < edm_goal, Vh, e
+
+    V = seed_metric(y, g)
+    edm = 0.5 * float(g @ V @ g)
+    restarts = 0
+    for it in range(1, 100000):
+        res.niter = it
+        if counter["f"] + counter["g"] > maxfcn:
+            res.message = "call limit reached"
+            break
+        if not (np.isfinite(f) and np.all(np.isfinite(g))):
+            res.message = "non-finite value or gradient"
+            break
+        if edm < edm_goal:
+            if not hesse:
+                res.converged = True
+                break
+            ok, Vh, e = verify(y, f, g, V)
+            if Vh is not None:
+                V, edm = Vh, e
+                if ok:
+                    res.converged = True
+                    break
+            elif restarts < 3:
+                restarts += 1
+                V = seed_metric(y, g)
+                edm = 0.5 * float(g @ V @ g)
+                if edm < edm_goal:  # the seed agrees that we are there; accept
+                    res.converged = True
+                    res.message = "converged (hesse not positive definite, seed metric used)"
+                    break
+            else:
+                res.message = "hesse failed: matrix not positive definite"
+                break
+        step = -V @ g
+        gdel = float(step @ g)
+        if gdel >= 0:  # metric not positive definite: reseed
+            V = seed_metric(y, g)
+            step = -V @ g
+            gdel = float(step @ g)
+            if gdel >= 0:
+                res.message = "no descent direction"
+                break
+        lam, f_new = line_search(y, step, f, gdel)
+        if lam == 0.0:
+            if restarts < 3:
+                restarts += 1
+                V = seed_metric(y, g)
+                edm = 0.5 * float(g @ V @ g)
+                if edm < edm_goal:
+                    continue
+                step = -V @ g
+                gdel = float(step @ g)
+                lam, f_new = line_search(y, step, f, gdel) if gdel < 0 else (0.0, f)
+            if lam == 0.0:
+                res.message = "line search failed to improve"
+                res.converged = edm < edm_goal
+                break
+        dy = lam * step
+        y_new = y + dy
+        g_new = g_int(y_new, f_new)
+        dg = g_new - g
+        # ---- DavidonErrorUpdator -----------------------------------------------------------------
+        delgam = float(dy @ dg)
+        Vg = V @ dg
+        gvg = float(dg @ Vg)
+        if delgam > 0 and gvg > 0:
+            V = V + np.outer(dy, dy) / delgam - np.outer(Vg, Vg) / gvg
+            if delgam > gvg:
+                flnu = dy / delgam - Vg / gvg
+                V = V + gvg * np.outer(flnu, flnu)
+        y, f, g = y_new, f_new, g_new
+        edm = 0.5 * float(g @ V @ g)
+        if verbose:
+            print(f"[migrad] it={it} f={f:.10g} edm={edm:.3g} lam={lam:.3g} nf={counter['f']} ng={counter['g']}")
+    x = tr.to_external(y)
+    res.x = x
+    res.fval = f
+    res.edm = edm
+    res.grad = g / np.where(np.abs(tr.dext_dint(y)) > 1e-300, tr.dext_dint(y), 1.0)
+    J = tr.dext_dint(y)
+    res.covariance = (V * J[:, None]) * J[None, :]
+    res.nfcn, res.ngrad = counter["f"], counter["g"]
+    res.valid = bool(res.converged and np.isfinite(f))
+    if res.converged and not res.message:
+        res.message = "converged"
+    return res
+
+
+def _hesse_internal(f_int, g_int, have_grad, y, f, g, V):
+    n = y.size
+    H = np.zeros((n, n))
+    sig = np.sqrt(np.maximum(np.diag(V), 1e-300))
+    if have_grad:
+        for i in range(n):
+            h = max(0.02 * sig[i], 1e-8)
+            yp, ym = y.copy(), y.copy()
+            yp[i] += h
+            ym[i] -= h
+            H[i, :] = (g_int(yp) - g_int(ym)) / (2 * h)
+        return 0.5 * (H + H.T)
+    hs = np.maximum(0.1 * sig, 1e-7)
+    fp = np.zeros(n)
+    fm = np.zeros(n)
+    for i in range(n):
+        yp, ym = y.copy(), y.copy()
+        yp[i] += hs[i]
+        ym[i] -= hs[i]
+        fp[i], fm[i] = f_int(yp), f_int(ym)
+        H[i, i] = (fp[i] + fm[i] - 2 * f) / hs[i] ** 2
+    for i in range(n):
+        for j in range(i + 1, n):
+            ypp = y.copy()
+            ypp[i] += hs[i]
+            ypp[j] += hs[j]
+            H[i, j] = H[j, i] = (f_int(ypp) + f - fp[i] - fp[j]) / (hs[i] * hs[j])
+    return H

@@ -66,6 +66,7 @@ SYMBOLS = {
     "znll_launch": (C.c_int, [C.c_void_p, _DP, C.c_uint32, C.c_double, C.c_void_p]),
     "znll_plan_acc_device": (C.c_void_p, [C.c_void_p]),
     "znll_collect": (C.c_int, [C.c_void_p, C.c_uint32, _DP, _DP, C.c_void_p]),
+    "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
     "znll_fp64_peak": (C.c_int, [C.c_int, C.c_double, _DP]),
 }
@@ -198,6 +199,12 @@ class Plan:
             )
         )
         return self._values.copy(), (self._grad[: self.total_slots].copy() if grad else None)
+
+    def pdf_values(self, ch: int, slots, n: int, stream=0):
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        out = np.empty(n, dtype=np.float64)
+        _check(lib().znll_pdf(self._h, ch, _dptr(slots), _dptr(out), C.c_void_p(stream)))
+        return out
 
     def launch(self, slots, *, grad=True, log_offset=0.0, stream=0):
         slots = np.ascontiguousarray(slots, dtype=np.float64)

@@ -21,6 +21,21 @@ cudaError_t launch_nll(const ZnllLaunchArgs& a, const double* consts, int grid, 
 }
 
 template <class M>
+cudaError_t launch_pdf(const ZnllLaunchArgs& a, const double* consts, int grid, cudaStream_t stream) {
+  KArgs<M::NC> k;
+  for (int i = 0; i < ZNLL_MAXCOL; ++i) k.cols[i] = a.cols[i];
+  k.w = a.w;
+  k.n = a.n;
+  k.log_offset = 0.0;
+  k.partials = a.partials;
+  k.ticket = a.ticket;
+  k.out = a.out;
+  for (int i = 0; i < M::NC; ++i) k.c[i] = consts[i];
+  pdf_kernel<M><<<grid, ZNLL_BLOCK, 0, stream>>>(k);
+  return cudaGetLastError();
+}
+
+template <class M>
 ZnllCatalogEntry make_entry(const char* name) {
   ZnllCatalogEntry e;
   e.name = name;
@@ -30,6 +45,7 @@ ZnllCatalogEntry make_entry(const char* name) {
   e.fn[0][1] = &launch_nll<M, false, true>;
   e.fn[1][0] = &launch_nll<M, true, false>;
   e.fn[1][1] = &launch_nll<M, true, true>;
+  e.pdf = &launch_pdf<M>;
   return e;
 }
 

@@ -486,6 +486,29 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 2) nll_kernel(const __grid_constan
   block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out);
 }
 
+// per-event normalised pdf values (BasePDF.pdf, core/basepdf.py:398-429): out[i] = P(x_i); args.partials = out
+template <class M>
+__global__ void __launch_bounds__(ZNLL_BLOCK, 2) pdf_kernel(const __grid_constant__ KArgs<M::NC> args) {
+  const double* __restrict__ c = args.c;
+  const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
+  for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < args.n; i += stride) {
+    double x[ZNLL_MAXCOL];
+#pragma unroll
+    for (int k = 0; k < ZNLL_MAXCOL; ++k)
+      if ((M::COLMASK >> k) & 1) x[k] = __ldg(args.cols[k] + i);
+    M m;
+    double p;
+    if constexpr (M::LOGNAT) {
+      bool neg = false;
+      const double lp = m.template fwd_log<0>(c, x, neg);
+      p = neg ? -exp(lp) : exp(lp);
+    } else {
+      p = m.template fwd_val<0>(c, x);
+    }
+    args.partials[i] = p;
+  }
+}
+
 // sum of weights with the same deterministic reduction (Data.samplesize, core/data.py:268-275)
 template <int UNUSED>
 __global__ void __launch_bounds__(ZNLL_BLOCK, 2)

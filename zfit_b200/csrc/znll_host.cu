@@ -240,6 +240,7 @@ struct Kernel {
   int origin = 0;  // 1 catalogue, 2 nvrtc
   const ZnllCatalogEntry* aot = nullptr;
   void* cufunc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // CUfunction, NVRTC path
+  void* cufunc_pdf = nullptr;
 };
 
 struct Channel {
@@ -523,6 +524,8 @@ static int build(const std::string& model, Kernel* out) {
       exprs[w][g] = "znll::nll_kernel<" + q + "," + (w ? "true" : "false") + "," + (g ? "true" : "false") + ">";
       a.addname(prog, exprs[w][g].c_str());
     }
+  const std::string pdf_expr = "znll::pdf_kernel<" + q + ">";
+  a.addname(prog, pdf_expr.c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const int rc = a.compile(prog, 3, opts);
   if (rc) {
@@ -555,21 +558,35 @@ static int build(const std::string& model, Kernel* out) {
         return fail("cuModuleGetFunction failed for '%s'", exprs[w][g].c_str());
       }
     }
+  {
+    const char* low = nullptr;
+    a.lowered(prog, pdf_expr.c_str(), &low);
+    if (!low || a.getfn(&k.cufunc_pdf, mod, low)) {
+      a.destroy(&prog);
+      return fail("cuModuleGetFunction failed for '%s'", pdf_expr.c_str());
+    }
+  }
   a.destroy(&prog);
   g_cache[model] = k;
   *out = k;
   return 0;
 }
 
+static int launch_fn(void* fn, const char* name, const ZnllLaunchArgs& la, const double* consts, int n_consts,
+                     int grid, cudaStream_t stream);
 static int launch(const Kernel& k, int w, int g, const ZnllLaunchArgs& la, const double* consts, int n_consts,
                   int grid, cudaStream_t stream) {
+  return launch_fn(k.cufunc[w][g], k.name.c_str(), la, consts, n_consts, grid, stream);
+}
+static int launch_fn(void* fn, const char* name, const ZnllLaunchArgs& la, const double* consts, int n_consts,
+                     int grid, cudaStream_t stream) {
   // parameter block == znll::KArgs<NC>: the ZnllLaunchArgs prefix followed by NC doubles
   std::vector<char> buf(sizeof(ZnllLaunchArgs) + sizeof(double) * (n_consts > 0 ? n_consts : 1));
   memcpy(buf.data(), &la, sizeof(la));
   memcpy(buf.data() + sizeof(la), consts, sizeof(double) * n_consts);
   void* params[] = {buf.data()};
-  const int rc = api().launch(k.cufunc[w][g], grid, 1, 1, 256, 1, 1, 0, stream, params, nullptr);
-  if (rc) return fail("cuLaunchKernel failed with CUresult %d for '%s'", rc, k.name.c_str());
+  const int rc = api().launch(fn, grid, 1, 1, 256, 1, 1, 0, stream, params, nullptr);
+  if (rc) return fail("cuLaunchKernel failed with CUresult %d for '%s'", rc, name);
   return 0;
 }
 }  // namespace rtc
@@ -832,6 +849,44 @@ int znll_eval(znll_plan* p, const double* slots, uint32_t flags, double log_offs
               double* grad_slots, void* stream) {
   if (znll_launch(p, slots, flags, log_offset, stream)) return 1;
   return znll_collect(p, flags, values, grad_slots, stream);
+}
+
+int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* stream) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size() || !slots || !out_host) return fail("znll_pdf: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  Channel& c = p->ch[ch];
+  if (c.nodes.empty() || !c.bound) return fail("znll_pdf: channel without model or data");
+  if (c.n == 0) return 0;
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  c.slots.assign(slots, slots + c.n_slots);
+  fill_consts(c, c.slots.data());
+  double* d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (size_t)c.n));
+  ZnllLaunchArgs la;
+  for (int i = 0; i < ZNLL_MAX_COLS; ++i) la.cols[i] = c.cols[i];
+  la.w = c.w;
+  la.n = c.n;
+  la.log_offset = 0.0;
+  la.partials = d_out;
+  la.ticket = c.d_ticket;
+  la.out = nullptr;
+  long long g = (c.n + 255) / 256;
+  if (g > p->max_grid * 4) g = p->max_grid * 4;
+  int rc = 0;
+  if (c.kernel.origin == 1) {
+    cudaError_t e = c.kernel.aot->pdf(la, c.consts.data(), (int)g, st);
+    if (e != cudaSuccess) rc = fail("pdf kernel launch failed: %s", cudaGetErrorString(e));
+  } else {
+    rc = rtc::launch_fn(c.kernel.cufunc_pdf, c.kernel.name.c_str(), la, c.consts.data(), c.n_consts, (int)g, st);
+  }
+  p->launches++;
+  cudaError_t e = cudaSuccess;
+  if (!rc) e = cudaMemcpyAsync(out_host, d_out, sizeof(double) * (size_t)c.n, cudaMemcpyDeviceToHost, st);
+  if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_out);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail("znll_pdf: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int znll_leaf_integral(const znll_node* leaf, const double* slots, double* integral, double* dintegral) {

@@ -19,6 +19,7 @@ struct ZnllCatalogEntry {
   const char* name;        // canonical type name, e.g. "Sum<CBall<0>,Expo<0>>"
   int n_slots, n_consts;
   znll_launcher_t fn[2][2];  // [weighted][grad]
+  znll_launcher_t pdf;       // per-event pdf values into args.partials
 };
 
 // each catalogue TU registers its instantiations at static-init time

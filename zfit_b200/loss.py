@@ -1,0 +1,712 @@
+"""``zfit.loss.UnbinnedNLL`` / ``ExtendedUnbinnedNLL`` on the fused CUDA kernel (``src/zfit/core/loss.py``).
+
+The minimizer-facing contract of ``BaseLoss`` is kept verbatim (``value``, ``gradient``,
+``value_gradient``, ``hessian``, ``value_gradient_hessian``, ``__call__``, ``get_params``, ``errordef``,
+``model`` / ``data`` / ``fit_range`` / ``constraints``, ``__add__``, ``create_new``).
+What changes is *how* a value + gradient is produced: instead of tracing ~25 TensorFlow ops per
+event and replaying them on a tape (``loss.py:73-142``, ``z/math.py:236-261``), one call
+
+  1. reads the current parameter values into the model trees' *slots*,
+  2. runs ONE fused kernel per channel (``znll_eval``: per-event composite pdf, analytic slot
+     derivatives, normalisation, log, weights, deterministic fp64 reduction),
+  3. applies d(slot)/d(theta) on the host (shared parameters, fractions from yields, user
+     ``ComposedParameter``), adds the extended Poisson term and the constraints.
+
+There is no CPU fallback: without the CUDA library / a GPU, evaluating raises.
+"""
+
+from __future__ import annotations
+
+import copy
+import math
+import warnings
+from collections.abc import Iterable, Mapping
+
+import numpy as np
+
+from . import distributed as _dist
+from .data import Data, convert_to_data
+from .exception import (
+    BreakingAPIChangeError,
+    IntentionAmbiguousError,
+    NotExtendedPDFError,
+    OutsideLimitsError,
+    ParamNameNotUniqueError,
+)
+from .parameter import OrderedSet, ZfitParameter, set_values
+from .pdf import BasePDF, CrystalBall
+from .space import Space
+
+DEFAULT_FULL_ARG = True  # loss.py:70
+
+
+# ------------------------------------------------------------------------------------------------
+# device engine
+# ------------------------------------------------------------------------------------------------
+class CudaEngine:
+    """Owns the ``znll_plan`` of a loss: lowered model trees, HBM-resident event columns, launches.
+
+    ``eval(slots, grad, log_offset) -> (values[n_channels], grad_slots[total_slots])`` -- already summed
+    over all ranks when ``torch.distributed`` is initialised with more than one rank (one NCCL all-reduce
+    of the raw ``sum(1 + n_slots)`` fp64 accumulators per call, issued on the launch stream).
+    """
+
+    def __init__(self, models, datas, fit_ranges, *, device=None, sort_events=True, deterministic_reduce=False):
+        from . import _znll as Z
+
+        self.Z = Z
+        self.distributed = _dist.is_distributed()
+        self.deterministic_reduce = deterministic_reduce
+        if device is None:
+            device = _dist.local_device()
+        self.device = device
+        self.plan = Z.Plan(len(models), device=device)
+        self.slot_params: list[ZfitParameter] = []
+        self.channel_slots: list[tuple[int, int]] = []
+        self._keep = []
+        self.n_local = []
+        import torch
+
+        self.torch = torch
+        for k, (model, data, rng) in enumerate(zip(models, datas, fit_ranges)):
+            if rng is not None:
+                data = data.with_obs(rng, guarantee_limits=False)
+            nodes, slots = model._lower(data.obs, rng)
+            self.plan.set_model(k, nodes)
+            start = len(self.slot_params)
+            self.slot_params.extend(slots)
+            self.channel_slots.append((start, len(self.slot_params)))
+            cols, w = data.device_columns(device)
+            n = data.num_entries
+            if sort_events and n > 1:
+                cols, w = self._sort_for_coherence(model, data, cols, w)
+            self._keep.append((cols, w))
+            self.plan.bind_device_ptrs(k, [c.data_ptr() for c in cols], 0 if w is None else w.data_ptr(), n)
+            self.n_local.append(n)
+        self.samplesize = [self.plan.sumw(k) for k in range(len(models))]
+        self.n_entries = list(self.n_local)
+        if self.distributed:
+            t = torch.tensor(self.samplesize + [float(n) for n in self.n_local], dtype=torch.float64, device=f"cuda:{device}")
+            _dist.all_reduce_sum_(t, deterministic=True)
+            t = t.cpu().numpy()
+            nch = len(models)
+            self.samplesize = [float(v) for v in t[:nch]]
+            self.n_entries = [int(round(v)) for v in t[nch:]]
+            for k in range(nch):
+                self.plan.set_sumw(k, self.samplesize[k])
+            self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
+        self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
+
+    def _sort_for_coherence(self, model, data, cols, w):
+        """Events are static for the whole fit and the NLL is a sum, so they may be reordered once at bind
+        time: sorting by the CrystalBall observable makes every warp uniformly core or tail."""
+        target = _first_leaf(model, CrystalBall)
+        if target is None:
+            return cols, w
+        torch = self.torch
+        i = data.obs.index(target.obs[0])
+        order = torch.argsort(cols[i])
+        cols = [c[order].contiguous() for c in cols]
+        if w is not None:
+            w = w[order].contiguous()
+        return cols, w
+
+    def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
+        if not self.distributed:
+            return self.plan.eval(slots, grad=grad, log_offset=log_offset, kahan=kahan)
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        self.plan.launch(slots, grad=grad, log_offset=log_offset, stream=stream)
+        _dist.all_reduce_sum_(self._acc, deterministic=self.deterministic_reduce)
+        return self.plan.collect(grad=grad, stream=stream)
+
+    def launch_count(self):
+        return self.plan.launch_count()
+
+    def close(self):
+        self.plan.close()
+
+
+def _first_leaf(model, cls):
+    if isinstance(model, cls):
+        return model
+    for m in getattr(model, "pdfs", []):
+        r = _first_leaf(m, cls)
+        if r is not None:
+            return r
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+def _to_list(x):
+    if x is None:
+        return []
+    if isinstance(x, (list,)):
+        return list(x)
+    return [x]
+
+
+class BaseLoss:
+    _name = "BaseLoss"
+
+    def __init__(self, model, data, fit_range=None, constraints=None, options=None):
+        if fit_range is not None and all(fr is not None for fr in _to_list(fit_range)):
+            warnings.warn(
+                "The fit_range argument is depreceated and will maybe removed in future releases. "
+                "It is preferred to define the range in the space"
+                " when creating the data and the model or directly cut the data correctly.",
+                stacklevel=2,
+            )
+        model, data, fit_range = self._input_check(model, data, fit_range)
+        self._model = model
+        self._data = data
+        self._fit_range = fit_range
+        self._options = self._check_init_options(options, data)
+        self._constraints = _constraint_check_convert(_to_list(constraints))
+        self._errordef = None
+        self._engine = None
+        self._engine_factory = None
+        self._assert_params_unique()
+
+    # ------------------------------------------------------------------ init helpers
+    def _check_init_options(self, options, data):  # loss.py:264-290
+        nevents = sum(d.num_entries for d in data)
+        options = {} if options is None else copy.copy(dict(options))
+        clean = copy.copy(options)
+        if options.pop("numhess", None) is None:
+            clean["numhess"] = True
+        if options.pop("numgrad", None) is None:
+            from . import settings
+
+            clean["numgrad"] = settings.options["numerical_grad"]
+        if options.pop("subtr_const", None) is None:
+            clean["subtr_const"] = True
+        if options.pop("sumtype", None) is None:
+            clean["sumtype"] = "kahan" if nevents > 200_000 else None
+        return clean
+
+    def _input_check(self, pdf, data, fit_range):  # loss.py:332-381, 413-480
+        if isinstance(pdf, tuple):
+            msg = "`pdf` has to be a pdf or a list of pdfs, not a tuple."
+            raise TypeError(msg)
+        if isinstance(data, tuple):
+            msg = "`data` has to be a data or a list of data, not a tuple."
+            raise TypeError(msg)
+        pdf, data = _to_list(pdf), _to_list(data)
+        is_simple = isinstance(self, SimpleLoss)
+        if not pdf and not is_simple:
+            msg = "At least one model must be provided to create a loss."
+            raise ValueError(msg)
+        if not data and not is_simple:
+            msg = "At least one dataset must be provided to create a loss."
+            raise ValueError(msg)
+        if len(pdf) != len(data):
+            msg = f"pdf, data don't have the same number of components:\npdf: {pdf}\ndata: {data}"
+            raise ValueError(msg)
+        pdf_checked, data_checked = [], []
+        for i, (mod, dat) in enumerate(zip(pdf, data)):
+            if not isinstance(mod, BasePDF):
+                msg = f"Model at index {i} must be a ZfitPDF, got {type(mod).__name__}"
+                raise TypeError(msg)
+            if not isinstance(dat, Data):
+                if fit_range is not None:
+                    msg = "Fit range should not be used if data is not ZfitData."
+                    raise TypeError(msg)
+                try:
+                    dat = convert_to_data(dat, obs=mod.space, check_limits=True)
+                except OutsideLimitsError as error:
+                    msg = (
+                        f"Data {dat} is not a zfit Data (and therefore has no Space that defines possible limits) "
+                        f"and is not fully within the limits {mod.space} of the model {mod}."
+                        f"If the data should be what it is, please convert to zfit Data (`zfit.Data(data, obs=obs)`) "
+                        f"or remove events outside the space"
+                    )
+                    raise IntentionAmbiguousError(msg) from error
+            if dat.num_entries == 0 and not _dist.is_distributed():
+                msg = f"Dataset at index {i} is empty (has 0 entries). Cannot create loss with empty data."
+                raise ValueError(msg)
+            if mod.space.obs != dat.space.obs:
+                if set(mod.space.obs) <= set(dat.space.obs) and len(mod.space.obs) == len(dat.space.obs):
+                    dat = dat.with_obs(mod.space.obs)
+                else:
+                    msg = (
+                        f"Model at index {i} has observables {mod.space.obs} but data has "
+                        f"observables {dat.space.obs}. The observables must match."
+                    )
+                    raise ValueError(msg)
+            pdf_checked.append(mod)
+            data_checked.append(dat)
+        if fit_range is None:
+            fit_range = [None] * len(pdf_checked)
+        else:
+            fit_range = fit_range if isinstance(fit_range, list) else [fit_range]
+            if len(fit_range) != len(pdf_checked):
+                msg = "pdf, data and fit_range don't have the same number of components"
+                raise ValueError(msg)
+            fit_range = [
+                None if r is None else (r if isinstance(r, Space) else p.space.with_limits(r))
+                for p, r in zip(pdf_checked, fit_range)
+            ]
+        return pdf_checked, data_checked, fit_range
+
+    def _assert_params_unique(self):
+        seen = {}
+        for p in self.get_params(floating=None, is_yield=None, extract_independent=True):
+            if p.name in seen and seen[p.name] is not p:
+                msg = f"The following parameter names appear more than once in {self}: {p.name}."
+                raise ParamNameNotUniqueError(msg)
+            seen[p.name] = p
+
+    # ------------------------------------------------------------------ description
+    @property
+    def name(self):
+        return type(self).__name__
+
+    @property
+    def model(self):
+        return self._model
+
+    @property
+    def data(self):
+        return self._data
+
+    @property
+    def fit_range(self):
+        return self._fit_range
+
+    @property
+    def constraints(self):
+        return self._constraints
+
+    @property
+    def errordef(self):
+        return self._errordef
+
+    @property
+    def is_weighted(self) -> bool:
+        return any(d.has_weights for d in self.data)
+
+    @property
+    def is_extended(self) -> bool:
+        return False
+
+    @property
+    def options(self):
+        return self._options
+
+    def get_params(self, floating=True, is_yield=None, extract_independent=True, **_):
+        """OrderedSet union over the models in list order, then constraints (``loss.py:296-321``);
+        the order defines the gradient layout."""
+        params = OrderedSet()
+        for m in self.model:
+            params = params.union(m.get_params(floating=floating, is_yield=is_yield, extract_independent=extract_independent))
+        for c in self.constraints:
+            params = params.union(c.get_params(floating=floating, is_yield=False, extract_independent=extract_independent))
+        return params
+
+    # ------------------------------------------------------------------ engine
+    def _get_engine(self):
+        if self._engine is None:
+            if self._engine_factory is not None:
+                self._engine = self._engine_factory(self.model, self.data, self.fit_range)
+            else:
+                self._engine = CudaEngine(
+                    self.model,
+                    self.data,
+                    self.fit_range,
+                    sort_events=self._options.get("sort_events", True),
+                    deterministic_reduce=self._options.get("deterministic_reduce", False),
+                )
+        return self._engine
+
+    def _set_engine_factory(self, factory):
+        """Test seam: ``factory(models, datas, fit_ranges) -> engine`` with the ``CudaEngine`` interface."""
+        self._engine_factory = factory
+        self._engine = None
+
+    # ------------------------------------------------------------------ core evaluation
+    def _nll_channels(self, want_grad, log_offset):
+        eng = self._get_engine()
+        slots = np.array([p.value() for p in eng.slot_params], dtype=np.float64)
+        kahan = self._options.get("sumtype") == "kahan" and not self.is_extended
+        values, gslots = eng.eval(slots, grad=want_grad, log_offset=0.0 if log_offset is False else float(log_offset), kahan=kahan)
+        total = 0.0
+        for v in values:
+            total += float(v)
+        grad = {}
+        if want_grad:
+            for p, g in zip(eng.slot_params, gslots):
+                if p.independent:
+                    grad[p] = grad.get(p, 0.0) + float(g)
+                else:
+                    for leaf, d in p._partials().items():
+                        grad[leaf] = grad.get(leaf, 0.0) + float(g) * d
+        return total, grad
+
+    def _extra_terms(self, want_grad, log_offset):
+        """Terms beyond the per-event sum (extended Poisson term); overridden by ExtendedUnbinnedNLL."""
+        return 0.0, {}
+
+    def _evaluate(self, params, want_grad, log_offset):
+        value, grad = self._nll_channels(want_grad, log_offset)
+        extra, egrad = self._extra_terms(want_grad, log_offset)
+        value += extra
+        for k, v in egrad.items():
+            grad[k] = grad.get(k, 0.0) + v
+        for c in self.constraints:
+            value += float(c.value())
+            if want_grad:
+                for k, v in c._partials().items():
+                    grad[k] = grad.get(k, 0.0) + v
+        if not want_grad:
+            return value, None
+        return value, np.array([grad.get(p, 0.0) for p in params], dtype=np.float64)
+
+    # ------------------------------------------------------------------ offsets (loss.py:383-411)
+    def check_precompile(self, *, params=None, force=False):
+        if self._options.get("_precompiled") and not force:
+            return params, False
+        with self._check_set_input_params(params):
+            do_subtr = self._options.get("subtr_const", False)
+            if do_subtr:
+                if do_subtr is not True:
+                    self._options["subtr_const_value"] = do_subtr
+                if self._options.get("subtr_const_value") is None:
+                    eng = self._get_engine()
+                    nevents_tot = float(sum(eng.n_entries))
+                    allp = list(self.get_params(floating=None))
+                    v0, _ = self._evaluate(allp, False, 0.0)
+                    self._options["subtr_const_value"] = -((v0 - 10000.0) / nevents_tot)
+        self._options["_precompiled"] = True
+        return params, True
+
+    def _check_set_input_params(self, params):
+        if params is None:
+            return _NullCtx()
+        if isinstance(params, Mapping):
+            byname = {p.name: p for p in self.get_params(floating=None, is_yield=None)}
+            keys = [k if isinstance(k, ZfitParameter) else byname[k] for k in params]
+            return set_values(keys, list(params.values()))
+        if hasattr(params, "params") and hasattr(params, "loss"):  # FitResult
+            return set_values(list(params.params), [v["value"] for v in params.params.values()])
+        if isinstance(params, Iterable):
+            allp = list(self.get_params(floating=None, is_yield=None))
+            vals = list(params)
+            if len(vals) != len(allp):
+                msg = "Length of params does not match the length of all parameters or provide a Mapping."
+                raise ValueError(msg)
+            return set_values(allp, vals)
+        msg = f"cannot interpret params {params}"
+        raise TypeError(msg)
+
+    def _input_check_params(self, params, only_independent=False):
+        if params is None:
+            return tuple(self.get_params())
+        if isinstance(params, ZfitParameter):
+            params = (params,)
+        params = tuple(params)
+        if only_independent and (bad := [p for p in params if not p.independent]):
+            msg = f"Parameters {bad} are not independent and `only_independent` is set to True."
+            raise ValueError(msg)
+        allp = self.get_params(floating=None, extract_independent=None, is_yield=None)
+        if not_in := [p for p in params if p not in allp]:
+            msg = f"Parameters {not_in} are not in the model."
+            raise ValueError(msg)
+        return params
+
+    # ------------------------------------------------------------------ public contract
+    def __call__(self, _x=None):
+        if isinstance(_x, dict):
+            msg = "Dicts are not supported when calling a loss, only array-like values."
+            raise TypeError(msg)
+        if _x is None:
+            return self.value(full=True)
+        params = list(self.get_params())
+        vals = np.atleast_1d(np.asarray(_x, dtype=np.float64)).reshape(-1)
+        if len(vals) != len(params):
+            msg = f"Incompatible length of parameters and values: {len(params)} vs {len(vals)}"
+            raise ValueError(msg)
+        with set_values(params, vals):
+            return self.value(full=True)
+
+    def value(self, *, params=None, full=None):
+        params, _ = self.check_precompile(params=params)
+        if full is None:
+            full = DEFAULT_FULL_ARG
+        log_offset = False if full else self._options.get("subtr_const_value", False)
+        if log_offset is None:
+            log_offset = False
+        with self._check_set_input_params(params):
+            return self._call_value(log_offset)
+
+    def _call_value(self, log_offset):
+        return self._evaluate((), False, log_offset)[0]
+
+    def gradient(self, params=None, *, numgrad=None, paramvals=None):
+        params = self._input_check_params(params, only_independent=True)
+        numgrad = self._options["numgrad"] if numgrad is None else numgrad
+        paramvals, _ = self.check_precompile(params=paramvals)
+        with self._check_set_input_params(paramvals):
+            return self._call_value_gradient(params, numgrad, full=False)[1]
+
+    def value_gradient(self, params=None, *, full=None, numgrad=None, paramvals=None):
+        params = self._input_check_params(params)
+        numgrad = self._options["numgrad"] if numgrad is None else numgrad
+        if full is None:
+            full = DEFAULT_FULL_ARG
+        paramvals, _ = self.check_precompile(params=paramvals)
+        with self._check_set_input_params(paramvals):
+            return self._call_value_gradient(params, numgrad, full)
+
+    def _call_value_gradient(self, params, numgrad, full):
+        log_offset = False if full else self._options.get("subtr_const_value", False)
+        if log_offset is None:
+            log_offset = False
+        if numgrad:
+            value = self._evaluate((), False, log_offset)[0]
+            return value, _numerical_gradient(lambda: self._evaluate((), False, log_offset)[0], params)
+        return self._evaluate(params, True, log_offset)
+
+    def hessian(self, params=None, hessian=None, *, numgrad=None, paramvals=None):
+        params = self._input_check_params(params)
+        numgrad = self._options["numgrad"] if numgrad is None else numgrad
+        paramvals, _ = self.check_precompile(params=paramvals)
+        with self._check_set_input_params(paramvals):
+            return self._call_hessian(params, hessian, numgrad)
+
+    def _call_hessian(self, params, hessian, numgrad):
+        """Central differences of the analytic gradient (2P fused-kernel calls).  The reference's default is a
+        numdifftools Hessian over ``loss.value`` (``numhess=True``, ``loss.py:271-272``, ``z/math.py:104-151``)."""
+        log_offset = self._options.get("subtr_const_value", False) or False
+
+        def grad_fn():
+            if numgrad:
+                return _numerical_gradient(lambda: self._evaluate((), False, log_offset)[0], params)
+            return self._evaluate(params, True, log_offset)[1]
+
+        H = _numerical_jacobian(grad_fn, params)
+        H = 0.5 * (H + H.T)
+        if hessian == "diag":
+            return np.diag(H).copy()
+        return H
+
+    def value_gradient_hessian(self, params=None, *, hessian=None, full=None, numgrad=None, paramvals=None):
+        params = self._input_check_params(params)
+        if full is None:
+            full = DEFAULT_FULL_ARG
+        paramvals, _ = self.check_precompile(params=paramvals)
+        with self._check_set_input_params(paramvals):
+            v, g = self._call_value_gradient(params, self._options["numgrad"] if numgrad is None else numgrad, full)
+            h = self._call_hessian(params, hessian, False)
+        return v, g, h
+
+    def gradients(self, *_, **__):
+        msg = "`gradients` is deprecated, use `gradient` instead."
+        raise BreakingAPIChangeError(msg)
+
+    def value_gradients(self, *_, **__):
+        msg = "`value_gradients` is deprecated, use `value_gradient` instead."
+        raise BreakingAPIChangeError(msg)
+
+    def __add__(self, other):
+        if not isinstance(other, BaseLoss):
+            msg = "Has to be a subclass of `BaseLoss` or overwrite `__add__`."
+            raise TypeError(msg)
+        if type(other) is not type(self):
+            msg = "cannot safely add two different kind of loss."
+            raise ValueError(msg)
+        kwargs = {
+            "model": self.model + other.model,
+            "data": self.data + other.data,
+            "constraints": self.constraints + other.constraints,
+        }
+        fit_range = self.fit_range + other.fit_range
+        if any(fr is not None for fr in fit_range):
+            kwargs["fit_range"] = fit_range
+        return type(self)(**kwargs)
+
+    def create_new(self, model=None, data=None, fit_range=None, constraints=None, options=None):
+        """New loss of the same kind taking over constants and options (``loss.py:923-1017``)."""
+        model = self.model if model is None else model
+        data = self.data if data is None else data
+        if fit_range is None and any(fr is not None for fr in self.fit_range):
+            fit_range = self.fit_range
+        constraints = self.constraints if constraints is None else constraints
+        if options is None:
+            options = {k: v for k, v in self._options.items() if not k.startswith("_")}
+        kwargs = {"model": model, "data": data, "constraints": constraints, "options": options}
+        if fit_range is not None:
+            kwargs["fit_range"] = fit_range
+        return type(self)(**kwargs)
+
+    def __repr__(self):
+        return (
+            f"<{type(self).__name__} model={[m.name for m in self.model]} data={[d.name for d in self.data]} "
+            f'constraints={self.constraints if len(self.constraints) <= 3 else "True"}>'
+        )
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _constraint_check_convert(constraints):
+    for c in constraints:
+        if not (hasattr(c, "value") and hasattr(c, "get_params") and hasattr(c, "_partials")):
+            msg = (
+                "Constraints have to be of type `Constraint`, a simple constraint from a function can be constructed"
+                " with `SimpleConstraint`."
+            )
+            raise BreakingAPIChangeError(msg)
+    return list(constraints)
+
+
+def _steps(params):
+    return [1e-5 * max(1.0, abs(p.value())) if not getattr(p, "has_stepsize", False) else min(p.stepsize * 1e-2, 1e-4 * max(1.0, abs(p.value()))) for p in params]
+
+
+def _numerical_gradient(func, params):
+    """Central differences with one Richardson step (stands in for numdifftools, ``z/math.py:43-79``)."""
+    g = np.zeros(len(params))
+    for i, p in enumerate(params):
+        v = p.value()
+        h = 1e-5 * max(1.0, abs(v))
+
+        def d(hh, p=p, v=v):
+            p.assign(v + hh)
+            up = func()
+            p.assign(v - hh)
+            dn = func()
+            p.assign(v)
+            return (up - dn) / (2 * hh)
+
+        g[i] = (4.0 * d(h) - d(2 * h)) / 3.0
+    return g
+
+
+def _numerical_jacobian(grad_fn, params):
+    n = len(params)
+    H = np.zeros((n, n))
+    for i, p in enumerate(params):
+        v = p.value()
+        h = 1e-4 * max(abs(v), p.stepsize if hasattr(p, "stepsize") else 1.0, 1e-3)
+        if p.has_limits:
+            lo = -np.inf if p.lower is None else p.lower
+            up = np.inf if p.upper is None else p.upper
+            h = min(h, 0.5 * (up - v) if np.isfinite(up) and up > v else h, 0.5 * (v - lo) if np.isfinite(lo) and v > lo else h)
+        p.assign(v + h)
+        gp = np.asarray(grad_fn(), dtype=np.float64)
+        p.assign(v - h)
+        gm = np.asarray(grad_fn(), dtype=np.float64)
+        p.assign(v)
+        H[i, :] = (gp - gm) / (2 * h)
+    return H
+
+
+class UnbinnedNLL(BaseLoss):
+    """``zfit.loss.UnbinnedNLL(model, data, fit_range=None, constraints=None, options=None)``
+    (``loss.py:1020-1170``): ignores yields (``is_yield=False``, :1160-1170)."""
+
+    def __init__(self, model, data, fit_range=None, constraints=None, options=None):
+        super().__init__(model=model, data=data, fit_range=fit_range, constraints=constraints, options=options)
+        self._errordef = 0.5
+        extended_pdfs = [pdf for pdf in self.model if pdf.is_extended]
+        if extended_pdfs and type(self) is UnbinnedNLL:
+            warnings.warn(
+                f"Extended PDFs ({extended_pdfs}) are given to a normal UnbinnedNLL. This won't take the yield "
+                "into account and simply treat the PDFs as non-extended PDFs. To create an "
+                "extended NLL, use the `ExtendedUnbinnedNLL`.",
+                stacklevel=2,
+            )
+
+    def get_params(self, floating=True, is_yield=None, extract_independent=True, **kw):
+        if not self.is_extended:
+            is_yield = False  # the loss does not depend on the yields
+        return super().get_params(floating, is_yield, extract_independent, **kw)
+
+
+class ExtendedUnbinnedNLL(UnbinnedNLL):
+    """``zfit.loss.ExtendedUnbinnedNLL`` (``loss.py:1178-1332``): adds, per channel,
+    ``tf.nn.log_poisson_loss(samplesize, log(yield), compute_full_loss=(log_offset is False))`` and, when an
+    offset is in use, ``+ log_offset`` (``:1301-1317``)."""
+
+    @property
+    def is_extended(self) -> bool:
+        return True
+
+    def _extra_terms(self, want_grad, log_offset):
+        eng = self._get_engine()
+        total = 0.0
+        grad = {}
+        for k, mod in enumerate(self.model):
+            if not mod.is_extended:
+                msg = f"The pdf {mod} is not extended but has to be (for an extended fit)"
+                raise NotExtendedPDFError(msg)
+            t = float(eng.samplesize[k])
+            yparam = mod.get_yield()
+            y = yparam.value()
+            log_y = math.log(y) if y > 0 else (float("-inf") if y == 0 else float("nan"))
+            term = math.exp(log_y) - log_y * t
+            if log_offset is False:
+                if not (0.0 <= t <= 1.0):
+                    term += t * math.log(t) - t + 0.5 * math.log(2.0 * math.pi * t)
+            else:
+                term += float(log_offset)
+            total += term
+            if want_grad:
+                dterm = 1.0 - t / y if y != 0 else float("nan")
+                for leaf, d in yparam._partials().items():
+                    grad[leaf] = grad.get(leaf, 0.0) + dterm * d
+        return total, grad
+
+
+class SimpleLoss(BaseLoss):
+    """``zfit.loss.SimpleLoss(func, params, errordef, *, gradient=None, hessian=None)`` (``loss.py:1340-1633``):
+    the generic callable slot -- lets any function (+ gradient) be driven by the minimizers."""
+
+    def __init__(self, func, params=None, errordef=None, *, gradient=None, hessian=None, jit=None, deps=None):
+        if deps is not None and params is None:
+            params = deps
+        if errordef is None:
+            errordef = getattr(func, "errordef", None)
+        if errordef is None:
+            msg = "errordef has to be given (or be an attribute of func): 0.5 for a NLL, 1 for a chi2"
+            raise ValueError(msg)
+        if params is None:
+            msg = "params have to be given"
+            raise ValueError(msg)
+        if isinstance(params, ZfitParameter):
+            params = [params]
+        self._simple_params = OrderedSet(params)
+        self._simple_func = func
+        self._simple_grad = None if gradient in (None, "num", "zfit") else gradient
+        self._simple_hess = None if hessian in (None, "num", "zfit") else hessian
+        super().__init__(model=[], data=[], options={"subtr_const": False})
+        self._errordef = errordef
+
+    def get_params(self, floating=True, is_yield=None, extract_independent=True, **_):
+        return OrderedSet(p for p in self._simple_params if floating is None or p.floating == floating)
+
+    def check_precompile(self, *, params=None, force=False):
+        return params, False
+
+    def _call_func(self):
+        try:
+            return float(self._simple_func(list(self._simple_params)))
+        except TypeError:
+            return float(self._simple_func())
+
+    def _evaluate(self, params, want_grad, log_offset):
+        value = self._call_func()
+        if not want_grad:
+            return value, None
+        if self._simple_grad is not None:
+            allp = list(self._simple_params)
+            g = np.asarray(self._simple_grad(allp), dtype=np.float64)
+            return value, np.array([g[allp.index(p)] for p in params])
+        return value, _numerical_gradient(self._call_func, params)

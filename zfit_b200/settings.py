@@ -1,0 +1,88 @@
+"""``zfit.settings`` / ``zfit.run`` for the hot path (``src/zfit/settings.py``, ``util/execution.py``):
+fp64 everywhere; the graph / autograd switches of the reference have no meaning without TensorFlow and
+are accepted as no-ops."""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+class _Options(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+options = _Options(numerical_grad=False, auto_update_params=True, epsilon=1e-8)
+
+
+class _ZTypes:
+    float = np.float64
+    int = np.int64
+    complex = np.complex128
+
+
+ztypes = _ZTypes()
+
+
+def set_seed(seed=None, numpy=None, backend=None):
+    if seed is None:
+        seed = np.random.randint(0, 2**31 - 1)
+    np.random.seed(int(seed) if numpy is None or numpy is True else int(numpy))
+    try:
+        import torch
+
+        torch.manual_seed(int(seed))
+    except Exception:
+        pass
+    return {"seed": seed}
+
+
+class RunManager:
+    """Subset of ``zfit.run`` (``util/execution.py:23-514``)."""
+
+    numeric_checks = False
+    chunking = None
+
+    def __init__(self):
+        self._n_cpu = None
+
+    def executing_eagerly(self):
+        return True
+
+    def set_graph_mode(self, graph=None):
+        return _Null()
+
+    def set_autograd_mode(self, autograd=None):
+        return _Null()
+
+    def set_n_cpu(self, n_cpu="auto", strict=False):
+        self._n_cpu = n_cpu
+
+    @property
+    def n_cpu(self):
+        import os
+
+        return self._n_cpu if isinstance(self._n_cpu, int) else len(os.sched_getaffinity(0))
+
+    def get_graph_mode(self):
+        return False
+
+    def get_autograd_mode(self):
+        return True
+
+    def assert_executing_eagerly(self):
+        return None
+
+    def clear_graph_cache(self):
+        return None
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+run = RunManager()
