@@ -112,9 +112,10 @@ class CudaEngine:
         return cols, w
 
     def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
-        if not self.distributed:
-            return self.plan.eval(slots, grad=grad, log_offset=log_offset, kahan=kahan)
+        # kernels go to torch's current stream (0 = default stream -> the plan's own stream)
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        if not self.distributed:
+            return self.plan.eval(slots, grad=grad, log_offset=log_offset, kahan=kahan, stream=stream)
         self.plan.launch(slots, grad=grad, log_offset=log_offset, stream=stream)
         _dist.all_reduce_sum_(self._acc, deterministic=self.deterministic_reduce)
         return self.plan.collect(grad=grad, stream=stream)
