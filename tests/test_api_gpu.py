@@ -42,7 +42,9 @@ def test_config_value_gradient_parity(cfg, n):
     v, _ = loss.value_gradient(params, full=False)
     r, _ = ref.value_gradient(params, full=False)
     assert abs(v - r) <= 1e-12 * max(abs(r_full), nev)
-    assert abs(v - 10000.0) < 1e-6 * nev  # offset brings the first value to ~1e4
+    # the offset brings the first value to ~1e4; the extended term adds the offset once more per channel (:1314-1316)
+    expect = 10000.0 + (loss.options["subtr_const_value"] * len(loss.model) if loss.is_extended else 0.0)
+    assert abs(v - expect) < 1e-9 * nev
     assert loss.value(full=False) == v and abs(loss.gradient(params) - g).max() <= 1e-10 * scale
 
 

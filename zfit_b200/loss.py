@@ -81,6 +81,9 @@ class CudaEngine:
             if sort_events and n > 1:
                 cols, w = self._sort_for_coherence(model, data, cols, w)
             self._keep.append((cols, w))
+            # the columns were produced by torch kernels on torch's stream (upload, cut, sort); the plan launches
+            # on its own stream, so make them visible first
+            torch.cuda.synchronize(device)
             self.plan.bind_device_ptrs(k, [c.data_ptr() for c in cols], 0 if w is None else w.data_ptr(), n)
             self.n_local.append(n)
         self.samplesize = [self.plan.sumw(k) for k in range(len(models))]

@@ -175,6 +175,9 @@ class BasePDF:
         try:
             plan.set_model(0, nodes)
             cols, _ = x.device_columns(plan.device)
+            import torch
+
+            torch.cuda.synchronize(plan.device)  # columns come from torch's stream, the plan has its own
             plan.bind_device_ptrs(0, [c.data_ptr() for c in cols], 0, n, keepalive=cols)
             return plan.pdf_values(0, slots, n)
         finally:
