@@ -145,6 +145,10 @@ int znll_pdf(znll_plan* plan, int ch, const double* slots, double* out_host, voi
  * (dist_tfp.py:113-120, basic.py:211-229, physics.py:83-142, polynomials.py:443-478). */
 int znll_leaf_integral(const znll_node* leaf, const double* slots, double* integral, double* dintegral);
 
+/* Test hook: out[i] = f(in[i]) on the device for the kernel's own fp64 elementary functions
+ * (kind 0: exp, 1: log, 2: reciprocal), so their accuracy can be checked against libm. */
+int znll_test_math(int kind, int64_t n, const double* in_host, double* out_host);
+
 /* Device micro-benchmark used for the roofline denominator: register-resident DFMA loop.
  * Returns achieved FP64 TFLOP/s over `ms` milliseconds of work (approx.). */
 int znll_fp64_peak(int device, double ms, double* tflops);

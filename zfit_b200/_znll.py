@@ -68,6 +68,7 @@ SYMBOLS = {
     "znll_collect": (C.c_int, [C.c_void_p, C.c_uint32, _DP, _DP, C.c_void_p]),
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
+    "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
     "znll_fp64_peak": (C.c_int, [C.c_int, C.c_double, _DP]),
 }
 
@@ -224,3 +225,11 @@ def fp64_peak(device: int = 0, ms: float = 200.0) -> float:
     out = np.zeros(1)
     _check(lib().znll_fp64_peak(device, float(ms), _dptr(out)))
     return float(out[0])
+
+
+def test_math(kind: int, x):
+    """Device evaluation of the kernel's fast exp (0) / log (1) / reciprocal (2) -- test hook."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    _check(lib().znll_test_math(kind, x.size, _dptr(x), _dptr(out)))
+    return out

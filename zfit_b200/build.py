@@ -53,7 +53,7 @@ def _digest(paths) -> str:
 
 def build(verbose: bool = False, force: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
-    deps = [CSRC / f for f in os.listdir(CSRC)] + [HERE.parent / "include" / "znll.h", Path(__file__)]
+    deps = [CSRC / f for f in os.listdir(CSRC) if (CSRC / f).is_file()] + [HERE.parent / "include" / "znll.h", Path(__file__)]
     stamp = OBJ / "stamp"
     digest = _digest(deps)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:

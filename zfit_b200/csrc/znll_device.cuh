@@ -24,9 +24,102 @@
 
 #define ZNLL_MAXCOL 8
 #define ZNLL_BLOCK 256
+#ifndef ZNLL_MIN_BLOCKS
+#define ZNLL_MIN_BLOCKS 3  // resident CTAs per SM the register allocation is tuned for
+#endif
 #define ZNLL_LOG_EPS 1e-307
 
 namespace znll {
+
+// ----------------------------------------------------------------------------------------------
+// fp64 elementary functions tuned for this kernel (the FP64 pipe is the roofline):
+//   * polynomial coefficients live in the constant bank, so every DFMA takes them as an operand
+//     (libdevice materialises each one with two UMOVs -> more issue slots than DP work);
+//   * log uses a 128-entry (1/c, log c) table in shared memory and a degree-7 log1p polynomial:
+//     13 DP instructions instead of ~35 (no division); exp: 15 DP instructions;
+//   * reciprocal: MUFU.RCP64H seed + two Newton steps (4 DFMA).
+// Accuracy (tests/test_math_gpu.py): exp, log <= 1 ulp-level relative error (measured ~2e-16),
+// far inside the 1e-12 NLL tolerance; arguments outside the fast range (|x| >= 700 for exp;
+// non-positive, subnormal, inf or NaN for log / rcp) take the libdevice path.
+// ----------------------------------------------------------------------------------------------
+static __constant__ double kExpC[10] = {
+    0.5000000000000001,     0.16666666666666669,    0.04166666666662413,   0.008333333333330062,
+    0.0013888888917213717,  0.00019841269863053618, 2.4801521295954376e-05, 2.7557268459997064e-06,
+    2.7620088445409746e-07, 2.510038549551032e-08};
+static __constant__ double kLogC[6] = {-0.5,
+                                       0.33333333333333337,
+                                       -0.24999999998288297,
+                                       0.19999999998478485,
+                                       -0.16666959217649738,
+                                       0.14285974331115564};
+static __constant__ double kMathC[8] = {
+    1.4426950408889634,        // 0 log2(e)
+    6755399441055744.0,        // 1 1.5 * 2^52
+    -6.93147180369123816490e-01,  // 2 -ln2_hi
+    -1.90821492927058770002e-10,  // 3 -ln2_lo
+    0x1.62e42fefa3800p-1,      // 4 ln2_hi (42 significant bits: k*ln2_hi is exact)
+    0x1.ef35793c76730p-45,     // 5 ln2_lo
+    4503601774854144.0,        // 6 2^52 + 2^31
+    0.0};
+
+struct Ctx {
+  const double2* logtab;  // shared memory: (1/c_i, log c_i) for 128 intervals of [0.6875, 1.375)
+};
+
+__device__ __forceinline__ double fast_exp(double x) {
+  const int hx = __double2hiint(x) & 0x7fffffff;
+  if (hx >= 0x4085E000) return exp(x);  // |x| >= 700, inf, NaN: rare
+  const double t = fma(x, kMathC[0], kMathC[1]);
+  const int n = __double2loint(t);
+  const double nd = t - kMathC[1];
+  double r = fma(nd, kMathC[2], x);
+  r = fma(nd, kMathC[3], r);
+  double p = kExpC[9];
+#pragma unroll
+  for (int k = 8; k >= 0; --k) p = fma(p, r, kExpC[k]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+__device__ __forceinline__ double fast_rcp(double x) {
+  const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+  if (ex - 1u >= 0x7fdu) return 1.0 / x;  // zero, subnormal, inf, NaN
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+__device__ __forceinline__ double fast_log(double x, const Ctx& cx) {
+  const int hi = __double2hiint(x);
+  if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);  // x <= 0, subnormal, inf, NaN
+  const int tmp = hi - 0x3fe60000;
+  const int i = (tmp >> 13) & 127;
+  const int k = tmp >> 20;
+  const double z = __hiloint2double(hi - (tmp & 0xfff00000), __double2loint(x));
+  const double2 tc = cx.logtab[i];
+  const double r = fma(z, tc.x, -1.0);
+  const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - kMathC[6];
+  double s = kLogC[5];
+#pragma unroll
+  for (int j = 4; j >= 0; --j) s = fma(s, r, kLogC[j]);
+  const double w = fma(kd, kMathC[4], tc.y);
+  const double t2 = fma(r * r, s, kd * kMathC[5]);
+  return w + (r + t2);
+}
+
+// one entry per thread < 128, then __syncthreads() by the caller
+__device__ __forceinline__ void init_logtab(double2* tab) {
+  if (threadIdx.x < 128) {
+    const int ha = 0x3fe60000 + ((int)threadIdx.x << 13);
+    const double a = __hiloint2double(ha, 0), b = __hiloint2double(ha + (1 << 13), 0);
+    const double invc = 1.0 / (0.5 * (a + b));
+    tab[threadIdx.x] = make_double2(invc, -log(invc));
+  }
+}
 
 // ----------------------------------------------------------------------------------------------
 // leaves.  c = const block, x = this event's column values, acc = per-thread accumulators.
@@ -42,14 +135,14 @@ struct Gauss {
   double t, P;
 
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const double* __restrict__ c, const double* x, bool&) {
+  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool&) {
     t = fma(x[COL], c[CO + 0], c[CO + 1]);  // x/sigma - mu/sigma (tfp Normal._log_prob)
     return fma(-0.5 * t, t, c[CO + 2]);
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const double* __restrict__ c, const double* x) {
+  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
     bool neg;
-    P = exp(fwd_log<CO>(c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
   template <int CO, int AO>
@@ -72,14 +165,14 @@ struct Expo {
   double xs, P;
 
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const double* __restrict__ c, const double* x, bool&) {
+  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool&) {
     xs = x[COL] - c[CO + 1];
     return fma(c[CO + 0], xs, c[CO + 2]);
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const double* __restrict__ c, const double* x) {
+  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
     bool neg;
-    P = exp(fwd_log<CO>(c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
   template <int CO, int AO>
@@ -104,14 +197,14 @@ struct CBall {
   bool tail;
 
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const double* __restrict__ c, const double* x, bool&) {
+  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool&) {
     t = (x[COL] - c[CO + 0]) * c[CO + 1];
     tail = t < -c[CO + 3];
     double lp;
     if (tail) {  // A*(B-t)^-n  ==  exp(ln A - n*ln(B-t))
       const double u = c[CO + 5] - t;
-      lu = log(u);
-      dt = c[CO + 4] / u;
+      lu = fast_log(u, cx);
+      dt = c[CO + 4] * fast_rcp(u);
       lp = fma(-c[CO + 4], lu, c[CO + 6]);
     } else {  // exp(-t^2/2)
       lu = 0.0;
@@ -121,9 +214,9 @@ struct CBall {
     return lp;
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const double* __restrict__ c, const double* x) {
+  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
     bool neg;
-    P = exp(fwd_log<CO>(c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
   template <int CO, int AO>
@@ -153,7 +246,7 @@ struct Cheb {
   double P;
 
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const double* __restrict__ c, const double* x) {
+  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
     const double z = fma(x[COL], c[CO + 0], c[CO + 1]);
     T[0] = 1.0;
     double p = c[CO + 3];
@@ -171,10 +264,10 @@ struct Cheb {
     return p;
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const double* __restrict__ c, const double* x, bool& neg) {
-    const double p = fwd_val<CO>(c, x);
+  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool& neg) {
+    const double p = fwd_val<CO>(cx, c, x);
     neg ^= (p < 0.0);
-    return log(fabs(p));
+    return fast_log(fabs(p), cx);
   }
   template <int CO, int AO>
   __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
@@ -185,7 +278,7 @@ struct Cheb {
   }
   template <int CO, int AO>
   __device__ __forceinline__ void bwd_log(double g, const double* __restrict__ c, double* acc) {
-    bwd_val<CO, AO>(g / P, c, acc);
+    bwd_val<CO, AO>(g * fast_rcp(P), c, acc);
   }
 };
 
@@ -220,11 +313,11 @@ struct Sum {
   double P;
 
   template <int CO, int I, int CK, class KD>
-  __device__ __forceinline__ void fwd_rec(KD& kd, const double* __restrict__ c, const double* x, double& tot) {
+  __device__ __forceinline__ void fwd_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const double* x, double& tot) {
     if constexpr (KD::N > 0) {
-      p[I] = kd.h.template fwd_val<CK>(c, x);
+      p[I] = kd.h.template fwd_val<CK>(cx, c, x);
       tot = fma(c[CO + I], p[I], tot);
-      fwd_rec<CO, I + 1, CK + decltype(kd.h)::NC>(kd.t, c, x, tot);
+      fwd_rec<CO, I + 1, CK + decltype(kd.h)::NC>(kd.t, cx, c, x, tot);
     }
   }
   template <int CO, int AO, int I, int CK, int AK, class KD>
@@ -236,17 +329,17 @@ struct Sum {
     }
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const double* __restrict__ c, const double* x) {
+  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
     double tot = 0.0;
-    fwd_rec<CO, 0, CO + K>(kids, c, x, tot);
+    fwd_rec<CO, 0, CO + K>(kids, cx, c, x, tot);
     P = tot;
     return tot;
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const double* __restrict__ c, const double* x, bool& neg) {
-    const double v = fwd_val<CO>(c, x);
+  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool& neg) {
+    const double v = fwd_val<CO>(cx, c, x);
     neg ^= (v < 0.0);
-    return log(fabs(v));
+    return fast_log(fabs(v), cx);
   }
   template <int CO, int AO>
   __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
@@ -254,7 +347,7 @@ struct Sum {
   }
   template <int CO, int AO>
   __device__ __forceinline__ void bwd_log(double g, const double* __restrict__ c, double* acc) {
-    bwd_val<CO, AO>(g / P, c, acc);
+    bwd_val<CO, AO>(g * fast_rcp(P), c, acc);
   }
 };
 
@@ -268,11 +361,11 @@ struct Prod {
   double P;
 
   template <int CK, class KD>
-  __device__ __forceinline__ void fwd_rec(KD& kd, const double* __restrict__ c, const double* x, double& tot,
-                                          bool& neg) {
+  __device__ __forceinline__ void fwd_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const double* x,
+                                          double& tot, bool& neg) {
     if constexpr (KD::N > 0) {
-      tot += kd.h.template fwd_log<CK>(c, x, neg);
-      fwd_rec<CK + decltype(kd.h)::NC>(kd.t, c, x, tot, neg);
+      tot += kd.h.template fwd_log<CK>(cx, c, x, neg);
+      fwd_rec<CK + decltype(kd.h)::NC>(kd.t, cx, c, x, tot, neg);
     }
   }
   template <int CK, int AK, class KD>
@@ -283,16 +376,16 @@ struct Prod {
     }
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const double* __restrict__ c, const double* x, bool& neg) {
+  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool& neg) {
     double tot = 0.0;
-    fwd_rec<CO>(kids, c, x, tot, neg);
+    fwd_rec<CO>(kids, cx, c, x, tot, neg);
     return tot;
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const double* __restrict__ c, const double* x) {
+  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
     bool neg = false;
-    const double lp = fwd_log<CO>(c, x, neg);
-    P = neg ? -exp(lp) : exp(lp);
+    const double lp = fwd_log<CO>(cx, c, x, neg);
+    P = neg ? -fast_exp(lp) : fast_exp(lp);
     return P;
   }
   template <int CO, int AO>
@@ -320,15 +413,16 @@ struct KArgs {
   double c[NC > 0 ? NC : 1];
 };
 
-// accumulators: [0] running sum of w*l - offset, [1] its Kahan compensation, [2..] slots
+// accumulators: [0] running sum of w*l - offset, [1] its Kahan compensation, [2..] slots.
+// Returns this event's term  w*l - offset  (the caller adds two of them, then one Kahan step).
 template <class M, bool WEIGHTED, bool GRAD>
-__device__ __forceinline__ void event(const double* __restrict__ c, const double* x, double w, double off,
-                                      double* acc) {
+__device__ __forceinline__ double event(const Ctx& cx, const double* __restrict__ c, const double* x, double w,
+                                        double off, double* acc) {
   M m;
   double l, g;
   if constexpr (M::LOGNAT) {
     bool neg = false;
-    const double lp = m.template fwd_log<0>(c, x, neg);
+    const double lp = m.template fwd_log<0>(cx, c, x, neg);
     l = lp;
     g = 1.0;
     if (lp < -690.0 || neg) {  // p + 1e-307 matters only here (loss.py:117)
@@ -340,21 +434,22 @@ __device__ __forceinline__ void event(const double* __restrict__ c, const double
     if constexpr (WEIGHTED) g *= w;
     if constexpr (GRAD) m.template bwd_log<0, 2>(g, c, acc);
   } else {
-    const double P = m.template fwd_val<0>(c, x);
+    const double P = m.template fwd_val<0>(cx, c, x);
     const double pp = P + ZNLL_LOG_EPS;
-    l = log(pp);
+    l = fast_log(pp, cx);
     if constexpr (GRAD) {
-      g = 1.0 / pp;
+      g = fast_rcp(pp);
       if constexpr (WEIGHTED) g *= w;
       m.template bwd_val<0, 2>(g, c, acc);
     }
   }
-  double term;
   if constexpr (WEIGHTED)
-    term = fma(w, l, -off);  // weights multiply first, then the unweighted offset (loss.py:134-137)
+    return fma(w, l, -off);  // weights multiply first, then the unweighted offset (loss.py:134-137)
   else
-    term = l - off;
-  // Kahan
+    return l - off;
+}
+
+__device__ __forceinline__ void kahan_add(double* acc, double term) {
   const double y = term - acc[1];
   const double s = acc[0] + y;
   acc[1] = (s - acc[0]) - y;
@@ -445,18 +540,12 @@ __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* par
   if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this stream
 }
 
-template <class M, bool WEIGHTED, bool GRAD>
-__global__ void __launch_bounds__(ZNLL_BLOCK, 2) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
-  constexpr int NACC = 2 + M::NS;
-  double acc[NACC];
-#pragma unroll
-  for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
-  const double* __restrict__ c = args.c;
-  const double off = args.log_offset;
-  const long long nvec = args.n >> 1;
-  const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
-  for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < nvec; i += stride) {
-    double xa[ZNLL_MAXCOL], xb[ZNLL_MAXCOL];
+template <class M, bool WEIGHTED>
+struct EventPair {
+  double xa[ZNLL_MAXCOL], xb[ZNLL_MAXCOL];
+  double wa, wb;
+  template <int NC>
+  __device__ __forceinline__ void load(const KArgs<NC>& args, long long i) {
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k) {
       if ((M::COLMASK >> k) & 1) {
@@ -465,14 +554,40 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 2) nll_kernel(const __grid_constan
         xb[k] = v.y;
       }
     }
-    double wa = 1.0, wb = 1.0;
+    wa = wb = 1.0;
     if constexpr (WEIGHTED) {
       const double2 v = __ldg(reinterpret_cast<const double2*>(args.w) + i);
       wa = v.x;
       wb = v.y;
     }
-    event<M, WEIGHTED, GRAD>(c, xa, wa, off, acc);
-    event<M, WEIGHTED, GRAD>(c, xb, wb, off, acc);
+  }
+};
+
+template <class M, bool WEIGHTED, bool GRAD>
+__global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
+  constexpr int NACC = 2 + M::NS;
+  __shared__ double2 logtab[128];
+  init_logtab(logtab);
+  __syncthreads();
+  Ctx cx;
+  cx.logtab = logtab;
+  double acc[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
+  const double* __restrict__ c = args.c;
+  const double off = args.log_offset;
+  const long long nvec = args.n >> 1;
+  const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
+  long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x;
+  EventPair<M, WEIGHTED> cur, nxt;
+  if (i < nvec) nxt.load(args, i);
+  while (i < nvec) {
+    cur = nxt;
+    i += stride;
+    if (i < nvec) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
+    const double ta = event<M, WEIGHTED, GRAD>(cx, c, cur.xa, cur.wa, off, acc);
+    const double tb = event<M, WEIGHTED, GRAD>(cx, c, cur.xb, cur.wb, off, acc);
+    kahan_add(acc, ta + tb);
   }
   if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event
     double xa[ZNLL_MAXCOL];
@@ -481,14 +596,19 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 2) nll_kernel(const __grid_constan
       if ((M::COLMASK >> k) & 1) xa[k] = args.cols[k][args.n - 1];
     double wa = 1.0;
     if constexpr (WEIGHTED) wa = args.w[args.n - 1];
-    event<M, WEIGHTED, GRAD>(c, xa, wa, off, acc);
+    kahan_add(acc, event<M, WEIGHTED, GRAD>(cx, c, xa, wa, off, acc));
   }
   block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out);
 }
 
 // per-event normalised pdf values (BasePDF.pdf, core/basepdf.py:398-429): out[i] = P(x_i); args.partials = out
 template <class M>
-__global__ void __launch_bounds__(ZNLL_BLOCK, 2) pdf_kernel(const __grid_constant__ KArgs<M::NC> args) {
+__global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) pdf_kernel(const __grid_constant__ KArgs<M::NC> args) {
+  __shared__ double2 logtab[128];
+  init_logtab(logtab);
+  __syncthreads();
+  Ctx cx;
+  cx.logtab = logtab;
   const double* __restrict__ c = args.c;
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
   for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < args.n; i += stride) {
@@ -500,10 +620,10 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 2) pdf_kernel(const __grid_constan
     double p;
     if constexpr (M::LOGNAT) {
       bool neg = false;
-      const double lp = m.template fwd_log<0>(c, x, neg);
+      const double lp = m.template fwd_log<0>(cx, c, x, neg);
       p = neg ? -exp(lp) : exp(lp);
     } else {
-      p = m.template fwd_val<0>(c, x);
+      p = m.template fwd_val<0>(cx, c, x);
     }
     args.partials[i] = p;
   }

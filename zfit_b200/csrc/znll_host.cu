@@ -618,7 +618,7 @@ int znll_plan_create(int device, int n_channels, znll_plan** out) {
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   p->sm_count = prop.multiProcessorCount;
-  p->max_grid = p->sm_count * 2;  // persistent: 2 resident CTAs of 256 threads per SM
+  p->max_grid = p->sm_count * ZNLL_BLOCKS_PER_SM;  // persistent grid: resident CTAs of 256 threads per SM
   p->ch.resize(n_channels);
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   *out = p;
@@ -911,6 +911,22 @@ __global__ void __launch_bounds__(256, 2) dfma_kernel(double* out, int iters, do
     }
   }
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int znll_test_math(int kind, int64_t n, const double* in_host, double* out_host) {
+  if (!in_host || !out_host || n < 0) return fail("znll_test_math: bad arguments");
+  if (znll_device_count() < 1) return fail("znll_test_math: no CUDA device");
+  if (n == 0) return 0;
+  double *d_in = nullptr, *d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_in, sizeof(double) * (size_t)n));
+  CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (size_t)n));
+  cudaError_t e = cudaMemcpy(d_in, in_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = znll_launch_test_math(kind, d_in, d_out, (long long)n, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail("znll_test_math: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 extern "C" int znll_fp64_peak(int device, double ms, double* tflops) {
