@@ -1,0 +1,445 @@
+"""CPU: host layer (API mirror, lowering, chain rule, minimizer protocol) and the C-ABI surface -- no GPU."""
+
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import zfit_b200 as zfit
+from oracle import nll as ON
+from oracle import pdfs as O
+from oracle.backend import TorchBackend
+from tests._oracle_engine import OracleEngine, use_oracle
+from zfit_b200 import _znll as Z
+from zfit_b200 import exception as zexc
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = Path(__file__).parent / "golden"
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    header = (ROOT / "include" / "znll.h").read_text()
+    declared = set(re.findall(r"\b(znll_[a-z0-9_]+)\s*\(", header))
+    declared -= {"znll_plan", "znll_node", "znll_kind"}
+    lib = Z.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/znll.h but not exported by libznll.so"
+    assert declared == set(Z.SYMBOLS), (declared ^ set(Z.SYMBOLS))
+    assert lib.znll_abi_version() == 1
+
+
+def test_no_cpu_fallback(have_gpu):
+    if have_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(Z.ZnllError, match="no CUDA device"):
+        Z.Plan(1)
+    obs = zfit.Space("x", -1, 1)
+    g = zfit.pdf.Gauss(zfit.Parameter("mu_nf", 0.0), zfit.Parameter("s_nf", 1.0), obs)
+    nll = zfit.loss.UnbinnedNLL(g, zfit.Data(np.zeros(10), obs=obs))
+    with pytest.raises(Z.ZnllError):
+        nll.value()
+
+
+def _autograd_integral(opdf, names, vals, lo, hi, norm):
+    import torch
+
+    B = TorchBackend()
+    leaves = [torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in vals]
+    I = opdf.integral(B, dict(zip(names, leaves)), lo, hi, norm)
+    g = torch.autograd.grad(I, leaves, allow_unused=True)
+    return float(I.detach()), np.array([0.0 if x is None else float(x) for x in g])
+
+
+@pytest.mark.parametrize(
+    "mu,s,a,n,lo,hi",
+    [(5275, 25, 1.2, 2.5, 5000, 5600), (5275, 25, -1.2, 2.5, 5000, 5600), (-0.3, 1.1, 0.8, 2, -6, 4),
+     (0, 1, 1.5, 1.000001, -6, -3), (0, 1, 1.5, 3.0, -6, -3), (0, 1, 1.5, 3.0, -1, 3), (0, 1, 1.5, 1.000002, -5, 3),
+     (0.0, -1.0, 1.5, 3.0, -5, 3)],
+)
+def test_host_prologue_crystalball_integral_and_derivatives(mu, s, a, n, lo, hi):
+    node = Z.Node(Z.CB, 0, 0, 0, lo, hi, 0, 0, 0)
+    I, dI = Z.leaf_integral(node, [mu, s, a, n])
+    rI, rdI = _autograd_integral(O.CrystalBall("mu", "s", "a", "n", "x", (lo, hi)), ["mu", "s", "a", "n"], [mu, s, a, n], lo, hi, (lo, hi))
+    assert abs(I - rI) <= 1e-14 * abs(rI)
+    np.testing.assert_allclose(dI, rdI, rtol=1e-12, atol=1e-14 * abs(rI))
+
+
+def test_host_prologue_other_leaf_integrals():
+    I, dI = Z.leaf_integral(Z.Node(Z.GAUSS, 0, 0, 0, -2, 3, 0, 0, 0), [1.2, 1.3])
+    rI, rdI = _autograd_integral(O.Gauss("mu", "sigma", "x", (-2, 3)), ["mu", "sigma"], [1.2, 1.3], -2, 3, (-2, 3))
+    assert abs(I - rI) <= 1e-15 and np.allclose(dI, rdI, rtol=1e-13)
+    I, dI = Z.leaf_integral(Z.Node(Z.EXP, 0, 0, 0, 5000, 5600, 0, 0, 5300.0), [-0.003])
+    rI, rdI = _autograd_integral(O.Exponential("l", "x", (5000, 5600)), ["l"], [-0.003], 5000, 5600, (5000, 5600))
+    assert abs(I - rI) <= 1e-13 * rI and np.allclose(dI, rdI, rtol=1e-12)
+    I, dI = Z.leaf_integral(Z.Node(Z.EXP, 0, 0, 0, 0, 5, 0, 0, 0.0), [-0.7])  # inside a ProductPDF: no shift
+    rI, rdI = _autograd_integral(O.Exponential("l", "x", (0, 5)), ["l"], [-0.7], 0, 5, False)
+    assert abs(I - rI) <= 1e-15 and np.allclose(dI, rdI, rtol=1e-13)
+    cn = ["c0", "c1", "c2", "c3", "c4"]
+    cv = [1.0, 0.2, -0.1, 0.05, 0.02]
+    I, dI = Z.leaf_integral(Z.Node(Z.CHEB, 0, 0, 4, -3, 7, -10, 10, 0), cv)
+    rI, rdI = _autograd_integral(O.Chebyshev(cn[1:], "x", (-10, 10), coeff0="c0"), cn, cv, -3, 7, (-3, 7))
+    assert abs(I - rI) <= 1e-14 * abs(rI) and np.allclose(dI, rdI, rtol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------ API mirror
+def test_space():
+    s = zfit.Space("x", -2, 3)
+    assert s.obs == ("x",) and s.n_obs == 1 and s.limit1d == (-2.0, 3.0) and s.volume == 5.0 and bool(s)
+    assert zfit.Space("x", (-2, 3)) == s and zfit.Space("x", limits=(-2, 3)) == s and zfit.Space(obs="x", lower=-2, upper=3) == s
+    assert not zfit.Space("x").has_limits
+    xy = s * zfit.Space("y", 0, 5)
+    assert xy.obs == ("x", "y") and xy.volume == 25.0 and xy.with_obs("y").limit1d == (0.0, 5.0)
+    assert xy.with_obs(["y", "x"]).obs == ("y", "x")
+    np.testing.assert_array_equal(s.inside(np.array([-2.0, -2.0000001, 3.0, 3.1])), [True, False, True, False])  # inclusive
+    assert s.lower.shape == (1, 1) and s.v1.limits[0][0] == -2.0
+    with pytest.raises(Exception):
+        zfit.Space("x", 3, -2)
+
+
+def test_parameter_semantics():
+    p = zfit.Parameter("p_sem", 1.0, 0, 2)
+    assert p.floating and p.independent and p.has_limits and p.stepsize == 0.01 and not p.has_stepsize
+    with pytest.raises(ValueError):
+        p.set_value(2.5)
+    p.set_value(2.5, clip=True)
+    assert p.value() == 2.0
+    with p.set_value(0.5):
+        assert p.value() == 0.5
+    assert p.value() == 2.0
+    q = zfit.Parameter("q_sem", 3.0)
+    with zfit.param.set_values([p, q], [1.5, -1.0]):
+        assert (p.value(), q.value()) == (1.5, -1.0)
+    assert (p.value(), q.value()) == (2.0, 3.0)
+    with pytest.raises(ValueError):
+        zfit.param.set_values([p, q], [1.0])
+    p.assign(5.0)  # unchecked fast path; value() clips with identity gradient (parameter.py:548-557)
+    assert p.value() == 2.0
+    c = zfit.param.convert_to_parameter(3.0)
+    assert not c.floating and not c.independent and list(c.get_params()) == []
+
+
+def test_composed_parameter_chain_rule():
+    a, b = zfit.Parameter("a_cp", 2.0), zfit.Parameter("b_cp", 3.0)
+    prod = zfit.ComposedParameter("prod_cp", lambda p: p["a"] * p["b"] ** 2, params={"a": a, "b": b})  # torch-traceable
+    assert prod.value() == 18.0
+    d = prod._partials()
+    assert abs(d[a] - 9.0) < 1e-12 and abs(d[b] - 12.0) < 1e-12
+    import math
+
+    nt = zfit.ComposedParameter("nt_cp", lambda p: math.sin(float(p["a"])) + float(p["b"]), params={"a": a, "b": b})  # numeric
+    d = nt._partials()
+    assert abs(d[a] - math.cos(2.0)) < 1e-8 and abs(d[b] - 1.0) < 1e-8
+    nested = zfit.ComposedParameter("nest_cp", lambda p: p["x"] + p["y"], params={"x": prod, "y": a})
+    assert abs(nested._partials()[a] - 10.0) < 1e-12
+    assert [p.name for p in nested.get_params()] == ["a_cp", "b_cp"]
+    with pytest.raises(zexc.ParameterNotIndependentError):
+        prod.set_value(1.0)
+
+
+def test_data_cut_weights_obs():
+    obs = zfit.Space("x", -1, 1) * zfit.Space("y", 0, 2)
+    arr = np.array([[0.0, 1.0], [-1.0, 2.0], [1.5, 1.0], [0.5, -0.1], [1.0, 0.0]])
+    w = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    d = zfit.Data(arr, obs=obs, weights=w)
+    assert d.num_entries == 3 and d.nentries == 3 and d.has_weights  # inclusive cut, weights cut alike
+    np.testing.assert_array_equal(d.weights, [1.0, 2.0, 5.0])
+    assert d.samplesize == 8.0
+    np.testing.assert_array_equal(d.value("y"), [1.0, 2.0, 0.0])
+    np.testing.assert_array_equal(d.with_obs(["y", "x"]).value()[:, 0], [1.0, 2.0, 0.0])
+    d1 = zfit.Data.from_numpy(obs="x", array=np.arange(5.0))
+    assert d1.value().shape == (5, 1) and d1.samplesize == 5.0
+    import pandas as pd
+
+    dp = zfit.Data.from_pandas(pd.DataFrame({"x": [0.0, 0.5], "y": [1.0, 1.5], "w": [2.0, 3.0]}), obs=obs, weights="w")
+    assert dp.num_entries == 2 and dp.samplesize == 5.0
+    with pytest.raises(ValueError):
+        zfit.Data(arr, obs=obs, weights=w[:3])
+    import torch
+
+    dt = zfit.Data(torch.tensor(arr), obs=obs, weights=torch.tensor(w))
+    assert dt.num_entries == 3 and dt.samplesize == 8.0
+
+
+def _sig_bkg(tag, extended=True):
+    obs = zfit.Space("m", 5000, 5600)
+    mu = zfit.Parameter("mu" + tag, 5275.0, 5200, 5350)
+    sigma = zfit.Parameter("sigma" + tag, 25.0, 5, 60)
+    alpha = zfit.Parameter("alpha" + tag, 1.2, 0.1, 5)
+    n = zfit.Parameter("n" + tag, 2.5, 1.05, 20)
+    lam = zfit.Parameter("lambda" + tag, -0.003, -0.02, -1e-5)
+    n_sig = zfit.Parameter("n_sig" + tag, 2500.0, 0, 1e5)
+    n_bkg = zfit.Parameter("n_bkg" + tag, 7500.0, 0, 1e5)
+    cb = zfit.pdf.CrystalBall(mu, sigma, alpha, n, obs, extended=n_sig if extended else None)
+    ex = zfit.pdf.Exponential(lam, obs, extended=n_bkg if extended else None)
+    return obs, cb, ex, [n_sig, n_bkg, mu, sigma, alpha, n, lam]
+
+
+def test_lowering_and_param_order():
+    obs, cb, ex, params = _sig_bkg("_lo")
+    model = zfit.pdf.SumPDF([cb, ex])
+    assert model.is_extended and abs(model.get_yield().value() - 10000.0) < 1e-9
+    assert [p.name for p in model.get_params()] == [p.name for p in params]  # yields, then daughters in order
+    assert [p.name for p in model.get_params(is_yield=False)] == [p.name for p in params]  # fracs depend on the yields
+    nodes, slots = model._lower()
+    assert [n.kind for n in nodes] == [Z.SUM, Z.CB, Z.EXP] and nodes[0].n_children == 2
+    assert nodes[2].shift == 5300.0 and (nodes[1].norm_lo, nodes[1].norm_hi) == (5000.0, 5600.0)
+    assert abs(slots[0].value() - 0.25) < 1e-15 and abs(slots[1].value() - 0.75) < 1e-15
+    assert [s.name for s in slots[2:]] == [p.name for p in params[2:]]
+    # product: Exponential unshifted, integrals over the product's range
+    oy = zfit.Space("y", 0, 5)
+    g = zfit.pdf.Gauss(zfit.Parameter("mu_p", 0.0), zfit.Parameter("s_p", 1.0), zfit.Space("x", -4, 4))
+    e = zfit.pdf.Exponential(zfit.Parameter("lam_p", -0.7), oy)
+    c = zfit.pdf.Chebyshev(zfit.Space("z", -2, 4), [zfit.Parameter("c1_p", 0.1), zfit.Parameter("c2_p", 0.2)])
+    prod = zfit.pdf.ProductPDF([g, e, c])
+    assert prod.obs == ("x", "y", "z")
+    nodes, slots = prod._lower(("z", "x", "y"))
+    assert [n.kind for n in nodes] == [Z.PROD, Z.GAUSS, Z.EXP, Z.CHEB]
+    assert [n.column for n in nodes[1:]] == [1, 2, 0] and nodes[2].shift == 0.0 and nodes[3].degree == 2
+    assert slots[3].value() == 1.0 and not slots[3].floating  # c_0 == 1 constant (polynomials.py:97-100)
+    assert [p.name for p in prod.get_params()] == ["mu_p", "s_p", "lam_p", "c1_p", "c2_p"]
+    # remainder fraction
+    s3 = zfit.pdf.SumPDF([g, zfit.pdf.Gauss(zfit.Parameter("mu_q", 1.0), zfit.Parameter("s_q", 2.0), zfit.Space("x", -4, 4))],
+                         fracs=zfit.Parameter("f_q", 0.3))
+    _, sl = s3._lower()
+    assert abs(sl[1].value() - 0.7) < 1e-15 and sl[1]._partials()[s3.params["frac_0"]] == -1.0
+
+
+def test_model_validation_errors():
+    obs = zfit.Space("x", -1, 1)
+    g = zfit.pdf.Gauss(zfit.Parameter("mu_v", 0.0), zfit.Parameter("s_v", 1.0), obs)
+    with pytest.raises(ValueError):
+        zfit.pdf.SumPDF([g])
+    with pytest.raises(zexc.ModelIncompatibleError):
+        zfit.pdf.SumPDF([g, g])  # not extended, no fracs
+    with pytest.raises(zexc.ObsIncompatibleError):
+        zfit.pdf.SumPDF([g, zfit.pdf.Gauss(1.0, 1.0, zfit.Space("y", -1, 1))], fracs=0.5)
+    with pytest.raises(zexc.ParamNameNotUniqueError):
+        zfit.pdf.Gauss(zfit.Parameter("dup", 0.0), zfit.Parameter("dup", 1.0), obs)
+    with pytest.raises(ValueError):
+        zfit.pdf.Chebyshev(zfit.Space("x"), [0.1])
+    ge = g.create_extended(zfit.Parameter("y_v", 10.0))
+    assert ge.is_extended and not g.is_extended and [p.name for p in ge.get_params()] == ["y_v", "mu_v", "s_v"]
+    with pytest.raises(zexc.AlreadyExtendedPDFError):
+        ge.create_extended(5.0)
+    # analytic integrals through the C library's host prologue
+    assert abs(float(g.integrate((-1, 1))[0]) - 1.0) < 1e-15
+    assert abs(float(g.integrate((-1, 0))[0]) - 0.5) < 1e-15
+
+
+def test_loss_validation_errors():
+    obs = zfit.Space("x", -1, 1)
+    g = zfit.pdf.Gauss(zfit.Parameter("mu_lv", 0.0), zfit.Parameter("s_lv", 1.0), obs)
+    d = zfit.Data(np.linspace(-0.9, 0.9, 50), obs=obs)
+    with pytest.raises(TypeError):
+        zfit.loss.UnbinnedNLL((g,), d)
+    with pytest.raises(TypeError):
+        zfit.loss.UnbinnedNLL(g, (d,))
+    with pytest.raises(ValueError):
+        zfit.loss.UnbinnedNLL([], [])
+    with pytest.raises(ValueError):
+        zfit.loss.UnbinnedNLL([g, g], [d])
+    with pytest.raises(TypeError):
+        zfit.loss.UnbinnedNLL("nope", d)
+    with pytest.raises(ValueError):
+        zfit.loss.UnbinnedNLL(g, zfit.Data(np.array([5.0]), obs=obs))  # empty after the cut
+    with pytest.raises(zexc.IntentionAmbiguousError):
+        zfit.loss.UnbinnedNLL(g, np.array([0.0, 3.0]))  # raw array outside the model space
+    with pytest.raises(ValueError):
+        zfit.loss.UnbinnedNLL(g, zfit.Data(np.zeros(3), obs=zfit.Space("y", -1, 1)))
+    nll = use_oracle(zfit.loss.ExtendedUnbinnedNLL(g, d))
+    with pytest.raises(zexc.NotExtendedPDFError):
+        nll.value()
+
+
+# ------------------------------------------------------------------------------------------------ loss host logic
+def _oracle_direct(extended, log_offset, x, vals):
+    cb = O.CrystalBall("mu", "sigma", "alpha", "n", "m", (5000, 5600), yield_="n_sig")
+    ex = O.Exponential("lam", "m", (5000, 5600), yield_="n_bkg")
+    m = O.SumPDF([cb, ex])
+    names = ["n_sig", "n_bkg", "mu", "sigma", "alpha", "n", "lam"]
+    return ON.value_and_gradient([m], [{"m": x}], vals, names, extended=extended, log_offset=log_offset)
+
+
+def test_loss_value_gradient_against_direct_oracle():
+    """Host layer (lowering to slots + chain rule through frac = yield/sum(yields) + Poisson term) == the oracle
+    evaluated directly on the reference's parametrisation."""
+    from tests._cases import cb_exp_case
+
+    x = cb_exp_case(n=4000).cols[0]
+    obs, cb, ex, params = _sig_bkg("_vg")
+    model = zfit.pdf.SumPDF([cb, ex])
+    vals = [p.value() for p in params]
+    ext = use_oracle(zfit.loss.ExtendedUnbinnedNLL(model, zfit.Data(x, obs=obs)))
+    assert [p.name for p in ext.get_params()] == [p.name for p in params]
+    v, g = ext.value_gradient(full=True)
+    rv, rg = _oracle_direct(True, False, x, vals)
+    assert abs(v - rv) < 1e-9 * abs(rv)
+    np.testing.assert_allclose(g, rg, rtol=1e-9, atol=1e-9 * np.abs(rg).max())
+    # full=False: constant from the first evaluation; extended adds the offset once per channel
+    off = ext.options["subtr_const_value"]
+    v2, g2 = ext.value_gradient(full=False)
+    rv2, rg2 = _oracle_direct(True, off, x, vals)
+    assert abs(v2 - rv2) < 1e-7 and np.allclose(g2, rg2, rtol=1e-9, atol=1e-9 * np.abs(rg).max())
+    assert abs(off - ON.initial_log_offset([_oracle_tree()], [{"m": x}], dict(zip(_names(), vals)), extended=True)) < 1e-12
+    # UnbinnedNLL ignores the yields as yields but still depends on them through the fractions
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plain = use_oracle(zfit.loss.UnbinnedNLL(model, zfit.Data(x, obs=obs)))
+    assert not plain.is_extended and [p.name for p in plain.get_params()] == [p.name for p in params]
+    pv, pg = plain.value_gradient(full=True)
+    rpv, rpg = _oracle_direct(False, False, x, vals)
+    assert abs(pv - rpv) < 1e-9 * abs(rpv) and np.allclose(pg, rpg, rtol=1e-9, atol=1e-9 * np.abs(rpg).max())
+    # call protocol (loss.py:532-568)
+    assert ext(np.array(vals)) == ext.value(full=True)
+    with pytest.raises(ValueError):
+        ext(vals[:-1])
+    with pytest.raises(TypeError):
+        ext({"a": 1})
+    sub = [params[3], params[0]]
+    gs = ext.gradient(sub)
+    assert gs[0] == g2[3] and gs[1] == g2[0]
+    with pytest.raises(ValueError):
+        ext.gradient([zfit.Parameter("alien", 1.0)])
+    # numerical gradient option and Hessian
+    gn = ext.gradient(numgrad=True)
+    np.testing.assert_allclose(gn, g2, rtol=2e-5, atol=2e-5 * np.abs(g2).max())
+    H = ext.hessian(params[2:5])
+    assert H.shape == (3, 3) and np.allclose(H, H.T) and np.all(np.linalg.eigvalsh(H[:2, :2]) > 0)
+    assert ext.hessian(params[2:5], hessian="diag").shape == (3,)
+
+
+def _names():
+    return ["n_sig", "n_bkg", "mu", "sigma", "alpha", "n", "lam"]
+
+
+def _oracle_tree():
+    cb = O.CrystalBall("mu", "sigma", "alpha", "n", "m", (5000, 5600), yield_="n_sig")
+    ex = O.Exponential("lam", "m", (5000, 5600), yield_="n_bkg")
+    return O.SumPDF([cb, ex])
+
+
+def test_simultaneous_shared_parameters_and_loss_addition():
+    rng = np.random.default_rng(0)
+    o1, o2 = zfit.Space("x", -5, 5), zfit.Space("y", -5, 5)
+    mu, sigma = zfit.Parameter("mu_sh", 0.3, -2, 2), zfit.Parameter("sigma_sh", 1.2, 0.2, 4)
+    g1 = zfit.pdf.Gauss(mu, sigma, o1)
+    g2 = zfit.pdf.Gauss(mu, zfit.Parameter("sigma2_sh", 2.0, 0.2, 6), o2)
+    d1 = zfit.Data(rng.normal(0.2, 1.0, 500), obs=o1)
+    d2 = zfit.Data(rng.normal(0.2, 2.2, 700), obs=o2)
+    both = use_oracle(zfit.loss.UnbinnedNLL([g1, g2], [d1, d2]))
+    l1, l2 = use_oracle(zfit.loss.UnbinnedNLL(g1, d1)), use_oracle(zfit.loss.UnbinnedNLL(g2, d2))
+    assert [p.name for p in both.get_params()] == ["mu_sh", "sigma_sh", "sigma2_sh"]
+    v, g = both.value_gradient(full=True)
+    v1, ga = l1.value_gradient(full=True)
+    v2, gb = l2.value_gradient(full=True)
+    assert abs(v - (v1 + v2)) < 1e-9
+    np.testing.assert_allclose(g, [ga[0] + gb[0], ga[1], gb[1]], rtol=1e-10)  # shared mu: two slots, one theta
+    added = l1 + l2
+    assert len(added.model) == 2 and isinstance(added, zfit.loss.UnbinnedNLL)
+    with pytest.raises(ValueError):
+        l1 + use_oracle(zfit.loss.ExtendedUnbinnedNLL(g1.create_extended(zfit.Parameter("y_sh", 500.0)), d1))
+
+
+def test_constraint_enters_value_and_gradient():
+    rng = np.random.default_rng(1)
+    obs = zfit.Space("x", -5, 5)
+    mu, sigma = zfit.Parameter("mu_c", 0.3, -2, 2), zfit.Parameter("sigma_c", 1.2, 0.2, 4)
+    g = zfit.pdf.Gauss(mu, sigma, obs)
+    d = zfit.Data(rng.normal(0.2, 1.0, 300), obs=obs)
+    plain = use_oracle(zfit.loss.UnbinnedNLL(g, d))
+    constr = zfit.constraint.GaussianConstraint(mu, observation=0.1, uncertainty=0.05)
+    con = use_oracle(zfit.loss.UnbinnedNLL(g, d, constraints=constr))
+    v0, g0 = plain.value_gradient(full=True)
+    v1, g1 = con.value_gradient(full=True)
+    assert abs((v1 - v0) - constr.value()) < 1e-10
+    assert abs((g1[0] - g0[0]) - (0.3 - 0.1) / 0.05**2) < 1e-8 and abs(g1[1] - g0[1]) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------ minimizers
+def test_golden_fit_through_host_layer_with_oracle_engine():
+    d = np.load(GOLDEN / "deterministic_fit_data.npz", allow_pickle=True)
+    stored = json.loads(str(d["fitted_params_json"]))
+    obs = zfit.Space("x", -10, 10)
+    mu = zfit.Parameter("mu", 0.5, -4, 6)
+    sigma = zfit.Parameter("sigma", 1.2, 0.1, 10)
+    lambd = zfit.Parameter("lambda", -0.05, -1, -0.01)
+    n_bkg = zfit.Parameter("n_bkg", 20000, 0, 50000)
+    n_sig = zfit.Parameter("n_sig", 1000, 0, 30000)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu=mu, sigma=sigma, obs=obs, extended=n_sig),
+                             zfit.pdf.Exponential(lambd, obs=obs, extended=n_bkg)])
+    nll = use_oracle(zfit.loss.ExtendedUnbinnedNLL(model=model, data=zfit.Data(d["data"], obs=obs)))
+    assert [p.name for p in nll.get_params()] == list(stored)
+    result = zfit.minimize.Minuit(gradient="zfit").minimize(nll).update_params()
+    assert result.valid and result.converged and result.edm < 1e-3
+    errs = result.hesse()
+    for p in result.params:
+        assert abs(result.params[p]["value"] - stored[p.name]) < 0.1 * errs[p]["error"], p.name
+    assert abs(result.fmin - 62323.84) < 0.05
+    assert "driver" in result.info and result.info["n_eval"] < 200
+    assert str(result).startswith("FitResult")
+    assert abs(result.params["mu"]["value"] - mu.value()) == 0.0
+
+
+@pytest.mark.parametrize("factory", [
+    lambda: zfit.minimize.Minuit(),                      # the driver's own numerical gradient (Minuit default)
+    lambda: zfit.minimize.Minuit(gradient="zfit"),
+    lambda: zfit.minimize.ScipyLBFGSB(),
+    lambda: zfit.minimize.ScipyTrustConstr(),
+    lambda: zfit.minimize.ScipySLSQP(),
+])
+def test_minimizers_acceptance_problem(factory):
+    """tests/minimize/test_minimizer.py:24-48: Gauss + Exponential SumPDF (frac 0.8), mu, sigma, lambda within 0.1."""
+    rng = np.random.default_rng(5)
+    n = 6000
+    sig = rng.normal(1.0, 0.5, int(0.8 * n))
+    u = rng.uniform(0, 1, n - sig.size)
+    lam_true, lo, hi = -0.4, -5.0, 5.0  # truncated exponential by inverse CDF
+    bkg = lo + np.log1p(u * np.expm1(lam_true * (hi - lo))) / lam_true
+    obs = zfit.Space("obs1", lo, hi)
+    tag = f"_{abs(hash(factory)) % 10**6}"
+    mu = zfit.Parameter("mu" + tag, 0.6, -2, 3)
+    sigma = zfit.Parameter("sigma" + tag, 0.8, 0.1, 3)
+    lam = zfit.Parameter("lambda" + tag, -0.7, -3, -0.01)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu, sigma, obs), zfit.pdf.Exponential(lam, obs)], fracs=0.8)
+    nll = use_oracle(zfit.loss.UnbinnedNLL(model, zfit.Data(np.concatenate([sig, bkg]), obs=obs)))
+    result = factory().minimize(nll)
+    assert result.valid, result.message
+    assert abs(mu.value() - 1.0) < 0.1 and abs(sigma.value() - 0.5) < 0.1 and abs(lam.value() - lam_true) < 0.1
+
+
+def test_nan_strategy_and_maxiter():
+    a = zfit.Parameter("a_nan", 1.0)
+
+    def f(params):
+        x = params[0].value()
+        return float("nan") if x > 1.5 else (x - 3.0) ** 2
+
+    loss = zfit.loss.SimpleLoss(f, [a], errordef=0.5)
+    ev = zfit.minimize.LossEval(loss, [a], zfit.minimize.PushbackStrategy(), False, maxiter=50)
+    assert ev.value(np.array([1.0])) == 4.0
+    assert ev.value(np.array([2.0])) == 4.0 + 100  # pushed back: last value + penalty (strategy.py:104-126)
+    assert ev.nan_counter == 1
+    ev2 = zfit.minimize.LossEval(loss, [a], zfit.minimize.PushbackStrategy(), False, maxiter=2)
+    ev2.value(np.array([1.0]))
+    ev2.value(np.array([1.0]))
+    with pytest.raises(zexc.MaximumIterationReached):
+        ev2.value(np.array([1.0]))
+
+
+def test_errors_profile_interval():
+    rng = np.random.default_rng(7)
+    obs = zfit.Space("x", -6, 6)
+    mu, sigma = zfit.Parameter("mu_er", 0.2, -2, 2), zfit.Parameter("sigma_er", 1.1, 0.3, 4)
+    nll = use_oracle(zfit.loss.UnbinnedNLL(zfit.pdf.Gauss(mu, sigma, obs), zfit.Data(rng.normal(0.0, 1.0, 400), obs=obs)))
+    result = zfit.minimize.Minuit(gradient="zfit", tol=1e-6).minimize(nll)
+    h = result.hesse()
+    e, _ = result.errors(params=[mu])
+    assert abs(h[mu]["error"] - 1.0 / np.sqrt(400)) < 0.01
+    assert abs(e[mu]["upper"] - h[mu]["error"]) < 0.1 * h[mu]["error"] and abs(e[mu]["lower"] + h[mu]["error"]) < 0.1 * h[mu]["error"]
+    cov = result.covariance()
+    assert cov.shape == (2, 2) and abs(cov[0, 0] - h[mu]["error"] ** 2) < 1e-12

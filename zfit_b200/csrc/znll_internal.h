@@ -31,7 +31,9 @@ const ZnllCatalogEntry* znll_catalog_at(int i);
 cudaError_t znll_launch_sumw(const double* w, long long n, double* partials, unsigned int* ticket, double* out,
                              int grid, cudaStream_t stream);
 
+#ifndef ZNLL_BLOCKS_PER_SM
 #define ZNLL_BLOCKS_PER_SM 3  // must match ZNLL_MIN_BLOCKS in znll_device.cuh
+#endif
 
 // test hook: out[i] = f(in[i]) with f = fast_exp (0), fast_log (1), fast_rcp (2) of znll_device.cuh
 cudaError_t znll_launch_test_math(int kind, const double* in, double* out, long long n, cudaStream_t stream);

@@ -171,6 +171,8 @@ class BaseLoss:
         self._errordef = None
         self._engine = None
         self._engine_factory = None
+        self._all_params = None
+        self._slot_plan = None
         self._assert_params_unique()
 
     # ------------------------------------------------------------------ init helpers
@@ -332,20 +334,25 @@ class BaseLoss:
     # ------------------------------------------------------------------ core evaluation
     def _nll_channels(self, want_grad, log_offset):
         eng = self._get_engine()
-        slots = np.array([p.value() for p in eng.slot_params], dtype=np.float64)
+        if self._slot_plan is None or self._slot_plan[0] is not eng:
+            sp = eng.slot_params
+            direct = [(j, p) for j, p in enumerate(sp) if p.independent]
+            composed = [(j, p) for j, p in enumerate(sp) if not p.independent and p._leaves()]
+            self._slot_plan = (eng, direct, composed, np.empty(len(sp), dtype=np.float64))
+        _, direct, composed, slots = self._slot_plan
+        for j, p in enumerate(eng.slot_params):
+            slots[j] = p.value()
         kahan = self._options.get("sumtype") == "kahan" and not self.is_extended
         values, gslots = eng.eval(slots, grad=want_grad, log_offset=0.0 if log_offset is False else float(log_offset), kahan=kahan)
-        total = 0.0
-        for v in values:
-            total += float(v)
+        total = float(values.sum()) if len(values) > 1 else float(values[0])
         grad = {}
         if want_grad:
-            for p, g in zip(eng.slot_params, gslots):
-                if p.independent:
-                    grad[p] = grad.get(p, 0.0) + float(g)
-                else:
-                    for leaf, d in p._partials().items():
-                        grad[leaf] = grad.get(leaf, 0.0) + float(g) * d
+            for j, p in direct:
+                grad[p] = grad.get(p, 0.0) + gslots[j]
+            for j, p in composed:
+                g = gslots[j]
+                for leaf, d in p._partials().items():
+                    grad[leaf] = grad.get(leaf, 0.0) + g * d
         return total, grad
 
     def _extra_terms(self, want_grad, log_offset):
@@ -404,6 +411,14 @@ class BaseLoss:
         msg = f"cannot interpret params {params}"
         raise TypeError(msg)
 
+    def _all_params_cached(self):
+        # membership of a parameter in the loss never changes after construction (only `floating` may)
+        if self._all_params is None:
+            self._all_params = self.get_params(floating=None, extract_independent=None, is_yield=None).union(
+                self.get_params(floating=None, extract_independent=True, is_yield=None)
+            )
+        return self._all_params
+
     def _input_check_params(self, params, only_independent=False):
         if params is None:
             return tuple(self.get_params())
@@ -413,7 +428,7 @@ class BaseLoss:
         if only_independent and (bad := [p for p in params if not p.independent]):
             msg = f"Parameters {bad} are not independent and `only_independent` is set to True."
             raise ValueError(msg)
-        allp = self.get_params(floating=None, extract_independent=None, is_yield=None)
+        allp = self._all_params_cached()
         if not_in := [p for p in params if p not in allp]:
             msg = f"Parameters {not_in} are not in the model."
             raise ValueError(msg)

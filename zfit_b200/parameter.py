@@ -83,15 +83,18 @@ class ZfitParameter:
 
 
 class OrderedSet(list):
-    """Insertion-ordered set with the little API the loss / minimizers use (``ordered_set.OrderedSet``)."""
+    """Insertion-ordered set with the little API the loss / minimizers use (``ordered_set.OrderedSet``).
+    Membership is by identity (parameters are unique objects), O(1) through an id index."""
 
     def __init__(self, it=()):
         super().__init__()
+        self._ids = set()
         for x in it:
             self.add(x)
 
     def add(self, x):
-        if not any(x is y for y in self):
+        if id(x) not in self._ids:
+            self._ids.add(id(x))
             self.append(x)
 
     def union(self, *others):
@@ -102,7 +105,7 @@ class OrderedSet(list):
         return out
 
     def __contains__(self, x):
-        return any(x is y for y in self)
+        return id(x) in self._ids
 
     def __sub__(self, other):
         return OrderedSet(x for x in self if x not in other)
