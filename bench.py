@@ -219,7 +219,9 @@ def run_product(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+
+        td.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
 
     import zfit_b200 as zfit  # noqa: F401
     from zfit_b200 import _znll as Z
@@ -366,6 +368,25 @@ def run_product(args):
             except Exception as exc:  # the checker failing must not void the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
                                         "sample": f"failed: {exc!r}"}
+    if not args.no_fit:
+        # ---- end-to-end fit wall time (all ranks run the same minimizer in lock-step) ---------------------------
+        for p, v in zip(params, theta0):
+            p.assign(v)
+        barrier()
+        t0 = time.perf_counter()
+        minimizer = zfit.minimize.Minuit(gradient="zfit")
+        result = minimizer.minimize(loss)
+        barrier()
+        fit_s = time.perf_counter() - t0
+        line["fit"] = {
+            "wall_s": fit_s,
+            "n_eval": int(result.info.get("n_eval", -1)),
+            "valid": bool(result.valid),
+            "edm": None if result.edm is None else float(result.edm),
+            "driver": result.info.get("driver"),
+            "minimizer": "zfit.minimize.Minuit(gradient='zfit'), tol=1e-3",
+            "fitted": {p.name: result.params[p]["value"] for p in result.params},
+        }
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -385,6 +406,7 @@ def main():
     ap.add_argument("--ref-events", type=int, default=2_000_000, help="bounded sample of the reference arm")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fit", action="store_true", help="skip the end-to-end Minuit fit after the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -123,7 +123,7 @@ int64_t znll_plan_launch_count(const znll_plan* plan);
  *               pass 0.0 for full=True
  *   values      [n_channels]    host out
  *   grad_slots  [total_slots]   host out (may be NULL without ZNLL_WANT_GRAD)
- *   stream      cudaStream_t as void* (NULL = the plan's own stream)
+ *   stream      cudaStream_t as void* (NULL = the default stream); all work of a call is enqueued there
  * Synchronous with respect to its outputs.  Replaces _unbinned_nll_tf + _nll_calc_unbinned_tf
  * (core/loss.py:73-142) and autodiff_value_gradient (z/math.py:236-261). */
 int znll_eval(znll_plan* plan, const double* slots, uint32_t flags, double log_offset,

@@ -1,0 +1,61 @@
+"""Multi-GPU worker (NCCL): event-sharded CUDA engine, one all-reduce of the raw accumulators per step."""
+
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import zfit_b200 as zfit  # noqa: E402
+from tests._dist_worker import build  # noqa: E402
+from zfit_b200 import distributed as D  # noqa: E402
+
+
+def main():
+    out = sys.argv[1]
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    import datetime
+
+    td.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
+    rank, world = td.get_rank(), td.get_world_size()
+    rng = np.random.default_rng(11)
+    n = 2_000_001
+    x = np.concatenate([rng.normal(1.0, 1.5, n // 3), rng.uniform(-10, 10, n - n // 3)])
+    x = x[(x >= -10) & (x <= 10)]
+    w = rng.normal(1.0, 0.6, x.size)
+    res = {}
+    for det in (False, True):
+        model, full, obs = build(x, w, f"_g{int(det)}")
+        nll = zfit.loss.UnbinnedNLL(model, D.shard(full), options={"deterministic_reduce": det})
+        params = list(nll.get_params())
+        v, g = nll.value_gradient(params, full=True)
+        mine = torch.tensor([v, *g], dtype=torch.float64, device=f"cuda:{local_rank}")
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        td.all_gather(gathered, mine)
+        assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree bitwise"
+        single = zfit.loss.UnbinnedNLL(model, full, options={"distributed": False})
+        sv, sg = single.value_gradient(params, full=True)
+        assert abs(v - sv) <= 1e-12 * abs(sv), (v, sv)
+        assert np.all(np.abs(g - sg) <= 1e-10 * np.abs(sg).max()), (g, sg)
+        result = zfit.minimize.Minuit(gradient="zfit").minimize(nll)
+        fitted = torch.tensor([result.params[p]["value"] for p in result.params], dtype=torch.float64, device=f"cuda:{local_rank}")
+        gathered = [torch.empty_like(fitted) for _ in range(world)]
+        td.all_gather(gathered, fitted)
+        assert all(torch.equal(gathered[0], t) for t in gathered)
+        res[f"det{int(det)}"] = {"value": v, "single": sv, "valid": bool(result.valid), "n_eval": int(result.info["n_eval"]),
+                                 "kernel": nll._get_engine().kernel_names}
+    if rank == 0:
+        json.dump(res, open(out, "w"))
+    td.barrier()
+    td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

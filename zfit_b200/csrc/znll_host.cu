@@ -264,7 +264,6 @@ struct Channel {
 struct znll_plan {
   int device = 0, sm_count = 148;
   std::vector<Channel> ch;
-  cudaStream_t stream = nullptr;
   double* d_acc = nullptr;
   double* h_acc = nullptr;  // pinned
   int total_acc = 0, total_slots = 0;
@@ -620,7 +619,6 @@ int znll_plan_create(int device, int n_channels, znll_plan** out) {
   p->sm_count = prop.multiProcessorCount;
   p->max_grid = p->sm_count * ZNLL_BLOCKS_PER_SM;  // persistent grid: resident CTAs of 256 threads per SM
   p->ch.resize(n_channels);
-  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   *out = p;
   return 0;
 }
@@ -641,7 +639,6 @@ void znll_plan_destroy(znll_plan* p) {
   }
   if (p->d_acc) cudaFree(p->d_acc);
   if (p->h_acc) cudaFreeHost(p->h_acc);
-  if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
 
@@ -704,11 +701,11 @@ static int compute_sumw(znll_plan* p, Channel& c) {
   CUDA_OK(cudaMalloc(&d_part, sizeof(double) * 2 * p->max_grid));
   CUDA_OK(cudaMalloc(&d_out, sizeof(double) * 2));
   const int grid = grid_for(p, c.n * 2);
-  cudaError_t e = znll_launch_sumw(c.w, c.n, d_part, c.d_ticket, d_out, grid, p->stream);
+  cudaError_t e = znll_launch_sumw(c.w, c.n, d_part, c.d_ticket, d_out, grid, 0);
   p->launches++;
   double h[2] = {0, 0};
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, p->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   cudaFree(d_part);
   cudaFree(d_out);
   if (e != cudaSuccess) return fail("sum of weights failed: %s", cudaGetErrorString(e));
@@ -802,7 +799,7 @@ double* znll_plan_acc_device(znll_plan* p) { return p ? p->d_acc : nullptr; }
 int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_offset, void* stream) {
   if (!p || !slots) return fail("znll_launch: bad arguments");
   CUDA_OK(cudaSetDevice(p->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the (legacy) default stream
   const int g = (flags & ZNLL_WANT_GRAD) ? 1 : 0;
   for (auto& c : p->ch) {
     if (c.nodes.empty() || !c.bound) return fail("znll_launch: channel without model or data");
@@ -835,7 +832,7 @@ int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_of
 
 int znll_collect(znll_plan* p, uint32_t flags, double* values, double* grad_slots, void* stream) {
   if (!p || !values) return fail("znll_collect: bad arguments");
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the (legacy) default stream
   CUDA_OK(cudaMemcpyAsync(p->h_acc, p->d_acc, sizeof(double) * p->total_acc, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   for (size_t k = 0; k < p->ch.size(); ++k) {
@@ -857,7 +854,7 @@ int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* 
   Channel& c = p->ch[ch];
   if (c.nodes.empty() || !c.bound) return fail("znll_pdf: channel without model or data");
   if (c.n == 0) return 0;
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the (legacy) default stream
   c.slots.assign(slots, slots + c.n_slots);
   fill_consts(c, c.slots.data());
   double* d_out = nullptr;

@@ -51,11 +51,12 @@ class CudaEngine:
     of the raw ``sum(1 + n_slots)`` fp64 accumulators per call, issued on the launch stream).
     """
 
-    def __init__(self, models, datas, fit_ranges, *, device=None, sort_events=True, deterministic_reduce=False):
+    def __init__(self, models, datas, fit_ranges, *, device=None, sort_events=True, deterministic_reduce=False,
+                 distributed=None):
         from . import _znll as Z
 
         self.Z = Z
-        self.distributed = _dist.is_distributed()
+        self.distributed = _dist.is_distributed() if distributed is None else bool(distributed)
         self.deterministic_reduce = deterministic_reduce
         if device is None:
             device = _dist.local_device()
@@ -115,7 +116,7 @@ class CudaEngine:
         return cols, w
 
     def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
-        # kernels go to torch's current stream (0 = default stream -> the plan's own stream)
+        # kernels go to torch's current stream, so torch ops (NCCL all-reduce, data preparation) order with them
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
         if not self.distributed:
             return self.plan.eval(slots, grad=grad, log_offset=log_offset, kahan=kahan, stream=stream)
@@ -323,6 +324,7 @@ class BaseLoss:
                     self.fit_range,
                     sort_events=self._options.get("sort_events", True),
                     deterministic_reduce=self._options.get("deterministic_reduce", False),
+                    distributed=self._options.get("distributed"),
                 )
         return self._engine
 
