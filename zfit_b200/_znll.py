@@ -12,7 +12,9 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libznll.so"
+import os as _os
+
+LIB_PATH = Path(_os.environ.get("ZNLL_LIB", _HERE / "libznll.so"))  # ZNLL_LIB: tuning experiments only
 
 GAUSS, EXP, CB, CHEB, SUM, PROD = 1, 2, 3, 4, 16, 17
 WANT_GRAD, KAHAN = 1, 2

@@ -17,10 +17,10 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "_build"
-LIB = HERE / "libznll.so"
+LIB = Path(os.environ.get("ZNLL_LIB_OUT", HERE / "libznll.so"))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-BPS = os.environ.get("ZNLL_BPS", "3")  # resident CTAs (256 threads) per SM the kernels are tuned for
+BPS = os.environ.get("ZNLL_BPS", "2")  # resident CTAs (256 threads) per SM the kernels are tuned for
 CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", f"-DZNLL_MIN_BLOCKS={BPS}", f"-DZNLL_BLOCKS_PER_SM={BPS}"]
 
 SOURCES = ["znll_host.cu", "znll_catalog_a.cu", "znll_catalog_b.cu", "znll_catalog_c.cu"]

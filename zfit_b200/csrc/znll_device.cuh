@@ -9,7 +9,13 @@
 // followed by a warp-shuffle / shared-memory block reduction and a deterministic fixed-order
 // cross-block reduce executed by the last block to finish (ticket counter).
 //
-// The same header is compiled ahead of time by nvcc (znll_catalog.cu) and, for tree shapes that
+// The FP64 pipe is the roofline, and its enemy is the dependent DFMA chain (Horner polynomials):
+// all node code is therefore written once over a value type V that is either `double` or `D2`
+// -- the two events a thread loads with one double2 -- so that every source-level operation
+// emits two independent instructions back to back (2-way ILP inside each warp) and every rare-path
+// branch (out-of-range exp/log arguments, CrystalBall tail) is taken once per pair.
+//
+// The same header is compiled ahead of time by nvcc (znll_catalog_*.cu) and, for tree shapes that
 // are not in the catalogue, at run time by NVRTC (znll_host.cu) -- so it only depends on CUDA
 // built-ins, no standard headers.
 //
@@ -25,25 +31,153 @@
 #define ZNLL_MAXCOL 8
 #define ZNLL_BLOCK 256
 #ifndef ZNLL_MIN_BLOCKS
-#define ZNLL_MIN_BLOCKS 3  // resident CTAs per SM the register allocation is tuned for
+#define ZNLL_MIN_BLOCKS 2  // resident CTAs per SM the register allocation is tuned for
 #endif
 #define ZNLL_LOG_EPS 1e-307
 
 namespace znll {
 
 // ----------------------------------------------------------------------------------------------
-// fp64 elementary functions tuned for this kernel (the FP64 pipe is the roofline):
+// two-lane value type
+// ----------------------------------------------------------------------------------------------
+struct D2 {
+  double a, b;
+};
+struct M2 {
+  bool a, b;
+};
+
+__device__ __forceinline__ double la(double x) { return x; }
+__device__ __forceinline__ double lb(double x) { return x; }
+__device__ __forceinline__ double la(D2 x) { return x.a; }
+__device__ __forceinline__ double lb(D2 x) { return x.b; }
+__device__ __forceinline__ bool la(bool x) { return x; }
+__device__ __forceinline__ bool lb(bool x) { return x; }
+__device__ __forceinline__ bool la(M2 x) { return x.a; }
+__device__ __forceinline__ bool lb(M2 x) { return x.b; }
+
+template <class V>
+struct Lanes;
+template <>
+struct Lanes<double> {
+  typedef bool Mask;
+  static __device__ __forceinline__ double make(double a, double) { return a; }
+  static __device__ __forceinline__ bool mask(bool a, bool) { return a; }
+  static constexpr int N = 1;
+};
+template <>
+struct Lanes<D2> {
+  typedef M2 Mask;
+  static __device__ __forceinline__ D2 make(double a, double b) {
+    D2 r;
+    r.a = a;
+    r.b = b;
+    return r;
+  }
+  static __device__ __forceinline__ M2 mask(bool a, bool b) {
+    M2 r;
+    r.a = a;
+    r.b = b;
+    return r;
+  }
+  static constexpr int N = 2;
+};
+
+// result type of a mixed scalar / two-lane expression
+template <class A, class B = double, class C = double>
+struct Wide {
+  typedef double T;
+};
+template <class B, class C>
+struct Wide<D2, B, C> {
+  typedef D2 T;
+};
+template <class C>
+struct Wide<double, D2, C> {
+  typedef D2 T;
+};
+template <>
+struct Wide<double, double, D2> {
+  typedef D2 T;
+};
+
+#define ZNLL_DEV __device__ __forceinline__
+
+template <class A, class B, class C>
+ZNLL_DEV typename Wide<A, B, C>::T zfma(A x, B y, C z) {
+  typedef typename Wide<A, B, C>::T R;
+  return Lanes<R>::make(fma(la(x), la(y), la(z)), fma(lb(x), lb(y), lb(z)));
+}
+template <class A, class B>
+ZNLL_DEV typename Wide<A, B>::T zmul(A x, B y) {
+  typedef typename Wide<A, B>::T R;
+  return Lanes<R>::make(la(x) * la(y), lb(x) * lb(y));
+}
+template <class A, class B>
+ZNLL_DEV typename Wide<A, B>::T zadd(A x, B y) {
+  typedef typename Wide<A, B>::T R;
+  return Lanes<R>::make(la(x) + la(y), lb(x) + lb(y));
+}
+template <class A, class B>
+ZNLL_DEV typename Wide<A, B>::T zsub(A x, B y) {
+  typedef typename Wide<A, B>::T R;
+  return Lanes<R>::make(la(x) - la(y), lb(x) - lb(y));
+}
+template <class V>
+ZNLL_DEV V zneg(V x) {
+  return Lanes<V>::make(-la(x), -lb(x));
+}
+template <class V>
+ZNLL_DEV V zabs(V x) {
+  return Lanes<V>::make(fabs(la(x)), fabs(lb(x)));
+}
+template <class V>
+ZNLL_DEV typename Lanes<V>::Mask zlt(V x, double y) {
+  return Lanes<V>::mask(la(x) < y, lb(x) < y);
+}
+template <class M>
+ZNLL_DEV bool zany(M m) {
+  return la(m) || lb(m);
+}
+template <class M>
+ZNLL_DEV bool zall(M m) {
+  return la(m) && lb(m);
+}
+ZNLL_DEV bool mxor(bool p, bool q) { return p != q; }
+ZNLL_DEV M2 mxor(M2 p, M2 q) {
+  M2 r;
+  r.a = p.a != q.a;
+  r.b = p.b != q.b;
+  return r;
+}
+template <class M, class V>
+ZNLL_DEV V zsel(M m, V x, V y) {
+  return Lanes<V>::make(la(m) ? la(x) : la(y), lb(m) ? lb(x) : lb(y));
+}
+template <class V>
+ZNLL_DEV V zbc(double x) {
+  return Lanes<V>::make(x, x);
+}
+// acc += sum over lanes of g*d
+ZNLL_DEV void zacc(double& acc, double g, double d) { acc = fma(g, d, acc); }
+ZNLL_DEV void zacc(double& acc, D2 g, D2 d) { acc = fma(g.b, d.b, fma(g.a, d.a, acc)); }
+ZNLL_DEV void zacc(double& acc, D2 g, double d) { acc = fma(g.a + g.b, d, acc); }
+ZNLL_DEV void zacc1(double& acc, double g) { acc += g; }
+ZNLL_DEV void zacc1(double& acc, D2 g) { acc += g.a + g.b; }
+
+// ----------------------------------------------------------------------------------------------
+// fp64 elementary functions tuned for this kernel:
 //   * polynomial coefficients live in the constant bank, so every DFMA takes them as an operand
 //     (libdevice materialises each one with two UMOVs -> more issue slots than DP work);
 //   * log uses a 128-entry (1/c, log c) table in shared memory and a degree-7 log1p polynomial:
 //     13 DP instructions instead of ~35 (no division); exp: 15 DP instructions;
-//   * reciprocal: MUFU.RCP64H seed + two Newton steps (4 DFMA).
-// Accuracy (tests/test_math_gpu.py): exp, log <= 1 ulp-level relative error (measured ~2e-16),
-// far inside the 1e-12 NLL tolerance; arguments outside the fast range (|x| >= 700 for exp;
-// non-positive, subnormal, inf or NaN for log / rcp) take the libdevice path.
+//   * reciprocal: MUFU.RCP64H seed + two Newton steps (4 DFMA);
+//   * both lanes of a D2 run interleaved; the libdevice path (|x| >= 700 for exp; non-positive,
+//     subnormal, inf or NaN for log / rcp) is taken once per pair.
+// Accuracy is tested on the GPU against libm (tests/test_math_gpu.py).
 // ----------------------------------------------------------------------------------------------
 static __constant__ double kExpC[10] = {
-    0.5000000000000001,     0.16666666666666669,    0.04166666666662413,   0.008333333333330062,
+    0.5000000000000001,     0.16666666666666669,    0.04166666666662413,    0.008333333333330062,
     0.0013888888917213717,  0.00019841269863053618, 2.4801521295954376e-05, 2.7557268459997064e-06,
     2.7620088445409746e-07, 2.510038549551032e-08};
 static __constant__ double kLogC[6] = {-0.5,
@@ -53,66 +187,86 @@ static __constant__ double kLogC[6] = {-0.5,
                                        -0.16666959217649738,
                                        0.14285974331115564};
 static __constant__ double kMathC[8] = {
-    1.4426950408889634,        // 0 log2(e)
-    6755399441055744.0,        // 1 1.5 * 2^52
+    1.4426950408889634,           // 0 log2(e)
+    6755399441055744.0,           // 1 1.5 * 2^52
     -6.93147180369123816490e-01,  // 2 -ln2_hi
     -1.90821492927058770002e-10,  // 3 -ln2_lo
-    0x1.62e42fefa3800p-1,      // 4 ln2_hi (42 significant bits: k*ln2_hi is exact)
-    0x1.ef35793c76730p-45,     // 5 ln2_lo
-    4503601774854144.0,        // 6 2^52 + 2^31
+    0x1.62e42fefa3800p-1,         // 4 ln2_hi (42 significant bits: k*ln2_hi is exact)
+    0x1.ef35793c76730p-45,        // 5 ln2_lo
+    4503601774854144.0,           // 6 2^52 + 2^31
     0.0};
 
 struct Ctx {
   const double2* logtab;  // shared memory: (1/c_i, log c_i) for 128 intervals of [0.6875, 1.375)
 };
 
-__device__ __forceinline__ double fast_exp(double x) {
-  const int hx = __double2hiint(x) & 0x7fffffff;
-  if (hx >= 0x4085E000) return exp(x);  // |x| >= 700, inf, NaN: rare
-  const double t = fma(x, kMathC[0], kMathC[1]);
-  const int n = __double2loint(t);
-  const double nd = t - kMathC[1];
-  double r = fma(nd, kMathC[2], x);
-  r = fma(nd, kMathC[3], r);
-  double p = kExpC[9];
-#pragma unroll
-  for (int k = 8; k >= 0; --k) p = fma(p, r, kExpC[k]);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
-
-__device__ __forceinline__ double fast_rcp(double x) {
-  const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
-  if (ex - 1u >= 0x7fdu) return 1.0 / x;  // zero, subnormal, inf, NaN
+ZNLL_DEV bool exp_in_range(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x4085E000; }  // |x| < 700
+ZNLL_DEV bool log_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u; }
+ZNLL_DEV bool rcp_in_range(double x) { return (((unsigned)__double2hiint(x) >> 20) & 0x7ffu) - 1u < 0x7fdu; }
+ZNLL_DEV double scale2n(double p, int n) { return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p)); }
+ZNLL_DEV double rcp_seed(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
+  return y;
 }
 
-__device__ __forceinline__ double fast_log(double x, const Ctx& cx) {
-  const int hi = __double2hiint(x);
-  if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);  // x <= 0, subnormal, inf, NaN
-  const int tmp = hi - 0x3fe60000;
-  const int i = (tmp >> 13) & 127;
-  const int k = tmp >> 20;
-  const double z = __hiloint2double(hi - (tmp & 0xfff00000), __double2loint(x));
-  const double2 tc = cx.logtab[i];
-  const double r = fma(z, tc.x, -1.0);
-  const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - kMathC[6];
-  double s = kLogC[5];
+template <class V>
+ZNLL_DEV V fast_exp(V x) {
+  if (!(exp_in_range(la(x)) && exp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
+  const V t = zfma(x, kMathC[0], kMathC[1]);
+  const V nd = zsub(t, kMathC[1]);
+  V r = zfma(nd, kMathC[2], x);
+  r = zfma(nd, kMathC[3], r);
+  V p = zfma(r, kExpC[9], kExpC[8]);
 #pragma unroll
-  for (int j = 4; j >= 0; --j) s = fma(s, r, kLogC[j]);
-  const double w = fma(kd, kMathC[4], tc.y);
-  const double t2 = fma(r * r, s, kd * kMathC[5]);
-  return w + (r + t2);
+  for (int k = 7; k >= 0; --k) p = zfma(p, r, kExpC[k]);
+  p = zfma(p, r, 1.0);
+  p = zfma(p, r, 1.0);
+  return Lanes<V>::make(scale2n(la(p), __double2loint(la(t))), scale2n(lb(p), __double2loint(lb(t))));
+}
+
+template <class V>
+ZNLL_DEV V fast_rcp(V x) {
+  if (!(rcp_in_range(la(x)) && rcp_in_range(lb(x)))) return Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));  // rare
+  V y = Lanes<V>::make(rcp_seed(la(x)), rcp_seed(lb(x)));
+  const V nx = zneg(x);
+  V e = zfma(nx, y, 1.0);
+  y = zfma(y, e, y);
+  e = zfma(nx, y, 1.0);
+  return zfma(y, e, y);
+}
+
+struct LogSplit {
+  double z, kd;
+  double2 tc;
+};
+ZNLL_DEV LogSplit log_split(double x, const Ctx& cx) {
+  LogSplit s;
+  const int hi = __double2hiint(x);
+  const int tmp = hi - 0x3fe60000;
+  s.z = __hiloint2double(hi - (tmp & 0xfff00000), __double2loint(x));
+  s.tc = cx.logtab[(tmp >> 13) & 127];
+  s.kd = __hiloint2double(0x43300000, (tmp >> 20) ^ 0x80000000);
+  return s;
+}
+
+template <class V>
+ZNLL_DEV V fast_log(V x, const Ctx& cx) {
+  if (!(log_in_range(la(x)) && log_in_range(lb(x)))) return Lanes<V>::make(log(la(x)), log(lb(x)));  // rare
+  const LogSplit sa = log_split(la(x), cx), sb = log_split(lb(x), cx);
+  const V z = Lanes<V>::make(sa.z, sb.z), invc = Lanes<V>::make(sa.tc.x, sb.tc.x), logc = Lanes<V>::make(sa.tc.y, sb.tc.y);
+  const V kd = zsub(Lanes<V>::make(sa.kd, sb.kd), kMathC[6]);
+  const V r = zfma(z, invc, -1.0);
+  V s = zfma(r, kLogC[5], kLogC[4]);
+#pragma unroll
+  for (int j = 3; j >= 0; --j) s = zfma(s, r, kLogC[j]);
+  const V w = zfma(kd, kMathC[4], logc);
+  const V t2 = zfma(zmul(r, r), s, zmul(kd, kMathC[5]));
+  return zadd(w, zadd(r, t2));
 }
 
 // one entry per thread < 128, then __syncthreads() by the caller
-__device__ __forceinline__ void init_logtab(double2* tab) {
+ZNLL_DEV void init_logtab(double2* tab) {
   if (threadIdx.x < 128) {
     const int ha = 0x3fe60000 + ((int)threadIdx.x << 13);
     const double a = __hiloint2double(ha, 0), b = __hiloint2double(ha + (1 << 13), 0);
@@ -122,280 +276,409 @@ __device__ __forceinline__ void init_logtab(double2* tab) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// leaves.  c = const block, x = this event's column values, acc = per-thread accumulators.
+// leaves.  c = const block, x = this event's (pair's) column values, acc = per-thread accumulators.
 // CO / AO are compile-time offsets into c / acc, so every access is a fixed register or a
-// constant-bank operand.
+// constant-bank operand.  `neg` tracks the sign of a product with non-positive factors.
 // ----------------------------------------------------------------------------------------------
 
 // Gauss: consts [1/sigma, -mu/sigma, -(0.5*ln(2pi)+ln sigma) - ln I];  slots [mu, sigma]
+template <int COL, class V>
+struct GaussN {
+  typedef typename Lanes<V>::Mask Mask;
+  V t, P;
+
+  template <int CO>
+  ZNLL_DEV V fwd_log(const Ctx&, const double* __restrict__ c, const V* x, Mask&) {
+    t = zfma(x[COL], c[CO + 0], c[CO + 1]);  // x/sigma - mu/sigma (tfp Normal._log_prob)
+    return zfma(zmul(t, -0.5), t, c[CO + 2]);
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg;
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    return P;
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    const V gi = zmul(g, c[CO + 0]);
+    zacc(acc[AO + 0], gi, t);                  // d/dmu    =  t/sigma
+    zacc(acc[AO + 1], gi, zfma(t, t, -1.0));   // d/dsigma = (t^2-1)/sigma
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
+  }
+};
 template <int COL>
 struct Gauss {
   static constexpr int NS = 2, NC = 3, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
-  double t, P;
+  template <class V>
+  using Node = GaussN<COL, V>;
+};
+
+// Exponential: consts [lambda, shift, -ln I];  slots [lambda]
+template <int COL, class V>
+struct ExpoN {
+  typedef typename Lanes<V>::Mask Mask;
+  V xs, P;
 
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool&) {
-    t = fma(x[COL], c[CO + 0], c[CO + 1]);  // x/sigma - mu/sigma (tfp Normal._log_prob)
-    return fma(-0.5 * t, t, c[CO + 2]);
+  ZNLL_DEV V fwd_log(const Ctx&, const double* __restrict__ c, const V* x, Mask&) {
+    xs = zsub(x[COL], c[CO + 1]);
+    return zfma(xs, c[CO + 0], c[CO + 2]);
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
-    bool neg;
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg;
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_log(double g, const double* __restrict__ c, double* acc) {
-    const double gi = g * c[CO + 0];
-    acc[AO + 0] = fma(gi, t, acc[AO + 0]);                  // d/dmu    =  t/sigma
-    acc[AO + 1] = fma(gi, fma(t, t, -1.0), acc[AO + 1]);    // d/dsigma = (t^2-1)/sigma
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__, double* acc) {
+    zacc(acc[AO + 0], g, xs);
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
-    bwd_log<CO, AO>(a * P, c, acc);
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
-
-// Exponential: consts [lambda, shift, -ln I];  slots [lambda]
 template <int COL>
 struct Expo {
   static constexpr int NS = 1, NC = 3, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
-  double xs, P;
-
-  template <int CO>
-  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool&) {
-    xs = x[COL] - c[CO + 1];
-    return fma(c[CO + 0], xs, c[CO + 2]);
-  }
-  template <int CO>
-  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
-    bool neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
-    return P;
-  }
-  template <int CO, int AO>
-  __device__ __forceinline__ void bwd_log(double g, const double* __restrict__, double* acc) {
-    acc[AO + 0] = fma(g, xs, acc[AO + 0]);
-  }
-  template <int CO, int AO>
-  __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
-    bwd_log<CO, AO>(a * P, c, acc);
-  }
+  template <class V>
+  using Node = ExpoN<COL, V>;
 };
 
 // CrystalBall: slots [mu, sigma, alpha, n]
 // consts [0 mu, 1 sign(alpha)/sigma, 2 1/sigma, 3 |alpha|, 4 n, 5 B=n/|alpha|-|alpha|,
 //         6 ln A - ln I, 7 -ln I, 8 ln(n/|alpha|)+1, 9 1/|alpha|, 10 -n/|alpha|-|alpha|,
 //         11 n/alpha^2+1, 12 sign(alpha)]
-template <int COL>
-struct CBall {
-  static constexpr int NS = 4, NC = 13, COLMASK = 1 << COL;
-  static constexpr bool LOGNAT = true;
-  double t, dt, lu, P;  // dt = d ln v / d t ; lu = ln(B-t) on the tail
-  bool tail;
+template <int COL, class V>
+struct CBallN {
+  typedef typename Lanes<V>::Mask Mask;
+  V t, dt, lu, P;  // dt = d ln v / d t ; lu = ln(B-t) on the tail
+  Mask tail;
+  bool any_tail;
 
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool&) {
-    t = (x[COL] - c[CO + 0]) * c[CO + 1];
-    tail = t < -c[CO + 3];
-    double lp;
-    if (tail) {  // A*(B-t)^-n  ==  exp(ln A - n*ln(B-t))
-      const double u = c[CO + 5] - t;
-      lu = fast_log(u, cx);
-      dt = c[CO + 4] * fast_rcp(u);
-      lp = fma(-c[CO + 4], lu, c[CO + 6]);
-    } else {  // exp(-t^2/2)
-      lu = 0.0;
-      dt = -t;
-      lp = fma(-0.5 * t, t, c[CO + 7]);
+  ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask&) {
+    t = zmul(zsub(x[COL], c[CO + 0]), c[CO + 1]);
+    tail = zlt(t, -c[CO + 3]);
+    any_tail = zany(tail);
+    const V lp_core = zfma(zmul(t, -0.5), t, c[CO + 7]);  // exp(-t^2/2)
+    if (!any_tail) {                                       // whole pair on the Gaussian core (events are sorted)
+      dt = zneg(t);
+      lu = zbc<V>(0.0);
+      return lp_core;
     }
-    return lp;
+    // A*(B-t)^-n == exp(ln A - n*ln(B-t)); a lane on the core gets the safe value u = 2 (z.safe_where)
+    const V u = zsel(tail, zsub(c[CO + 5], t), zbc<V>(2.0));
+    lu = fast_log(u, cx);
+    const V dtt = zmul(fast_rcp(u), c[CO + 4]);
+    const V lp_tail = zfma(lu, -c[CO + 4], c[CO + 6]);
+    dt = zsel(tail, dtt, zneg(t));
+    return zsel(tail, lp_tail, lp_core);
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
-    bool neg;
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg;
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_log(double g, const double* __restrict__ c, double* acc) {
-    const double gd = g * dt;
-    acc[AO + 0] = fma(-gd, c[CO + 1], acc[AO + 0]);          // dt/dmu    = -sign/sigma
-    acc[AO + 1] = fma(-gd * t, c[CO + 2], acc[AO + 1]);      // dt/dsigma = -t/sigma
-    if (tail) {
-      // d ln v/d|alpha| = -n/a - a + (n/u)(n/a^2+1) ; d ln v/dn = ln(n/a)+1 - ln u - (n/u)/a
-      acc[AO + 2] = fma(g * c[CO + 12], fma(dt, c[CO + 11], c[CO + 10]), acc[AO + 2]);
-      acc[AO + 3] = fma(g, (c[CO + 8] - lu) - dt * c[CO + 9], acc[AO + 3]);
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    const V gd = zmul(g, dt);
+    zacc(acc[AO + 0], zneg(gd), c[CO + 1]);             // dt/dmu    = -sign/sigma
+    zacc(acc[AO + 1], zmul(zneg(gd), t), c[CO + 2]);    // dt/dsigma = -t/sigma
+    if (any_tail) {
+      // d ln v/d|alpha| = -n/a - a + (n/u)(n/a^2+1) ; d ln v/dn = ln(n/a)+1 - ln u - (n/u)/a ; 0 on the core
+      const V gt = zsel(tail, g, zbc<V>(0.0));
+      zacc(acc[AO + 2], zmul(gt, c[CO + 12]), zfma(dt, c[CO + 11], c[CO + 10]));
+      zacc(acc[AO + 3], gt, zsub(zsub(c[CO + 8], lu), zmul(dt, c[CO + 9])));
     }
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
-    bwd_log<CO, AO>(a * P, c, acc);
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
+};
+template <int COL>
+struct CBall {
+  static constexpr int NS = 4, NC = 13, COLMASK = 1 << COL;
+  static constexpr bool LOGNAT = true;
+  template <class V>
+  using Node = CBallN<COL, V>;
 };
 
 // Chebyshev of degree DEG: slots [c_0 .. c_DEG]
 // consts [0 2/(hi-lo), 1 -(lo+hi)/(hi-lo), 2 1/I, 3.. c_k/I]
-template <int COL, int DEG>
-struct Cheb {
-  static constexpr int NS = DEG + 1, NC = 3 + DEG + 1, COLMASK = 1 << COL;
-  static constexpr bool LOGNAT = false;
-  double T[DEG + 1];
-  double P;
+template <int COL, int DEG, class V>
+struct ChebN {
+  typedef typename Lanes<V>::Mask Mask;
+  V T[DEG + 1];
+  V P;
 
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
-    const double z = fma(x[COL], c[CO + 0], c[CO + 1]);
-    T[0] = 1.0;
-    double p = c[CO + 3];
+  ZNLL_DEV V fwd_val(const Ctx&, const double* __restrict__ c, const V* x) {
+    const V z = zfma(x[COL], c[CO + 0], c[CO + 1]);
+    T[0] = zbc<V>(1.0);
+    V p = zbc<V>(c[CO + 3]);
     if constexpr (DEG >= 1) {
       T[1] = z;
-      p = fma(c[CO + 4], z, p);
+      p = zfma(z, c[CO + 4], p);
     }
-    const double z2 = z + z;
+    const V z2 = zadd(z, z);
 #pragma unroll
     for (int k = 2; k <= DEG; ++k) {
-      T[k] = fma(z2, T[k - 1], -T[k - 2]);
-      p = fma(c[CO + 3 + k], T[k], p);
+      T[k] = zfma(z2, T[k - 1], zneg(T[k - 2]));
+      p = zfma(T[k], c[CO + 3 + k], p);
     }
     P = p;
     return p;
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool& neg) {
-    const double p = fwd_val<CO>(cx, c, x);
-    neg ^= (p < 0.0);
-    return fast_log(fabs(p), cx);
+  ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
+    const V p = fwd_val<CO>(cx, c, x);
+    neg = mxor(neg, zlt(p, 0.0));
+    return fast_log(zabs(p), cx);
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
-    const double ai = a * c[CO + 2];
-    acc[AO + 0] += ai;
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    const V ai = zmul(a, c[CO + 2]);
+    zacc1(acc[AO + 0], ai);
 #pragma unroll
-    for (int k = 1; k <= DEG; ++k) acc[AO + k] = fma(ai, T[k], acc[AO + k]);
+    for (int k = 1; k <= DEG; ++k) zacc(acc[AO + k], ai, T[k]);
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_log(double g, const double* __restrict__ c, double* acc) {
-    bwd_val<CO, AO>(g * fast_rcp(P), c, acc);
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    bwd_val<CO, AO>(zmul(g, fast_rcp(P)), c, acc);
   }
+};
+template <int COL, int DEG>
+struct Cheb {
+  static constexpr int NS = DEG + 1, NC = 3 + DEG + 1, COLMASK = 1 << COL;
+  static constexpr bool LOGNAT = false;
+  template <class V>
+  using Node = ChebN<COL, DEG, V>;
 };
 
 // ----------------------------------------------------------------------------------------------
 // functors
 // ----------------------------------------------------------------------------------------------
 template <class... Cs>
-struct Kids;
+struct Meta;
 template <>
-struct Kids<> {
-  static constexpr int NS = 0, NC = 0, COLMASK = 0, N = 0;
+struct Meta<> {
+  static constexpr int NS = 0, NC = 0, COLMASK = 0;
 };
 template <class H, class... T>
-struct Kids<H, T...> {
-  H h;
-  Kids<T...> t;
-  static constexpr int NS = H::NS + Kids<T...>::NS;
-  static constexpr int NC = H::NC + Kids<T...>::NC;
-  static constexpr int COLMASK = H::COLMASK | Kids<T...>::COLMASK;
+struct Meta<H, T...> {
+  static constexpr int NS = H::NS + Meta<T...>::NS;
+  static constexpr int NC = H::NC + Meta<T...>::NC;
+  static constexpr int COLMASK = H::COLMASK | Meta<T...>::COLMASK;
+};
+
+template <class V, class... Cs>
+struct Kids;
+template <class V>
+struct Kids<V> {
+  static constexpr int N = 0;
+};
+template <class V, class H, class... T>
+struct Kids<V, H, T...> {
+  typedef H Head;
+  typename H::template Node<V> h;
+  Kids<V, T...> t;
   static constexpr int N = 1 + sizeof...(T);
 };
 
 // SumPDF: consts [f_0..f_{K-1}]; slots [f_0..f_{K-1}]; then the children
-template <class... Cs>
-struct Sum {
+template <class V, class... Cs>
+struct SumN {
+  typedef typename Lanes<V>::Mask Mask;
   static constexpr int K = sizeof...(Cs);
-  static constexpr int NS = K + Kids<Cs...>::NS, NC = K + Kids<Cs...>::NC;
-  static constexpr int COLMASK = Kids<Cs...>::COLMASK;
-  static constexpr bool LOGNAT = false;
-  Kids<Cs...> kids;
-  double p[K];
-  double P;
+  Kids<V, Cs...> kids;
+  V p[K];
+  V P;
 
   template <int CO, int I, int CK, class KD>
-  __device__ __forceinline__ void fwd_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const double* x, double& tot) {
+  ZNLL_DEV void fwd_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const V* x, V& tot) {
     if constexpr (KD::N > 0) {
       p[I] = kd.h.template fwd_val<CK>(cx, c, x);
-      tot = fma(c[CO + I], p[I], tot);
-      fwd_rec<CO, I + 1, CK + decltype(kd.h)::NC>(kd.t, cx, c, x, tot);
+      tot = zfma(p[I], c[CO + I], tot);
+      fwd_rec<CO, I + 1, CK + KD::Head::NC>(kd.t, cx, c, x, tot);
     }
   }
   template <int CO, int AO, int I, int CK, int AK, class KD>
-  __device__ __forceinline__ void bwd_rec(KD& kd, double a, const double* __restrict__ c, double* acc) {
+  ZNLL_DEV void bwd_rec(KD& kd, V a, const double* __restrict__ c, double* acc) {
     if constexpr (KD::N > 0) {
-      acc[AO + I] = fma(a, p[I], acc[AO + I]);
-      kd.h.template bwd_val<CK, AK>(a * c[CO + I], c, acc);
-      bwd_rec<CO, AO, I + 1, CK + decltype(kd.h)::NC, AK + decltype(kd.h)::NS>(kd.t, a, c, acc);
+      zacc(acc[AO + I], a, p[I]);
+      kd.h.template bwd_val<CK, AK>(zmul(a, c[CO + I]), c, acc);
+      bwd_rec<CO, AO, I + 1, CK + KD::Head::NC, AK + KD::Head::NS>(kd.t, a, c, acc);
     }
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
-    double tot = 0.0;
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    V tot = zbc<V>(0.0);
     fwd_rec<CO, 0, CO + K>(kids, cx, c, x, tot);
     P = tot;
     return tot;
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool& neg) {
-    const double v = fwd_val<CO>(cx, c, x);
-    neg ^= (v < 0.0);
-    return fast_log(fabs(v), cx);
+  ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
+    const V v = fwd_val<CO>(cx, c, x);
+    neg = mxor(neg, zlt(v, 0.0));
+    return fast_log(zabs(v), cx);
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
     bwd_rec<CO, AO, 0, CO + K, AO + K>(kids, a, c, acc);
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_log(double g, const double* __restrict__ c, double* acc) {
-    bwd_val<CO, AO>(g * fast_rcp(P), c, acc);
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    bwd_val<CO, AO>(zmul(g, fast_rcp(P)), c, acc);
+  }
+};
+// SumPDF of exactly two log-native children (the signal + background case), in log-sum-exp form:
+//   ln P = m + ln S,  m = max(l0, l1),  S = f0*e^(l0-m) + f1*e^(l1-m)
+// One of the two exponentials is exp(0) = 1, so a single exp is evaluated per event instead of two, it can
+// neither overflow nor lose the event to underflow, and the Sum becomes log-native itself (no exp at all
+// when it sits under a ProductPDF).  d ln P/d f_i = e_i/S;  the adjoint of child i is g*f_i*e_i/S.
+template <class V, class C0, class C1>
+struct SumLseN {
+  typedef typename Lanes<V>::Mask Mask;
+  typename C0::template Node<V> k0;
+  typename C1::template Node<V> k1;
+  V q0, q1;  // e_i / S
+  V P;
+
+  template <int CO>
+  ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
+    Mask n0 = Lanes<V>::mask(false, false), n1 = n0;
+    const V l0 = k0.template fwd_log<CO + 2>(cx, c, x, n0);
+    const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
+    const V d = zsub(l0, l1);
+    const Mask lt = zlt(d, 0.0);  // l0 < l1
+    const V e = fast_exp(zneg(zabs(d)));
+    const V one = zbc<V>(1.0);
+    V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
+    e0 = zsel(n0, zneg(e0), e0);  // children that are themselves products with a negative factor
+    e1 = zsel(n1, zneg(e1), e1);
+    const V S = zfma(e0, c[CO + 0], zmul(e1, c[CO + 1]));
+    neg = mxor(neg, zlt(S, 0.0));
+    const V rS = fast_rcp(S);
+    q0 = zmul(e0, rS);
+    q1 = zmul(e1, rS);
+    return zadd(zsel(lt, l1, l0), fast_log(zabs(S), cx));
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg = Lanes<V>::mask(false, false);
+    const V e = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = zsel(neg, zneg(e), e);
+    return P;
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    const V g0 = zmul(g, q0), g1 = zmul(g, q1);
+    zacc1(acc[AO + 0], g0);
+    zacc1(acc[AO + 1], g1);
+    k0.template bwd_log<CO + 2, AO + 2>(zmul(g0, c[CO + 0]), c, acc);
+    k1.template bwd_log<CO + 2 + C0::NC, AO + 2 + C0::NS>(zmul(g1, c[CO + 1]), c, acc);
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
 
-// ProductPDF over disjoint observables: no consts, no slots of its own
+template <bool B, class T, class F>
+struct If {
+  typedef T type;
+};
+template <class T, class F>
+struct If<false, T, F> {
+  typedef F type;
+};
+template <class V, class... Cs>
+struct SumPick {
+  typedef SumN<V, Cs...> type;
+};
+template <class V, class C0, class C1>
+struct SumPick<V, C0, C1> {
+  typedef typename If<C0::LOGNAT && C1::LOGNAT, SumLseN<V, C0, C1>, SumN<V, C0, C1>>::type type;
+};
 template <class... Cs>
-struct Prod {
-  static constexpr int NS = Kids<Cs...>::NS, NC = Kids<Cs...>::NC;
-  static constexpr int COLMASK = Kids<Cs...>::COLMASK;
-  static constexpr bool LOGNAT = true;
-  Kids<Cs...> kids;
-  double P;
+struct AllLog {
+  static constexpr bool value = false;
+};
+template <class C0, class C1>
+struct AllLog<C0, C1> {
+  static constexpr bool value = C0::LOGNAT && C1::LOGNAT;
+};
+
+template <class... Cs>
+struct Sum {
+  static constexpr int K = sizeof...(Cs);
+  static constexpr int NS = K + Meta<Cs...>::NS, NC = K + Meta<Cs...>::NC;
+  static constexpr int COLMASK = Meta<Cs...>::COLMASK;
+  static constexpr bool LOGNAT = AllLog<Cs...>::value;
+  template <class V>
+  using Node = typename SumPick<V, Cs...>::type;
+};
+
+// ProductPDF over disjoint observables: no consts, no slots of its own
+template <class V, class... Cs>
+struct ProdN {
+  typedef typename Lanes<V>::Mask Mask;
+  Kids<V, Cs...> kids;
+  V P;
 
   template <int CK, class KD>
-  __device__ __forceinline__ void fwd_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const double* x,
-                                          double& tot, bool& neg) {
+  ZNLL_DEV void fwd_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const V* x, V& tot, Mask& neg) {
     if constexpr (KD::N > 0) {
-      tot += kd.h.template fwd_log<CK>(cx, c, x, neg);
-      fwd_rec<CK + decltype(kd.h)::NC>(kd.t, cx, c, x, tot, neg);
+      tot = zadd(tot, kd.h.template fwd_log<CK>(cx, c, x, neg));
+      fwd_rec<CK + KD::Head::NC>(kd.t, cx, c, x, tot, neg);
     }
   }
   template <int CK, int AK, class KD>
-  __device__ __forceinline__ void bwd_rec(KD& kd, double g, const double* __restrict__ c, double* acc) {
+  ZNLL_DEV void bwd_rec(KD& kd, V g, const double* __restrict__ c, double* acc) {
     if constexpr (KD::N > 0) {
       kd.h.template bwd_log<CK, AK>(g, c, acc);
-      bwd_rec<CK + decltype(kd.h)::NC, AK + decltype(kd.h)::NS>(kd.t, g, c, acc);
+      bwd_rec<CK + KD::Head::NC, AK + KD::Head::NS>(kd.t, g, c, acc);
     }
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_log(const Ctx& cx, const double* __restrict__ c, const double* x, bool& neg) {
-    double tot = 0.0;
+  ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
+    V tot = zbc<V>(0.0);
     fwd_rec<CO>(kids, cx, c, x, tot, neg);
     return tot;
   }
   template <int CO>
-  __device__ __forceinline__ double fwd_val(const Ctx& cx, const double* __restrict__ c, const double* x) {
-    bool neg = false;
-    const double lp = fwd_log<CO>(cx, c, x, neg);
-    P = neg ? -fast_exp(lp) : fast_exp(lp);
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg = Lanes<V>::mask(false, false);
+    const V e = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = zsel(neg, zneg(e), e);
     return P;
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_log(double g, const double* __restrict__ c, double* acc) {
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
     bwd_rec<CO, AO>(kids, g, c, acc);
   }
   template <int CO, int AO>
-  __device__ __forceinline__ void bwd_val(double a, const double* __restrict__ c, double* acc) {
-    bwd_log<CO, AO>(a * P, c, acc);
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
+};
+template <class... Cs>
+struct Prod {
+  static constexpr int NS = Meta<Cs...>::NS, NC = Meta<Cs...>::NC;
+  static constexpr int COLMASK = Meta<Cs...>::COLMASK;
+  static constexpr bool LOGNAT = true;
+  template <class V>
+  using Node = ProdN<V, Cs...>;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -414,56 +697,65 @@ struct KArgs {
 };
 
 // accumulators: [0] running sum of w*l - offset, [1] its Kahan compensation, [2..] slots.
-// Returns this event's term  w*l - offset  (the caller adds two of them, then one Kahan step).
-template <class M, bool WEIGHTED, bool GRAD>
-__device__ __forceinline__ double event(const Ctx& cx, const double* __restrict__ c, const double* x, double w,
-                                        double off, double* acc) {
-  M m;
-  double l, g;
+// Returns the term(s)  w*l - offset  of this event (pair).
+template <class M, class V, bool WEIGHTED, bool GRAD>
+ZNLL_DEV V event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, double off, double* acc) {
+  typedef typename Lanes<V>::Mask Mask;
+  typename M::template Node<V> m;
+  V l;
   if constexpr (M::LOGNAT) {
-    bool neg = false;
-    const double lp = m.template fwd_log<0>(cx, c, x, neg);
+    Mask neg = Lanes<V>::mask(false, false);
+    const V lp = m.template fwd_log<0>(cx, c, x, neg);
     l = lp;
-    g = 1.0;
-    if (lp < -690.0 || neg) {  // p + 1e-307 matters only here (loss.py:117)
-      const double p = neg ? -exp(lp) : exp(lp);
-      const double pp = p + ZNLL_LOG_EPS;
-      l = log(pp);
-      g = p / pp;
+    V g = zbc<V>(1.0);
+    if (zany(zlt(lp, -690.0)) || zany(neg)) {  // p + 1e-307 matters only here (loss.py:117); rare
+      double ll[2] = {la(lp), lb(lp)}, gg[2] = {1.0, 1.0};
+      const bool ng[2] = {la(neg), lb(neg)};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (ll[k] < -690.0 || ng[k]) {
+          const double p = ng[k] ? -exp(ll[k]) : exp(ll[k]);
+          const double pp = p + ZNLL_LOG_EPS;
+          ll[k] = log(pp);
+          gg[k] = p / pp;
+        }
+      }
+      l = Lanes<V>::make(ll[0], ll[1]);
+      g = Lanes<V>::make(gg[0], gg[1]);
     }
-    if constexpr (WEIGHTED) g *= w;
+    if constexpr (WEIGHTED) g = zmul(g, w);
     if constexpr (GRAD) m.template bwd_log<0, 2>(g, c, acc);
   } else {
-    const double P = m.template fwd_val<0>(cx, c, x);
-    const double pp = P + ZNLL_LOG_EPS;
+    const V P = m.template fwd_val<0>(cx, c, x);
+    const V pp = zadd(P, ZNLL_LOG_EPS);
     l = fast_log(pp, cx);
     if constexpr (GRAD) {
-      g = fast_rcp(pp);
-      if constexpr (WEIGHTED) g *= w;
+      V g = fast_rcp(pp);
+      if constexpr (WEIGHTED) g = zmul(g, w);
       m.template bwd_val<0, 2>(g, c, acc);
     }
   }
   if constexpr (WEIGHTED)
-    return fma(w, l, -off);  // weights multiply first, then the unweighted offset (loss.py:134-137)
+    return zfma(w, l, -off);  // weights multiply first, then the unweighted offset (loss.py:134-137)
   else
-    return l - off;
+    return zsub(l, off);
 }
 
-__device__ __forceinline__ void kahan_add(double* acc, double term) {
+ZNLL_DEV void kahan_add(double* acc, double term) {
   const double y = term - acc[1];
   const double s = acc[0] + y;
   acc[1] = (s - acc[0]) - y;
   acc[0] = s;
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
+ZNLL_DEV double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   return v;
 }
 
 // error-free merge of two compensated sums (s - c is the value)
-__device__ __forceinline__ void kahan_merge(double& s, double& c, double s2, double c2) {
+ZNLL_DEV void kahan_merge(double& s, double& c, double s2, double c2) {
   const double t = s + s2;
   const double bp = t - s;
   const double e = (s - (t - bp)) + (s2 - bp);  // TwoSum error of s + s2
@@ -472,8 +764,7 @@ __device__ __forceinline__ void kahan_merge(double& s, double& c, double s2, dou
 }
 
 template <int NACC>
-__device__ __forceinline__ void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket,
-                                                        double* out) {
+ZNLL_DEV void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket, double* out) {
   __shared__ double sm[ZNLL_BLOCK / 32][NACC];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -542,23 +833,23 @@ __device__ __forceinline__ void block_reduce_and_finish(double* acc, double* par
 
 template <class M, bool WEIGHTED>
 struct EventPair {
-  double xa[ZNLL_MAXCOL], xb[ZNLL_MAXCOL];
-  double wa, wb;
+  D2 x[ZNLL_MAXCOL];
+  D2 w;
   template <int NC>
-  __device__ __forceinline__ void load(const KArgs<NC>& args, long long i) {
+  ZNLL_DEV void load(const KArgs<NC>& args, long long i) {
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k) {
       if ((M::COLMASK >> k) & 1) {
         const double2 v = __ldg(reinterpret_cast<const double2*>(args.cols[k]) + i);
-        xa[k] = v.x;
-        xb[k] = v.y;
+        x[k].a = v.x;
+        x[k].b = v.y;
       }
     }
-    wa = wb = 1.0;
+    w.a = w.b = 1.0;
     if constexpr (WEIGHTED) {
       const double2 v = __ldg(reinterpret_cast<const double2*>(args.w) + i);
-      wa = v.x;
-      wb = v.y;
+      w.a = v.x;
+      w.b = v.y;
     }
   }
 };
@@ -585,18 +876,17 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
     cur = nxt;
     i += stride;
     if (i < nvec) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
-    const double ta = event<M, WEIGHTED, GRAD>(cx, c, cur.xa, cur.wa, off, acc);
-    const double tb = event<M, WEIGHTED, GRAD>(cx, c, cur.xb, cur.wb, off, acc);
-    kahan_add(acc, ta + tb);
+    const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, off, acc);
+    kahan_add(acc, t.a + t.b);
   }
-  if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event
+  if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event: scalar instantiation
     double xa[ZNLL_MAXCOL];
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k)
       if ((M::COLMASK >> k) & 1) xa[k] = args.cols[k][args.n - 1];
     double wa = 1.0;
     if constexpr (WEIGHTED) wa = args.w[args.n - 1];
-    kahan_add(acc, event<M, WEIGHTED, GRAD>(cx, c, xa, wa, off, acc));
+    kahan_add(acc, event<M, double, WEIGHTED, GRAD>(cx, c, xa, wa, off, acc));
   }
   block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out);
 }
@@ -616,7 +906,7 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) pdf_kernel(const 
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k)
       if ((M::COLMASK >> k) & 1) x[k] = __ldg(args.cols[k] + i);
-    M m;
+    typename M::template Node<double> m;
     double p;
     if constexpr (M::LOGNAT) {
       bool neg = false;
@@ -631,16 +921,11 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) pdf_kernel(const 
 
 // sum of weights with the same deterministic reduction (Data.samplesize, core/data.py:268-275)
 template <int UNUSED>
-__global__ void __launch_bounds__(ZNLL_BLOCK, 2)
+__global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS)
 sumw_kernel(const double* __restrict__ w, long long n, double* partials, unsigned int* ticket, double* out) {
   double acc[2] = {0.0, 0.0};
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
-  for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < n; i += stride) {
-    const double y = w[i] - acc[1];
-    const double s = acc[0] + y;
-    acc[1] = (s - acc[0]) - y;
-    acc[0] = s;
-  }
+  for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < n; i += stride) kahan_add(acc, w[i]);
   block_reduce_and_finish<2>(acc, partials, ticket, out);
 }
 

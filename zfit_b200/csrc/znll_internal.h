@@ -32,7 +32,7 @@ cudaError_t znll_launch_sumw(const double* w, long long n, double* partials, uns
                              int grid, cudaStream_t stream);
 
 #ifndef ZNLL_BLOCKS_PER_SM
-#define ZNLL_BLOCKS_PER_SM 3  // must match ZNLL_MIN_BLOCKS in znll_device.cuh
+#define ZNLL_BLOCKS_PER_SM 2  // must match ZNLL_MIN_BLOCKS in znll_device.cuh
 #endif
 
 // test hook: out[i] = f(in[i]) with f = fast_exp (0), fast_log (1), fast_rcp (2) of znll_device.cuh
