@@ -351,9 +351,10 @@ class BaseLoss:
         if want_grad:
             for j, p in direct:
                 grad[p] = grad.get(p, 0.0) + gslots[j]
+            memo = {}
             for j, p in composed:
                 g = gslots[j]
-                for leaf, d in p._partials().items():
+                for leaf, d in p._partials(memo).items():
                     grad[leaf] = grad.get(leaf, 0.0) + g * d
         return total, grad
 

@@ -367,12 +367,24 @@ class ComposedParameter(ZfitParameter):
             partials[k] = (4.0 * d(h) - d(2 * h)) / 3.0
         return partials
 
-    def _partials(self):
+    def _partials(self, memo=None):
+        """{independent leaf: d value / d leaf}; ``memo`` shares sub-results within one loss evaluation."""
+        if memo is not None:
+            hit = memo.get(id(self))
+            if hit is not None:
+                return hit
         local = self._local_partials()
         out: dict = {}
         for k, p in self.params.items():
-            for leaf, d in p._partials().items():
-                out[leaf] = out.get(leaf, 0.0) + local.get(k, 0.0) * d
+            lk = local.get(k, 0.0)
+            if p._independent:
+                out[p] = out.get(p, 0.0) + lk
+            elif lk != 0.0 or True:
+                sub = p._partials(memo) if isinstance(p, ComposedParameter) else p._partials()
+                for leaf, d in sub.items():
+                    out[leaf] = out.get(leaf, 0.0) + lk * d
+        if memo is not None:
+            memo[id(self)] = out
         return out
 
     def set_value(self, value):
