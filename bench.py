@@ -231,6 +231,8 @@ def run_product(args):
     events = args.events or W.FULL_SIZES[cfg]
     w = W.build(cfg, n=events, device=f"cuda:{local}", rank=rank)
     loss = w["loss"]
+    if args.nccl:
+        loss.options["fused_reduce"] = False
     params = list(loss.get_params())
     theta0 = np.array([p.value() for p in params])
     n_events = w["n_events"]  # events evaluated per step on this rank
@@ -296,7 +298,7 @@ def run_product(args):
             "n_params": len(params),
             "kernel": eng.kernel_names,
             "l2": "inputs (%.0f MB per GPU) are larger than the 126 MB L2; no flush needed" % (n_events * w["bytes_per_event"] / 1e6),
-            "parallelism": f"event-sharded x{world}, one all-reduce of {plan.total_acc()} fp64 per step" if world > 1 else "single GPU",
+            "parallelism": f"event-sharded x{world}, {plan.total_acc()} fp64 accumulators reduced per step via {eng.reduce_mode}" if world > 1 else "single GPU",
             "minuit_driver": "n/a (evaluation benchmark)",
         },
         "clocks": clocks.summary(),
@@ -429,6 +431,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="skip timing the one-time host->HBM bind of the event columns")
+    ap.add_argument("--nccl", action="store_true", help="multi-GPU: NCCL all-reduce instead of the fused NVLink exchange")
     ap.add_argument("--no-fit", action="store_true", help="skip the end-to-end Minuit fit after the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -136,6 +136,15 @@ int znll_launch(znll_plan* plan, const double* slots, uint32_t flags, double log
 double* znll_plan_acc_device(znll_plan* plan);
 int znll_collect(znll_plan* plan, uint32_t flags, double* values, double* grad_slots, void* stream);
 
+/* Fused multi-GPU reduction (no reference equivalent; the reference has no multi-device path).  peer_bufs[r] is rank
+ * r's exchange buffer of at least znll_plan_exchange_bytes() bytes, zero-initialised, peer-mapped into this process
+ * (CUDA IPC / VMM symmetric memory; the host obtains it from torch.distributed._symmetric_memory).  Once set, the last
+ * block of each evaluation's (last) kernel pushes the raw accumulators to all peers over NVLink, waits for theirs and
+ * sums in fixed rank order, so znll_eval returns world-reduced, bit-identical results on every rank without any
+ * collective library call on the step path.  All ranks must call znll_eval the same number of times.  world <= 1 clears. */
+int znll_plan_set_peers(znll_plan* plan, int rank, int world, void* const* peer_bufs, size_t buf_bytes);
+size_t znll_plan_exchange_bytes(const znll_plan* plan, int world);
+
 /* Per-event normalised pdf values of channel ch on its bound events: out_host[n_events].
  * Replaces BasePDF.pdf (core/basepdf.py:398-429) for plotting / diagnostics; not on the fit's hot path. */
 int znll_pdf(znll_plan* plan, int ch, const double* slots, double* out_host, void* stream);

@@ -31,9 +31,9 @@ def main():
     x = x[(x >= -10) & (x <= 10)]
     w = rng.normal(1.0, 0.6, x.size)
     res = {}
-    for det in (False, True):
-        model, full, obs = build(x, w, f"_g{int(det)}")
-        nll = zfit.loss.UnbinnedNLL(model, D.shard(full), options={"deterministic_reduce": det})
+    for mode, opts in (("fused", {}), ("nccl", {"fused_reduce": False}), ("nccl_det", {"fused_reduce": False, "deterministic_reduce": True})):
+        model, full, obs = build(x, w, f"_g{mode}")
+        nll = zfit.loss.UnbinnedNLL(model, D.shard(full), options=opts)
         params = list(nll.get_params())
         v, g = nll.value_gradient(params, full=True)
         mine = torch.tensor([v, *g], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -49,8 +49,10 @@ def main():
         gathered = [torch.empty_like(fitted) for _ in range(world)]
         td.all_gather(gathered, fitted)
         assert all(torch.equal(gathered[0], t) for t in gathered)
-        res[f"det{int(det)}"] = {"value": v, "single": sv, "valid": bool(result.valid), "n_eval": int(result.info["n_eval"]),
-                                 "kernel": nll._get_engine().kernel_names}
+        eng = nll._get_engine()
+        res[mode] = {"value": v, "single": sv, "valid": bool(result.valid), "n_eval": int(result.info["n_eval"]),
+                     "kernel": eng.kernel_names, "reduce_mode": eng.reduce_mode,
+                     "fallback": getattr(eng, "reduce_fallback_reason", None)}
     if rank == 0:
         json.dump(res, open(out, "w"))
     td.barrier()

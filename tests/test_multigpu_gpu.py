@@ -26,4 +26,8 @@ def test_two_gpu_nccl_matches_single_gpu(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     got = json.loads(out.read_text())
-    assert got["det0"]["valid"] and got["det1"]["valid"]
+    assert all(got[m]["valid"] for m in ("fused", "nccl", "nccl_det"))
+    assert got["nccl"]["reduce_mode"] == "nccl"
+    # the fused NVLink exchange is the product path; if symmetric memory is unavailable the reason must be visible
+    assert got["fused"]["reduce_mode"] == "fused-nvlink", got["fused"]["fallback"]
+    assert abs(got["fused"]["value"] - got["nccl"]["value"]) <= 1e-12 * abs(got["nccl"]["value"])

@@ -68,6 +68,8 @@ SYMBOLS = {
     "znll_launch": (C.c_int, [C.c_void_p, _DP, C.c_uint32, C.c_double, C.c_void_p]),
     "znll_plan_acc_device": (C.c_void_p, [C.c_void_p]),
     "znll_collect": (C.c_int, [C.c_void_p, C.c_uint32, _DP, _DP, C.c_void_p]),
+    "znll_plan_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
+    "znll_plan_exchange_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
     "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
@@ -170,6 +172,14 @@ class Plan:
 
     def set_sumw(self, ch: int, v: float):
         _check(lib().znll_plan_set_sumw(self._h, ch, float(v)))
+
+    def exchange_bytes(self, world: int) -> int:
+        return int(lib().znll_plan_exchange_bytes(self._h, world))
+
+    def set_peers(self, rank: int, world: int, peer_ptrs, nbytes: int, keepalive=None):
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
+        _check(lib().znll_plan_set_peers(self._h, rank, world, arr, nbytes))
+        self._keep.append(keepalive)
 
     def n_slots(self, ch: int) -> int:
         return lib().znll_plan_n_slots(self._h, ch)

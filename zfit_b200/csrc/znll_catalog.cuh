@@ -1,5 +1,7 @@
 // znll_catalog.cuh -- helper to instantiate and register kernels ahead of time (nvcc, sm_100a).
 #pragma once
+#include <cstring>
+
 #include "znll_device.cuh"
 #include "znll_internal.h"
 
@@ -15,6 +17,8 @@ cudaError_t launch_nll(const ZnllLaunchArgs& a, const double* consts, int grid, 
   k.partials = a.partials;
   k.ticket = a.ticket;
   k.out = a.out;
+  static_assert(sizeof(Xchg) == sizeof(ZnllXchg), "Xchg layout");
+  memcpy(&k.xc, &a.xc, sizeof(Xchg));
   for (int i = 0; i < M::NC; ++i) k.c[i] = consts[i];
   nll_kernel<M, W, G><<<grid, ZNLL_BLOCK, 0, stream>>>(k);
   return cudaGetLastError();
@@ -30,6 +34,7 @@ cudaError_t launch_pdf(const ZnllLaunchArgs& a, const double* consts, int grid, 
   k.partials = a.partials;
   k.ticket = a.ticket;
   k.out = a.out;
+  memset(&k.xc, 0, sizeof(Xchg));
   for (int i = 0; i < M::NC; ++i) k.c[i] = consts[i];
   pdf_kernel<M><<<grid, ZNLL_BLOCK, 0, stream>>>(k);
   return cudaGetLastError();

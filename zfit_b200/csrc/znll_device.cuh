@@ -684,6 +684,57 @@ struct Prod {
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
+// Cross-GPU exchange fused into the last block of the (last channel's) kernel: every rank pushes its raw
+// accumulators into all peers' exchange buffers with plain stores over NVLink (peer-mapped symmetric memory),
+// publishes a sequence flag with release semantics at system scope, waits for the peers' flags, and sums the
+// world's contributions in fixed rank order -- bit-identical on every rank, no NCCL call on the step path.
+// Buffer layout per rank: [128 B: u64 flag per source rank][2 parities][world][total] doubles.
+#define ZNLL_MAXPEERS 8
+#define ZNLL_XFLAG_BYTES 128
+struct Xchg {
+  double* buf[ZNLL_MAXPEERS];  // buf[r]: rank r's exchange buffer as mapped into this process
+  double* acc;                 // this rank's accumulators of ALL channels (plan-wide), reduced in place
+  unsigned long long seq;      // evaluation counter (> 0), identical on all ranks
+  int rank, world, total, pad;
+};
+
+ZNLL_DEV void peer_exchange(const Xchg& xc) {
+  __shared__ int timed_out;
+  const int t = threadIdx.x;
+  if (t == 0) timed_out = 0;
+  __syncthreads();  // all of this kernel's out[] stores are done (and earlier channels' kernels have completed)
+  const int par = (int)(xc.seq & 1ull);
+  if (t < xc.total) {
+    const double v = __ldcg(xc.acc + t);
+    for (int p = 0; p < xc.world; ++p) {
+      double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(xc.buf[p]) + ZNLL_XFLAG_BYTES) +
+                    ((size_t)(par * xc.world + xc.rank) * xc.total + t);
+      *reinterpret_cast<volatile double*>(dst) = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < xc.world) {
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(xc.buf[t]) + xc.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(xc.seq) : "memory");
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(xc.buf[xc.rank]) + t;
+    unsigned long long v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    } while (v < xc.seq && (clock64() - t0) < 60000000000ll);  // ~30 s: a dead peer must not hang the GPU
+    if (v < xc.seq) timed_out = 1;
+  }
+  __syncthreads();
+  if (t < xc.total) {
+    const double* src = reinterpret_cast<const double*>(reinterpret_cast<const char*>(xc.buf[xc.rank]) + ZNLL_XFLAG_BYTES) +
+                        (size_t)par * xc.world * xc.total + t;
+    double s = 0.0;
+    for (int r = 0; r < xc.world; ++r) s += __ldcg(src + (size_t)r * xc.total);  // fixed rank order
+    xc.acc[t] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : s;
+  }
+}
+
 template <int NC>
 struct KArgs {
   const double* cols[ZNLL_MAXCOL];
@@ -693,6 +744,7 @@ struct KArgs {
   double* partials;        // [gridDim.x][NACC]
   unsigned int* ticket;    // zero before launch; reset by the last block
   double* out;             // [NACC]
+  Xchg xc;                 // cross-GPU exchange (world == 0: none)
   double c[NC > 0 ? NC : 1];
 };
 
@@ -764,7 +816,7 @@ ZNLL_DEV void kahan_merge(double& s, double& c, double s2, double c2) {
 }
 
 template <int NACC>
-ZNLL_DEV void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket, double* out) {
+ZNLL_DEV void block_reduce_and_finish(double* acc, double* partials, unsigned int* ticket, double* out, const Xchg* xc) {
   __shared__ double sm[ZNLL_BLOCK / 32][NACC];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -829,6 +881,7 @@ ZNLL_DEV void block_reduce_and_finish(double* acc, double* partials, unsigned in
     }
   }
   if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this stream
+  if (xc != nullptr && xc->world > 1) peer_exchange(*xc);
 }
 
 template <class M, bool WEIGHTED>
@@ -888,7 +941,7 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
     if constexpr (WEIGHTED) wa = args.w[args.n - 1];
     kahan_add(acc, event<M, double, WEIGHTED, GRAD>(cx, c, xa, wa, off, acc));
   }
-  block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out);
+  block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out, &args.xc);
 }
 
 // per-event normalised pdf values (BasePDF.pdf, core/basepdf.py:398-429): out[i] = P(x_i); args.partials = out
@@ -926,7 +979,7 @@ sumw_kernel(const double* __restrict__ w, long long n, double* partials, unsigne
   double acc[2] = {0.0, 0.0};
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
   for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < n; i += stride) kahan_add(acc, w[i]);
-  block_reduce_and_finish<2>(acc, partials, ticket, out);
+  block_reduce_and_finish<2>(acc, partials, ticket, out, nullptr);
 }
 
 }  // namespace znll

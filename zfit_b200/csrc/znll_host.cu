@@ -269,6 +269,10 @@ struct znll_plan {
   int total_acc = 0, total_slots = 0;
   long long launches = 0;
   int max_grid = 0;
+  // fused cross-GPU exchange (znll_plan_set_peers)
+  int x_rank = 0, x_world = 0;
+  double* x_buf[8] = {nullptr};
+  unsigned long long x_seq = 0;
 };
 
 static void relayout(znll_plan* p) {
@@ -783,6 +787,31 @@ int znll_plan_set_sumw(znll_plan* p, int ch, double sumw) {
   return 0;
 }
 
+int znll_plan_set_peers(znll_plan* p, int rank, int world, void* const* peer_bufs, size_t buf_bytes) {
+  if (!p) return fail("znll_plan_set_peers: bad arguments");
+  if (world <= 1) {
+    p->x_world = 0;
+    return 0;
+  }
+  if (world > 8 || rank < 0 || rank >= world || !peer_bufs) return fail("znll_plan_set_peers: bad rank/world (max 8 peers)");
+  if (p->total_acc > 256) return fail("znll_plan_set_peers: too many accumulators (%d) for the fused exchange", p->total_acc);
+  const size_t need = znll_plan_exchange_bytes(p, world);
+  if (buf_bytes < need) return fail("znll_plan_set_peers: exchange buffer too small (%zu < %zu bytes)", buf_bytes, need);
+  for (int r = 0; r < world; ++r) {
+    if (!peer_bufs[r] || ((uintptr_t)peer_bufs[r] & 15)) return fail("znll_plan_set_peers: peer buffer %d null or misaligned", r);
+    p->x_buf[r] = (double*)peer_bufs[r];
+  }
+  p->x_rank = rank;
+  p->x_world = world;
+  p->x_seq = 0;
+  return 0;
+}
+
+size_t znll_plan_exchange_bytes(const znll_plan* p, int world) {
+  if (!p || world < 1) return 0;
+  return 128 + sizeof(double) * 2 * (size_t)world * (size_t)p->total_acc;
+}
+
 int znll_plan_n_slots(const znll_plan* p, int ch) { return (p && ch >= 0 && ch < (int)p->ch.size()) ? p->ch[ch].n_slots : -1; }
 int znll_plan_n_acc(const znll_plan* p, int ch) { return (p && ch >= 0 && ch < (int)p->ch.size()) ? p->ch[ch].n_acc : -1; }
 int znll_plan_total_slots(const znll_plan* p) { return p ? p->total_slots : -1; }
@@ -805,7 +834,7 @@ int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_of
     if (c.nodes.empty() || !c.bound) return fail("znll_launch: channel without model or data");
     c.slots.assign(slots + c.slot_off, slots + c.slot_off + c.n_slots);
     fill_consts(c, c.slots.data());
-    if (c.n == 0) {  // empty shard: contributes exact zeros
+    if (c.n == 0 && p->x_world <= 1) {  // empty shard: contributes exact zeros
       CUDA_OK(cudaMemsetAsync(p->d_acc + c.acc_off, 0, sizeof(double) * c.n_acc, st));
       continue;
     }
@@ -817,6 +846,15 @@ int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_of
     la.partials = c.d_partials;
     la.ticket = c.d_ticket;
     la.out = p->d_acc + c.acc_off;
+    memset(&la.xc, 0, sizeof(la.xc));
+    if (p->x_world > 1 && &c == &p->ch.back()) {  // the last channel's kernel also performs the exchange
+      for (int r = 0; r < p->x_world; ++r) la.xc.buf[r] = p->x_buf[r];
+      la.xc.acc = p->d_acc;
+      la.xc.seq = ++p->x_seq;
+      la.xc.rank = p->x_rank;
+      la.xc.world = p->x_world;
+      la.xc.total = p->total_acc;
+    }
     const int w = c.w ? 1 : 0;
     const int grid = grid_for(p, c.n);
     if (c.kernel.origin == 1) {
@@ -867,6 +905,7 @@ int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* 
   la.partials = d_out;
   la.ticket = c.d_ticket;
   la.out = nullptr;
+  memset(&la.xc, 0, sizeof(la.xc));
   long long g = (c.n + 255) / 256;
   if (g > p->max_grid * 4) g = p->max_grid * 4;
   int rc = 0;

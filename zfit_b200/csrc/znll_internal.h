@@ -2,7 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 
-struct ZnllLaunchArgs {
+struct ZnllXchg {  // == znll::Xchg
+  double* buf[8];
+  double* acc;
+  unsigned long long seq;
+  int rank, world, total, pad;
+};
+
+struct ZnllLaunchArgs {  // == the prefix of znll::KArgs<NC> (the NVRTC path copies it verbatim)
   const double* cols[8];
   const double* w;
   long long n;
@@ -10,6 +17,7 @@ struct ZnllLaunchArgs {
   double* partials;
   unsigned int* ticket;
   double* out;
+  ZnllXchg xc;
 };
 
 // launches nll_kernel<M, WEIGHTED, GRAD> with `grid` blocks of 256 threads on `stream`

@@ -52,11 +52,12 @@ class CudaEngine:
     """
 
     def __init__(self, models, datas, fit_ranges, *, device=None, sort_events=True, deterministic_reduce=False,
-                 distributed=None):
+                 distributed=None, fused_reduce=True):
         from . import _znll as Z
 
         self.Z = Z
         self.distributed = _dist.is_distributed() if distributed is None else bool(distributed)
+        self.reduce_mode = "none"
         self.deterministic_reduce = deterministic_reduce
         if device is None:
             device = _dist.local_device()
@@ -98,7 +99,15 @@ class CudaEngine:
             self.n_entries = [int(round(v)) for v in t[nch:]]
             for k in range(nch):
                 self.plan.set_sumw(k, self.samplesize[k])
-            self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
+            self.reduce_mode = "nccl"
+            if fused_reduce:
+                try:
+                    self._setup_fused_exchange(device)
+                    self.reduce_mode = "fused-nvlink"
+                except Exception as exc:  # symmetric memory unavailable: keep the NCCL all-reduce
+                    self.reduce_fallback_reason = repr(exc)
+            if self.reduce_mode == "nccl":
+                self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
         self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
 
     def _sort_for_coherence(self, model, data, cols, w):
@@ -115,10 +124,31 @@ class CudaEngine:
             w = w[order].contiguous()
         return cols, w
 
+    def _setup_fused_exchange(self, device):
+        """Peer-mapped exchange buffers through torch's symmetric memory (allocation + handle exchange only); the
+        reduction itself runs inside the NLL kernel (csrc/znll_device.cuh::peer_exchange)."""
+        import torch.distributed as td
+        import torch.distributed._symmetric_memory as symm
+
+        torch = self.torch
+        world, rank = _dist.world_size(), _dist.rank()
+        nbytes = self.plan.exchange_bytes(world)
+        n = (nbytes + 7) // 8
+        buf = symm.empty(n, dtype=torch.float64, device=torch.device("cuda", device))
+        buf.zero_()
+        handle = symm.rendezvous(buf, td.group.WORLD)
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        if len(ptrs) != world:
+            msg = f"symmetric memory returned {len(ptrs)} peers for world {world}"
+            raise RuntimeError(msg)
+        torch.cuda.synchronize(device)
+        td.barrier()  # every rank has zeroed its flags before anyone publishes
+        self.plan.set_peers(rank, world, ptrs, n * 8, keepalive=(buf, handle))
+
     def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
         # kernels go to torch's current stream, so torch ops (NCCL all-reduce, data preparation) order with them
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
-        if not self.distributed:
+        if not self.distributed or self.reduce_mode == "fused-nvlink":
             return self.plan.eval(slots, grad=grad, log_offset=log_offset, kahan=kahan, stream=stream)
         self.plan.launch(slots, grad=grad, log_offset=log_offset, stream=stream)
         _dist.all_reduce_sum_(self._acc, deterministic=self.deterministic_reduce)
@@ -325,6 +355,7 @@ class BaseLoss:
                     sort_events=self._options.get("sort_events", True),
                     deterministic_reduce=self._options.get("deterministic_reduce", False),
                     distributed=self._options.get("distributed"),
+                    fused_reduce=self._options.get("fused_reduce", True),
                 )
         return self._engine
 
