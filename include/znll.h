@@ -22,6 +22,9 @@
  *       ZNLL_EXP    lambda                    (src/zfit/models/basic.py:34-243)
  *       ZNLL_CB     mu, sigma, alpha, n       (src/zfit/models/physics.py:31-45,83-142,233-336)
  *       ZNLL_CHEB   c_0 .. c_degree           (src/zfit/models/polynomials.py:334-482)
+ *       ZNLL_LEGENDRE, ZNLL_CHEB2  c_0 .. c_degree   (polynomials.py:181-332, 487-600; "next" row f.3)
+ *       ZNLL_GCB    mu, sigmal, alphal, nl, sigmar, alphar, nr   (GeneralizedCB, physics.py:47-80,186-232;
+ *                   DoubleCB is the same node with the sigma slot given twice)
  *       ZNLL_SUM    frac_0 .. frac_{k-1}      (src/zfit/models/functor.py:74-313; ALL k fractions)
  *       ZNLL_PROD   (none)                    (src/zfit/models/functor.py:331-483)
  *   The library differentiates with respect to slots; the host applies d(slot)/d(theta)
@@ -45,6 +48,9 @@ enum znll_kind {
   ZNLL_EXP = 2,
   ZNLL_CB = 3,
   ZNLL_CHEB = 4,
+  ZNLL_LEGENDRE = 5,
+  ZNLL_CHEB2 = 6,
+  ZNLL_GCB = 7,
   ZNLL_SUM = 16,
   ZNLL_PROD = 17
 };
@@ -55,10 +61,10 @@ typedef struct znll_node {
   int32_t kind;       /* enum znll_kind */
   int32_t n_children; /* functors: number of direct children; leaves: 0 */
   int32_t column;     /* leaves: index of the bound data column this leaf reads */
-  int32_t degree;     /* ZNLL_CHEB: polynomial degree d (slots c_0..c_d); else 0 */
+  int32_t degree;     /* polynomials: degree d (slots c_0..c_d); else 0 */
   double norm_lo;     /* leaves: normalisation integral limits (BasePDF.normalization, basepdf.py:198-251) */
   double norm_hi;
-  double space_lo;    /* ZNLL_CHEB: rescale limits (rescale_minus_plus_one, polynomials.py:32-43) */
+  double space_lo;    /* polynomials: rescale limits (rescale_minus_plus_one, polynomials.py:32-43) */
   double space_hi;
   double shift;       /* ZNLL_EXP: numerics data shift s (basic.py:128-154): centre of the norm, or 0
                          inside a ProductPDF */

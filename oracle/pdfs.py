@@ -186,8 +186,8 @@ class CrystalBall(_Leaf):
         use_log = B.abs(n - one) < 1e-05
         abs_sigma = B.abs(sigma)
         abs_alpha = B.abs(alpha)
-        tmin = (B.const(lo) - mu) / abs_sigma
-        tmax = (B.const(hi) - mu) / abs_sigma
+        tmin = ((lo if hasattr(lo, "dtype") else B.const(lo)) - mu) / abs_sigma
+        tmax = ((hi if hasattr(hi, "dtype") else B.const(hi)) - mu) / abs_sigma
         alpha_negative = alpha < 0
         tmax, tmin = B.where(alpha_negative, -tmin, tmax), B.where(alpha_negative, -tmax, tmin)
 
@@ -284,6 +284,99 @@ class Chebyshev(_Leaf):
             integral = integral + (indefinite(upper) - indefinite(lower))
         volume = B.const(self.limits[1] - self.limits[0])
         return integral * (B.const(0.5) * volume)
+
+
+class Legendre(Chebyshev):
+    """``zfit.pdf.Legendre`` (``src/zfit/models/polynomials.py:181-332``)."""
+
+    @staticmethod
+    def _recurrence(B, x, degree):  # legendre_recurrence, polynomials.py:181-190
+        polys = [B.ones_like(x), x]
+        for n in range(1, degree):
+            polys.append((B.const(2.0 * n + 1.0) * (x * polys[-1]) - B.const(float(n)) * polys[-2]) / B.const(n + 1.0))
+        return polys
+
+    def integral(self, B, P, lo, hi, norm):  # legendre_integral, polynomials.py:193-228
+        coeffs = [_val(B, P, c) for c in self.coeffs]
+        lower = self._rescale(B, B.const(lo))
+        upper = self._rescale(B, B.const(hi))
+        integral = coeffs[0] * (upper - lower)
+        if self.degree >= 1:
+
+            def indefinite(lim):
+                polys = self._recurrence(B, lim, self.degree + 1)
+                tot = None
+                for degree in range(1, self.degree + 1):
+                    term = coeffs[degree] * (polys[degree + 1] - polys[degree - 1]) / B.const(2.0 * degree + 1.0)
+                    tot = term if tot is None else tot + term
+                return tot
+
+            integral = indefinite(upper) - indefinite(lower) + integral
+        return integral * (B.const(0.5) * B.const(self.limits[1] - self.limits[0]))
+
+
+class Chebyshev2(Chebyshev):
+    """``zfit.pdf.Chebyshev2`` (``src/zfit/models/polynomials.py:487-600``): U_0 = 1, U_1 = 2x, same recurrence."""
+
+    @staticmethod
+    def _recurrence(B, x, degree):
+        polys = [B.ones_like(x), x * B.const(2.0)]
+        for _ in range(1, degree):
+            polys.append(B.const(2.0) * (x * polys[-1]) - polys[-2])
+        return polys
+
+    def integral(self, B, P, lo, hi, norm):  # func_integral_chebyshev2, polynomials.py:565-590
+        coeffs = [_val(B, P, c) for c in self.coeffs]
+        lower = self._rescale(B, B.const(lo))
+        upper = self._rescale(B, B.const(hi))
+
+        def indefinite(lim):  # integral of U_n is T_{n+1}/(n+1): a first-kind sum with c_0 = 0
+            polys = Chebyshev._recurrence(B, lim, self.degree + 1)
+            tot = None
+            for n, c in enumerate(coeffs):
+                term = (c / B.const(n + 1.0)) * polys[n + 1]
+                tot = term if tot is None else tot + term
+            return tot
+
+        integral = indefinite(upper) - indefinite(lower)
+        return integral * (B.const(0.5) * B.const(self.limits[1] - self.limits[0]))
+
+
+class GeneralizedCB(_Leaf):
+    """``zfit.pdf.GeneralizedCB`` (``src/zfit/models/physics.py:47-80,186-232``); ``DoubleCB`` = ``sigmal is sigmar``."""
+
+    def __init__(self, mu, sigmal, alphal, nl, sigmar, alphar, nr, obs, limits, yield_=None):
+        super().__init__(obs, limits, yield_)
+        self.p = (mu, sigmal, alphal, nl, sigmar, alphar, nr)
+
+    def param_names(self):
+        out = []
+        for q in self.p:
+            for n in _names(q):
+                if n not in out:
+                    out.append(n)
+        return out
+
+    def _sides(self, B, P):
+        mu, sl, al, nl, sr, ar, nr = (_val(B, P, q) for q in self.p)
+        left = CrystalBall(lambda _: mu, lambda _: sl, lambda _: al, lambda _: nl, self.obs, self.limits)
+        right = CrystalBall(lambda _: mu, lambda _: sr, lambda _: -ar, lambda _: nr, self.obs, self.limits)
+        return mu, left, right
+
+    def unnorm(self, B, x, P, norm):  # generalized_crystalball_func, physics.py:69-80
+        mu, left, right = self._sides(B, P)
+        return B.where(x < mu, left.unnorm(B, x, P, norm), right.unnorm(B, x, P, norm))
+
+    def integral(self, B, P, lo, hi, norm):  # generalized_crystalball_mu_integral_func, physics.py:218-232
+        mu, left, right = self._sides(B, P)
+        lo_c, hi_c = B.const(lo), B.const(hi)
+        upper_of_lowerint = B.where(mu < hi_c, mu, hi_c)
+        lower_of_upperint = B.where(mu > lo_c, mu, lo_c)
+        il = left.integral(B, P, lo_c, upper_of_lowerint, norm)
+        ir = right.integral(B, P, lower_of_upperint, hi_c, norm)
+        il = B.where(mu < lo_c, B.zeros_like(il), il)
+        ir = B.where(mu > hi_c, B.zeros_like(ir), ir)
+        return il + ir
 
 
 class SumPDF:
@@ -393,7 +486,7 @@ def leaf_get_yield(pdf, B, P):
     return _val(B, P, pdf.yield_)
 
 
-for _cls in (Gauss, Exponential, CrystalBall, Chebyshev):
+for _cls in (Gauss, Exponential, CrystalBall, Chebyshev, Legendre, Chebyshev2, GeneralizedCB):
     _cls.get_yield = lambda self, B, P: _val(B, P, self.yield_)
 
 

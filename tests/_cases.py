@@ -186,6 +186,43 @@ def nested_case(n=50_000, seed=8):
                 kernel="Sum<Prod<Gauss<0>,Expo<1>>,Prod<Cheb<0,1>,Expo<1>>>")
 
 
+def gcb_exp_case(n=100_000, seed=9):
+    """Generalized (two-sided) CrystalBall + exponential background."""
+    rng = np.random.default_rng(seed)
+    lo, hi = 5000.0, 5600.0
+    sig = _trunc(rng, lambda k: np.concatenate([_cb_sample(rng, k // 2, 5280, 18, 1.4, 3), 2 * 5280 - _cb_sample(rng, k // 2, 5280, 24, 1.1, 4)]), lo, hi, int(0.4 * n))
+    bkg = _trunc(rng, lambda k: lo + rng.exponential(1 / 0.002, k), lo, hi, n - sig.size)
+    x = rng.permutation(np.concatenate([sig, bkg]))
+    nodes = [
+        Z.Node(Z.SUM, 2, 0, 0, 0, 0, 0, 0, 0),
+        Z.Node(Z.GCB, 0, 0, 0, lo, hi, 0, 0, 0),
+        Z.Node(Z.EXP, 0, 0, 0, lo, hi, 0, 0, 0.5 * (lo + hi)),
+    ]
+    names = ["f0", "f1", "mu", "sl", "al", "nl", "sr", "ar", "nr", "lam"]
+    g = O.GeneralizedCB("mu", "sl", "al", "nl", "sr", "ar", "nr", "m", (lo, hi))
+    m = O.SumPDF([g, O.Exponential("lam", "m", (lo, hi))], fracs=["f0", "f1"])
+    slots = [0.35, 0.65, 5277.0, 20.0, 1.2, 2.5, 22.0, 1.3, 3.5, -0.0025]
+    return Case("gcb_exp", nodes, names, slots, [x], m, ["m"], kernel="Sum<GCBall<0>,Expo<0>>")
+
+
+def poly_case(kind, n=100_000, seed=10):
+    """Gauss + Legendre / Chebyshev2 background (degree 3: outside the catalogue -> NVRTC; degree 2: catalogue)."""
+    rng = np.random.default_rng(seed)
+    lo, hi = -6.0, 8.0
+    x = _trunc(rng, lambda k: np.concatenate([rng.normal(1, 1.2, k // 3), rng.uniform(lo, hi, k - k // 3)]), lo, hi, n)
+    zk, ocls, tname, deg = {"legendre": (Z.LEGENDRE, O.Legendre, "Legd", 3), "cheb2": (Z.CHEB2, O.Chebyshev2, "Chb2", 2)}[kind]
+    nodes = [
+        Z.Node(Z.SUM, 2, 0, 0, 0, 0, 0, 0, 0),
+        Z.Node(Z.GAUSS, 0, 0, 0, lo, hi, 0, 0, 0),
+        Z.Node(zk, 0, 0, deg, lo, hi, lo, hi, 0),
+    ]
+    cn = [f"c{k + 1}" for k in range(deg)]
+    m = O.SumPDF([O.Gauss("mu", "sigma", "x", (lo, hi)), ocls(cn, "x", (lo, hi))], fracs=["f0", "f1"])
+    names = ["f0", "f1", "mu", "sigma", None, *cn]
+    slots = [0.3, 0.7, 0.8, 1.3, 1.0, *([0.12, -0.07, 0.05][:deg])]
+    return Case(f"gauss_{kind}", nodes, names, slots, [x], m, ["x"], kernel=f"Sum<Gauss<0>,{tname}<0,{deg}>>")
+
+
 class _SumOfProducts:
     """SumPDF over N-D ProductPDFs (functor.py:197-206: sum_i frac_i * pdf_i.pdf(x))."""
 
@@ -208,4 +245,7 @@ ALL_CASES = {
     "product": product_case,
     "rtc": rtc_case,
     "nested": nested_case,
+    "gcb_exp": gcb_exp_case,
+    "legendre": lambda **kw: poly_case("legendre", **kw),
+    "cheb2": lambda **kw: poly_case("cheb2", **kw),
 }

@@ -42,10 +42,14 @@ def _translate(nodes, obs, i, slot, in_prod):
         return O.Exponential(f"s{slot}", o, lim), i + 1, slot + 1
     if nd.kind == Z.CB:
         return O.CrystalBall(f"s{slot}", f"s{slot + 1}", f"s{slot + 2}", f"s{slot + 3}", o, lim), i + 1, slot + 4
-    if nd.kind == Z.CHEB:
-        assert (nd.space_lo, nd.space_hi) == lim, "oracle translation needs norm == space for Chebyshev"
+    if nd.kind in (Z.CHEB, Z.LEGENDRE, Z.CHEB2):
+        assert (nd.space_lo, nd.space_hi) == lim, "oracle translation needs norm == space for polynomials"
         names = [f"s{slot + k}" for k in range(nd.degree + 1)]
-        return O.Chebyshev(names[1:], o, lim, coeff0=names[0]), i + 1, slot + nd.degree + 1
+        cls = {Z.CHEB: O.Chebyshev, Z.LEGENDRE: O.Legendre, Z.CHEB2: O.Chebyshev2}[nd.kind]
+        return cls(names[1:], o, lim, coeff0=names[0]), i + 1, slot + nd.degree + 1
+    if nd.kind == Z.GCB:
+        names = [f"s{slot + k}" for k in range(7)]
+        return O.GeneralizedCB(*names, o, lim), i + 1, slot + 7
     raise AssertionError(nd.kind)
 
 

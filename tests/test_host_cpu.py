@@ -84,6 +84,39 @@ def test_host_prologue_other_leaf_integrals():
     assert abs(I - rI) <= 1e-14 * abs(rI) and np.allclose(dI, rdI, rtol=1e-13)
 
 
+def test_host_prologue_next_row_leaves():
+    """Legendre / Chebyshev2 / GeneralizedCB integrals + derivatives vs the oracle tape."""
+    cn, cv = ["c0", "c1", "c2", "c3"], [1.0, 0.3, -0.2, 0.1]
+    for kind, cls in ((Z.LEGENDRE, O.Legendre), (Z.CHEB2, O.Chebyshev2)):
+        I, dI = Z.leaf_integral(Z.Node(kind, 0, 0, 3, -3, 7, -10, 10, 0), cv)
+        rI, rdI = _autograd_integral(cls(cn[1:], "x", (-10, 10), coeff0="c0"), cn, cv, -3, 7, (-3, 7))
+        assert abs(I - rI) <= 1e-14 * abs(rI) and np.allclose(dI, rdI, rtol=1e-13)
+    gn = ["mu", "sl", "al", "nl", "sr", "ar", "nr"]
+    for vals, lo, hi in [([0.2, 1.1, 1.2, 2.5, 0.9, 1.5, 3.0], -8, 7), ([0.2, 1.1, 1.2, 2.5, 0.9, 1.5, 3.0], 0.5, 7),
+                         ([0.2, 1.1, 1.2, 2.5, 0.9, 1.5, 3.0], -8, 0.1), ([5280, 20, 1.3, 2.2, 25, 1.1, 4.0], 5000, 5600)]:
+        I, dI = Z.leaf_integral(Z.Node(Z.GCB, 0, 0, 0, lo, hi, 0, 0, 0), vals)
+        rI, rdI = _autograd_integral(O.GeneralizedCB(*gn, "x", (lo, hi)), gn, vals, lo, hi, (lo, hi))
+        assert abs(I - rI) <= 1e-14 * abs(rI)
+        np.testing.assert_allclose(dI, rdI, rtol=1e-11, atol=1e-13 * abs(rI))
+
+
+def test_double_cb_shares_sigma_slot():
+    obs = zfit.Space("m", 5000, 5600)
+    mu, sigma = zfit.Parameter("mu_dcb", 5280.0), zfit.Parameter("sigma_dcb", 20.0)
+    pars = [zfit.Parameter(n + "_dcb", v) for n, v in (("al", 1.2), ("nl", 2.5), ("ar", 1.4), ("nr", 3.0))]
+    dcb = zfit.pdf.DoubleCB(mu, sigma, pars[0], pars[1], pars[2], pars[3], obs)
+    nodes, slots = dcb._lower()
+    assert nodes[0].kind == Z.GCB and slots[1] is sigma and slots[4] is sigma and len(slots) == 7
+    assert [p.name for p in dcb.get_params()] == ["mu_dcb", "sigma_dcb", "al_dcb", "nl_dcb", "ar_dcb", "nr_dcb"]
+    rng = np.random.default_rng(0)
+    x = rng.normal(5280, 30, 3000)
+    nll = use_oracle(zfit.loss.UnbinnedNLL(dcb, zfit.Data(x, obs=obs)))
+    v, g = nll.value_gradient(full=True)
+    gn = nll.gradient(numgrad=True)
+    np.testing.assert_allclose(g, gn, rtol=2e-5, atol=1e-5 * np.abs(g).max())  # sigma: two slots, one theta
+    assert abs(float(dcb.integrate((5000, 5600))[0]) - 1.0) < 1e-13
+
+
 # ------------------------------------------------------------------------------------------------ API mirror
 def test_space():
     s = zfit.Space("x", -2, 3)

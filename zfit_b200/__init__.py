@@ -30,6 +30,10 @@ pdf = _types.SimpleNamespace(
     Exponential=_pdf_mod.Exponential,
     CrystalBall=_pdf_mod.CrystalBall,
     Chebyshev=_pdf_mod.Chebyshev,
+    Legendre=_pdf_mod.Legendre,
+    Chebyshev2=_pdf_mod.Chebyshev2,
+    DoubleCB=_pdf_mod.DoubleCB,
+    GeneralizedCB=_pdf_mod.GeneralizedCB,
     SumPDF=_pdf_mod.SumPDF,
     ProductPDF=_pdf_mod.ProductPDF,
 )

@@ -9,6 +9,10 @@ static const ZnllCatalogEntry kEntries[] = {
     ZNLL_ENTRY(Prod<Gauss<0>,Expo<1>>),
     ZNLL_ENTRY(Prod<Gauss<0>,Cheb<1,2>>),
     ZNLL_ENTRY(Sum<Prod<Gauss<0>,Expo<1>>,Prod<Cheb<0,1>,Expo<1>>>),
+    ZNLL_ENTRY(GCBall<0>),
+    ZNLL_ENTRY(Sum<GCBall<0>,Expo<0>>),
+    ZNLL_ENTRY(Sum<Gauss<0>,Legd<0,2>>),
+    ZNLL_ENTRY(Sum<Gauss<0>,Chb2<0,2>>),
 };
 static Registrar reg_c(kEntries, sizeof(kEntries) / sizeof(kEntries[0]));
 

@@ -412,10 +412,12 @@ struct CBall {
   using Node = CBallN<COL, V>;
 };
 
-// Chebyshev of degree DEG: slots [c_0 .. c_DEG]
+// Orthogonal-polynomial sums of degree DEG (models/polynomials.py:46-175): slots [c_0 .. c_DEG]
 // consts [0 2/(hi-lo), 1 -(lo+hi)/(hi-lo), 2 1/I, 3.. c_k/I]
-template <int COL, int DEG, class V>
-struct ChebN {
+// KIND 0: Chebyshev T_n (T_{n+1} = 2zT_n - T_{n-1}, polynomials.py:338-343); 1: Legendre
+// ((n+1)P_{n+1} = (2n+1)zP_n - nP_{n-1}, :181-190); 2: Chebyshev of the second kind U_n (U_1 = 2z, :487-560)
+template <int COL, int DEG, int KIND, class V>
+struct PolyN {
   typedef typename Lanes<V>::Mask Mask;
   V T[DEG + 1];
   V P;
@@ -425,14 +427,19 @@ struct ChebN {
     const V z = zfma(x[COL], c[CO + 0], c[CO + 1]);
     T[0] = zbc<V>(1.0);
     V p = zbc<V>(c[CO + 3]);
-    if constexpr (DEG >= 1) {
-      T[1] = z;
-      p = zfma(z, c[CO + 4], p);
-    }
     const V z2 = zadd(z, z);
+    if constexpr (DEG >= 1) {
+      T[1] = KIND == 2 ? z2 : z;
+      p = zfma(T[1], c[CO + 4], p);
+    }
 #pragma unroll
     for (int k = 2; k <= DEG; ++k) {
-      T[k] = zfma(z2, T[k - 1], zneg(T[k - 2]));
+      if constexpr (KIND == 1) {
+        const double n = (double)(k - 1);
+        T[k] = zsub(zmul(zmul(z, T[k - 1]), (2.0 * n + 1.0) / (n + 1.0)), zmul(T[k - 2], n / (n + 1.0)));
+      } else {
+        T[k] = zfma(z2, T[k - 1], zneg(T[k - 2]));
+      }
       p = zfma(T[k], c[CO + 3 + k], p);
     }
     P = p;
@@ -456,12 +463,96 @@ struct ChebN {
     bwd_val<CO, AO>(zmul(g, fast_rcp(P)), c, acc);
   }
 };
-template <int COL, int DEG>
-struct Cheb {
+template <int COL, int DEG, int KIND>
+struct Poly {
   static constexpr int NS = DEG + 1, NC = 3 + DEG + 1, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = false;
   template <class V>
-  using Node = ChebN<COL, DEG, V>;
+  using Node = PolyN<COL, DEG, KIND, V>;
+};
+template <int COL, int DEG>
+using Cheb = Poly<COL, DEG, 0>;
+template <int COL, int DEG>
+using Legd = Poly<COL, DEG, 1>;
+template <int COL, int DEG>
+using Chb2 = Poly<COL, DEG, 2>;
+
+// Generalized (two-sided) CrystalBall (models/physics.py:47-80, 186-232): x < mu -> CrystalBall(mu, sigmal, alphal, nl),
+// else CrystalBall(mu, sigmar, -alphar, nr); DoubleCB is the same node with sigmal = sigmar = sigma.
+// slots [mu, sigmal, alphal, nl, sigmar, alphar, nr]
+// consts [0 mu, 1 -ln I, then per side (L at 2, R at 13):
+//         +0 sign(alpha_eff)/sigma, +1 1/sigma, +2 |alpha|, +3 n, +4 B, +5 ln A - ln I, +6 ln(n/a)+1, +7 1/a,
+//         +8 -n/a-a, +9 n/a^2+1, +10 sign(alpha slot)]
+template <int COL, class V>
+struct GCBallN {
+  typedef typename Lanes<V>::Mask Mask;
+  V t, dt, lu, P;
+  Mask left, tail;
+  bool any_tail;
+
+  template <int K>
+  ZNLL_DEV V side(const double* __restrict__ c) const {  // per-lane selection of a side constant
+    return zsel(left, zbc<V>(c[2 + K]), zbc<V>(c[13 + K]));
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask&) {
+    const double* cc = c + CO;
+    const V dx = zsub(x[COL], cc[0]);
+    left = zlt(dx, 0.0);
+    t = zmul(dx, side<0>(cc));
+    const V a = side<2>(cc);
+    tail = Lanes<V>::mask(la(t) < -la(a), lb(t) < -lb(a));
+    any_tail = zany(tail);
+    const V lp_core = zfma(zmul(t, -0.5), t, cc[1]);
+    if (!any_tail) {
+      dt = zneg(t);
+      lu = zbc<V>(0.0);
+      return lp_core;
+    }
+    const V u = zsel(tail, zsub(side<4>(cc), t), zbc<V>(2.0));
+    lu = fast_log(u, cx);
+    const V n = side<3>(cc);
+    const V dtt = zmul(fast_rcp(u), n);
+    const V lp_tail = zfma(lu, zneg(n), side<5>(cc));
+    dt = zsel(tail, dtt, zneg(t));
+    return zsel(tail, lp_tail, lp_core);
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg;
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    return P;
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    const double* cc = c + CO;
+    const V zero = zbc<V>(0.0);
+    const V gd = zneg(zmul(g, dt));
+    zacc(acc[AO + 0], gd, side<0>(cc));  // dt/dmu = -sign/sigma
+    const V gs = zmul(zmul(gd, t), side<1>(cc));  // dt/dsigma = -t/sigma, to the side's own sigma
+    zacc1(acc[AO + 1], zsel(left, gs, zero));
+    zacc1(acc[AO + 4], zsel(left, zero, gs));
+    if (any_tail) {
+      const V gt = zsel(tail, g, zero);
+      const V ga = zmul(zmul(gt, side<10>(cc)), zfma(dt, side<9>(cc), side<8>(cc)));
+      const V gn = zmul(gt, zsub(zsub(side<6>(cc), lu), zmul(dt, side<7>(cc))));
+      zacc1(acc[AO + 2], zsel(left, ga, zero));
+      zacc1(acc[AO + 5], zsel(left, zero, ga));
+      zacc1(acc[AO + 3], zsel(left, gn, zero));
+      zacc1(acc[AO + 6], zsel(left, zero, gn));
+    }
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
+  }
+};
+template <int COL>
+struct GCBall {
+  static constexpr int NS = 7, NC = 24, COLMASK = 1 << COL;
+  static constexpr bool LOGNAT = true;
+  template <class V>
+  using Node = GCBallN<COL, V>;
 };
 
 // ----------------------------------------------------------------------------------------------

@@ -197,12 +197,72 @@ static void cb_integral(double mu, double sigma, double alpha, double n, double 
   dI[3] = dIn;
 }
 
+// Legendre: src/zfit/models/polynomials.py:193-228;  Chebyshev2: :565-590 (integral of U_n is T_{n+1}/(n+1))
+static void poly_integral(int kind, const double* c, int deg, double lo, double hi, double slo, double shi, double* I,
+                          double* dI) {
+  if (kind == ZNLL_CHEB) return cheb_integral(c, deg, lo, hi, slo, shi, I, dI);
+  const double zl = (2.0 * lo - slo - shi) / (shi - slo), zu = (2.0 * hi - slo - shi) / (shi - slo);
+  std::vector<double> Pu(deg + 3), Pl(deg + 3), J(deg + 1);
+  if (kind == ZNLL_LEGENDRE) {
+    auto rec = [&](double z, double* P) {
+      P[0] = 1.0;
+      P[1] = z;
+      for (int n = 1; n <= deg; ++n) P[n + 1] = ((2.0 * n + 1.0) * (z * P[n]) - n * P[n - 1]) / (n + 1.0);
+    };
+    rec(zu, Pu.data());
+    rec(zl, Pl.data());
+    J[0] = zu - zl;
+    for (int k = 1; k <= deg; ++k) J[k] = (Pu[k + 1] - Pu[k - 1]) / (2.0 * k + 1.0) - (Pl[k + 1] - Pl[k - 1]) / (2.0 * k + 1.0);
+  } else {  // Chebyshev2
+    cheb_T(zu, deg + 1, Pu.data());
+    cheb_T(zl, deg + 1, Pl.data());
+    for (int k = 0; k <= deg; ++k) J[k] = (Pu[k + 1] - Pl[k + 1]) / (k + 1.0);
+  }
+  double integral = 0.0;
+  for (int k = 0; k <= deg; ++k) integral += c[k] * J[k];
+  const double scale = 0.5 * (shi - slo);
+  *I = integral * scale;
+  for (int k = 0; k <= deg; ++k) dI[k] = J[k] * scale;
+}
+
+// GeneralizedCB: double_crystalball_mu_integral_func / generalized_..., src/zfit/models/physics.py:166-232
+// slots [mu, sigmal, alphal, nl, sigmar, alphar, nr]
+static void gcb_integral(const double* s, double lo, double hi, double* I, double* dI) {
+  const double mu = s[0];
+  for (int i = 0; i < 7; ++i) dI[i] = 0.0;
+  double total = 0.0;
+  if (!(mu < lo)) {  // left part: [lo, min(mu, hi)]
+    double Il, d[4];
+    cb_integral(mu, s[1], s[2], s[3], lo, mu < hi ? mu : hi, &Il, d);
+    total += Il;
+    dI[0] += d[0];
+    dI[1] += d[1];
+    dI[2] += d[2];
+    dI[3] += d[3];
+    if (mu < hi) dI[0] += 1.0;  // the upper limit is mu itself: + f(t=0) = 1
+  }
+  if (!(mu > hi)) {  // right part: [max(mu, lo), hi] with alpha -> -alphar
+    double Ir, d[4];
+    cb_integral(mu, s[4], -s[5], s[6], mu > lo ? mu : lo, hi, &Ir, d);
+    total += Ir;
+    dI[0] += d[0];
+    dI[4] += d[1];
+    dI[5] -= d[2];
+    dI[6] += d[3];
+    if (mu > lo) dI[0] -= 1.0;  // the lower limit is mu itself: - f(t=0) = -1
+  }
+  *I = total;
+}
+
 static int leaf_n_slots(const znll_node& nd) {
   switch (nd.kind) {
     case ZNLL_GAUSS: return 2;
     case ZNLL_EXP: return 1;
     case ZNLL_CB: return 4;
-    case ZNLL_CHEB: return nd.degree + 1;
+    case ZNLL_CHEB:
+    case ZNLL_LEGENDRE:
+    case ZNLL_CHEB2: return nd.degree + 1;
+    case ZNLL_GCB: return 7;
     default: return -1;
   }
 }
@@ -211,7 +271,10 @@ static int leaf_n_consts(const znll_node& nd) {
     case ZNLL_GAUSS: return 3;
     case ZNLL_EXP: return 3;
     case ZNLL_CB: return 13;
-    case ZNLL_CHEB: return 3 + nd.degree + 1;
+    case ZNLL_CHEB:
+    case ZNLL_LEGENDRE:
+    case ZNLL_CHEB2: return 3 + nd.degree + 1;
+    case ZNLL_GCB: return 24;
     default: return -1;
   }
 }
@@ -221,7 +284,10 @@ static int leaf_integral(const znll_node& nd, const double* s, double* I, double
     case ZNLL_GAUSS: gauss_integral(s[0], s[1], nd.norm_lo, nd.norm_hi, I, dI); return 0;
     case ZNLL_EXP: exp_integral(s[0], nd.norm_lo, nd.norm_hi, nd.shift, I, dI); return 0;
     case ZNLL_CB: cb_integral(s[0], s[1], s[2], s[3], nd.norm_lo, nd.norm_hi, I, dI); return 0;
-    case ZNLL_CHEB: cheb_integral(s, nd.degree, nd.norm_lo, nd.norm_hi, nd.space_lo, nd.space_hi, I, dI); return 0;
+    case ZNLL_CHEB:
+    case ZNLL_LEGENDRE:
+    case ZNLL_CHEB2: poly_integral(nd.kind, s, nd.degree, nd.norm_lo, nd.norm_hi, nd.space_lo, nd.space_hi, I, dI); return 0;
+    case ZNLL_GCB: gcb_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
     default: return fail("znll_leaf_integral: node kind %d is not a leaf", nd.kind);
   }
 }
@@ -320,7 +386,7 @@ static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int par
   const int ns = leaf_n_slots(nd), nc = leaf_n_consts(nd);
   if (ns < 0 || nd.n_children != 0) return -1;
   if (nd.column < 0 || nd.column >= ZNLL_MAX_COLS) return -1;
-  if (nd.kind == ZNLL_CHEB && (nd.degree < 0 || nd.degree > 16)) return -1;
+  if ((nd.kind == ZNLL_CHEB || nd.kind == ZNLL_LEGENDRE || nd.kind == ZNLL_CHEB2) && (nd.degree < 0 || nd.degree > 16)) return -1;
   c.n_slots += ns;
   c.n_consts += nc;
   c.nodes.push_back(ni);
@@ -328,6 +394,9 @@ static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int par
     case ZNLL_GAUSS: snprintf(buf, sizeof buf, "Gauss<%d>", nd.column); break;
     case ZNLL_EXP: snprintf(buf, sizeof buf, "Expo<%d>", nd.column); break;
     case ZNLL_CB: snprintf(buf, sizeof buf, "CBall<%d>", nd.column); break;
+    case ZNLL_GCB: snprintf(buf, sizeof buf, "GCBall<%d>", nd.column); break;
+    case ZNLL_LEGENDRE: snprintf(buf, sizeof buf, "Legd<%d,%d>", nd.column, nd.degree); break;
+    case ZNLL_CHEB2: snprintf(buf, sizeof buf, "Chb2<%d,%d>", nd.column, nd.degree); break;
     default: snprintf(buf, sizeof buf, "Cheb<%d,%d>", nd.column, nd.degree); break;
   }
   name += buf;
@@ -383,7 +452,31 @@ static void fill_consts(Channel& c, const double* slots) {
         k[12] = sg;
         break;
       }
-      case ZNLL_CHEB: {
+      case ZNLL_GCB: {
+        k[0] = s[0];
+        k[1] = -lnI;
+        for (int side = 0; side < 2; ++side) {
+          const double sigma = s[side ? 4 : 1], alpha = s[side ? 5 : 2], n = s[side ? 6 : 3];
+          const double aeff = side ? -alpha : alpha;  // crystalball_func(x, mu, sigmar, -alphar, nr) on the right
+          const double a = fabs(alpha);
+          double* q = k + (side ? 13 : 2);
+          q[0] = (aeff > 0 ? 1.0 : (aeff < 0 ? -1.0 : 0.0)) / sigma;
+          q[1] = 1.0 / sigma;
+          q[2] = a;
+          q[3] = n;
+          q[4] = n / a - a;
+          q[5] = n * log(n / a) - 0.5 * a * a - lnI;
+          q[6] = log(n / a) + 1.0;
+          q[7] = 1.0 / a;
+          q[8] = -n / a - a;
+          q[9] = n / (a * a) + 1.0;
+          q[10] = alpha > 0 ? 1.0 : (alpha < 0 ? -1.0 : 0.0);
+        }
+        break;
+      }
+      case ZNLL_CHEB:
+      case ZNLL_LEGENDRE:
+      case ZNLL_CHEB2: {
         k[0] = 2.0 / (nd.space_hi - nd.space_lo);
         k[1] = -(nd.space_lo + nd.space_hi) / (nd.space_hi - nd.space_lo);
         k[2] = 1.0 / I;

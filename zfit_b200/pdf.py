@@ -376,16 +376,13 @@ class CrystalBall(_Leaf1D):
         super().__init__(obs, params, extended=extended, norm=norm, name=name, label=label)
 
 
-class Chebyshev(_Leaf1D):
-    """``zfit.pdf.Chebyshev(obs, coeffs, apply_scaling=True, coeff0=None, *, extended, norm, name, label)``
-    (``models/polynomials.py:334-482``): ``sum_k c_k T_k(z)`` with ``c_0 = 1`` unless ``coeff0`` is given."""
+class _RecursivePolynomial(_Leaf1D):
+    """``RecursivePolynomial`` (``models/polynomials.py:46-144``): ``sum_k c_k Poly_k(z)`` on the rescaled observable,
+    ``c_0 = 1`` unless ``coeff0`` is given."""
 
-    _KIND = Z.CHEB
-
-    def __init__(self, obs, coeffs, apply_scaling=True, coeff0=None, *, extended=None, norm=None, name="Chebyshev",
-                 label=None):
+    def __init__(self, obs, coeffs, apply_scaling=True, coeff0=None, *, extended=None, norm=None, name=None, label=None):
         if not apply_scaling:
-            msg = "Chebyshev without rescaling is not lowered to the fused kernel"
+            msg = f"{type(self).__name__} without rescaling is not lowered to the fused kernel"
             raise ModelNotOnDeviceError(msg)
         space = obs if isinstance(obs, Space) else Space(obs)
         if not space.has_limits:
@@ -395,11 +392,11 @@ class Chebyshev(_Leaf1D):
         c0 = convert_to_parameter(1.0 if coeff0 is None else coeff0)
         allc = [c0] + [convert_to_parameter(c) for c in coeffs]
         if len(allc) - 1 > 16:
-            msg = "Chebyshev degree > 16 is not supported by the fused kernel"
+            msg = "polynomial degree > 16 is not supported by the fused kernel"
             raise ModelNotOnDeviceError(msg)
         self._degree = len(allc) - 1
-        super().__init__(space, {f"c_{i}": c for i, c in enumerate(allc)}, extended=extended, norm=norm, name=name,
-                         label=label)
+        super().__init__(space, {f"c_{i}": c for i, c in enumerate(allc)}, extended=extended, norm=norm,
+                         name=name or type(self).__name__, label=label)
 
     @property
     def degree(self):
@@ -407,7 +404,68 @@ class Chebyshev(_Leaf1D):
 
     def _node(self, column, lo, hi, shift):
         slo, shi = self._space.limit1d
-        return Z.Node(Z.CHEB, 0, column, self._degree, lo, hi, slo, shi, 0.0)
+        return Z.Node(self._KIND, 0, column, self._degree, lo, hi, slo, shi, 0.0)
+
+
+class Chebyshev(_RecursivePolynomial):
+    """``zfit.pdf.Chebyshev(obs, coeffs, apply_scaling=True, coeff0=None, *, extended, norm, name, label)``
+    (``models/polynomials.py:334-482``)."""
+
+    _KIND = Z.CHEB
+
+
+class Legendre(_RecursivePolynomial):
+    """``zfit.pdf.Legendre`` (``models/polynomials.py:181-332``)."""
+
+    _KIND = Z.LEGENDRE
+
+
+class Chebyshev2(_RecursivePolynomial):
+    """``zfit.pdf.Chebyshev2`` -- second kind, ``U_1 = 2x`` (``models/polynomials.py:487-600``)."""
+
+    _KIND = Z.CHEB2
+
+
+class GeneralizedCB(_Leaf1D):
+    """``zfit.pdf.GeneralizedCB(mu, sigmal, alphal, nl, sigmar, alphar, nr, obs, ...)`` (``models/physics.py:47-80,
+    186-232, 506-640``): CrystalBall(mu, sigmal, alphal, nl) below ``mu``, CrystalBall(mu, sigmar, -alphar, nr) above."""
+
+    _KIND = Z.GCB
+
+    def __init__(self, mu, sigmal, alphal, nl, sigmar, alphar, nr, obs, *, extended=None, norm=None,
+                 name="GeneralizedCB", label=None):
+        params = {
+            "mu": convert_to_parameter(mu),
+            "sigmal": convert_to_parameter(sigmal),
+            "alphal": convert_to_parameter(alphal),
+            "nl": convert_to_parameter(nl),
+            "sigmar": convert_to_parameter(sigmar),
+            "alphar": convert_to_parameter(alphar),
+            "nr": convert_to_parameter(nr),
+        }
+        super().__init__(obs, params, extended=extended, norm=norm, name=name, label=label)
+
+
+class DoubleCB(_Leaf1D):
+    """``zfit.pdf.DoubleCB(mu, sigma, alphal, nl, alphar, nr, obs, ...)`` (``models/physics.py:339-503``): the
+    generalized node with one ``sigma`` feeding both sides (two slots, one parameter)."""
+
+    _KIND = Z.GCB
+
+    def __init__(self, mu, sigma, alphal, nl, alphar, nr, obs, *, extended=None, norm=None, name="DoubleCB", label=None):
+        params = {
+            "mu": convert_to_parameter(mu),
+            "sigma": convert_to_parameter(sigma),
+            "alphal": convert_to_parameter(alphal),
+            "nl": convert_to_parameter(nl),
+            "alphar": convert_to_parameter(alphar),
+            "nr": convert_to_parameter(nr),
+        }
+        super().__init__(obs, params, extended=extended, norm=norm, name=name, label=label)
+
+    def _slot_params(self):
+        p = self._params
+        return [p["mu"], p["sigma"], p["alphal"], p["nl"], p["sigma"], p["alphar"], p["nr"]]
 
 
 # ------------------------------------------------------------------------------------------------
