@@ -142,6 +142,14 @@ int znll_launch(znll_plan* plan, const double* slots, uint32_t flags, double log
 double* znll_plan_acc_device(znll_plan* plan);
 int znll_collect(znll_plan* plan, uint32_t flags, double* values, double* grad_slots, void* stream);
 
+/* Weighted-covariance pass: value, slot gradient and, per channel, the (n_slots+1)^2 matrix
+ *      [ sum_i w_i^2 g_i g_i^T    sum_i w_i^2 g_i ]        g_i = d log pdf(x_i) / d slot  (normalisation included)
+ *      [ (sum_i w_i^2 g_i)^T      sum_i w_i^2     ]
+ * row-major, channels concatenated, in ONE extra pass over the events.  Replaces the per-event Jacobian of
+ * covariance_with_weights (src/zfit/minimizers/errors.py:333-464), which costs P forward-mode passes there. */
+int znll_eval_cov(znll_plan* plan, const double* slots, double log_offset, double* values, double* grad_slots,
+                  double* cov, void* stream);
+
 /* Fused multi-GPU reduction (no reference equivalent; the reference has no multi-device path).  peer_bufs[r] is rank
  * r's exchange buffer of at least znll_plan_exchange_bytes() bytes, zero-initialised, peer-mapped into this process
  * (CUDA IPC / VMM symmetric memory; the host obtains it from torch.distributed._symmetric_memory).  Once set, the last

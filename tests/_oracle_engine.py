@@ -123,6 +123,36 @@ class OracleEngine:
             values, gs = t[: len(values)].numpy().copy(), t[len(values) :].numpy().copy()
         return values, (gs if grad else None)
 
+    def eval_cov(self, slots):
+        """Reference-style per-event Jacobian (errors.py:406-452) -> sum_i w_i^2 [g_i;1][g_i;1]^T per channel."""
+        import torch
+
+        from oracle.backend import TorchBackend
+
+        B = TorchBackend()
+        mats = []
+        for tree, cols, w, off, ns in self.channels:
+            names = [f"s{k}" for k in range(ns)]
+            theta = torch.tensor(np.asarray(slots[off : off + ns], dtype=np.float64), requires_grad=True)
+            x = {k: B.asarray(v) for k, v in cols.items()}
+
+            def logp(th):
+                return torch.log(tree.pdf(B, x, {n: th[i] for i, n in enumerate(names)}))
+
+            J = torch.autograd.functional.jacobian(logp, theta, vectorize=True).numpy()  # (N, ns)
+            ww = np.ones(J.shape[0]) if w is None else np.asarray(w)
+            G = np.concatenate([J, np.ones((J.shape[0], 1))], axis=1)
+            mats.append((G * (ww**2)[:, None]).T @ G)
+        if self.distributed:
+            t = torch.from_numpy(np.concatenate([m.ravel() for m in mats]))
+            D.all_reduce_sum_(t, deterministic=True)
+            out, o = [], 0
+            for m in mats:
+                out.append(t[o : o + m.size].numpy().reshape(m.shape).copy())
+                o += m.size
+            mats = out
+        return mats
+
     def launch_count(self):
         return 0
 

@@ -176,3 +176,29 @@ def test_full_size_properties_1e8():
     assert np.all(np.abs(ga - gb) <= 1e-10 * np.maximum(np.abs(gb), np.abs(gb).max()))
     del x, data
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("cfg,n", [(5, 6_000), (4, 6_000), (2, 6_000), (3, 4_000)])
+def test_weighted_score_outer_matches_oracle(cfg, n):
+    """One fused pass (znll_eval_cov) against the reference-style per-event Jacobian (errors.py:406-452)."""
+    w = W.build(cfg, n=n, device="cuda:0")
+    loss = w["loss"]
+    ref = _twin(loss)
+    params = list(loss.get_params())
+    C = loss.weighted_score_outer(params)
+    R = ref.weighted_score_outer(params)
+    scale = np.sqrt(np.outer(np.diag(R), np.diag(R)))
+    assert np.all(np.abs(C - R) <= 1e-9 * scale + 1e-12 * np.abs(R).max()), np.abs(C - R).max()
+    assert np.allclose(C, C.T, rtol=1e-13, atol=0)
+
+
+def test_weighted_fit_asymptotic_covariance():
+    w = W.build(5, n=200_000, device="cuda:0")
+    loss = w["loss"]
+    result = zfit.minimize.Minuit(gradient="zfit", tol=1e-5).minimize(loss)
+    assert result.valid
+    corr = result.covariance()
+    plain = result.covariance(weightcorr=False)
+    # sWeight-like weights with mean 1 and rms 0.6: the corrected errors are larger by roughly sum w^2 / sum w
+    ratio = np.diag(corr) / np.diag(plain)
+    assert np.all(ratio > 1.05) and np.all(ratio < 2.5)

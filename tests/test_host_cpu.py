@@ -476,3 +476,49 @@ def test_errors_profile_interval():
     assert abs(e[mu]["upper"] - h[mu]["error"]) < 0.1 * h[mu]["error"] and abs(e[mu]["lower"] + h[mu]["error"]) < 0.1 * h[mu]["error"]
     cov = result.covariance()
     assert cov.shape == (2, 2) and abs(cov[0, 0] - h[mu]["error"] ** 2) < 1e-12
+
+
+def test_weighted_covariance_correction_host_logic():
+    """covariance_with_weights (errors.py:333-464) through the host layer: C from the engine's per-event score outer
+    product, mapped slots -> theta (incl. the log-yield term of extended fits), cov = H^-1 C H^-1."""
+    rng = np.random.default_rng(12)
+    obs = zfit.Space("x", -6, 6)
+    x = np.concatenate([rng.normal(0.3, 1.0, 1500), rng.uniform(-6, 6, 1500)])
+    w = rng.normal(1.0, 0.5, x.size)
+    mu, sigma = zfit.Parameter("mu_wc", 0.2, -2, 2), zfit.Parameter("sigma_wc", 1.1, 0.3, 4)
+    lam = zfit.Parameter("lam_wc", -0.05, -1, 1)
+    ns, nb = zfit.Parameter("ns_wc", 1500.0, 0, 1e5), zfit.Parameter("nb_wc", 1500.0, 0, 1e5)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu, sigma, obs, extended=ns), zfit.pdf.Exponential(lam, obs, extended=nb)])
+    data = zfit.Data(x, obs=obs, weights=w)
+    nll = use_oracle(zfit.loss.ExtendedUnbinnedNLL(model, data))
+    params = list(nll.get_params())
+    C = nll.weighted_score_outer(params)
+    # independent: finite-difference Jacobian of v_i = log pdf(x_i) + log(yield) in theta space
+    from oracle.backend import NumpyBackend
+
+    NB = NumpyBackend()
+    tree = O.SumPDF([O.Gauss("mu", "sigma", "x", (-6, 6), yield_="ns"), O.Exponential("lam", "x", (-6, 6), yield_="nb")])
+    names = ["ns", "nb", "mu", "sigma", "lam"]
+    th = np.array([p.value() for p in params])
+
+    def v(t):
+        P = dict(zip(names, map(np.float64, t)))
+        return np.log(tree.pdf(NB, {"x": data.value("x")}, P)) + np.log(P["ns"] + P["nb"])
+
+    J = np.zeros((len(th), data.num_entries))
+    for i in range(len(th)):
+        h = 1e-6 * max(1.0, abs(th[i]))
+        tp, tm = th.copy(), th.copy()
+        tp[i] += h
+        tm[i] -= h
+        J[i] = (v(tp) - v(tm)) / (2 * h)
+    Cref = (J * data.weights**2) @ J.T
+    np.testing.assert_allclose(C, Cref, rtol=2e-6, atol=1e-8 * np.abs(Cref).max())
+    result = zfit.minimize.Minuit(gradient="zfit", tol=1e-6).minimize(nll)
+    cov_corr = result.covariance()
+    cov_none = result.covariance(weightcorr=False)
+    cov_sumw2 = result.covariance(weightcorr="sumw2")
+    assert np.all(np.diag(cov_corr) > 0) and not np.allclose(cov_corr, cov_none)
+    np.testing.assert_allclose(cov_sumw2, cov_none * (np.sum(w**2) / np.sum(w)), rtol=1e-12)
+    h = result.hesse()
+    assert abs(h[mu]["error"] - np.sqrt(cov_corr[2, 2])) < 1e-12

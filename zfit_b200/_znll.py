@@ -70,6 +70,7 @@ SYMBOLS = {
     "znll_collect": (C.c_int, [C.c_void_p, C.c_uint32, _DP, _DP, C.c_void_p]),
     "znll_plan_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
     "znll_plan_exchange_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "znll_eval_cov": (C.c_int, [C.c_void_p, _DP, C.c_double, _DP, _DP, _DP, C.c_void_p]),
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
     "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
@@ -212,6 +213,19 @@ class Plan:
             )
         )
         return self._values.copy(), (self._grad[: self.total_slots].copy() if grad else None)
+
+    def eval_cov(self, slots, *, log_offset=0.0, stream=0):
+        """-> (values, grad_slots, [per channel (n_slots+1, n_slots+1) matrix]); see znll_eval_cov."""
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        sizes = [self.n_slots(k) + 1 for k in range(self.n_channels)]
+        cov = np.zeros(sum(n * n for n in sizes))
+        _check(lib().znll_eval_cov(self._h, _dptr(slots), float(log_offset), _dptr(self._values), _dptr(self._grad),
+                                   _dptr(cov), C.c_void_p(stream)))
+        mats, off = [], 0
+        for n in sizes:
+            mats.append(cov[off : off + n * n].reshape(n, n).copy())
+            off += n * n
+        return self._values.copy(), self._grad[: self.total_slots].copy(), mats
 
     def pdf_values(self, ch: int, slots, n: int, stream=0):
         slots = np.ascontiguousarray(slots, dtype=np.float64)

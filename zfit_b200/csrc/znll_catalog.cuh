@@ -40,6 +40,22 @@ cudaError_t launch_pdf(const ZnllLaunchArgs& a, const double* consts, int grid, 
   return cudaGetLastError();
 }
 
+template <class M, bool W>
+cudaError_t launch_cov(const ZnllLaunchArgs& a, const double* consts, int grid, cudaStream_t stream) {
+  KArgs<M::NC> k;
+  for (int i = 0; i < ZNLL_MAXCOL; ++i) k.cols[i] = a.cols[i];
+  k.w = a.w;
+  k.n = a.n;
+  k.log_offset = a.log_offset;
+  k.partials = a.partials;
+  k.ticket = a.ticket;
+  k.out = a.out;
+  memset(&k.xc, 0, sizeof(Xchg));
+  for (int i = 0; i < M::NC; ++i) k.c[i] = consts[i];
+  cov_kernel<M, W><<<grid, ZNLL_BLOCK, 0, stream>>>(k);
+  return cudaGetLastError();
+}
+
 template <class M>
 ZnllCatalogEntry make_entry(const char* name) {
   ZnllCatalogEntry e;
@@ -51,6 +67,8 @@ ZnllCatalogEntry make_entry(const char* name) {
   e.fn[1][0] = &launch_nll<M, true, false>;
   e.fn[1][1] = &launch_nll<M, true, true>;
   e.pdf = &launch_pdf<M>;
+  e.cov[0] = &launch_cov<M, false>;
+  e.cov[1] = &launch_cov<M, true>;
   return e;
 }
 

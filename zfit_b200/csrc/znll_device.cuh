@@ -1035,6 +1035,51 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
   block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out, &args.xc);
 }
 
+// Weighted-covariance pass (reference: covariance_with_weights,
+// src/zfit/minimizers/errors.py:333-464, C = sum_i w_i^2 grad(log p_i) grad(log p_i)^T): besides the usual
+// accumulators it sums the outer product of the per-event vector e_i = [c_i0 .. c_i,NS-1, w_i] with
+// c_ij = w_i * d l_i / d slot_j (normalisation constants held fixed; the host applies the same linear map as for
+// the gradient).  One event per thread step (scalar instantiation): a once-per-fit pass, not the step kernel.
+// out: [0,1] value pair, [2, 2+NS) slot sums, then the upper triangle of sum e e^T, row-major, (NS+1)(NS+2)/2 entries.
+template <class M, bool WEIGHTED>
+__global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constant__ KArgs<M::NC> args) {
+  constexpr int NS = M::NS, NE = NS + 1, NQ = NE * (NE + 1) / 2, NACC = 2 + NS + NQ;
+  __shared__ double2 logtab[128];
+  init_logtab(logtab);
+  __syncthreads();
+  Ctx cx;
+  cx.logtab = logtab;
+  double acc[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
+  const double* __restrict__ c = args.c;
+  const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
+  for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < args.n; i += stride) {
+    double x[ZNLL_MAXCOL];
+#pragma unroll
+    for (int k = 0; k < ZNLL_MAXCOL; ++k)
+      if ((M::COLMASK >> k) & 1) x[k] = __ldg(args.cols[k] + i);
+    double w = 1.0;
+    if constexpr (WEIGHTED) w = __ldg(args.w + i);
+    double e[2 + NE];
+#pragma unroll
+    for (int j = 0; j < 2 + NE; ++j) e[j] = 0.0;
+    kahan_add(acc, event<M, double, WEIGHTED, true>(cx, c, x, w, args.log_offset, e));
+    e[2 + NS] = w;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acc[2 + j] += e[2 + j];
+    int q = 2 + NS;
+#pragma unroll
+    for (int a = 0; a < NE; ++a)
+#pragma unroll
+      for (int b = a; b < NE; ++b) {
+        acc[q] = fma(e[2 + a], e[2 + b], acc[q]);
+        ++q;
+      }
+  }
+  block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out, nullptr);
+}
+
 // per-event normalised pdf values (BasePDF.pdf, core/basepdf.py:398-429): out[i] = P(x_i); args.partials = out
 template <class M>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) pdf_kernel(const __grid_constant__ KArgs<M::NC> args) {

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -307,6 +308,7 @@ struct Kernel {
   const ZnllCatalogEntry* aot = nullptr;
   void* cufunc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // CUfunction, NVRTC path
   void* cufunc_pdf = nullptr;
+  void* cufunc_cov[2] = {nullptr, nullptr};
 };
 
 struct Channel {
@@ -622,6 +624,9 @@ static int build(const std::string& model, Kernel* out) {
     }
   const std::string pdf_expr = "znll::pdf_kernel<" + q + ">";
   a.addname(prog, pdf_expr.c_str());
+  const std::string cov_expr[2] = {"znll::cov_kernel<" + q + ",false>", "znll::cov_kernel<" + q + ",true>"};
+  a.addname(prog, cov_expr[0].c_str());
+  a.addname(prog, cov_expr[1].c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const int rc = a.compile(prog, 3, opts);
   if (rc) {
@@ -660,6 +665,14 @@ static int build(const std::string& model, Kernel* out) {
     if (!low || a.getfn(&k.cufunc_pdf, mod, low)) {
       a.destroy(&prog);
       return fail("cuModuleGetFunction failed for '%s'", pdf_expr.c_str());
+    }
+  }
+  for (int w = 0; w < 2; ++w) {
+    const char* low = nullptr;
+    a.lowered(prog, cov_expr[w].c_str(), &low);
+    if (!low || a.getfn(&k.cufunc_cov[w], mod, low)) {
+      a.destroy(&prog);
+      return fail("cuModuleGetFunction failed for '%s'", cov_expr[w].c_str());
     }
   }
   a.destroy(&prog);
@@ -977,6 +990,88 @@ int znll_eval(znll_plan* p, const double* slots, uint32_t flags, double log_offs
               double* grad_slots, void* stream) {
   if (znll_launch(p, slots, flags, log_offset, stream)) return 1;
   return znll_collect(p, flags, values, grad_slots, stream);
+}
+
+int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* values, double* grad_slots,
+                  double* cov, void* stream) {
+  if (!p || !slots || !values || !cov) return fail("znll_eval_cov: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t cov_off = 0;
+  for (size_t k = 0; k < p->ch.size(); ++k) {
+    Channel& c = p->ch[k];
+    if (c.nodes.empty() || !c.bound) return fail("znll_eval_cov: channel without model or data");
+    const int NS = c.n_slots, NE = NS + 1, NQ = NE * (NE + 1) / 2, NACC = 2 + NS + NQ;
+    if (NACC > 256) return fail("znll_eval_cov: too many slots (%d) for the covariance pass", NS);
+    c.slots.assign(slots + c.slot_off, slots + c.slot_off + NS);
+    fill_consts(c, c.slots.data());
+    std::vector<double> acc(NACC, 0.0);
+    if (c.n > 0) {
+      const int grid = (int)std::min<long long>(p->sm_count, (c.n + 255) / 256);
+      double *d_part = nullptr, *d_out = nullptr;
+      CUDA_OK(cudaMalloc(&d_part, sizeof(double) * (size_t)grid * NACC));
+      CUDA_OK(cudaMalloc(&d_out, sizeof(double) * NACC));
+      ZnllLaunchArgs la;
+      for (int i = 0; i < ZNLL_MAX_COLS; ++i) la.cols[i] = c.cols[i];
+      la.w = c.w;
+      la.n = c.n;
+      la.log_offset = log_offset;
+      la.partials = d_part;
+      la.ticket = c.d_ticket;
+      la.out = d_out;
+      memset(&la.xc, 0, sizeof(la.xc));
+      const int w = c.w ? 1 : 0;
+      int rc = 0;
+      if (c.kernel.origin == 1) {
+        cudaError_t e = c.kernel.aot->cov[w](la, c.consts.data(), grid, st);
+        if (e != cudaSuccess) rc = fail("cov kernel launch failed: %s", cudaGetErrorString(e));
+      } else {
+        rc = rtc::launch_fn(c.kernel.cufunc_cov[w], c.kernel.name.c_str(), la, c.consts.data(), c.n_consts, grid, st);
+      }
+      p->launches++;
+      cudaError_t e = cudaSuccess;
+      if (!rc) e = cudaMemcpyAsync(acc.data(), d_out, sizeof(double) * NACC, cudaMemcpyDeviceToHost, st);
+      if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(st);
+      cudaFree(d_part);
+      cudaFree(d_out);
+      if (rc) return rc;
+      if (e != cudaSuccess) return fail("znll_eval_cov: %s", cudaGetErrorString(e));
+    }
+    finish(c, acc.data(), ZNLL_WANT_GRAD, &values[k], grad_slots ? grad_slots + c.slot_off : nullptr);
+    // Q = sum e e^T (symmetric), e = [c_0..c_{NS-1}, w];  per-event d log p/d slot = M e  with the same normalisation
+    // map as the gradient epilogue:  G_j = c_j - k_leaf * dlnI_j,  k_leaf = f_b * c_{frac_b}  or  w
+    std::vector<double> Q((size_t)NE * NE), Mx((size_t)NE * NE, 0.0), T((size_t)NE * NE);
+    int q = 2 + NS;
+    for (int a = 0; a < NE; ++a)
+      for (int b = a; b < NE; ++b) Q[(size_t)a * NE + b] = Q[(size_t)b * NE + a] = acc[q++];
+    for (int j = 0; j < NE; ++j) Mx[(size_t)j * NE + j] = 1.0;
+    for (auto& ni : c.nodes) {
+      if (ni.nd.kind == ZNLL_SUM || ni.nd.kind == ZNLL_PROD) continue;
+      const int ns = leaf_n_slots(ni.nd);
+      for (int i = 0; i < ns; ++i) {
+        const int j = ni.slot_off + i;
+        if (ni.parent_sum_frac_slot >= 0)
+          Mx[(size_t)j * NE + ni.parent_sum_frac_slot] -= c.dlnI[j] * c.slots[ni.parent_sum_frac_slot];
+        else
+          Mx[(size_t)j * NE + NS] -= c.dlnI[j];
+      }
+    }
+    for (int a = 0; a < NE; ++a)
+      for (int b = 0; b < NE; ++b) {
+        double t = 0.0;
+        for (int m = 0; m < NE; ++m) t += Mx[(size_t)a * NE + m] * Q[(size_t)m * NE + b];
+        T[(size_t)a * NE + b] = t;
+      }
+    double* out = cov + cov_off;
+    for (int a = 0; a < NE; ++a)
+      for (int b = 0; b < NE; ++b) {
+        double t = 0.0;
+        for (int m = 0; m < NE; ++m) t += T[(size_t)a * NE + m] * Mx[(size_t)b * NE + m];
+        out[(size_t)a * NE + b] = t;
+      }
+    cov_off += (size_t)NE * NE;
+  }
+  return 0;
 }
 
 int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* stream) {

@@ -28,6 +28,7 @@ struct ZnllCatalogEntry {
   int n_slots, n_consts;
   znll_launcher_t fn[2][2];  // [weighted][grad]
   znll_launcher_t pdf;       // per-event pdf values into args.partials
+  znll_launcher_t cov[2];    // weighted-covariance pass [weighted]
 };
 
 // each catalogue TU registers its instantiations at static-init time

@@ -154,6 +154,21 @@ class CudaEngine:
         _dist.all_reduce_sum_(self._acc, deterministic=self.deterministic_reduce)
         return self.plan.collect(grad=grad, stream=stream)
 
+    def eval_cov(self, slots):
+        """Per channel the (n_slots+1)^2 matrix sum_i w_i^2 [g_i;1][g_i;1]^T (g_i = d log pdf_i/d slot), world-summed."""
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        _, _, mats = self.plan.eval_cov(slots, stream=stream)
+        if self.distributed:
+            flat = self.torch.from_numpy(np.concatenate([m.ravel() for m in mats])).to(f"cuda:{self.device}")
+            _dist.all_reduce_sum_(flat, deterministic=True)
+            flat = flat.cpu().numpy()
+            out, off = [], 0
+            for m in mats:
+                out.append(flat[off : off + m.size].reshape(m.shape).copy())
+                off += m.size
+            mats = out
+        return mats
+
     def launch_count(self):
         return self.plan.launch_count()
 
@@ -407,6 +422,50 @@ class BaseLoss:
         if not want_grad:
             return value, None
         return value, np.array([grad.get(p, 0.0) for p in params], dtype=np.float64)
+
+    # ------------------------------------------------------------------ weighted-fit covariance ingredient
+    def weighted_score_outer(self, params=None):
+        """``C = sum_i w_i^2 grad_theta(v_i) grad_theta(v_i)^T`` with ``v_i = log pdf(x_i) [+ log yield]`` plus one
+        unit-weight term per constraint -- the matrix ``covariance_with_weights`` builds from a per-event Jacobian
+        (``minimizers/errors.py:406-452``); here it is ONE extra fused pass over the events (``znll_eval_cov``)."""
+        params = list(self._input_check_params(params))
+        eng = self._get_engine()
+        slots = np.array([p.value() for p in eng.slot_params], dtype=np.float64)
+        mats = eng.eval_cov(slots)
+        index = {id(p): i for i, p in enumerate(params)}
+        npar = len(params)
+        C = np.zeros((npar, npar))
+        for k, (E, (lo, hi)) in enumerate(zip(mats, self._channel_slot_ranges(eng))):
+            ns = hi - lo
+            B = np.zeros((ns + 1, npar))
+            for j, sp in enumerate(eng.slot_params[lo:hi]):
+                for leaf, d in (sp._partials().items() if not sp.independent else [(sp, 1.0)]):
+                    if id(leaf) in index:
+                        B[j, index[id(leaf)]] += d
+            if self.is_extended:
+                yparam = self.model[k].get_yield()
+                y = yparam.value()
+                for leaf, d in yparam._partials().items():
+                    if id(leaf) in index:
+                        B[ns, index[id(leaf)]] += d / y
+            C += B.T @ E @ B
+        for con in self.constraints:
+            g = np.zeros(npar)
+            for leaf, d in con._partials().items():
+                if id(leaf) in index:
+                    g[index[id(leaf)]] += d
+            C += np.outer(g, g)
+        return C
+
+    def _channel_slot_ranges(self, eng):
+        if hasattr(eng, "channel_slots"):
+            return eng.channel_slots
+        out, off = [], 0
+        for model, data, rng in zip(self.model, self.data, self.fit_range):
+            n = len(model._lower(data.obs, rng)[1])
+            out.append((off, off + n))
+            off += n
+        return out
 
     # ------------------------------------------------------------------ offsets (loss.py:383-411)
     def check_precompile(self, *, params=None, force=False):

@@ -372,13 +372,23 @@ class FitResult:
         return False
 
     # -- uncertainties -----------------------------------------------------------------------------
-    def covariance(self, params=None, method=None, as_dict=False):
+    def covariance(self, params=None, method=None, as_dict=False, weightcorr=None):
         """Covariance = inverse Hessian of the NLL at the minimum (``hesse_np``, ``fitresult.py:234-244, 1600-1671``)
-        -- 2P fused-kernel gradient calls; ``method="approx"`` returns the minimizer's own estimate."""
+        -- 2P fused-kernel gradient calls; ``method="approx"`` returns the minimizer's own estimate.  For weighted
+        data the estimate is corrected (``weightcorr``: ``"asymptotic"`` (default) -> ``H^-1 C H^-1`` with
+        ``C = sum w_i^2 grad grad^T`` from one extra fused pass, ``"sumw2"`` -> ``H^-1 * sum w^2 / sum w``, ``False`` ->
+        none; ``minimizers/errors.py:333-464``)."""
         allp = list(self.params)
         params = allp if params is None else ([params] if isinstance(params, ZfitParameter) else list(params))
         method = method or "hesse_np"
-        if method not in self._covariance:
+        weighted = bool(getattr(self.loss, "is_weighted", False)) and method != "approx"
+        if weightcorr is None:
+            weightcorr = "asymptotic" if weighted else False
+        if weightcorr not in (False, "asymptotic", "sumw2"):
+            msg = f"Unknown method {weightcorr}, has to be one of False, 'asymptotic', 'sumw2'"
+            raise ValueError(msg)
+        key = (method, weightcorr if weighted else False)
+        if key not in self._covariance:
             if method == "approx":
                 cov = self.approx.get("inv_hessian")
                 if cov is None:
@@ -386,9 +396,17 @@ class FitResult:
             if method != "approx":
                 with set_values(allp, [self.params[p]["value"] for p in allp]):
                     hess = np.asarray(self.loss.hessian(allp), dtype=np.float64)
-                cov = np.linalg.inv(hess) * (2.0 * self.loss.errordef)
-            self._covariance[method] = np.asarray(cov)
-        cov = self._covariance[method]
+                    cov = np.linalg.inv(hess) * (2.0 * self.loss.errordef)
+                    if weighted and weightcorr == "asymptotic":
+                        C = self.loss.weighted_score_outer(allp)
+                        cov = cov @ C @ cov
+                    elif weighted and weightcorr == "sumw2":
+                        sw = sum(float(np.sum(d.weights)) if d.has_weights else float(d.num_entries) for d in self.loss.data)
+                        sw2 = sum(float(np.sum(d.weights**2)) if d.has_weights else float(d.num_entries) for d in self.loss.data)
+                        ncon = len(self.loss.constraints)
+                        cov = cov * ((sw2 + ncon) / (sw + ncon))
+            self._covariance[key] = np.asarray(cov)
+        cov = self._covariance[key]
         idx = [allp.index(p) for p in params]
         sub = cov[np.ix_(idx, idx)]
         if as_dict:
@@ -411,7 +429,7 @@ class FitResult:
             from scipy import stats
 
             scale = stats.norm.ppf(0.5 + cl / 2)
-        cov = self.covariance(params, method)
+        cov = self.covariance(params, method, weightcorr=weightcorr)
         out = {}
         for i, p in enumerate(params):
             err = {"error": float(math.sqrt(cov[i, i])) * scale, "cl": 0.68268949 if cl is None else cl}
