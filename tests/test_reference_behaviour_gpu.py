@@ -1,0 +1,193 @@
+"""The reference's own loss tests, re-expressed against the CUDA loss (behavioural spec: tests/test_loss.py).
+
+Same problems, same statistical tolerances as upstream; the arithmetic under test is the fused kernel."""
+
+import numpy as np
+import pytest
+
+import zfit_b200 as zfit
+from zfit_b200.minimize import Minuit
+
+pytestmark = pytest.mark.gpu
+
+rng = np.random.default_rng(519)  # tests/conftest.py:20 seeds with 519
+mu_true, sigma_true = 1.2, 4.1
+mu_true2, sigma_true2 = 1.01, 3.5
+yield_true = 3000
+test_values_np = rng.normal(loc=mu_true, scale=sigma_true, size=(yield_true, 1))
+test_values_np2 = rng.normal(loc=mu_true2, scale=sigma_true2, size=yield_true)
+obs1 = zfit.Space("obs1", (min(test_values_np.min(), test_values_np2.min()) - 1.4, max(test_values_np.max(), test_values_np2.max()) + 2.4))
+mu_constr, sigma_constr = [1.6, 0.02], [3.5, 0.01]
+
+_n = {"i": 0}
+
+
+def _tag():
+    _n["i"] += 1
+    return f"_rb{_n['i']}"
+
+
+def create_params(prefix):
+    t = _tag()
+    mu = zfit.Parameter(prefix + "mu" + t, mu_true - 0.2, mu_true - 1.0, mu_true + 1.0)
+    sigma = zfit.Parameter(prefix + "sigma" + t, sigma_true - 0.3, sigma_true - 2.0, sigma_true + 2.0)
+    return mu, sigma
+
+
+def create_gauss(prefix):
+    mu, sigma = create_params(prefix)
+    return zfit.pdf.Gauss(mu, sigma, obs=obs1, name="gaussian" + prefix), mu, sigma
+
+
+@pytest.mark.parametrize("size", [None, 5000, 50000, 300000, 3_000_000])
+def test_extended_unbinned_nll(size):  # tests/test_loss.py:133-156
+    if size is None:
+        values = test_values_np
+        size = values.shape[0]
+    else:
+        values = np.random.default_rng(size).normal(mu_true, sigma_true, size=(size, 1))
+    data = zfit.Data.from_tensor(obs=obs1, tensor=values)
+    gauss, mu3, sigma3 = create_gauss("3")
+    yield3 = zfit.Parameter("yield35" + _tag(), yield_true + 300, 0, 10000000)
+    gaussian3 = gauss.create_extended(yield3)
+    with pytest.warns(UserWarning, match="fit_range"):
+        nll = zfit.loss.ExtendedUnbinnedNLL(model=gaussian3, data=data, fit_range=(-20, 20))
+    assert {mu3, sigma3, yield3} == nll.get_params()
+    status = Minuit(tol=1e-4).minimize(loss=nll)  # Minuit's default: the driver's own numerical gradient
+    params = status.params
+    inside = values[(values >= -20) & (values <= 20)]
+    assert pytest.approx(np.mean(data.value()), rel=0.05) == params[mu3]["value"]
+    assert pytest.approx(np.std(data.value()), rel=0.05) == params[sigma3]["value"]
+    assert pytest.approx(inside.size, rel=0.005) == params[yield3]["value"]
+
+
+def test_unbinned_simultaneous_nll():  # tests/test_loss.py:159-169
+    data1 = zfit.Data.from_tensor(obs=obs1, tensor=test_values_np)
+    data2 = zfit.Data.from_tensor(obs=obs1, tensor=test_values_np2)
+    gaussian1, mu1, sigma1 = create_gauss("1")
+    gaussian2, mu2, sigma2 = create_gauss("2")
+    gaussian2 = gaussian2.create_extended(zfit.Parameter("yield_gauss2" + _tag(), 5))
+    with pytest.warns(UserWarning, match="Extended PDFs"):
+        nll = zfit.loss.UnbinnedNLL(model=[gaussian1, gaussian2], data=[data1, data2])
+    status = Minuit(tol=1e-5).minimize(loss=nll, params=[mu1, sigma1, mu2, sigma2])
+    params = status.params
+    assert set(nll.get_params()) == {mu1, mu2, sigma1, sigma2}
+    assert pytest.approx(np.mean(test_values_np), rel=0.007) == params[mu1]["value"]
+    assert pytest.approx(np.mean(test_values_np2), rel=0.007) == params[mu2]["value"]
+    assert pytest.approx(np.std(test_values_np), rel=0.007) == params[sigma1]["value"]
+    assert pytest.approx(np.std(test_values_np2), rel=0.007) == params[sigma2]["value"]
+
+
+@pytest.mark.parametrize("weights", (None, np.random.default_rng(1).normal(loc=1.0, scale=0.2, size=yield_true)), ids=["noweights", "weights"])
+@pytest.mark.parametrize("sigma", (lambda: [mu_constr[1] ** 2, sigma_constr[1] ** 2],
+                                   lambda: np.array([[mu_constr[1] ** 2, 0], [0, sigma_constr[1] ** 2]])), ids=["cov1d", "cov2d"])
+@pytest.mark.parametrize("options", ({"subtr_const": False}, {"subtr_const": True}))
+def test_unbinned_nll(weights, sigma, options):  # tests/test_loss.py:172-212
+    gaussian1, mu1, sigma1 = create_gauss("1")
+    gaussian2, mu2, sigma2 = create_gauss("2")
+    data = zfit.Data.from_tensor(obs=obs1, tensor=test_values_np, weights=weights)
+    nll_object = zfit.loss.UnbinnedNLL(model=gaussian1, data=data, options=options)
+    status = Minuit(tol=1e-5).minimize(loss=nll_object, params=[mu1, sigma1])
+    params = status.params
+    rel_error = 0.12 if weights is None else 0.1
+    assert pytest.approx(np.mean(test_values_np), rel=rel_error) == params[mu1]["value"]
+    assert pytest.approx(np.std(test_values_np), rel=rel_error) == params[sigma1]["value"]
+    constraints = zfit.constraint.GaussianConstraint(params=[mu2, sigma2], observation=[mu_constr[0], sigma_constr[0]], cov=sigma())
+    nll_object = zfit.loss.UnbinnedNLL(model=gaussian2, data=data, constraints=constraints, options=options)
+    status = Minuit(tol=1e-4).minimize(loss=nll_object, params=[mu2, sigma2])
+    params = status.params
+    if weights is None:
+        assert params[mu2]["value"] > np.average(test_values_np, weights=weights)
+        assert params[sigma2]["value"] < np.std(test_values_np)
+
+
+def test_add():  # tests/test_loss.py:215-275
+    params = [create_params(str(i)) for i in range(4)]
+    pdfs = [zfit.pdf.Gauss(mu, sigma, obs=obs1) for mu, sigma in params]
+    datas = [zfit.Data.from_tensor(obs=obs1, tensor=rng.normal(1.0, 3.0, size=500)) for _ in range(4)]
+    nll = zfit.loss.UnbinnedNLL(model=pdfs[0], data=datas[0])
+    nll2 = zfit.loss.UnbinnedNLL(model=pdfs[1], data=datas[1])
+    nll3 = zfit.loss.UnbinnedNLL(model=[pdfs[2], pdfs[3]], data=[datas[2], datas[3]])
+    simult = nll + nll2 + nll3
+    assert simult.model == pdfs and simult.data == datas
+    assert abs(simult.value(full=True) - (nll.value(full=True) + nll2.value(full=True) + nll3.value(full=True))) < 1e-9
+    assert len(simult.get_params()) == 8
+    with pytest.raises(ValueError):
+        _ = nll + zfit.loss.ExtendedUnbinnedNLL(pdfs[0].create_extended(zfit.Parameter("y" + _tag(), 400.0)), datas[0])
+
+
+@pytest.mark.parametrize("numgrad", [True, False], ids=["numgrad", "analytic"])
+def test_gradients(numgrad):  # tests/test_loss.py:278-335
+    t = _tag()
+    initial1, initial2 = 1.0, 2.0
+    param1, param2 = zfit.Parameter("param1" + t, initial1), zfit.Parameter("param2" + t, initial2)
+    gauss1 = zfit.pdf.Gauss(param1, 4, obs=obs1)
+    gauss2 = zfit.pdf.Gauss(param2, 5, obs=obs1)
+    data1 = zfit.Data.from_tensor(obs=obs1, tensor=np.full(100, 1.0))
+    data2 = zfit.Data.from_tensor(obs=obs1, tensor=np.full(100, 1.0))
+    nll = zfit.loss.UnbinnedNLL(model=[gauss1, gauss2], data=[data1, data2])
+
+    def loss_funcparam1and2(values):
+        with zfit.param.set_values([param2, param1], values):
+            return nll.value()
+
+    def central(f, x0, i, h=1e-4):
+        xp, xm = np.array(x0, float), np.array(x0, float)
+        xp[i] += h
+        xm[i] -= h
+        d1 = (f(xp) - f(xm)) / (2 * h)
+        xp[i] += h
+        xm[i] -= h
+        d2 = (f(xp) - f(xm)) / (4 * h)
+        return (4 * d1 - d2) / 3
+
+    truth = np.array([central(loss_funcparam1and2, [initial2, initial1], i) for i in range(2)])
+    gradient1 = nll.gradient(params=param2, numgrad=numgrad)
+    np.testing.assert_allclose(gradient1, truth[:1], rtol=1e-6)
+    gradient2 = nll.gradient(params=[param2, param1], numgrad=numgrad)
+    np.testing.assert_allclose(gradient2, truth, rtol=1e-5)
+    params3 = list(nll.get_params())
+    gradient3 = nll.gradient(params3)
+    expected = [gradient2[[param2, param1].index(p)] for p in params3]  # order of get_params defines the layout
+    np.testing.assert_allclose(gradient3, expected, rtol=1e-5)
+
+
+def test_simple_loss():  # tests/test_loss.py:338-420
+    t = _tag()
+    true_a, true_b, true_c = 1.0, 4.0, -0.3
+    a = zfit.Parameter("variable_a15151" + t, 1.5, -1.0, 20.0, stepsize=0.1)
+    b = zfit.Parameter("variable_b15151" + t, 3.5, 0, 20)
+    c = zfit.Parameter("variable_c15151" + t, -0.23, -1, 1)
+    params = [a, b, c]
+
+    def loss_func(params):
+        a, b, c = (p.value() for p in params)
+        return (a - true_a) ** 2 + (b - true_b) ** 2 + (c - true_c) ** 4 + 0.42
+
+    loss_func.errordef = 1.0
+    loss = zfit.loss.SimpleLoss(func=loss_func, params=params)
+    assert loss.errordef == 1.0 and set(loss.get_params()) == set(params)
+    result = Minuit(gradient="zfit").minimize(loss=loss)
+    assert result.valid
+    assert abs(result.params[a]["value"] - true_a) < 0.05 and abs(result.params[b]["value"] - true_b) < 0.05  # EDM < 1e-3
+    assert abs(result.params[c]["value"] - true_c) < 0.2
+    assert abs(result.fmin - 0.42) < 1e-3
+
+
+def test_callable_loss_and_iminuit_protocol():  # tests/test_loss.py:501-547
+    gaussian1, mu1, sigma1 = create_gauss("1")
+    data = zfit.Data.from_tensor(obs=obs1, tensor=test_values_np)
+    nll = zfit.loss.UnbinnedNLL(model=gaussian1, data=data)
+    x = np.array([p.value() for p in nll.get_params()])
+    assert nll(x) == pytest.approx(nll.value(full=True))
+    assert nll(x + 0.1) == pytest.approx(nll.value(params=dict(zip(nll.get_params(), x + 0.1)), full=True))
+    with pytest.raises(ValueError):
+        nll(x[:1])
+    assert nll.errordef == 0.5
+    # any driver that only knows f(x) and grad(x) can minimise it (what raw iminuit.Minuit(loss, x) does upstream)
+    from scipy import optimize
+
+    ev = zfit.minimize.LossEval(nll, list(nll.get_params()), zfit.minimize.DefaultStrategy(), False, maxiter=500, numpy_converter=np.array)
+    opt = optimize.minimize(ev.value, x, jac=ev.gradient, method="BFGS")
+    assert opt.success or opt.status == 2
+    assert opt.x[0] == pytest.approx(np.mean(test_values_np), rel=0.01) and opt.x[1] == pytest.approx(np.std(test_values_np), rel=0.01)

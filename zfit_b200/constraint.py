@@ -35,14 +35,28 @@ class GaussianConstraint(BaseConstraint):
         params = [params] if isinstance(params, ZfitParameter) else list(params)
         super().__init__(params)
         self.observation = np.atleast_1d(np.asarray(observation, dtype=np.float64))
+        if cov is not None and (sigma is not None or uncertainty is not None):
+            msg = "Either `sigma` or `cov` can be given, not both."
+            raise ValueError(msg)
         if cov is None:
             s = uncertainty if uncertainty is not None else sigma
             if s is None:
                 msg = "one of uncertainty / sigma / cov is required"
                 raise ValueError(msg)
             s = np.atleast_1d(np.asarray(s, dtype=np.float64))
-            cov = np.diag(s**2) if s.ndim == 1 else s
+            if s.ndim == 1 and s.size == 1 and len(params) > 1:
+                s = np.full(len(params), s[0])
+            cov = np.diag(s**2) if s.ndim == 1 else s  # legacy `uncertainty`: 2-D means a covariance (constraint.py:311-320)
+        else:
+            cov = np.atleast_1d(np.asarray(cov, dtype=np.float64))
+            if cov.ndim == 1:  # 1-D: the diagonal of the covariance matrix (constraint.py:296-299)
+                cov = np.diag(np.full(len(params), cov[0]) if cov.size == 1 and len(params) > 1 else cov)
         self.cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+        if self.cov.shape != (len(params), len(params)) or self.observation.size != len(params):
+            from .exception import ShapeIncompatibleError
+
+            msg = f"params ({len(params)}), observation ({self.observation.size}) and covariance {self.cov.shape} do not match"
+            raise ShapeIncompatibleError(msg)
         self._icov = np.linalg.inv(self.cov)
         self._lognorm = 0.5 * (len(params) * np.log(2 * np.pi) + np.linalg.slogdet(self.cov)[1])
 

@@ -683,11 +683,15 @@ def _steps(params):
 
 
 def _numerical_gradient(func, params):
-    """Central differences with one Richardson step (stands in for numdifftools, ``z/math.py:43-79``)."""
+    """Central differences with two Richardson levels, O(h^6) (stands in for numdifftools, ``z/math.py:43-79``)."""
     g = np.zeros(len(params))
     for i, p in enumerate(params):
         v = p.value()
-        h = 1e-5 * max(1.0, abs(v))
+        h = 1e-4 * max(1.0, abs(v))
+        if p.has_limits:  # stay inside the limits (value() clips)
+            room = min(v - p.lower if p.lower is not None else np.inf, p.upper - v if p.upper is not None else np.inf)
+            if room > 0:
+                h = min(h, room / 4.5)
 
         def d(hh, p=p, v=v):
             p.assign(v + hh)
@@ -697,7 +701,9 @@ def _numerical_gradient(func, params):
             p.assign(v)
             return (up - dn) / (2 * hh)
 
-        g[i] = (4.0 * d(h) - d(2 * h)) / 3.0
+        d1, d2, d4 = d(h), d(2 * h), d(4 * h)
+        r1, r2 = (4.0 * d1 - d2) / 3.0, (4.0 * d2 - d4) / 3.0
+        g[i] = (16.0 * r1 - r2) / 15.0
     return g
 
 
