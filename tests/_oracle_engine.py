@@ -76,6 +76,7 @@ class OracleEngine:
     def __init__(self, models, datas, fit_ranges):
         self.slot_params = []
         self.channels = []
+        datas = [d if r is None else d.with_obs(r, guarantee_limits=False) for d, r in zip(datas, fit_ranges)]
         for model, data, rng in zip(models, datas, fit_ranges):
             nodes, slots = model._lower(data.obs, rng)
             tree, end, ns = _translate(nodes, data.obs, 0, 0, False)

@@ -202,3 +202,22 @@ def test_weighted_fit_asymptotic_covariance():
     # sWeight-like weights with mean 1 and rms 0.6: the corrected errors are larger by roughly sum w^2 / sum w
     ratio = np.diag(corr) / np.diag(plain)
     assert np.all(ratio > 1.05) and np.all(ratio < 2.5)
+
+
+def test_sum_pdf_with_fit_range_parity():
+    """Deprecated fit_range on a SumPDF (loss.py:112-114): cut to the range and normalise over it."""
+    rng = np.random.default_rng(21)
+    obs = zfit.Space("x", -10, 10)
+    x = np.concatenate([rng.normal(1.0, 1.5, 15000), rng.exponential(4.0, 25000) - 10])
+    mu, sigma = zfit.Parameter("mu_frg", 0.8, -5, 5), zfit.Parameter("sigma_frg", 1.7, 0.3, 6)
+    lam, frac = zfit.Parameter("lam_frg", -0.2, -2, 2), zfit.Parameter("frac_frg", 0.4, 0, 1)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu, sigma, obs), zfit.pdf.Exponential(lam, obs)], fracs=frac)
+    with pytest.warns(UserWarning, match="fit_range"):
+        loss = zfit.loss.UnbinnedNLL(model, zfit.Data(x, obs=obs), fit_range=(-4, 6))
+    with pytest.warns(UserWarning, match="fit_range"):
+        ref = _twin(loss)
+    params = list(loss.get_params())
+    v, g = loss.value_gradient(params, full=True)
+    r, rg = ref.value_gradient(params, full=True)
+    assert abs(v - r) <= 1e-12 * abs(r)
+    assert np.all(np.abs(g - rg) <= 1e-10 * np.maximum(np.abs(rg), np.abs(rg).max()))

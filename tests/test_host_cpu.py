@@ -522,3 +522,70 @@ def test_weighted_covariance_correction_host_logic():
     np.testing.assert_allclose(cov_sumw2, cov_none * (np.sum(w**2) / np.sum(w)), rtol=1e-12)
     h = result.hesse()
     assert abs(h[mu]["error"] - np.sqrt(cov_corr[2, 2])) < 1e-12
+
+
+def test_sum_pdf_with_explicit_norm_fit_range():
+    """fit_range / explicit norm on a SumPDF: sum_i f_i pdf_i(x) / sum_j f_j int_norm pdf_j (functor.py:189-206,
+    loss.py:112-114), lowered as leaves normalised over the range + renormalised composed fractions."""
+    from oracle.backend import NumpyBackend
+
+    NB = NumpyBackend()
+    rng = np.random.default_rng(21)
+    obs = zfit.Space("x", -10, 10)
+    x = np.concatenate([rng.normal(1.0, 1.5, 1500), rng.exponential(4.0, 2500) - 10])
+    mu, sigma = zfit.Parameter("mu_fr", 0.8, -5, 5), zfit.Parameter("sigma_fr", 1.7, 0.3, 6)
+    lam, frac = zfit.Parameter("lam_fr", -0.2, -2, 2), zfit.Parameter("frac_fr", 0.4, 0, 1)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu, sigma, obs), zfit.pdf.Exponential(lam, obs)], fracs=frac)
+    data = zfit.Data(x, obs=obs)
+    with pytest.warns(UserWarning, match="fit_range"):
+        nll = use_oracle(zfit.loss.UnbinnedNLL(model, data, fit_range=(-4, 6)))
+    params = list(nll.get_params())
+    v, g = nll.value_gradient(params, full=True)
+    # direct restatement of the reference route on the cut data
+    xin = data.value("x")
+    xin = xin[(xin >= -4) & (xin <= 6)]
+    og, oe = O.Gauss("mu", "sigma", "x", (-10, 10)), O.Exponential("lam", "x", (-10, 10))
+
+    def ref(theta):
+        P = dict(zip(["frac", "mu", "sigma", "lam"], map(np.float64, theta)))
+        f = [P["frac"], 1 - P["frac"]]
+        num = f[0] * og.pdf(NB, {"x": xin}, P) + f[1] * oe.pdf(NB, {"x": xin}, P)
+        den = f[0] * og.integral(NB, P, -4, 6, (-10, 10)) / og.integral(NB, P, -10, 10, (-10, 10)) + f[1] * oe.integral(
+            NB, P, -4, 6, (-10, 10)) / oe.integral(NB, P, -10, 10, (-10, 10))
+        return float(-np.sum(np.log(num / den + 1e-307)))
+
+    th = [p.value() for p in params]
+    assert [p.name for p in params] == ["frac_fr", "mu_fr", "sigma_fr", "lam_fr"]
+    assert abs(v - ref(th)) < 1e-9 * abs(v)
+    np.testing.assert_allclose(g, ON.numeric_gradient(ref, th), rtol=1e-6, atol=1e-6 * np.abs(g).max())
+
+
+def test_constraints_values_and_partials():
+    from scipy import stats
+
+    a, b = zfit.Parameter("a_con", 4.2, 0, 100), zfit.Parameter("b_con", 7.5, 0, 100)
+    g = zfit.constraint.GaussianConstraint([a, b], observation=[4.0, 8.0], cov=[[0.04, 0.01], [0.01, 0.09]])
+    assert abs(g.value() + stats.multivariate_normal([4.2, 7.5], [[0.04, 0.01], [0.01, 0.09]]).logpdf([4.0, 8.0])) < 1e-12
+    g1 = zfit.constraint.GaussianConstraint([a, b], observation=[4.0, 8.0], cov=[0.04, 0.09])  # 1-D: diagonal of the covariance
+    g2 = zfit.constraint.GaussianConstraint([a, b], observation=[4.0, 8.0], sigma=[0.2, 0.3])
+    assert abs(g1.value() - g2.value()) < 1e-14
+    p = zfit.constraint.PoissonConstraint([a, b], observation=[5.0, 6.0])
+    assert abs(p.value() + np.sum(stats.gamma.logpdf([5.0, 6.0], 1) * 0 + np.array([4.2, 7.5]) * np.log([5.0, 6.0]) - np.array([5.0, 6.0])
+                                   - np.array([stats.loggamma.logpdf(0, 1) * 0 + __import__("scipy").special.gammaln(v + 1) for v in (4.2, 7.5)]))) < 1e-12
+    ln = zfit.constraint.LogNormalConstraint([a], observation=[1.4], uncertainty=[0.2])
+    assert abs(ln.value() + stats.lognorm.logpdf(4.2, s=0.2, scale=np.exp(1.4))) < 1e-12
+    for con in (g, p, ln):
+        num = {}
+        for leaf in con.get_params():
+            v = leaf.value()
+            leaf.assign(v + 1e-6)
+            up = con.value()
+            leaf.assign(v - 1e-6)
+            dn = con.value()
+            leaf.assign(v)
+            num[leaf] = (up - dn) / 2e-6
+        ana = con._partials()
+        for leaf in num:
+            assert abs(ana[leaf] - num[leaf]) < 1e-6 * max(1.0, abs(num[leaf]))
+    with pytest.raises(ValueError):
+        zfit.constraint.GaussianConstraint([a], observation=[1.0], sigma=[0.1], cov=[0.01])

@@ -16,7 +16,7 @@ from . import loss as _loss_mod
 from . import minimize as _min_mod
 from . import parameter as _param_mod
 from . import pdf as _pdf_mod
-from .constraint import GaussianConstraint, SimpleConstraint
+from .constraint import GaussianConstraint, LogNormalConstraint, PoissonConstraint, SimpleConstraint
 from .data import Data, convert_to_data
 from .parameter import ComposedParameter, ConstantParameter, Parameter, convert_to_parameter
 from .settings import run, ztypes
@@ -63,5 +63,10 @@ param = _types.SimpleNamespace(
     assign_values=_param_mod.assign_values,
 )
 data = _types.SimpleNamespace(Data=Data, concat=_data_mod.concat, convert_to_data=convert_to_data)
-constraint = _types.SimpleNamespace(GaussianConstraint=GaussianConstraint, SimpleConstraint=SimpleConstraint)
+constraint = _types.SimpleNamespace(
+    GaussianConstraint=GaussianConstraint,
+    PoissonConstraint=PoissonConstraint,
+    LogNormalConstraint=LogNormalConstraint,
+    SimpleConstraint=SimpleConstraint,
+)
 dimension = _types.SimpleNamespace(combine_spaces=combine_spaces)

@@ -103,3 +103,65 @@ class SimpleConstraint(BaseConstraint):
             leaf.assign(v)
             out[leaf] = (up - dn) / (2 * h)
         return out
+
+
+class PoissonConstraint(BaseConstraint):
+    """``zfit.constraint.PoissonConstraint(params, observation)`` (``constraint.py:407-440``):
+    ``-sum log Poisson(rate=observation).prob(params)`` -- the parameters are the counts, as in the reference."""
+
+    def __init__(self, params, observation):
+        params = [params] if isinstance(params, ZfitParameter) else list(params)
+        super().__init__(params)
+        self.observation = np.atleast_1d(np.asarray(observation, dtype=np.float64))
+        if self.observation.size != len(params):
+            from .exception import ShapeIncompatibleError
+
+            msg = "params and observation have to have the same length"
+            raise ShapeIncompatibleError(msg)
+
+    def value(self):
+        from scipy import special
+
+        k = np.array([p.value() for p in self._params])
+        return float(-np.sum(k * np.log(self.observation) - self.observation - special.gammaln(k + 1.0)))
+
+    def _partials(self):
+        from scipy import special
+
+        out = {}
+        for p, obs in zip(self._params, self.observation):
+            g = -(np.log(obs) - special.digamma(p.value() + 1.0))
+            for leaf, dd in p._partials().items():
+                out[leaf] = out.get(leaf, 0.0) + float(g) * dd
+        return out
+
+
+class LogNormalConstraint(BaseConstraint):
+    """``zfit.constraint.LogNormalConstraint(params, observation, uncertainty)`` (``constraint.py:457-523``):
+    ``-sum log LogNormal(loc=observation, scale=uncertainty).prob(params)``."""
+
+    def __init__(self, params, observation, uncertainty):
+        params = [params] if isinstance(params, ZfitParameter) else list(params)
+        super().__init__(params)
+        self.observation = np.atleast_1d(np.asarray(observation, dtype=np.float64))
+        self.uncertainty = np.broadcast_to(np.atleast_1d(np.asarray(uncertainty, dtype=np.float64)), self.observation.shape).copy()
+        if self.observation.size != len(params):
+            from .exception import ShapeIncompatibleError
+
+            msg = "params, observation and uncertainty have to have the same length"
+            raise ShapeIncompatibleError(msg)
+
+    def value(self):
+        x = np.array([p.value() for p in self._params])
+        s = self.uncertainty
+        lp = -np.log(x) - np.log(s) - 0.5 * np.log(2 * np.pi) - 0.5 * ((np.log(x) - self.observation) / s) ** 2
+        return float(-np.sum(lp))
+
+    def _partials(self):
+        out = {}
+        for p, loc, s in zip(self._params, self.observation, self.uncertainty):
+            x = p.value()
+            g = 1.0 / x + (np.log(x) - loc) / (s * s * x)
+            for leaf, dd in p._partials().items():
+                out[leaf] = out.get(leaf, 0.0) + float(g) * dd
+        return out

@@ -574,9 +574,20 @@ class SumPDF(BaseFunctor):
 
     def _emit(self, colmap, ctx, limits, nodes, slots):
         if ctx == "norm" and limits is not None and any(p.norm != limits.with_obs(p.obs) for p in self.pdfs):
-            # reference: SpecificFunctionNotImplemented -> unnormalised / normalization(norm) (functor.py:197-206)
-            msg = "SumPDF with a norm that differs from its daughters' norm is not lowered to the fused kernel yet"
-            raise ModelNotOnDeviceError(msg)
+            # reference: SpecificFunctionNotImplemented -> _unnormalized_pdf / normalization(norm) (functor.py:189-206):
+            #   sum_i f_i pdf_i(x) / sum_j f_j int_norm pdf_j
+            # == sum_i f'_i U_i(x)/I_i(norm)  with  f'_i = f_i r_i / sum_j f_j r_j,  r_i = I_i(norm)/I_i(own norm):
+            # leaves normalised over the requested range + composed fractions (their slot derivatives come from the
+            # analytic integral derivatives of the C library's host prologue).
+            if not all(isinstance(p, _Leaf1D) for p in self.pdfs):
+                msg = "a SumPDF of functors with a norm that differs from its daughters' norm is not lowered yet"
+                raise ModelNotOnDeviceError(msg)
+            rng = limits.with_obs(self.obs)
+            nodes.append(Z.Node(Z.SUM, len(self.pdfs), 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0))
+            slots.extend(_renormalised_fracs(self, rng))
+            for p in self.pdfs:
+                p._emit(colmap, "norm", rng, nodes, slots)
+            return
         if ctx == "prod":
             rng = limits.with_obs(self.obs)
             if not self._fracs_sum_to_one or any(p.norm != rng for p in self.pdfs):
@@ -596,6 +607,57 @@ class SumPDF(BaseFunctor):
         for p, f in zip(self.pdfs, self._fracs):
             tot += f.value() * float(p.integrate(limits)[0])
         return tot
+
+
+def _renormalised_fracs(sumpdf, rng):
+    """f'_i = f_i r_i / sum_j f_j r_j with r_i = I_i(rng) / I_i(own norm), as ComposedParameters with analytic partials."""
+    pdfs, fracs = sumpdf.pdfs, sumpdf._fracs
+    k = len(pdfs)
+    deps = {}
+    layout = []  # per daughter: (keys of its slot params, keys of its frac)
+    for i, (p, f) in enumerate(zip(pdfs, fracs)):
+        skeys = []
+        for j, sp in enumerate(p._slot_params()):
+            key = f"s{i}_{j}"
+            deps[key] = sp
+            skeys.append(key)
+        deps[f"f{i}"] = f
+        layout.append(skeys)
+
+    def ratios(vals):
+        r, dr = [], []
+        for i, p in enumerate(pdfs):
+            sv = [vals[key] for key in layout[i]]
+            lo, hi = rng.limit1d
+            olo, ohi = p.norm.limit1d
+            shift = p._shift("norm", p.norm)  # both integrals of the SAME unnormalised function (one data shift)
+            I1, d1 = Z.leaf_integral(p._node(0, lo, hi, shift), sv)
+            I0, d0 = Z.leaf_integral(p._node(0, olo, ohi, shift), sv)
+            r.append(I1 / I0)
+            dr.append((d1 - (I1 / I0) * d0) / I0)
+        return r, dr
+
+    def make(i):
+        def value(vals):
+            r, _ = ratios(vals)
+            tot = sum(float(vals[f"f{j}"]) * r[j] for j in range(k))
+            return float(vals[f"f{i}"]) * r[i] / tot
+
+        def grad(vals):
+            r, dr = ratios(vals)
+            f = [float(vals[f"f{j}"]) for j in range(k)]
+            tot = sum(f[j] * r[j] for j in range(k))
+            fi = f[i] * r[i] / tot
+            out = {}
+            for j in range(k):
+                out[f"f{j}"] = ((r[i] if j == i else 0.0) - fi * r[j]) / tot
+                for key, d in zip(layout[j], dr[j]):
+                    out[key] = ((f[i] * d if j == i else 0.0) - fi * f[j] * d) / tot
+            return out
+
+        return ComposedParameter(f"Composed_autoparam_renorm_frac_{i}_{sumpdf.name}", value, params=deps, grad=grad)
+
+    return [make(i) for i in range(k)]
 
 
 class ProductPDF(BaseFunctor):
