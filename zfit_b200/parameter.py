@@ -400,6 +400,82 @@ class ComposedParameter(ZfitParameter):
         return self is other
 
 
+class SumOfParameters(ComposedParameter):
+    """``sum_yields`` of an automatically extended SumPDF (``models/basefunctor.py:231-236``), with a direct fast path."""
+
+    def __init__(self, name, terms):
+        terms = [convert_to_parameter(t) for t in terms]
+        super().__init__(name, lambda params: sum(params.values()), params={f"yield_{i}": t for i, t in enumerate(terms)},
+                         grad=lambda vals: dict.fromkeys(vals, 1.0))
+        self._terms = terms
+        self._plain = all(t._independent for t in terms)
+
+    def value(self):
+        tot = 0.0
+        for t in self._terms:
+            tot += t.value()
+        return tot
+
+    def _partials(self, memo=None):
+        if self._plain:
+            out = {}
+            for t in self._terms:
+                out[t] = out.get(t, 0.0) + 1.0
+            return out
+        return super()._partials(memo)
+
+
+class FractionOfSum(ComposedParameter):
+    """``frac_i = yield_i / sum(yields)`` (``models/basefunctor.py:237-244``), with a direct fast path."""
+
+    def __init__(self, name, term, total: SumOfParameters):
+        term = convert_to_parameter(term)
+        super().__init__(name, lambda params: params["yield_"] / params["sum_yields"],
+                         params={"sum_yields": total, "yield_": term},
+                         grad=lambda v: {"yield_": 1.0 / v["sum_yields"], "sum_yields": -v["yield_"] / v["sum_yields"] ** 2})
+        self._term, self._total = term, total
+        self._plain = term._independent and total._plain
+
+    def value(self):
+        return self._term.value() / self._total.value()
+
+    def _partials(self, memo=None):
+        if not self._plain:
+            return super()._partials(memo)
+        tot = self._total.value()
+        y = self._term.value()
+        out = {}
+        for t in self._total._terms:
+            out[t] = out.get(t, 0.0) - y / (tot * tot)
+        out[self._term] = out.get(self._term, 0.0) + 1.0 / tot
+        return out
+
+
+class OneMinusSum(ComposedParameter):
+    """Remaining fraction ``1 - sum(fracs)`` (``models/basefunctor.py:189-205``), with a direct fast path."""
+
+    def __init__(self, name, terms):
+        terms = [convert_to_parameter(t) for t in terms]
+        super().__init__(name, lambda params: 1.0 - sum(params.values()), params={f"frac_{i}": t for i, t in enumerate(terms)},
+                         grad=lambda vals: dict.fromkeys(vals, -1.0))
+        self._terms = terms
+        self._plain = all(t._independent for t in terms)
+
+    def value(self):
+        tot = 1.0
+        for t in self._terms:
+            tot -= t.value()
+        return tot
+
+    def _partials(self, memo=None):
+        if self._plain:
+            out = {}
+            for t in self._terms:
+                out[t] = out.get(t, 0.0) - 1.0
+            return out
+        return super()._partials(memo)
+
+
 _auto_names = {"n": 0}
 
 

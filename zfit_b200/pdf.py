@@ -25,7 +25,15 @@ from .exception import (
     ObsIncompatibleError,
     ParamNameNotUniqueError,
 )
-from .parameter import ComposedParameter, OrderedSet, ZfitParameter, convert_to_parameter
+from .parameter import (
+    ComposedParameter,
+    FractionOfSum,
+    OneMinusSum,
+    OrderedSet,
+    SumOfParameters,
+    ZfitParameter,
+    convert_to_parameter,
+)
 from .space import Space, combine_spaces, convert_to_obs_str
 
 
@@ -513,13 +521,7 @@ class SumPDF(BaseFunctor):
         if fracs:
             if len(fracs) == len(pdfs) - 1:
                 self._frac_param_created = True
-                keys = {f"frac_{i}": f for i, f in enumerate(fracs)}
-                remaining = ComposedParameter(
-                    "Composed_autoparam_remaining_frac",
-                    lambda params: 1.0 - sum(params.values()),
-                    params=keys,
-                    grad=lambda vals: dict.fromkeys(vals, -1.0),
-                )
+                remaining = OneMinusSum("Composed_autoparam_remaining_frac", fracs)
                 param_fracs = [*fracs, remaining]
             elif len(fracs) == len(pdfs):
                 param_fracs = fracs
@@ -535,21 +537,8 @@ class SumPDF(BaseFunctor):
                 msg = f"Not all pdf {pdfs} are extended and no fracs {fracs} are provided."
                 raise ModelIncompatibleError(msg)
             yields = [p.get_yield() for p in pdfs]
-            sum_yields = ComposedParameter(
-                "Composed_autoparam_sum_yields",
-                lambda params: sum(params.values()),
-                params={f"yield_{i}": y for i, y in enumerate(yields)},
-                grad=lambda vals: dict.fromkeys(vals, 1.0),
-            )
-            param_fracs = [
-                ComposedParameter(
-                    f"Composed_autoparam_frac_{i}",
-                    lambda params: params["yield_"] / params["sum_yields"],
-                    params={"sum_yields": sum_yields, "yield_": y},
-                    grad=lambda v: {"yield_": 1.0 / v["sum_yields"], "sum_yields": -v["yield_"] / v["sum_yields"] ** 2},
-                )
-                for i, y in enumerate(yields)
-            ]
+            sum_yields = SumOfParameters("Composed_autoparam_sum_yields", yields)
+            param_fracs = [FractionOfSum(f"Composed_autoparam_frac_{i}", y, sum_yields) for i, y in enumerate(yields)]
             fracs_cleaned = None
         self._fracs = param_fracs
         self._original_fracs = fracs_cleaned
