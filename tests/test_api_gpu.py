@@ -221,3 +221,16 @@ def test_sum_pdf_with_fit_range_parity():
     r, rg = ref.value_gradient(params, full=True)
     assert abs(v - r) <= 1e-12 * abs(r)
     assert np.all(np.abs(g - rg) <= 1e-10 * np.maximum(np.abs(rg), np.abs(rg).max()))
+
+
+def test_misaligned_view_and_device_born_data():
+    import torch
+
+    obs = zfit.Space("x", -5, 5)
+    base = torch.randn(20_001, dtype=torch.float64, device="cuda:0").clamp_(-4.9, 4.9)
+    view = base[1:]  # starts 8 bytes into the allocation: not 16-byte aligned
+    mu, sigma = zfit.Parameter("mu_mis", 0.1, -1, 1), zfit.Parameter("sigma_mis", 1.1, 0.3, 3)
+    g = zfit.pdf.Gauss(mu, sigma, obs)
+    a = zfit.loss.UnbinnedNLL(g, zfit.Data(view, obs=obs)).value(full=True)
+    b = zfit.loss.UnbinnedNLL(g, zfit.Data(view.cpu().numpy(), obs=obs)).value(full=True)
+    assert a == b

@@ -269,9 +269,10 @@ class Data:
         dev = torch.device("cuda", device)
 
         def up(c):
-            if _is_torch(c):
-                return c.to(dev).contiguous()
-            return torch.from_numpy(np.ascontiguousarray(c)).to(dev)
+            t = c.to(dev).contiguous() if _is_torch(c) else torch.from_numpy(np.ascontiguousarray(c)).to(dev)
+            if t.data_ptr() % 16:  # e.g. a view starting at an odd element: the kernel reads double2
+                t = t.clone()
+            return t
 
         cols = [up(c) for c in self._cols]
         w = None if self._weights is None else up(self._weights)
