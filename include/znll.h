@@ -25,6 +25,8 @@
  *       ZNLL_LEGENDRE, ZNLL_CHEB2  c_0 .. c_degree   (polynomials.py:181-332, 487-600; "next" row f.3)
  *       ZNLL_GCB    mu, sigmal, alphal, nl, sigmar, alphar, nr   (GeneralizedCB, physics.py:47-80,186-232;
  *                   DoubleCB is the same node with the sigma slot given twice)
+ *       ZNLL_GET    mu, sigma, alpha          (GaussExpTail, physics.py:608-623,636-686,727-805)
+ *       ZNLL_GGET   mu, sigmal, alphal, sigmar, alphar   (GeneralizedGaussExpTail, physics.py:625-634,689-724,819-923)
  *       ZNLL_SUM    frac_0 .. frac_{k-1}      (src/zfit/models/functor.py:74-313; ALL k fractions)
  *       ZNLL_PROD   (none)                    (src/zfit/models/functor.py:331-483)
  *   The library differentiates with respect to slots; the host applies d(slot)/d(theta)
@@ -51,6 +53,8 @@ enum znll_kind {
   ZNLL_LEGENDRE = 5,
   ZNLL_CHEB2 = 6,
   ZNLL_GCB = 7,
+  ZNLL_GET = 8,
+  ZNLL_GGET = 9,
   ZNLL_SUM = 16,
   ZNLL_PROD = 17
 };

@@ -379,6 +379,80 @@ class GeneralizedCB(_Leaf):
         return il + ir
 
 
+class GaussExpTail(_Leaf):
+    """``zfit.pdf.GaussExpTail`` (``src/zfit/models/physics.py:608-623,636-686``)."""
+
+    def __init__(self, mu, sigma, alpha, obs, limits, yield_=None):
+        super().__init__(obs, limits, yield_)
+        self.mu, self.sigma, self.alpha = mu, sigma, alpha
+
+    def param_names(self):
+        return _names(self.mu) + _names(self.sigma) + _names(self.alpha)
+
+    def unnorm(self, B, x, P, norm):  # gaussexptail_func, physics.py:610-623
+        mu, sigma, alpha = _val(B, P, self.mu), _val(B, P, self.sigma), _val(B, P, self.alpha)
+        t = (x - mu) / sigma * B.sign(alpha)
+        abs_alpha = B.abs(alpha)
+        cond = t < -abs_alpha
+        t_tail = B.where(cond, t, B.ones_like(t) * abs_alpha)
+        t_core = B.where(cond, B.ones_like(t) * abs_alpha, t)
+        func = B.where(cond, B.const(0.5) * B.square(abs_alpha) + abs_alpha * t_tail, B.const(-0.5) * B.square(t_core))
+        return B.exp(func)
+
+    def integral(self, B, P, lo, hi, norm):  # gaussexptail_integral_func, physics.py:647-686
+        mu, sigma, alpha = _val(B, P, self.mu), _val(B, P, self.sigma), _val(B, P, self.alpha)
+        sqrt_pi_over_two = B.const(math.sqrt(math.pi / 2))
+        sqrt2 = B.const(SQRT2)
+        abs_sigma, abs_alpha = B.abs(sigma), B.abs(alpha)
+        tmin = ((lo if hasattr(lo, "dtype") else B.const(lo)) - mu) / abs_sigma
+        tmax = ((hi if hasattr(hi, "dtype") else B.const(hi)) - mu) / abs_sigma
+        alpha_negative = alpha < 0
+        tmax, tmin = B.where(alpha_negative, -tmin, tmax), B.where(alpha_negative, -tmax, tmin)
+        gauss_tmin_tmax = abs_sigma * sqrt_pi_over_two * (B.erf(tmax / sqrt2) - B.erf(tmin / sqrt2))
+        pref = abs_sigma / abs_alpha * B.exp(B.const(0.5) * B.square(abs_alpha))
+        exp_tmin_tmax = pref * (B.exp(abs_alpha * tmax) - B.exp(abs_alpha * tmin))
+        gauss_minus_a_tmax = abs_sigma * sqrt_pi_over_two * (B.erf(tmax / sqrt2) - B.erf(-abs_alpha / sqrt2))
+        exp_tmin_minus_a = pref * (B.exp(-B.square(abs_alpha)) - B.exp(abs_alpha * tmin))
+        integral_sum = exp_tmin_minus_a + gauss_minus_a_tmax
+        conditional = B.where(tmax <= -abs_alpha, exp_tmin_tmax, integral_sum)
+        return B.where(tmin >= -abs_alpha, gauss_tmin_tmax, conditional)
+
+
+class GeneralizedGaussExpTail(_Leaf):
+    """``zfit.pdf.GeneralizedGaussExpTail`` (``src/zfit/models/physics.py:625-634,712-724``)."""
+
+    def __init__(self, mu, sigmal, alphal, sigmar, alphar, obs, limits, yield_=None):
+        super().__init__(obs, limits, yield_)
+        self.p = (mu, sigmal, alphal, sigmar, alphar)
+
+    def param_names(self):
+        out = []
+        for q in self.p:
+            for n in _names(q):
+                if n not in out:
+                    out.append(n)
+        return out
+
+    def _sides(self, B, P):
+        mu, sl, al, sr, ar = (_val(B, P, q) for q in self.p)
+        left = GaussExpTail(lambda _: mu, lambda _: sl, lambda _: al, self.obs, self.limits)
+        right = GaussExpTail(lambda _: mu, lambda _: sr, lambda _: -ar, self.obs, self.limits)
+        return mu, left, right
+
+    def unnorm(self, B, x, P, norm):
+        mu, left, right = self._sides(B, P)
+        return B.where(x < mu, left.unnorm(B, x, P, norm), right.unnorm(B, x, P, norm))
+
+    def integral(self, B, P, lo, hi, norm):
+        mu, left, right = self._sides(B, P)
+        lo_c, hi_c = B.const(lo), B.const(hi)
+        il = left.integral(B, P, lo_c, B.where(mu < hi_c, mu, hi_c), norm)
+        ir = right.integral(B, P, B.where(mu > lo_c, mu, lo_c), hi_c, norm)
+        il = B.where(mu < lo_c, B.zeros_like(il), il)
+        ir = B.where(mu > hi_c, B.zeros_like(ir), ir)
+        return il + ir
+
+
 class SumPDF:
     """``zfit.pdf.SumPDF`` (``src/zfit/models/functor.py:74-313``, ``basefunctor.py:160-255``).
 
@@ -486,7 +560,7 @@ def leaf_get_yield(pdf, B, P):
     return _val(B, P, pdf.yield_)
 
 
-for _cls in (Gauss, Exponential, CrystalBall, Chebyshev, Legendre, Chebyshev2, GeneralizedCB):
+for _cls in (Gauss, Exponential, CrystalBall, Chebyshev, Legendre, Chebyshev2, GeneralizedCB, GaussExpTail, GeneralizedGaussExpTail):
     _cls.get_yield = lambda self, B, P: _val(B, P, self.yield_)
 
 

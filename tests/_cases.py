@@ -223,6 +223,27 @@ def poly_case(kind, n=100_000, seed=10):
     return Case(f"gauss_{kind}", nodes, names, slots, [x], m, ["x"], kernel=f"Sum<Gauss<0>,{tname}<0,{deg}>>")
 
 
+def get_exp_case(generalized, n=100_000, seed=13):
+    """(Generalized) GaussExpTail + exponential background."""
+    rng = np.random.default_rng(seed)
+    lo, hi = -12.0, 10.0
+    sig = _trunc(rng, lambda k: np.concatenate([rng.normal(0.5, 1.2, k // 2), 0.5 - rng.exponential(2.0, k // 4), 0.5 + rng.exponential(2.5, k // 4)]), lo, hi, int(0.5 * n))
+    bkg = _trunc(rng, lambda k: lo + rng.exponential(1 / 0.1, k), lo, hi, n - sig.size)
+    x = rng.permutation(np.concatenate([sig, bkg]))
+    if generalized:
+        leaf = Z.Node(Z.GGET, 0, 0, 0, lo, hi, 0, 0, 0)
+        o = O.GeneralizedGaussExpTail("mu", "sl", "al", "sr", "ar", "x", (lo, hi))
+        names, vals, kern = ["mu", "sl", "al", "sr", "ar"], [0.4, 1.3, 1.1, 1.0, 1.4], "GGETail<0>"
+    else:
+        leaf = Z.Node(Z.GET, 0, 0, 0, lo, hi, 0, 0, 0)
+        o = O.GaussExpTail("mu", "s", "a", "x", (lo, hi))
+        names, vals, kern = ["mu", "s", "a"], [0.4, 1.3, 1.1], "GETail<0>"
+    nodes = [Z.Node(Z.SUM, 2, 0, 0, 0, 0, 0, 0, 0), leaf, Z.Node(Z.EXP, 0, 0, 0, lo, hi, 0, 0, 0.5 * (lo + hi))]
+    m = O.SumPDF([o, O.Exponential("lam", "x", (lo, hi))], fracs=["f0", "f1"])
+    return Case("gget_exp" if generalized else "get_exp", nodes, ["f0", "f1", *names, "lam"], [0.45, 0.55, *vals, -0.08],
+                [x], m, ["x"], kernel=f"Sum<{kern},Expo<0>>")
+
+
 class _SumOfProducts:
     """SumPDF over N-D ProductPDFs (functor.py:197-206: sum_i frac_i * pdf_i.pdf(x))."""
 
@@ -248,4 +269,6 @@ ALL_CASES = {
     "gcb_exp": gcb_exp_case,
     "legendre": lambda **kw: poly_case("legendre", **kw),
     "cheb2": lambda **kw: poly_case("cheb2", **kw),
+    "get_exp": lambda **kw: get_exp_case(False, **kw),
+    "gget_exp": lambda **kw: get_exp_case(True, **kw),
 }

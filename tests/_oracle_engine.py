@@ -47,6 +47,11 @@ def _translate(nodes, obs, i, slot, in_prod):
         names = [f"s{slot + k}" for k in range(nd.degree + 1)]
         cls = {Z.CHEB: O.Chebyshev, Z.LEGENDRE: O.Legendre, Z.CHEB2: O.Chebyshev2}[nd.kind]
         return cls(names[1:], o, lim, coeff0=names[0]), i + 1, slot + nd.degree + 1
+    if nd.kind == Z.GET:
+        return O.GaussExpTail(f"s{slot}", f"s{slot + 1}", f"s{slot + 2}", o, lim), i + 1, slot + 3
+    if nd.kind == Z.GGET:
+        names = [f"s{slot + k}" for k in range(5)]
+        return O.GeneralizedGaussExpTail(*names, o, lim), i + 1, slot + 5
     if nd.kind == Z.GCB:
         names = [f"s{slot + k}" for k in range(7)]
         return O.GeneralizedCB(*names, o, lim), i + 1, slot + 7

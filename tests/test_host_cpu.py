@@ -100,6 +100,23 @@ def test_host_prologue_next_row_leaves():
         np.testing.assert_allclose(dI, rdI, rtol=1e-11, atol=1e-13 * abs(rI))
 
 
+def test_host_prologue_gaussexptail_family():
+    for vals, lo, hi in [([0.2, 1.1, 1.2], -8, 7), ([0.2, 1.1, -1.2], -8, 7), ([0.2, 1.1, 1.2], -8, -2), ([0.2, 1.1, 1.2], 0, 7)]:
+        I, dI = Z.leaf_integral(Z.Node(Z.GET, 0, 0, 0, lo, hi, 0, 0, 0), vals)
+        rI, rdI = _autograd_integral(O.GaussExpTail("mu", "s", "a", "x", (lo, hi)), ["mu", "s", "a"], vals, lo, hi, (lo, hi))
+        assert abs(I - rI) <= 1e-14 * abs(rI)
+        np.testing.assert_allclose(dI, rdI, rtol=1e-11, atol=1e-13 * abs(rI))
+    gn = ["mu", "sl", "al", "sr", "ar"]
+    for vals, lo, hi in [([0.2, 1.1, 1.2, 0.9, 1.5], -8, 7), ([0.2, 1.1, 1.2, 0.9, 1.5], 0.5, 7), ([0.2, 1.1, 1.2, 0.9, 1.5], -8, 0.1)]:
+        I, dI = Z.leaf_integral(Z.Node(Z.GGET, 0, 0, 0, lo, hi, 0, 0, 0), vals)
+        rI, rdI = _autograd_integral(O.GeneralizedGaussExpTail(*gn, "x", (lo, hi)), gn, vals, lo, hi, (lo, hi))
+        assert abs(I - rI) <= 1e-14 * abs(rI)
+        np.testing.assert_allclose(dI, rdI, rtol=1e-10, atol=1e-13 * abs(rI))
+    obs = zfit.Space("x", -8, 7)
+    pdf = zfit.pdf.GeneralizedGaussExpTail(0.2, 1.1, 1.2, 0.9, 1.5, obs)
+    assert abs(float(pdf.integrate((-8, 7))[0]) - 1.0) < 1e-13 and pdf._lower()[0][0].kind == Z.GGET
+
+
 def test_double_cb_shares_sigma_slot():
     obs = zfit.Space("m", 5000, 5600)
     mu, sigma = zfit.Parameter("mu_dcb", 5280.0), zfit.Parameter("sigma_dcb", 20.0)

@@ -34,6 +34,8 @@ pdf = _types.SimpleNamespace(
     Chebyshev2=_pdf_mod.Chebyshev2,
     DoubleCB=_pdf_mod.DoubleCB,
     GeneralizedCB=_pdf_mod.GeneralizedCB,
+    GaussExpTail=_pdf_mod.GaussExpTail,
+    GeneralizedGaussExpTail=_pdf_mod.GeneralizedGaussExpTail,
     SumPDF=_pdf_mod.SumPDF,
     ProductPDF=_pdf_mod.ProductPDF,
 )

@@ -13,6 +13,8 @@ static const ZnllCatalogEntry kEntries[] = {
     ZNLL_ENTRY(Sum<GCBall<0>,Expo<0>>),
     ZNLL_ENTRY(Sum<Gauss<0>,Legd<0,2>>),
     ZNLL_ENTRY(Sum<Gauss<0>,Chb2<0,2>>),
+    ZNLL_ENTRY(Sum<GETail<0>,Expo<0>>),
+    ZNLL_ENTRY(Sum<GGETail<0>,Expo<0>>),
 };
 static Registrar reg_c(kEntries, sizeof(kEntries) / sizeof(kEntries[0]));
 

@@ -412,6 +412,104 @@ struct CBall {
   using Node = CBallN<COL, V>;
 };
 
+// GaussExpTail (models/physics.py:608-623, 727-805): Gaussian core, exponential tail  exp(a^2/2 + a t)  for t < -|alpha|.
+// slots [mu, sigma, alpha];  consts [0 mu, 1 sign(alpha)/sigma, 2 1/sigma, 3 |alpha|, 4 a^2/2 - ln I, 5 -ln I, 6 sign(alpha)]
+template <int COL, class V>
+struct GETailN {
+  typedef typename Lanes<V>::Mask Mask;
+  V t, dt, P;
+  Mask tail;
+
+  template <int CO>
+  ZNLL_DEV V fwd_log(const Ctx&, const double* __restrict__ c, const V* x, Mask&) {
+    t = zmul(zsub(x[COL], c[CO + 0]), c[CO + 1]);
+    tail = zlt(t, -c[CO + 3]);
+    dt = zsel(tail, zbc<V>(c[CO + 3]), zneg(t));  // d ln v / d t
+    return zsel(tail, zfma(t, c[CO + 3], c[CO + 4]), zfma(zmul(t, -0.5), t, c[CO + 5]));
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg;
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    return P;
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    const V gd = zneg(zmul(g, dt));
+    zacc(acc[AO + 0], gd, c[CO + 1]);
+    zacc(acc[AO + 1], zmul(gd, t), c[CO + 2]);
+    zacc(acc[AO + 2], zsel(tail, g, zbc<V>(0.0)), zmul(zadd(t, c[CO + 3]), c[CO + 6]));  // d ln v/d|alpha| = a + t
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
+  }
+};
+template <int COL>
+struct GETail {
+  static constexpr int NS = 3, NC = 7, COLMASK = 1 << COL;
+  static constexpr bool LOGNAT = true;
+  template <class V>
+  using Node = GETailN<COL, V>;
+};
+
+// GeneralizedGaussExpTail (models/physics.py:625-634, 819-923): x < mu -> GaussExpTail(mu, sigmal, alphal), else
+// GaussExpTail(mu, sigmar, -alphar).  slots [mu, sigmal, alphal, sigmar, alphar]
+// consts [0 mu, 1 -ln I, per side (L at 2, R at 7): +0 sign(alpha_eff)/sigma, +1 1/sigma, +2 |alpha|, +3 a^2/2 - ln I,
+//         +4 sign(alpha slot)]
+template <int COL, class V>
+struct GGETailN {
+  typedef typename Lanes<V>::Mask Mask;
+  V t, dt, P;
+  Mask left, tail;
+
+  template <int K>
+  ZNLL_DEV V side(const double* __restrict__ c) const {
+    return zsel(left, zbc<V>(c[2 + K]), zbc<V>(c[7 + K]));
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_log(const Ctx&, const double* __restrict__ c, const V* x, Mask&) {
+    const double* cc = c + CO;
+    const V dx = zsub(x[COL], cc[0]);
+    left = zlt(dx, 0.0);
+    t = zmul(dx, side<0>(cc));
+    const V a = side<2>(cc);
+    tail = Lanes<V>::mask(la(t) < -la(a), lb(t) < -lb(a));
+    dt = zsel(tail, a, zneg(t));
+    return zsel(tail, zfma(t, a, side<3>(cc)), zfma(zmul(t, -0.5), t, cc[1]));
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg;
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    return P;
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+    const double* cc = c + CO;
+    const V zero = zbc<V>(0.0);
+    const V gd = zneg(zmul(g, dt));
+    zacc(acc[AO + 0], gd, side<0>(cc));
+    const V gs = zmul(zmul(gd, t), side<1>(cc));
+    zacc1(acc[AO + 1], zsel(left, gs, zero));
+    zacc1(acc[AO + 3], zsel(left, zero, gs));
+    const V ga = zmul(zmul(zsel(tail, g, zero), side<4>(cc)), zadd(t, side<2>(cc)));
+    zacc1(acc[AO + 2], zsel(left, ga, zero));
+    zacc1(acc[AO + 4], zsel(left, zero, ga));
+  }
+  template <int CO, int AO>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
+  }
+};
+template <int COL>
+struct GGETail {
+  static constexpr int NS = 5, NC = 12, COLMASK = 1 << COL;
+  static constexpr bool LOGNAT = true;
+  template <class V>
+  using Node = GGETailN<COL, V>;
+};
+
 // Orthogonal-polynomial sums of degree DEG (models/polynomials.py:46-175): slots [c_0 .. c_DEG]
 // consts [0 2/(hi-lo), 1 -(lo+hi)/(hi-lo), 2 1/I, 3.. c_k/I]
 // KIND 0: Chebyshev T_n (T_{n+1} = 2zT_n - T_{n-1}, polynomials.py:338-343); 1: Legendre

@@ -255,6 +255,65 @@ static void gcb_integral(const double* s, double lo, double hi, double* I, doubl
   *I = total;
 }
 
+// GaussExpTail: gaussexptail_integral_func, src/zfit/models/physics.py:647-686, plus its derivative
+static void get_integral(double mu, double sigma, double alpha, double lo, double hi, double* I, double* dI) {
+  const double s = fabs(sigma), a = fabs(alpha);
+  const double sgn_sigma = sigma < 0 ? -1.0 : 1.0, sgn_alpha = alpha < 0 ? -1.0 : 1.0;
+  double tmin = (lo - mu) / s, tmax = (hi - mu) / s;
+  if (alpha < 0) {
+    const double tm = tmin;
+    tmin = -tmax;
+    tmax = -tm;
+  }
+  auto f_at = [&](double t) { return t < -a ? exp(0.5 * a * a + a * t) : exp(-0.5 * t * t); };
+  const double ea = exp(0.5 * a * a);
+  double Ival, dIa = 0.0;
+  if (tmin >= -a) {
+    Ival = s * kSqrtPiOver2 * (erf(tmax / kSqrt2) - erf(tmin / kSqrt2));
+  } else {
+    const bool all_tail = tmax <= -a;
+    const double eh = all_tail ? exp(a * tmax) : exp(-a * a), el = exp(a * tmin);
+    const double th = all_tail ? tmax : -a;
+    const double tailI = s / a * ea * (eh - el);
+    double gaussI = 0.0;
+    if (!all_tail) gaussI = s * kSqrtPiOver2 * (erf(tmax / kSqrt2) - erf(-a / kSqrt2));
+    Ival = tailI + gaussI;
+    // d/da of the tail integral; the moving break point cancels against the Gaussian part (continuity at t = -a)
+    dIa = s * ea * (eh * (1.0 + th / a - 1.0 / (a * a)) - el * (1.0 + tmin / a - 1.0 / (a * a)));
+  }
+  const double fmax = f_at(tmax), fmin = f_at(tmin);
+  *I = Ival;
+  dI[0] = -sgn_alpha * (fmax - fmin);
+  dI[1] = sgn_sigma * (Ival / s - (tmax * fmax - tmin * fmin));
+  dI[2] = sgn_alpha * dIa;
+}
+
+// GeneralizedGaussExpTail: generalized_gaussexptail_integral_func, physics.py:712-724; slots [mu, sl, al, sr, ar]
+static void gget_integral(const double* s, double lo, double hi, double* I, double* dI) {
+  const double mu = s[0];
+  for (int i = 0; i < 5; ++i) dI[i] = 0.0;
+  double total = 0.0;
+  if (!(mu < lo)) {
+    double Il, d[3];
+    get_integral(mu, s[1], s[2], lo, mu < hi ? mu : hi, &Il, d);
+    total += Il;
+    dI[0] += d[0];
+    dI[1] += d[1];
+    dI[2] += d[2];
+    if (mu < hi) dI[0] += 1.0;
+  }
+  if (!(mu > hi)) {
+    double Ir, d[3];
+    get_integral(mu, s[3], -s[4], mu > lo ? mu : lo, hi, &Ir, d);
+    total += Ir;
+    dI[0] += d[0];
+    dI[3] += d[1];
+    dI[4] -= d[2];
+    if (mu > lo) dI[0] -= 1.0;
+  }
+  *I = total;
+}
+
 static int leaf_n_slots(const znll_node& nd) {
   switch (nd.kind) {
     case ZNLL_GAUSS: return 2;
@@ -264,6 +323,8 @@ static int leaf_n_slots(const znll_node& nd) {
     case ZNLL_LEGENDRE:
     case ZNLL_CHEB2: return nd.degree + 1;
     case ZNLL_GCB: return 7;
+    case ZNLL_GET: return 3;
+    case ZNLL_GGET: return 5;
     default: return -1;
   }
 }
@@ -276,6 +337,8 @@ static int leaf_n_consts(const znll_node& nd) {
     case ZNLL_LEGENDRE:
     case ZNLL_CHEB2: return 3 + nd.degree + 1;
     case ZNLL_GCB: return 24;
+    case ZNLL_GET: return 7;
+    case ZNLL_GGET: return 12;
     default: return -1;
   }
 }
@@ -289,6 +352,8 @@ static int leaf_integral(const znll_node& nd, const double* s, double* I, double
     case ZNLL_LEGENDRE:
     case ZNLL_CHEB2: poly_integral(nd.kind, s, nd.degree, nd.norm_lo, nd.norm_hi, nd.space_lo, nd.space_hi, I, dI); return 0;
     case ZNLL_GCB: gcb_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
+    case ZNLL_GET: get_integral(s[0], s[1], s[2], nd.norm_lo, nd.norm_hi, I, dI); return 0;
+    case ZNLL_GGET: gget_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
     default: return fail("znll_leaf_integral: node kind %d is not a leaf", nd.kind);
   }
 }
@@ -397,6 +462,8 @@ static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int par
     case ZNLL_EXP: snprintf(buf, sizeof buf, "Expo<%d>", nd.column); break;
     case ZNLL_CB: snprintf(buf, sizeof buf, "CBall<%d>", nd.column); break;
     case ZNLL_GCB: snprintf(buf, sizeof buf, "GCBall<%d>", nd.column); break;
+    case ZNLL_GET: snprintf(buf, sizeof buf, "GETail<%d>", nd.column); break;
+    case ZNLL_GGET: snprintf(buf, sizeof buf, "GGETail<%d>", nd.column); break;
     case ZNLL_LEGENDRE: snprintf(buf, sizeof buf, "Legd<%d,%d>", nd.column, nd.degree); break;
     case ZNLL_CHEB2: snprintf(buf, sizeof buf, "Chb2<%d,%d>", nd.column, nd.degree); break;
     default: snprintf(buf, sizeof buf, "Cheb<%d,%d>", nd.column, nd.degree); break;
@@ -452,6 +519,32 @@ static void fill_consts(Channel& c, const double* slots) {
         k[10] = -n / a - a;
         k[11] = n / (a * a) + 1.0;
         k[12] = sg;
+        break;
+      }
+      case ZNLL_GET: {
+        const double a = fabs(s[2]), sg = s[2] > 0 ? 1.0 : (s[2] < 0 ? -1.0 : 0.0);
+        k[0] = s[0];
+        k[1] = sg / s[1];
+        k[2] = 1.0 / s[1];
+        k[3] = a;
+        k[4] = 0.5 * a * a - lnI;
+        k[5] = -lnI;
+        k[6] = sg;
+        break;
+      }
+      case ZNLL_GGET: {
+        k[0] = s[0];
+        k[1] = -lnI;
+        for (int side = 0; side < 2; ++side) {
+          const double sigma = s[side ? 3 : 1], alpha = s[side ? 4 : 2];
+          const double aeff = side ? -alpha : alpha, a = fabs(alpha);
+          double* q = k + (side ? 7 : 2);
+          q[0] = (aeff > 0 ? 1.0 : (aeff < 0 ? -1.0 : 0.0)) / sigma;
+          q[1] = 1.0 / sigma;
+          q[2] = a;
+          q[3] = 0.5 * a * a - lnI;
+          q[4] = alpha > 0 ? 1.0 : (alpha < 0 ? -1.0 : 0.0);
+        }
         break;
       }
       case ZNLL_GCB: {

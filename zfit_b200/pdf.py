@@ -476,6 +476,33 @@ class DoubleCB(_Leaf1D):
         return [p["mu"], p["sigma"], p["alphal"], p["nl"], p["sigma"], p["alphar"], p["nr"]]
 
 
+class GaussExpTail(_Leaf1D):
+    """``zfit.pdf.GaussExpTail(mu, sigma, alpha, obs, ...)`` (``models/physics.py:727-805``)."""
+
+    _KIND = Z.GET
+
+    def __init__(self, mu, sigma, alpha, obs, *, extended=None, norm=None, name="GaussExpTail", label=None):
+        params = {"mu": convert_to_parameter(mu), "sigma": convert_to_parameter(sigma), "alpha": convert_to_parameter(alpha)}
+        super().__init__(obs, params, extended=extended, norm=norm, name=name, label=label)
+
+
+class GeneralizedGaussExpTail(_Leaf1D):
+    """``zfit.pdf.GeneralizedGaussExpTail(mu, sigmal, alphal, sigmar, alphar, obs, ...)`` (``models/physics.py:819-923``)."""
+
+    _KIND = Z.GGET
+
+    def __init__(self, mu, sigmal, alphal, sigmar, alphar, obs, *, extended=None, norm=None,
+                 name="GeneralizedGaussExpTail", label=None):
+        params = {
+            "mu": convert_to_parameter(mu),
+            "sigmal": convert_to_parameter(sigmal),
+            "alphal": convert_to_parameter(alphal),
+            "sigmar": convert_to_parameter(sigmar),
+            "alphar": convert_to_parameter(alphar),
+        }
+        super().__init__(obs, params, extended=extended, norm=norm, name=name, label=label)
+
+
 # ------------------------------------------------------------------------------------------------
 # functors
 # ------------------------------------------------------------------------------------------------
