@@ -191,3 +191,75 @@ def test_callable_loss_and_iminuit_protocol():  # tests/test_loss.py:501-547
     opt = optimize.minimize(ev.value, x, jac=ev.gradient, method="BFGS")
     assert opt.success or opt.status == 2
     assert opt.x[0] == pytest.approx(np.mean(test_values_np), rel=0.01) and opt.x[1] == pytest.approx(np.std(test_values_np), rel=0.01)
+
+
+def test_exact_yields_toys():  # tests/highstats/test_exact_yields.py:12-125 (fewer toys; the fits run on the GPU)
+    obs = zfit.Space("x", -10, 10)
+    t = _tag()
+    mu = zfit.Parameter("mu" + t, 1.0, -4, 6)
+    sigma = zfit.Parameter("sigma" + t, 1.0, 0.1, 10)
+    lambd = zfit.Parameter("lambda" + t, -0.06, -1, -0.01)
+    n_bkg = zfit.Parameter("n_bkg" + t, 20000, 0, 500000)
+    n_sig = zfit.Parameter("n_sig" + t, 1000, 0, 300000)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu, sigma, obs, extended=n_sig), zfit.pdf.Exponential(lambd, obs, extended=n_bkg)])
+    toy_rng = np.random.default_rng(7)
+    true_vals = [20000.0, 1000.0, 1.0, 1.0, -0.06]
+    minimizer = Minuit(gradient=False, tol=1e-05)  # as upstream: the loss' own gradient, tight tolerance
+    for _ in range(15):
+        n = toy_rng.poisson(21000)
+        nsig = toy_rng.binomial(n, 1000 / 21000)
+        sig = toy_rng.normal(1.0, 1.0, nsig)
+        u = toy_rng.uniform(0, 1, n - nsig)
+        bkg = -10 + np.log1p(u * np.expm1(-0.06 * 20)) / -0.06
+        data = zfit.Data(np.concatenate([sig, bkg]), obs=obs)
+        zfit.param.set_values([n_bkg, n_sig, mu, sigma, lambd], true_vals)
+        nll = zfit.loss.ExtendedUnbinnedNLL(model=model, data=data)
+        result = minimizer.minimize(nll)
+        assert result.valid
+        fitted = result.params[n_sig]["value"] + result.params[n_bkg]["value"]
+        assert abs(fitted - data.num_entries) < 0.6  # the extended term pins the total yield to N
+
+
+def test_weights_one_equal_no_weights():  # tests/result/test_uncertainties.py:180,671
+    data = zfit.Data.from_tensor(obs=obs1, tensor=test_values_np)
+    dataw = zfit.Data.from_tensor(obs=obs1, tensor=test_values_np, weights=np.ones(yield_true))
+    gaussian1, mu1, sigma1 = create_gauss("1")
+    a = zfit.loss.UnbinnedNLL(gaussian1, data)
+    b = zfit.loss.UnbinnedNLL(gaussian1, dataw)
+    va, ga = a.value_gradient(full=True)
+    vb, gb = b.value_gradient(full=True)
+    assert va == vb and np.array_equal(ga, gb)
+    assert b.is_weighted and not a.is_weighted
+
+
+def test_exponential_numerics_far_from_zero():  # tests/test_pdfs.py:302-321
+    t = _tag()
+    lam = zfit.Parameter("lambda" + t, -0.3, -5, 5)
+    obs = zfit.Space("obs1", 5000, 6000)
+    exp1 = zfit.pdf.Exponential(lam, obs=obs)
+    x = np.linspace(5000, 6000, 200001)
+    p = exp1.pdf(x)  # exp(-0.3 * 5500) would underflow without the data shift of basic.py:128-154
+    assert np.all(np.isfinite(p)) and np.all(p >= 0)
+    assert abs(np.trapezoid(p, x) - 1.0) < 1e-3
+    data = zfit.Data(5000 + np.random.default_rng(3).exponential(1 / 0.3, 10000), obs=obs)
+    nll = zfit.loss.UnbinnedNLL(exp1, data)
+    v, g = nll.value_gradient(full=True)
+    assert np.isfinite(v) and np.all(np.isfinite(g))
+    result = Minuit(gradient="zfit").minimize(nll)
+    assert abs(result.params[lam]["value"] + 0.3) < 0.02
+
+
+def test_product_pdf_values_are_product_of_factors():  # tests/test_pdfs.py:204-227
+    t = _tag()
+    ox, oy, oz = zfit.Space("x", -4, 4), zfit.Space("y", 0, 5), zfit.Space("z", -2, 4)
+    g = zfit.pdf.Gauss(zfit.Parameter("mu" + t, 0.3), zfit.Parameter("sigma" + t, 1.2), ox)
+    e = zfit.pdf.Exponential(zfit.Parameter("lam" + t, -0.7), oy)
+    c = zfit.pdf.Chebyshev(oz, [zfit.Parameter("c1" + t, 0.2), zfit.Parameter("c2" + t, -0.1)])
+    prod = zfit.pdf.ProductPDF([g, e, c])
+    r = np.random.default_rng(0)
+    pts = np.stack([r.uniform(-4, 4, 500), r.uniform(0, 5, 500), r.uniform(-2, 4, 500)], axis=1)
+    data = zfit.Data(pts, obs=ox * oy * oz)
+    expected = g.pdf(pts[:, 0]) * e.pdf(pts[:, 1]) * c.pdf(pts[:, 2])
+    np.testing.assert_allclose(prod.pdf(data), expected, rtol=1e-12)
+    np.testing.assert_allclose(prod.pdf(data.with_obs(["z", "x", "y"])), expected, rtol=1e-12)  # obs are matched by name
+    assert abs(float(prod.integrate(ox * oy * oz)[0]) - 1.0) < 1e-12
