@@ -885,7 +885,19 @@ struct Xchg {
   double* acc;                 // this rank's accumulators of ALL channels (plan-wide), reduced in place
   unsigned long long seq;      // evaluation counter (> 0), identical on all ranks
   int rank, world, total, pad;
+  double* hout;                // host-mapped pinned copy of acc (zero-copy result path), or null
+  unsigned long long* hflag;   // host-mapped flag: set to seq after hout is complete
 };
+
+// Result hand-off without a D2H copy or a stream synchronisation: the last block writes the final accumulators
+// straight into host-mapped pinned memory and then publishes the evaluation's sequence number; the host spins on it.
+ZNLL_DEV void host_publish(const Xchg& xc) {
+  __syncthreads();
+  if (threadIdx.x < xc.total) xc.hout[threadIdx.x] = __ldcg(xc.acc + threadIdx.x);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(xc.hflag), "l"(xc.seq) : "memory");
+}
 
 ZNLL_DEV void peer_exchange(const Xchg& xc) {
   __shared__ int timed_out;
@@ -1071,6 +1083,7 @@ ZNLL_DEV void block_reduce_and_finish(double* acc, double* partials, unsigned in
   }
   if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this stream
   if (xc != nullptr && xc->world > 1) peer_exchange(*xc);
+  if (xc != nullptr && xc->hout != nullptr) host_publish(*xc);
 }
 
 template <class M, bool WEIGHTED>

@@ -406,6 +406,11 @@ struct znll_plan {
   int x_rank = 0, x_world = 0;
   double* x_buf[8] = {nullptr};
   unsigned long long x_seq = 0;
+  // zero-copy result path: pinned host memory mapped into the device address space
+  double* h_acc_dev = nullptr;
+  unsigned long long* h_flag = nullptr;
+  unsigned long long* h_flag_dev = nullptr;
+  bool direct_pending = false;
 };
 
 static void relayout(znll_plan* p) {
@@ -842,6 +847,7 @@ void znll_plan_destroy(znll_plan* p) {
   }
   if (p->d_acc) cudaFree(p->d_acc);
   if (p->h_acc) cudaFreeHost(p->h_acc);
+  if (p->h_flag) cudaFreeHost(p->h_flag);
   delete p;
 }
 
@@ -879,7 +885,13 @@ int znll_plan_set_model(znll_plan* p, int ch, const znll_node* nodes, int n_node
   if (p->h_acc) cudaFreeHost(p->h_acc), p->h_acc = nullptr;
   CUDA_OK(cudaMalloc(&p->d_acc, sizeof(double) * p->total_acc));
   CUDA_OK(cudaMemset(p->d_acc, 0, sizeof(double) * p->total_acc));
-  CUDA_OK(cudaMallocHost(&p->h_acc, sizeof(double) * p->total_acc));
+  CUDA_OK(cudaHostAlloc(&p->h_acc, sizeof(double) * p->total_acc, cudaHostAllocMapped));
+  CUDA_OK(cudaHostGetDevicePointer((void**)&p->h_acc_dev, p->h_acc, 0));
+  if (!p->h_flag) {
+    CUDA_OK(cudaHostAlloc(&p->h_flag, sizeof(unsigned long long), cudaHostAllocMapped));
+    *p->h_flag = 0ull;
+    CUDA_OK(cudaHostGetDevicePointer((void**)&p->h_flag_dev, p->h_flag, 0));
+  }
   return 0;
 }
 
@@ -1024,8 +1036,16 @@ int znll_plan_kernel_origin(const znll_plan* p, int ch) {
 int64_t znll_plan_launch_count(const znll_plan* p) { return p ? p->launches : 0; }
 double* znll_plan_acc_device(znll_plan* p) { return p ? p->d_acc : nullptr; }
 
+static int launch_impl(znll_plan* p, const double* slots, uint32_t flags, double log_offset, void* stream, bool direct);
+
 int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_offset, void* stream) {
+  return launch_impl(p, slots, flags, log_offset, stream, false);
+}
+
+static int launch_impl(znll_plan* p, const double* slots, uint32_t flags, double log_offset, void* stream, bool direct) {
   if (!p || !slots) return fail("znll_launch: bad arguments");
+  if (direct && (p->total_acc > 256 || p->ch.back().n == 0)) direct = false;
+  p->direct_pending = direct;
   CUDA_OK(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the (legacy) default stream
   const int g = (flags & ZNLL_WANT_GRAD) ? 1 : 0;
@@ -1046,13 +1066,20 @@ int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_of
     la.ticket = c.d_ticket;
     la.out = p->d_acc + c.acc_off;
     memset(&la.xc, 0, sizeof(la.xc));
-    if (p->x_world > 1 && &c == &p->ch.back()) {  // the last channel's kernel also performs the exchange
-      for (int r = 0; r < p->x_world; ++r) la.xc.buf[r] = p->x_buf[r];
+    if (&c == &p->ch.back() && (p->x_world > 1 || direct)) {
+      // the last channel's kernel also performs the cross-GPU exchange and / or the zero-copy hand-off to the host
       la.xc.acc = p->d_acc;
       la.xc.seq = ++p->x_seq;
-      la.xc.rank = p->x_rank;
-      la.xc.world = p->x_world;
       la.xc.total = p->total_acc;
+      if (p->x_world > 1) {
+        for (int r = 0; r < p->x_world; ++r) la.xc.buf[r] = p->x_buf[r];
+        la.xc.rank = p->x_rank;
+        la.xc.world = p->x_world;
+      }
+      if (direct) {
+        la.xc.hout = p->h_acc_dev;
+        la.xc.hflag = p->h_flag_dev;
+      }
     }
     const int w = c.w ? 1 : 0;
     const int grid = grid_for(p, c.n);
@@ -1070,8 +1097,23 @@ int znll_launch(znll_plan* p, const double* slots, uint32_t flags, double log_of
 int znll_collect(znll_plan* p, uint32_t flags, double* values, double* grad_slots, void* stream) {
   if (!p || !values) return fail("znll_collect: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the (legacy) default stream
-  CUDA_OK(cudaMemcpyAsync(p->h_acc, p->d_acc, sizeof(double) * p->total_acc, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
+  if (p->direct_pending) {
+    // the kernel's last block wrote the accumulators into mapped pinned memory and then the sequence flag
+    p->direct_pending = false;
+    volatile unsigned long long* flag = p->h_flag;
+    unsigned long long spins = 0;
+    while (*flag != p->x_seq) {
+      if ((++spins & 0xfffffull) == 0) {  // every ~1M polls: has the stream failed or finished without publishing?
+        cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess && *flag != p->x_seq) return fail("znll_collect: kernel finished without publishing its result");
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail("znll_collect: %s", cudaGetErrorString(q));
+      }
+    }
+    __sync_synchronize();
+  } else {
+    CUDA_OK(cudaMemcpyAsync(p->h_acc, p->d_acc, sizeof(double) * p->total_acc, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
   for (size_t k = 0; k < p->ch.size(); ++k) {
     const Channel& c = p->ch[k];
     finish(c, p->h_acc + c.acc_off, flags, &values[k], grad_slots ? grad_slots + c.slot_off : nullptr);
@@ -1081,7 +1123,7 @@ int znll_collect(znll_plan* p, uint32_t flags, double* values, double* grad_slot
 
 int znll_eval(znll_plan* p, const double* slots, uint32_t flags, double log_offset, double* values,
               double* grad_slots, void* stream) {
-  if (znll_launch(p, slots, flags, log_offset, stream)) return 1;
+  if (launch_impl(p, slots, flags, log_offset, stream, true)) return 1;
   return znll_collect(p, flags, values, grad_slots, stream);
 }
 

@@ -7,6 +7,8 @@ struct ZnllXchg {  // == znll::Xchg
   double* acc;
   unsigned long long seq;
   int rank, world, total, pad;
+  double* hout;
+  unsigned long long* hflag;
 };
 
 struct ZnllLaunchArgs {  // == the prefix of znll::KArgs<NC> (the NVRTC path copies it verbatim)
