@@ -383,6 +383,7 @@ def run_product(args):
         line["fit"] = {
             "wall_s": fit_s,
             "n_eval": int(result.info.get("n_eval", -1)),
+            "n_pass": int(result.info.get("n_pass", -1)),
             "valid": bool(result.valid),
             "edm": None if result.edm is None else float(result.edm),
             "driver": result.info.get("driver"),

@@ -110,10 +110,13 @@ def _num_grad(value, x, steps, fx):
     return g
 
 
-def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000, hesse=True, verbose=False):
+def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000, hesse=True, verbose=False,
+             value_gradient=None):
     """Variable-metric minimisation in Minuit's internal coordinates.
 
-    value(x_ext) -> float; gradient(x_ext) -> array or None (None: finite differences of value).
+    value(x_ext) -> float; gradient(x_ext) -> array or None (None: finite differences of value);
+    value_gradient(x_ext) -> (float, array) or None: when the loss returns both in one pass (the fused kernel does),
+    line-search probes use it, so an accepted step costs ONE pass instead of a value pass plus a gradient pass.
     """
     tr = _Transform(lower, upper)
     res = MigradResult()
@@ -133,6 +136,12 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             fy = f_int(y)
         return _num_grad(f_int, y, num_steps, fy)
 
+    def fg_int(y):
+        counter["f"] += 1
+        counter["g"] += 1
+        fv, gv = value_gradient(tr.to_external(y))
+        return float(fv), np.asarray(gv, dtype=np.float64) * tr.dext_dint(y)
+
     x0 = np.asarray(x0, dtype=np.float64)
     y = tr.to_internal(x0)
     n = y.size
@@ -142,8 +151,11 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
     ysteps = np.minimum(ysteps, 0.5)
     num_steps = np.maximum(ysteps * 0.1, 1e-8)
 
-    f = f_int(y)
-    g = g_int(y, f)
+    if value_gradient is not None and gradient is not None:
+        f, g = fg_int(y)
+    else:
+        f = f_int(y)
+        g = g_int(y, f)
 
     def seed_metric(y, g):
         """Diagonal seed from second derivatives along each axis (MnSeedGenerator)."""
@@ -203,6 +215,38 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             return 0.0, f0
         return best
 
+    def line_search_fg(y, step, f0, gdel):
+        """Line search with value+gradient probes: the secant of the directional derivative locates the minimum of the
+        quadratic model along the step; returns (lambda, f, g) with f < f0, or (0, f0, None)."""
+        cands = []
+
+        def probe(lam):
+            fl, gl = fg_int(y + lam * step)
+            if np.isfinite(fl) and np.all(np.isfinite(gl)):
+                cands.append((lam, fl, gl))
+                return fl, float(gl @ step)
+            return np.inf, None
+
+        f1, d1 = probe(1.0)
+        if d1 is not None:
+            lam2 = gdel / (gdel - d1) if d1 > gdel else 2.5  # still descending at lambda = 1 -> extend
+            lam2 = min(max(lam2, 0.05), 6.0)
+            far = abs(lam2 - 1.0) > 0.25
+            if f1 >= f0 or far:
+                probe(lam2)
+        lam = min([c[0] for c in cands], default=1.0)
+        tries = 0
+        while (not cands or min(c[1] for c in cands) >= f0) and tries < 10:
+            tries += 1
+            lam *= 0.2
+            probe(lam)
+        if not cands:
+            return 0.0, f0, None
+        best = min(cands, key=lambda c: c[1])
+        if best[1] >= f0:
+            return 0.0, f0, None
+        return best
+
     def verify(y, f, g, V):
         """HESSE in internal coordinates; returns (converged, V, edm)."""
         H = _hesse_internal(f_int, g_int, gradient is not None, y, f, g, V)
@@ -219,6 +263,8 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
     V = seed_metric(y, g)
     edm = 0.5 * float(g @ V @ g)
     restarts = 0
+    use_fg = value_gradient is not None and gradient is not None
+    hesse_iter = None  # iteration at which V was last replaced by an exact inverse Hessian
     for it in range(1, 100000):
         res.niter = it
         if counter["f"] + counter["g"] > maxfcn:
@@ -228,12 +274,14 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             res.message = "non-finite value or gradient"
             break
         if edm < edm_goal:
-            if not hesse:
+            if not hesse or (hesse_iter is not None and it - hesse_iter <= 4):
+                # strategy 1: no second HESSE when the metric descends from a recent exact inverse Hessian
                 res.converged = True
                 break
             ok, Vh, e = verify(y, f, g, V)
             if Vh is not None:
                 V, edm = Vh, e
+                hesse_iter = it
                 if ok:
                     res.converged = True
                     break
@@ -257,7 +305,11 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             if gdel >= 0:
                 res.message = "no descent direction"
                 break
-        lam, f_new = line_search(y, step, f, gdel)
+        g_acc = None
+        if use_fg:
+            lam, f_new, g_acc = line_search_fg(y, step, f, gdel)
+        else:
+            lam, f_new = line_search(y, step, f, gdel)
         if lam == 0.0:
             if restarts < 3:
                 restarts += 1
@@ -267,14 +319,17 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
                     continue
                 step = -V @ g
                 gdel = float(step @ g)
-                lam, f_new = line_search(y, step, f, gdel) if gdel < 0 else (0.0, f)
+                if gdel < 0 and use_fg:
+                    lam, f_new, g_acc = line_search_fg(y, step, f, gdel)
+                elif gdel < 0:
+                    lam, f_new = line_search(y, step, f, gdel)
             if lam == 0.0:
                 res.message = "line search failed to improve"
                 res.converged = edm < edm_goal
                 break
         dy = lam * step
         y_new = y + dy
-        g_new = g_int(y_new, f_new)
+        g_new = g_acc if g_acc is not None else g_int(y_new, f_new)
         dg = g_new - g
         # ---- DavidonErrorUpdator -----------------------------------------------------------------
         delgam = float(dy @ dg)

@@ -95,6 +95,7 @@ class LossEval:
         self.maxiter = maxiter
         self._ignoring_maxiter = False
         self._nfunc_eval = self._ngrad_eval = self._nhess_eval = 0
+        self.npass = 0  # calls that reached the loss (one fused pass over the events each, hessian calls excepted)
         self.loss = loss
         self.hesse_fn = loss.hessian if hesse_fn is None else hesse_fn
         if grad_fn is not None:
@@ -143,6 +144,7 @@ class LossEval:
     nhess_eval = property(lambda self: self._nhess_eval)
 
     def _count(self, f=0, g=0, h=0):
+        self.npass += 1
         if not self._ignoring_maxiter:
             self._nfunc_eval += f
             self._ngrad_eval += g
@@ -715,7 +717,7 @@ class Minuit(BaseMinimizer):
         res = _migrad.minimize(
             evaluator.value, grad, [p.value() for p in params], steps, [p.lower for p in params],
             [p.upper for p in params], edm_goal=self.tol, maxfcn=evaluator.maxiter or 100000, hesse=self.mode >= 1,
-            verbose=self.verbosity > 6,
+            verbose=self.verbosity > 6, value_gradient=None if self.minuit_grad else evaluator.value_gradient,
         )
         assign_values(params, res.x)
         criterion.last_value = res.edm
@@ -724,7 +726,7 @@ class Minuit(BaseMinimizer):
             edm=res.edm, fminopt=res.fval, message=res.message, criterion=criterion,
             approx={"inv_hessian": res.covariance * (2.0 * loss.errordef), "gradient": res.grad}, evaluator=evaluator,
             info={"n_eval": evaluator.niter, "n_value": evaluator.nfunc_eval, "n_gradient": evaluator.ngrad_eval,
-                  "n_iter": res.niter, "driver": "native-migrad (iminuit not installed)"},
+                  "n_pass": evaluator.npass, "n_iter": res.niter, "driver": "native-migrad (iminuit not installed)"},
         )
 
 
