@@ -160,8 +160,18 @@ def run_reference(args):
 
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    n_sample = int(min(total_events, args.ref_events))
-    per_channel = n_sample // (2 if cfg == 3 else 1)
+    # bounded sample per step, sized so that the whole (warmup + steps) run stays within ~2 minutes of CPU time
+    nch = 2 if cfg == 3 else 1
+    probe_n = 1_000_000
+    w, loss = _oracle_case(cfg, probe_n // nch)
+    params = list(loss.get_params())
+    loss.value_gradient(params, full=False)
+    t0 = time.perf_counter()
+    loss.value_gradient(params, full=False)
+    t_probe = max(time.perf_counter() - t0, 1e-4)
+    budget = args.ref_budget / max(1, args.steps + max(1, args.warmup))
+    n_sample = int(min(total_events, args.ref_events, max(200_000, probe_n * budget / t_probe)))
+    per_channel = n_sample // nch
     w, loss = _oracle_case(cfg, per_channel)
     params = list(loss.get_params())
     theta0 = np.array([p.value() for p in params])
@@ -429,6 +439,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--events", type=int, default=None, help="events per GPU (per channel for config 3)")
     ap.add_argument("--ref-events", type=int, default=10_000_000, help="bounded sample of the reference arm")
+    ap.add_argument("--ref-budget", type=float, default=120.0, help="CPU seconds the reference arm may spend in total")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="skip timing the one-time host->HBM bind of the event columns")
