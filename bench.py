@@ -324,62 +324,63 @@ def run_product(args):
         "gpu_launches": int(launches),
     }
 
-    if rank == 0 and world == 1:
-        # ---- roofline of the dominant kernel: back-to-back launches, CUDA events on the launch stream -----------
-        peaks, peak_src = _peaks()
-        with torch.cuda.stream(stream):
-            reps = max(5, min(args.steps, 50))
-            for _ in range(3):
-                plan.launch(slots, grad=True, log_offset=off, stream=stream.cuda_stream)
-            torch.cuda.synchronize(local)
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record(stream)
-            for _ in range(reps):
-                plan.launch(slots, grad=True, log_offset=off, stream=stream.cuda_stream)
-            k1.record(stream)
-            torch.cuda.synchronize(local)
-            kern_ms = k0.elapsed_time(k1) / reps
-        fp64_peak = Z.fp64_peak(local, 300.0)
-        flops = W.F_ALG[cfg] * n_events
-        bytes_alg = w["bytes_per_event"] * n_events
-        achieved_tf = flops / (kern_ms * 1e-3) / 1e12
-        achieved_gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
-        t_fp64 = flops / (fp64_peak * 1e12)
-        t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
-        bound = "fp64" if t_fp64 >= t_hbm else "hbm"
-        traffic = None
-        tr = ROOT / "profiles" / "traffic.json"
-        if tr.exists():
-            try:
-                traffic = json.loads(tr.read_text()).get(f"cfg{cfg}")
-            except Exception:
-                traffic = None
-        line["roofline"] = {
-            "bound": bound,
-            "achieved": achieved_tf if bound == "fp64" else achieved_gbs,
-            "peak": fp64_peak if bound == "fp64" else peaks["hbm_gbs"],
-            "unit": "TFLOP/s" if bound == "fp64" else "GB/s",
-            "frac": max(t_fp64, t_hbm) / (kern_ms * 1e-3),
-            "traffic": traffic,
-            "kernel": eng.kernel_names[0],
-            "kernel_ms": kern_ms,
-            "launches_per_step": len(eng.kernel_names),
-            "algorithmic_flops_per_event": W.F_ALG[cfg],
-            "algorithmic_bytes_per_event": w["bytes_per_event"],
-            "fp64_peak_tflops": fp64_peak,
-            "fp64_peak_source": "measured live: register-resident DFMA loop (znll_fp64_peak), 300 ms",
-            "hbm_achieved_gbs": achieved_gbs,
-            "hbm_peak_gbs": peaks["hbm_gbs"],
-            "hbm_peak_source": peak_src,
-            "note": "roofline = slower of (bytes at HBM bandwidth, algorithmic fp64 flops at the DFMA peak), per north_star; "
-                    "no tensor cores: elementwise transcendental map-reduce",
-        }
-        if not args.no_cpu_baseline:
-            try:
-                line["cpu_baseline"] = time_cpu_port(cfg, n_events, budget_s=args.cpu_budget)
-            except Exception as exc:  # the checker failing must not void the GPU number
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
-                                        "sample": f"failed: {exc!r}"}
+    # ---- roofline of the dominant kernel: back-to-back launches, CUDA events on the launch stream -----------
+    # every rank runs it in lock-step (with the fused exchange a launch waits for its peers); rank 0 reports its own
+    peaks, peak_src = _peaks()
+    barrier()
+    with torch.cuda.stream(stream):
+        reps = max(5, min(args.steps, 50))
+        for _ in range(3):
+            plan.launch(slots, grad=True, log_offset=off, stream=stream.cuda_stream)
+        torch.cuda.synchronize(local)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(reps):
+            plan.launch(slots, grad=True, log_offset=off, stream=stream.cuda_stream)
+        k1.record(stream)
+        torch.cuda.synchronize(local)
+        kern_ms = k0.elapsed_time(k1) / reps
+    fp64_peak = Z.fp64_peak(local, 300.0)
+    flops = W.F_ALG[cfg] * n_events
+    bytes_alg = w["bytes_per_event"] * n_events
+    achieved_tf = flops / (kern_ms * 1e-3) / 1e12
+    achieved_gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
+    t_fp64 = flops / (fp64_peak * 1e12)
+    t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
+    bound = "fp64" if t_fp64 >= t_hbm else "hbm"
+    traffic = None
+    tr = ROOT / "profiles" / "traffic.json"
+    if tr.exists():
+        try:
+            traffic = json.loads(tr.read_text()).get(f"cfg{cfg}")
+        except Exception:
+            traffic = None
+    line["roofline"] = {
+        "bound": bound,
+        "achieved": achieved_tf if bound == "fp64" else achieved_gbs,
+        "peak": fp64_peak if bound == "fp64" else peaks["hbm_gbs"],
+        "unit": "TFLOP/s" if bound == "fp64" else "GB/s",
+        "frac": max(t_fp64, t_hbm) / (kern_ms * 1e-3),
+        "traffic": traffic,
+        "kernel": eng.kernel_names[0],
+        "kernel_ms": kern_ms,
+        "launches_per_step": len(eng.kernel_names),
+        "algorithmic_flops_per_event": W.F_ALG[cfg],
+        "algorithmic_bytes_per_event": w["bytes_per_event"],
+        "fp64_peak_tflops": fp64_peak,
+        "fp64_peak_source": "measured live: register-resident DFMA loop (znll_fp64_peak), 300 ms",
+        "hbm_achieved_gbs": achieved_gbs,
+        "hbm_peak_gbs": peaks["hbm_gbs"],
+        "hbm_peak_source": peak_src,
+        "note": "roofline = slower of (bytes at HBM bandwidth, algorithmic fp64 flops at the DFMA peak), per north_star; "
+                "no tensor cores: elementwise transcendental map-reduce",
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = time_cpu_port(cfg, n_events, budget_s=args.cpu_budget)
+        except Exception as exc:  # the checker failing must not void the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                                    "sample": f"failed: {exc!r}"}
     if not args.no_fit:
         # ---- end-to-end fit wall time (all ranks run the same minimizer in lock-step) ---------------------------
         for p, v in zip(params, theta0):
