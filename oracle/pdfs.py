@@ -531,16 +531,23 @@ class ProductPDF:
         self.pdfs = list(pdfs)
         self.yield_ = yield_
 
+    limits = None  # a product integrates each daughter over the daughter's own limits
+
     def pdf(self, B, x, P, norm=None):
         prob = None
         for pdf in self.pdfs:
             v = pdf.pdf(B, x, P, norm=False)
             prob = v if prob is None else prob * v
+        if norm is False:  # as a daughter of another product: ``_unnormalized_pdf`` (functor.py:408-411)
+            return prob
+        return prob / self.integrate(B, P, None, norm=False)
+
+    def integrate(self, B, P, limits, norm=False):  # functor.py:423-433: product of the daughters' integrals
         integral = None
         for pdf in self.pdfs:
             i = pdf.integrate(B, P, pdf.limits, norm=False)
             integral = i if integral is None else integral * i
-        return prob / integral
+        return integral
 
     def get_yield(self, B, P):
         return _val(B, P, self.yield_)
