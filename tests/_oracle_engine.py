@@ -145,7 +145,8 @@ class OracleEngine:
             def logp(th):
                 return torch.log(tree.pdf(B, x, {n: th[i] for i, n in enumerate(names)}))
 
-            J = torch.autograd.functional.jacobian(logp, theta, vectorize=True).numpy()  # (N, ns)
+            # forward mode: ns tangent passes, O(N * ns) memory (reverse mode would need an N x N basis)
+            J = torch.autograd.functional.jacobian(logp, theta, vectorize=True, strategy="forward-mode").detach().numpy()  # (N, ns)
             ww = np.ones(J.shape[0]) if w is None else np.asarray(w)
             G = np.concatenate([J, np.ones((J.shape[0], 1))], axis=1)
             mats.append((G * (ww**2)[:, None]).T @ G)

@@ -9,8 +9,14 @@ it is not installed in this image and cannot be.  This module implements the sam
   parabolic line search,
 * convergence on the estimated distance to minimum ``EDM = g^T V g / 2 < 0.002 * tol * errordef``
   (with zfit's ``tol`` pre-divided by ``0.002 * errordef``, :313-315, that is ``EDM < zfit tol``),
-* a final HESSE (finite differences of the gradient) whose inverse is the covariance, with MIGRAD restarted
-  from it when the verified EDM is still above the goal (strategy 1 behaviour),
+* Minuit2's bookkeeping of the metric's uncertainty (``Dcovar``: 1 for a seed, 0 after HESSE, averaged with the relative
+  size of every DFP update): the stop test is ``EDM (1 + 3 Dcovar) < goal`` and, as in strategy 1, HESSE (differences of
+  the analytic gradient: P passes forward, 2P central when the forward matrix is not symmetric to 1e-3) verifies the
+  result only while ``Dcovar > 0.05``; MIGRAD continues from the HESSE metric when the verified EDM is above the goal,
+* when the loss can supply its information matrix (summed outer product of the per-event scores, ONE fused pass), that
+  seeds the metric instead of Minuit's diagonal seed (P passes, no correlations) and refreshes it once when the
+  inflated EDM first drops below 1 (about one sigma from the minimum, where the information matrix is the Hessian up
+  to O(1/sqrt(N))) -- a B200-side addition: the pass is cheap here and removes most DFP iterations,
 * ``grad=None`` -> the driver's own finite-difference gradient of ``value`` (Minuit's default, :139-141).
 
 The driver only sees ``value(x)`` and ``gradient(x)`` callbacks of a ``LossEval``.
@@ -21,6 +27,9 @@ from __future__ import annotations
 import math
 
 import numpy as np
+
+
+REFRESH_EDM = 1.0  # refresh the metric from the information matrix once the inflated EDM drops below this
 
 
 class _Transform:
@@ -111,12 +120,15 @@ def _num_grad(value, x, steps, fx):
 
 
 def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000, hesse=True, verbose=False,
-             value_gradient=None):
+             value_gradient=None, information=None):
     """Variable-metric minimisation in Minuit's internal coordinates.
 
     value(x_ext) -> float; gradient(x_ext) -> array or None (None: finite differences of value);
     value_gradient(x_ext) -> (float, array) or None: when the loss returns both in one pass (the fused kernel does),
     line-search probes use it, so an accepted step costs ONE pass instead of a value pass plus a gradient pass.
+    information(x_ext) -> (P, P) array or None: an approximate Hessian of ``value`` in external coordinates that costs
+    about one pass (for a likelihood: the summed outer product of the per-event scores).  When given it seeds the
+    metric instead of Minuit's diagonal seed (which costs P gradient passes and knows no correlations).
     """
     tr = _Transform(lower, upper)
     res = MigradResult()
@@ -157,8 +169,36 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
         f = f_int(y)
         g = g_int(y, f)
 
-    def seed_metric(y, g):
+    def information_metric(y):
+        if information is None:
+            return None
+        try:
+            H = information(tr.to_external(y))
+        except Exception:  # the seed is an optimisation; any trouble falls back to Minuit's own seed
+            return None
+        if H is None:
+            return None
+        J = tr.dext_dint(y)
+        H = np.asarray(H, dtype=np.float64) * J[:, None] * J[None, :]
+        if H.shape != (n, n) or not np.all(np.isfinite(H)):
+            return None
+        H = 0.5 * (H + H.T)
+        d = np.sqrt(np.maximum(np.diag(H), 1e-300))
+        C = H / d[:, None] / d[None, :]
+        try:
+            w = np.linalg.eigvalsh(C)
+            if w[0] < 1e-10 * w[-1]:
+                return None
+            return np.linalg.inv(C) / d[:, None] / d[None, :]
+        except np.linalg.LinAlgError:
+            return None
+
+    def seed_metric(y, g, first=False):
         """Diagonal seed from second derivatives along each axis (MnSeedGenerator)."""
+        if first:
+            Vi = information_metric(y)
+            if Vi is not None:
+                return Vi
         V = np.zeros((n, n))
         for i in range(n):
             h = max(ysteps[i] * 0.05, 1e-7)
@@ -260,11 +300,12 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
         e = 0.5 * float(g @ Vh @ g)
         return e < edm_goal, Vh, e
 
-    V = seed_metric(y, g)
+    V = seed_metric(y, g, first=True)
     edm = 0.5 * float(g @ V @ g)
+    dcovar = 1.0  # Minuit2's estimate of the relative error of V: 1 for a seed, 0 after HESSE, updated by DFP
     restarts = 0
+    refreshed = False
     use_fg = value_gradient is not None and gradient is not None
-    hesse_iter = None  # iteration at which V was last replaced by an exact inverse Hessian
     for it in range(1, 100000):
         res.niter = it
         if counter["f"] + counter["g"] > maxfcn:
@@ -273,15 +314,14 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
         if not (np.isfinite(f) and np.all(np.isfinite(g))):
             res.message = "non-finite value or gradient"
             break
-        if edm < edm_goal:
-            if not hesse or (hesse_iter is not None and it - hesse_iter <= 4):
-                # strategy 1: no second HESSE when the metric descends from a recent exact inverse Hessian
+        if edm * (1.0 + 3.0 * dcovar) < edm_goal:  # VariableMetricBuilder: the EDM is inflated by the metric's uncertainty
+            if not hesse or dcovar <= 0.05:
+                # strategy 1: HESSE verifies the result only while the metric is still uncertain (Dcovar > 0.05)
                 res.converged = True
                 break
             ok, Vh, e = verify(y, f, g, V)
             if Vh is not None:
-                V, edm = Vh, e
-                hesse_iter = it
+                V, edm, dcovar = Vh, e, 0.0
                 if ok:
                     res.converged = True
                     break
@@ -289,6 +329,7 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
                 restarts += 1
                 V = seed_metric(y, g)
                 edm = 0.5 * float(g @ V @ g)
+                dcovar = 1.0
                 if edm < edm_goal:  # the seed agrees that we are there; accept
                     res.converged = True
                     res.message = "converged (hesse not positive definite, seed metric used)"
@@ -296,10 +337,19 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             else:
                 res.message = "hesse failed: matrix not positive definite"
                 break
+        if information is not None and not refreshed and it > 1 and edm * (1.0 + 3.0 * dcovar) < REFRESH_EDM:
+            # within about one sigma of the minimum the score outer product IS the Hessian up to O(1/sqrt(N)): one pass
+            # replaces the correlations DFP would need several more iterations to learn
+            refreshed = True
+            Vi = information_metric(y)
+            if Vi is not None and float(g @ Vi @ g) > 0:
+                V, dcovar = Vi, 0.5
+                edm = 0.5 * float(g @ V @ g)
         step = -V @ g
         gdel = float(step @ g)
         if gdel >= 0:  # metric not positive definite: reseed
             V = seed_metric(y, g)
+            dcovar = 1.0
             step = -V @ g
             gdel = float(step @ g)
             if gdel >= 0:
@@ -315,6 +365,7 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
                 restarts += 1
                 V = seed_metric(y, g)
                 edm = 0.5 * float(g @ V @ g)
+                dcovar = 1.0
                 if edm < edm_goal:
                     continue
                 step = -V @ g
@@ -336,14 +387,16 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
         Vg = V @ dg
         gvg = float(dg @ Vg)
         if delgam > 0 and gvg > 0:
-            V = V + np.outer(dy, dy) / delgam - np.outer(Vg, Vg) / gvg
+            upd = np.outer(dy, dy) / delgam - np.outer(Vg, Vg) / gvg
             if delgam > gvg:
                 flnu = dy / delgam - Vg / gvg
-                V = V + gvg * np.outer(flnu, flnu)
+                upd = upd + gvg * np.outer(flnu, flnu)
+            V = V + upd
+            dcovar = 0.5 * (dcovar + float(np.abs(upd).sum()) / max(float(np.abs(V).sum()), 1e-300))
         y, f, g = y_new, f_new, g_new
         edm = 0.5 * float(g @ V @ g)
         if verbose:
-            print(f"[migrad] it={it} f={f:.10g} edm={edm:.3g} lam={lam:.3g} nf={counter['f']} ng={counter['g']}")
+            print(f"[migrad] it={it} f={f:.10g} edm={edm:.3g} dcovar={dcovar:.3g} lam={lam:.3g} nf={counter['f']} ng={counter['g']}")
     x = tr.to_external(y)
     res.x = x
     res.fval = f
@@ -363,12 +416,24 @@ def _hesse_internal(f_int, g_int, have_grad, y, f, g, V):
     H = np.zeros((n, n))
     sig = np.sqrt(np.maximum(np.diag(V), 1e-300))
     if have_grad:
+        # rows of the Hessian from differences of the analytic gradient.  Forward differences reuse g(y): P passes.
+        # Their O(h) truncation error shows up as asymmetry of the matrix; when that exceeds 1e-3 (small samples, far from
+        # quadratic) the backward points are added and the differences become central (2P passes).
+        hs = np.maximum(0.02 * sig, 1e-8)
+        gp = []
         for i in range(n):
-            h = max(0.02 * sig[i], 1e-8)
-            yp, ym = y.copy(), y.copy()
-            yp[i] += h
-            ym[i] -= h
-            H[i, :] = (g_int(yp) - g_int(ym)) / (2 * h)
+            yp = y.copy()
+            yp[i] += hs[i]
+            gp.append(g_int(yp))
+            H[i, :] = (gp[i] - g) / hs[i]
+        d = np.sqrt(np.maximum(np.abs(np.diag(H)), 1e-300))
+        C = H / d[:, None] / d[None, :]
+        if np.all(np.isfinite(C)) and np.linalg.norm(C - C.T) <= 1e-3 * np.linalg.norm(C):
+            return 0.5 * (H + H.T)
+        for i in range(n):
+            ym = y.copy()
+            ym[i] -= hs[i]
+            H[i, :] = (gp[i] - g_int(ym)) / (2 * hs[i])
         return 0.5 * (H + H.T)
     hs = np.maximum(0.1 * sig, 1e-7)
     fp = np.zeros(n)

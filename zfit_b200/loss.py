@@ -424,7 +424,13 @@ class BaseLoss:
         return value, np.array([grad.get(p, 0.0) for p in params], dtype=np.float64)
 
     # ------------------------------------------------------------------ weighted-fit covariance ingredient
-    def weighted_score_outer(self, params=None):
+    def information_matrix(self, params=None):
+        """Observed-information estimate ``sum_i w_i grad(v_i) grad(v_i)^T`` (+ the constraints' outer products): the
+        expected Hessian of the NLL at the true parameters, from the same single pass as ``weighted_score_outer``
+        (weighted channels are rescaled by ``sum w / sum w^2``).  The native MIGRAD driver seeds its metric with it."""
+        return self.weighted_score_outer(params, _unit_scale=True)
+
+    def weighted_score_outer(self, params=None, _unit_scale=False):
         """``C = sum_i w_i^2 grad_theta(v_i) grad_theta(v_i)^T`` with ``v_i = log pdf(x_i) [+ log yield]`` plus one
         unit-weight term per constraint -- the matrix ``covariance_with_weights`` builds from a per-event Jacobian
         (``minimizers/errors.py:406-452``); here it is ONE extra fused pass over the events (``znll_eval_cov``)."""
@@ -448,6 +454,8 @@ class BaseLoss:
                 for leaf, d in yparam._partials().items():
                     if id(leaf) in index:
                         B[ns, index[id(leaf)]] += d / y
+            if _unit_scale and self.data[k].has_weights and E[ns, ns] > 0:
+                E = E * (eng.samplesize[k] / E[ns, ns])  # sum w / sum w^2
             C += B.T @ E @ B
         for con in self.constraints:
             g = np.zeros(npar)

@@ -706,6 +706,20 @@ class Minuit(BaseMinimizer):
             info={"n_eval": evaluator.niter, "driver": "iminuit", "original": m, "minuit": m},
         )
 
+    @staticmethod
+    def _information_seed(loss, params, evaluator):
+        """Seed metric for the native driver: the loss's summed score outer product (one extra fused pass)."""
+        fn = getattr(loss, "information_matrix", None)
+        if fn is None:
+            return None
+
+        def information(x):
+            assign_values(params, x)
+            evaluator.npass += 1
+            return fn(params)
+
+        return information
+
     def _minimize_native(self, loss, params, init):
         evaluator = self.create_evaluator(loss, params, numpy_converter=np.array)
         criterion = self.create_criterion(loss, params)
@@ -718,6 +732,7 @@ class Minuit(BaseMinimizer):
             evaluator.value, grad, [p.value() for p in params], steps, [p.lower for p in params],
             [p.upper for p in params], edm_goal=self.tol, maxfcn=evaluator.maxiter or 100000, hesse=self.mode >= 1,
             verbose=self.verbosity > 6, value_gradient=None if self.minuit_grad else evaluator.value_gradient,
+            information=None if self.minuit_grad else self._information_seed(loss, params, evaluator),
         )
         assign_values(params, res.x)
         criterion.last_value = res.edm
