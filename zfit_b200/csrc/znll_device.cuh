@@ -162,6 +162,19 @@ ZNLL_DEV V zbc(double x) {
 ZNLL_DEV void zacc(double& acc, double g, double d) { acc = fma(g, d, acc); }
 ZNLL_DEV void zacc(double& acc, D2 g, D2 d) { acc = fma(g.b, d.b, fma(g.a, d.a, acc)); }
 ZNLL_DEV void zacc(double& acc, D2 g, double d) { acc = fma(g.a + g.b, d, acc); }
+// per-lane accumulators (covariance pass: the two events of a pair keep separate score vectors)
+ZNLL_DEV void zacc(D2& acc, D2 g, D2 d) {
+  acc.a = fma(g.a, d.a, acc.a);
+  acc.b = fma(g.b, d.b, acc.b);
+}
+ZNLL_DEV void zacc(D2& acc, D2 g, double d) {
+  acc.a = fma(g.a, d, acc.a);
+  acc.b = fma(g.b, d, acc.b);
+}
+ZNLL_DEV void zacc1(D2& acc, D2 g) {
+  acc.a += g.a;
+  acc.b += g.b;
+}
 ZNLL_DEV void zacc1(double& acc, double g) { acc += g; }
 ZNLL_DEV void zacc1(double& acc, D2 g) { acc += g.a + g.b; }
 
@@ -298,14 +311,14 @@ struct GaussN {
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     const V gi = zmul(g, c[CO + 0]);
     zacc(acc[AO + 0], gi, t);                  // d/dmu    =  t/sigma
     zacc(acc[AO + 1], gi, zfma(t, t, -1.0));   // d/dsigma = (t^2-1)/sigma
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -334,12 +347,12 @@ struct ExpoN {
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__, A* acc) {
     zacc(acc[AO + 0], g, xs);
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -387,8 +400,8 @@ struct CBallN {
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     const V gd = zmul(g, dt);
     zacc(acc[AO + 0], zneg(gd), c[CO + 1]);             // dt/dmu    = -sign/sigma
     zacc(acc[AO + 1], zmul(zneg(gd), t), c[CO + 2]);    // dt/dsigma = -t/sigma
@@ -399,8 +412,8 @@ struct CBallN {
       zacc(acc[AO + 3], gt, zsub(zsub(c[CO + 8], lu), zmul(dt, c[CO + 9])));
     }
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -433,15 +446,15 @@ struct GETailN {
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     const V gd = zneg(zmul(g, dt));
     zacc(acc[AO + 0], gd, c[CO + 1]);
     zacc(acc[AO + 1], zmul(gd, t), c[CO + 2]);
     zacc(acc[AO + 2], zsel(tail, g, zbc<V>(0.0)), zmul(zadd(t, c[CO + 3]), c[CO + 6]));  // d ln v/d|alpha| = a + t
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -484,8 +497,8 @@ struct GGETailN {
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     const double* cc = c + CO;
     const V zero = zbc<V>(0.0);
     const V gd = zneg(zmul(g, dt));
@@ -497,8 +510,8 @@ struct GGETailN {
     zacc1(acc[AO + 2], zsel(left, ga, zero));
     zacc1(acc[AO + 4], zsel(left, zero, ga));
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -549,15 +562,15 @@ struct PolyN {
     neg = mxor(neg, zlt(p, 0.0));
     return fast_log(zabs(p), cx);
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     const V ai = zmul(a, c[CO + 2]);
     zacc1(acc[AO + 0], ai);
 #pragma unroll
     for (int k = 1; k <= DEG; ++k) zacc(acc[AO + k], ai, T[k]);
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     bwd_val<CO, AO>(zmul(g, fast_rcp(P)), c, acc);
   }
 };
@@ -621,8 +634,8 @@ struct GCBallN {
     P = fast_exp(fwd_log<CO>(cx, c, x, neg));
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     const double* cc = c + CO;
     const V zero = zbc<V>(0.0);
     const V gd = zneg(zmul(g, dt));
@@ -640,8 +653,8 @@ struct GCBallN {
       zacc1(acc[AO + 6], zsel(left, zero, gn));
     }
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -700,8 +713,8 @@ struct SumN {
       fwd_rec<CO, I + 1, CK + KD::Head::NC>(kd.t, cx, c, x, tot);
     }
   }
-  template <int CO, int AO, int I, int CK, int AK, class KD>
-  ZNLL_DEV void bwd_rec(KD& kd, V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, int I, int CK, int AK, class KD, class A>
+  ZNLL_DEV void bwd_rec(KD& kd, V a, const double* __restrict__ c, A* acc) {
     if constexpr (KD::N > 0) {
       zacc(acc[AO + I], a, p[I]);
       kd.h.template bwd_val<CK, AK>(zmul(a, c[CO + I]), c, acc);
@@ -721,12 +734,12 @@ struct SumN {
     neg = mxor(neg, zlt(v, 0.0));
     return fast_log(zabs(v), cx);
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_rec<CO, AO, 0, CO + K, AO + K>(kids, a, c, acc);
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     bwd_val<CO, AO>(zmul(g, fast_rcp(P)), c, acc);
   }
 };
@@ -769,16 +782,16 @@ struct SumLseN {
     P = zsel(neg, zneg(e), e);
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     const V g0 = zmul(g, q0), g1 = zmul(g, q1);
     zacc1(acc[AO + 0], g0);
     zacc1(acc[AO + 1], g1);
     k0.template bwd_log<CO + 2, AO + 2>(zmul(g0, c[CO + 0]), c, acc);
     k1.template bwd_log<CO + 2 + C0::NC, AO + 2 + C0::NS>(zmul(g1, c[CO + 1]), c, acc);
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -832,8 +845,8 @@ struct ProdN {
       fwd_rec<CK + KD::Head::NC>(kd.t, cx, c, x, tot, neg);
     }
   }
-  template <int CK, int AK, class KD>
-  ZNLL_DEV void bwd_rec(KD& kd, V g, const double* __restrict__ c, double* acc) {
+  template <int CK, int AK, class KD, class A>
+  ZNLL_DEV void bwd_rec(KD& kd, V g, const double* __restrict__ c, A* acc) {
     if constexpr (KD::N > 0) {
       kd.h.template bwd_log<CK, AK>(g, c, acc);
       bwd_rec<CK + KD::Head::NC, AK + KD::Head::NS>(kd.t, g, c, acc);
@@ -852,12 +865,12 @@ struct ProdN {
     P = zsel(neg, zneg(e), e);
     return P;
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     bwd_rec<CO, AO>(kids, g, c, acc);
   }
-  template <int CO, int AO>
-  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, double* acc) {
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
 };
@@ -951,8 +964,8 @@ struct KArgs {
 
 // accumulators: [0] running sum of w*l - offset, [1] its Kahan compensation, [2..] slots.
 // Returns the term(s)  w*l - offset  of this event (pair).
-template <class M, class V, bool WEIGHTED, bool GRAD>
-ZNLL_DEV V event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, double off, double* acc) {
+template <class M, class V, bool WEIGHTED, bool GRAD, class A>
+ZNLL_DEV V event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, double off, A* acc) {
   typedef typename Lanes<V>::Mask Mask;
   typename M::template Node<V> m;
   V l;
@@ -1150,7 +1163,7 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
 // src/zfit/minimizers/errors.py:333-464, C = sum_i w_i^2 grad(log p_i) grad(log p_i)^T): besides the usual
 // accumulators it sums the outer product of the per-event vector e_i = [c_i0 .. c_i,NS-1, w_i] with
 // c_ij = w_i * d l_i / d slot_j (normalisation constants held fixed; the host applies the same linear map as for
-// the gradient).  One event per thread step (scalar instantiation): a once-per-fit pass, not the step kernel.
+// the gradient).  Runs once or twice per fit (metric seed / weighted covariance), not on the step path.
 // out: [0,1] value pair, [2, 2+NS) slot sums, then the upper triangle of sum e e^T, row-major, (NS+1)(NS+2)/2 entries.
 template <class M, bool WEIGHTED>
 __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constant__ KArgs<M::NC> args) {
@@ -1164,14 +1177,40 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constan
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
   const double* __restrict__ c = args.c;
+  const long long nvec = args.n >> 1;
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
-  for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < args.n; i += stride) {
+  long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x;
+  // two events per thread in lock-step like the step kernel; the pair keeps per-lane score vectors e.a / e.b
+  EventPair<M, WEIGHTED> cur, nxt;
+  if (i < nvec) nxt.load(args, i);
+  while (i < nvec) {
+    cur = nxt;
+    i += stride;
+    if (i < nvec) nxt.load(args, i);
+    D2 e[2 + NE];
+#pragma unroll
+    for (int j = 0; j < 2 + NE; ++j) e[j] = zbc<D2>(0.0);
+    const D2 t = event<M, D2, WEIGHTED, true>(cx, c, cur.x, cur.w, args.log_offset, e);
+    kahan_add(acc, t.a + t.b);
+    e[2 + NS] = cur.w;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acc[2 + j] += e[2 + j].a + e[2 + j].b;
+    int q = 2 + NS;
+#pragma unroll
+    for (int a = 0; a < NE; ++a)
+#pragma unroll
+      for (int b = a; b < NE; ++b) {
+        acc[q] = fma(e[2 + a].b, e[2 + b].b, fma(e[2 + a].a, e[2 + b].a, acc[q]));
+        ++q;
+      }
+  }
+  if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event
     double x[ZNLL_MAXCOL];
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k)
-      if ((M::COLMASK >> k) & 1) x[k] = __ldg(args.cols[k] + i);
+      if ((M::COLMASK >> k) & 1) x[k] = args.cols[k][args.n - 1];
     double w = 1.0;
-    if constexpr (WEIGHTED) w = __ldg(args.w + i);
+    if constexpr (WEIGHTED) w = args.w[args.n - 1];
     double e[2 + NE];
 #pragma unroll
     for (int j = 0; j < 2 + NE; ++j) e[j] = 0.0;
