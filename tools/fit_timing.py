@@ -1,4 +1,11 @@
+"""Full-size Minuit fits of the BASELINE configs on cuda:0: wall time, fused passes, information-pass cost.
+
+usage: python tools/fit_timing.py 1,2,3,4,5 [verbose]
+"""
+import os
+sys_path = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import sys, time, numpy as np, torch
+sys.path.insert(0, sys_path)
 import zfit_b200 as zfit
 from zfit_b200 import workloads as W
 cfgs = [int(c) for c in sys.argv[1].split(',')]

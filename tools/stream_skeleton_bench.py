@@ -1,5 +1,6 @@
 # achievable read bandwidth of the step kernel's access pattern with (almost) no arithmetic: Prod of Exponentials
-import sys, time, numpy as np, torch
+import os, sys, time, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import zfit_b200 as zfit
 n = 100_000_000
 for ncol in (1, 2, 3, 4):
