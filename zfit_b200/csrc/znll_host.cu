@@ -388,6 +388,8 @@ struct Channel {
   double sumw = 0.0;
   std::vector<void*> owned;
   double* d_partials = nullptr;
+  double* d_cov = nullptr;  // covariance pass: [grid][NACC] partials followed by [NACC] results, allocated on first use
+  size_t d_cov_len = 0;
   unsigned int* d_ticket = nullptr;
   // per-call scratch
   std::vector<double> consts, dlnI;  // dlnI: per slot, d ln I_leaf / d slot (0 for functor slots)
@@ -843,6 +845,7 @@ void znll_plan_destroy(znll_plan* p) {
   for (auto& c : p->ch) {
     free_channel_data(c);
     if (c.d_partials) cudaFree(c.d_partials);
+    if (c.d_cov) cudaFree(c.d_cov);
     if (c.d_ticket) cudaFree(c.d_ticket);
   }
   if (p->d_acc) cudaFree(p->d_acc);
@@ -875,6 +878,7 @@ int znll_plan_set_model(znll_plan* p, int ch, const znll_node* nodes, int n_node
   }
   c.kernel = k;
   if (c.d_partials) cudaFree(c.d_partials), c.d_partials = nullptr;
+  if (c.d_cov) cudaFree(c.d_cov), c.d_cov = nullptr, c.d_cov_len = 0;
   if (!c.d_ticket) {
     CUDA_OK(cudaMalloc(&c.d_ticket, sizeof(unsigned int)));
     CUDA_OK(cudaMemset(c.d_ticket, 0, sizeof(unsigned int)));
@@ -1142,10 +1146,14 @@ int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* 
     fill_consts(c, c.slots.data());
     std::vector<double> acc(NACC, 0.0);
     if (c.n > 0) {
-      const int grid = (int)std::min<long long>(p->sm_count, (c.n + 255) / 256);
-      double *d_part = nullptr, *d_out = nullptr;
-      CUDA_OK(cudaMalloc(&d_part, sizeof(double) * (size_t)grid * NACC));
-      CUDA_OK(cudaMalloc(&d_out, sizeof(double) * NACC));
+      const int grid = (int)std::min<long long>(p->sm_count, std::max<long long>(1, ((c.n + 1) / 2 + 255) / 256));
+      const size_t need = ((size_t)p->sm_count + 1) * NACC;
+      if (c.d_cov_len < need) {
+        if (c.d_cov) cudaFree(c.d_cov), c.d_cov = nullptr, c.d_cov_len = 0;
+        CUDA_OK(cudaMalloc(&c.d_cov, sizeof(double) * need));
+        c.d_cov_len = need;
+      }
+      double *d_part = c.d_cov, *d_out = c.d_cov + (size_t)p->sm_count * NACC;
       ZnllLaunchArgs la;
       for (int i = 0; i < ZNLL_MAX_COLS; ++i) la.cols[i] = c.cols[i];
       la.w = c.w;
@@ -1167,8 +1175,6 @@ int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* 
       cudaError_t e = cudaSuccess;
       if (!rc) e = cudaMemcpyAsync(acc.data(), d_out, sizeof(double) * NACC, cudaMemcpyDeviceToHost, st);
       if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(st);
-      cudaFree(d_part);
-      cudaFree(d_out);
       if (rc) return rc;
       if (e != cudaSuccess) return fail("znll_eval_cov: %s", cudaGetErrorString(e));
     }

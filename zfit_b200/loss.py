@@ -118,6 +118,8 @@ class CudaEngine:
             return cols, w
         torch = self.torch
         i = data.obs.index(target.obs[0])
+        if len(cols) == 1 and w is None:
+            return [torch.sort(cols[0]).values], None  # nothing to carry along: no permutation gather needed
         order = torch.argsort(cols[i])
         cols = [c[order].contiguous() for c in cols]
         if w is not None:
