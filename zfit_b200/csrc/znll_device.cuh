@@ -1122,6 +1122,17 @@ struct EventPair {
   }
 };
 
+#ifndef ZNLL_PINGPONG
+#define ZNLL_PINGPONG 1
+#endif
+__host__ __device__ constexpr int zpopc(unsigned m) {
+  int n = 0;
+  while (m) {
+    n += (int)(m & 1u);
+    m >>= 1;
+  }
+  return n;
+}
 template <class M, bool WEIGHTED, bool GRAD>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NACC = 2 + M::NS;
@@ -1138,14 +1149,37 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
   const long long nvec = args.n >> 1;
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
   long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x;
-  EventPair<M, WEIGHTED> cur, nxt;
-  if (i < nvec) nxt.load(args, i);
-  while (i < nvec) {
-    cur = nxt;
-    i += stride;
-    if (i < nvec) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
-    const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, off, acc);
-    kahan_add(acc, t.a + t.b);
+  if constexpr ((ZNLL_PINGPONG != 0) && (zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0) >= 3)) {
+    // three or more 8-byte streams per event: two register buffers used alternately -- the loop body exists twice and no
+    // buffer is ever copied (the copy is 12+ moves per pair there; measured -10 % on cfg 4, while one- and two-stream
+    // trees lose 1 % to the doubled loop body and keep the copying loop below)
+    EventPair<M, WEIGHTED> b0, b1;
+    if (i < nvec) b0.load(args, i);
+    while (i < nvec) {
+      i += stride;
+      if (i < nvec) b1.load(args, i);
+      {
+        const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, b0.x, b0.w, off, acc);
+        kahan_add(acc, t.a + t.b);
+      }
+      if (i >= nvec) break;
+      i += stride;
+      if (i < nvec) b0.load(args, i);
+      {
+        const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, b1.x, b1.w, off, acc);
+        kahan_add(acc, t.a + t.b);
+      }
+    }
+  } else {
+    EventPair<M, WEIGHTED> cur, nxt;
+    if (i < nvec) nxt.load(args, i);
+    while (i < nvec) {
+      cur = nxt;
+      i += stride;
+      if (i < nvec) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
+      const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, off, acc);
+      kahan_add(acc, t.a + t.b);
+    }
   }
   if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event: scalar instantiation
     double xa[ZNLL_MAXCOL];
