@@ -178,10 +178,11 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             return None
         if H is None:
             return None
-        J = tr.dext_dint(y)
-        H = np.asarray(H, dtype=np.float64) * J[:, None] * J[None, :]
+        H = np.asarray(H, dtype=np.float64)
         if H.shape != (n, n) or not np.all(np.isfinite(H)):
             return None
+        J = tr.dext_dint(y)
+        H = H * J[:, None] * J[None, :]
         H = 0.5 * (H + H.T)
         d = np.sqrt(np.maximum(np.diag(H), 1e-300))
         C = H / d[:, None] / d[None, :]
