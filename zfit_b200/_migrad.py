@@ -29,6 +29,7 @@ import math
 import numpy as np
 
 
+FAR = 0.5  # a second line-search probe only when the secant puts the line minimum this far from the unit step
 REFRESH_EDM = 1.0  # refresh the metric from the information matrix once the inflated EDM drops below this
 
 
@@ -272,7 +273,7 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
         if d1 is not None:
             lam2 = gdel / (gdel - d1) if d1 > gdel else 2.5  # still descending at lambda = 1 -> extend
             lam2 = min(max(lam2, 0.05), 6.0)
-            far = abs(lam2 - 1.0) > 0.25
+            far = abs(lam2 - 1.0) > FAR
             if f1 >= f0 or far:
                 probe(lam2)
         lam = min([c[0] for c in cands], default=1.0)
