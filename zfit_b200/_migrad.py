@@ -70,7 +70,7 @@ class _Transform:
         m = self.up_only
         if m.any():
             x[m] = self.up[m] + 1.0 - np.sqrt(y[m] ** 2 + 1.0)
-        return x
+        return np.minimum(np.maximum(x, self.lo), self.up)  # rounding must not step an ulp outside the limits
 
     def dext_dint(self, y):
         y = np.asarray(y, dtype=np.float64)

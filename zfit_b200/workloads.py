@@ -11,6 +11,8 @@ import math
 
 import numpy as np
 
+from . import distributed as D
+
 FULL_SIZES = {1: 10_000, 2: 100_000_000, 3: 50_000_000, 4: 100_000_000, 5: 125_000_000}
 NAMES = {
     1: "cfg1: Gauss UnbinnedNLL, 10k events (examples/simple_fit.py)",
@@ -153,8 +155,10 @@ def build(cfg: int, n: int | None = None, device="cpu", rank: int = 0, zfit=None
         alpha = zfit.Parameter("alpha" + tag, 1.2, 0.1, 5)
         nn = zfit.Parameter("n" + tag, 2.5, 1.05, 20)
         lam = zfit.Parameter("lambda" + tag, -0.003, -0.02, -1e-5)
-        n_sig = zfit.Parameter("n_sig" + tag, 0.25 * n, 0, 2.0 * n, stepsize=max(1.0, math.sqrt(n)))
-        n_bkg = zfit.Parameter("n_bkg" + tag, 0.75 * n, 0, 2.0 * n, stepsize=max(1.0, math.sqrt(n)))
+        # the yields count the events of ALL ranks (each rank holds its own n-event shard of one sample)
+        ntot = float(n) * D.world_size()
+        n_sig = zfit.Parameter("n_sig" + tag, 0.25 * ntot, 0, 2.0 * ntot, stepsize=max(1.0, math.sqrt(ntot)))
+        n_bkg = zfit.Parameter("n_bkg" + tag, 0.75 * ntot, 0, 2.0 * ntot, stepsize=max(1.0, math.sqrt(ntot)))
         cb = zfit.pdf.CrystalBall(mu=mu, sigma=sigma, alpha=alpha, n=nn, obs=obs, extended=n_sig)
         ex = zfit.pdf.Exponential(lam, obs=obs, extended=n_bkg)
         model = zfit.pdf.SumPDF([cb, ex])
