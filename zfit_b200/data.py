@@ -288,6 +288,15 @@ _STAGE_ELEMS = 2 << 20  # 16 MB of fp64 per buffer
 _STAGE_BUFS = 4
 
 
+def _copy_threads():
+    """Host threads for filling the staging buffers: the cores this process may use, shared among the ranks of the node."""
+    import os
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(16, cores // local_world))
+
+
 def _upload_numpy(a, dev):
     """Pageable host column -> HBM through a ring of pinned staging buffers: host threads fill one buffer while the
     copy engine drains the others (measured on the B200 box: 800 MB in 16 ms = 51 GB/s, against 70 ms for a plain
@@ -305,15 +314,25 @@ def _upload_numpy(a, dev):
     bufs, events = _STAGE[key]
     out = torch.empty(n, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
-    for k, off in enumerate(range(0, n, _STAGE_ELEMS)):
-        m = min(_STAGE_ELEMS, n - off)
-        b = k % _STAGE_BUFS
-        if events[b] is not None:
-            events[b].synchronize()
-        bufs[b][:m].copy_(src[off : off + m])
-        out[off : off + m].copy_(bufs[b][:m], non_blocking=True)
-        events[b] = torch.cuda.Event()
-        events[b].record(stream)
+    # the fill is torch's parallel CPU copy; torchrun exports OMP_NUM_THREADS=1, which would leave one thread to move
+    # every rank's gigabytes (measured 0.46 s instead of 0.05 s for 2 GB), so the thread count is raised for the upload
+    prev = torch.get_num_threads()
+    want = _copy_threads()
+    if want != prev:
+        torch.set_num_threads(want)
+    try:
+        for k, off in enumerate(range(0, n, _STAGE_ELEMS)):
+            m = min(_STAGE_ELEMS, n - off)
+            b = k % _STAGE_BUFS
+            if events[b] is not None:
+                events[b].synchronize()
+            bufs[b][:m].copy_(src[off : off + m])
+            out[off : off + m].copy_(bufs[b][:m], non_blocking=True)
+            events[b] = torch.cuda.Event()
+            events[b].record(stream)
+    finally:
+        if want != prev:
+            torch.set_num_threads(prev)
     return out
 
 
