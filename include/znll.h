@@ -27,6 +27,8 @@
  *                   DoubleCB is the same node with the sigma slot given twice)
  *       ZNLL_GET    mu, sigma, alpha          (GaussExpTail, physics.py:608-623,636-686,727-805)
  *       ZNLL_GGET   mu, sigmal, alphal, sigmar, alphar   (GeneralizedGaussExpTail, physics.py:625-634,689-724,819-923)
+ *       ZNLL_BERNSTEIN  c_0 .. c_degree       (Bernstein, polynomials.py:872-1028; every coefficient is a slot)
+ *       ZNLL_TGAUSS mu, sigma, low, high      (TruncatedGauss, dist_tfp.py:357-417: zero outside [low, high])
  *       ZNLL_SUM    frac_0 .. frac_{k-1}      (src/zfit/models/functor.py:74-313; ALL k fractions)
  *       ZNLL_PROD   (none)                    (src/zfit/models/functor.py:331-483)
  *   The library differentiates with respect to slots; the host applies d(slot)/d(theta)
@@ -55,6 +57,8 @@ enum znll_kind {
   ZNLL_GCB = 7,
   ZNLL_GET = 8,
   ZNLL_GGET = 9,
+  ZNLL_BERNSTEIN = 10,
+  ZNLL_TGAUSS = 11,
   ZNLL_SUM = 16,
   ZNLL_PROD = 17
 };

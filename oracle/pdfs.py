@@ -342,6 +342,95 @@ class Chebyshev2(Chebyshev):
         return integral * (B.const(0.5) * B.const(self.limits[1] - self.limits[0]))
 
 
+class Bernstein(_Leaf):
+    """``zfit.pdf.Bernstein`` (``src/zfit/models/polynomials.py:872-1028``): De Casteljau's algorithm on the observable
+    rescaled to (0, 1) with the pdf's *space* limits; every coefficient is a parameter."""
+
+    def __init__(self, coeffs, obs, limits, yield_=None):
+        super().__init__(obs, limits, yield_)
+        self.coeffs = list(coeffs)
+        self.degree = len(self.coeffs) - 1
+
+    def param_names(self):
+        out = []
+        for c in self.coeffs:
+            out += _names(c)
+        return out
+
+    def _rescale(self, B, x):  # rescale_zero_one, polynomials.py:872-885
+        lim_low, lim_high = B.const(self.limits[0]), B.const(self.limits[1])
+        return (x - lim_low) / (lim_high - lim_low)
+
+    @staticmethod
+    def _de_casteljau(B, x, coeffs):  # polynomials.py:888-900
+        beta = list(coeffs)
+        n = len(beta)
+        for j in range(1, n):
+            for k in range(n - j):
+                beta[k] = beta[k] * (B.const(1.0) - x) + beta[k + 1] * x
+        if n == 1:
+            beta[0] = beta[0] * B.ones_like(x)
+        return beta[0]
+
+    def unnorm(self, B, x, P, norm):  # _pdf, polynomials.py:969-978
+        return self._de_casteljau(B, self._rescale(B, x), [_val(B, P, c) for c in self.coeffs])
+
+    def integral(self, B, P, lo, hi, norm):  # func_integral_bernstein + _coeffs_int, polynomials.py:1000-1025
+        coeffs = [_val(B, P, c) for c in self.coeffs]
+        n = len(coeffs)
+        r = [B.const(0.0)] * (n + 1)
+        for j in range(1, n + 1):
+            for k in range(j):
+                r[j] = r[j] + coeffs[k]
+        r = [rj / B.const(float(n)) for rj in r]
+        volume = B.const(self.limits[1]) - B.const(self.limits[0])
+        upper = self._de_casteljau(B, self._rescale(B, B.const(hi)), r) * volume
+        lower = self._de_casteljau(B, self._rescale(B, B.const(lo)), r) * volume
+        return upper - lower
+
+
+class TruncatedGauss(_Leaf):
+    """``zfit.pdf.TruncatedGauss`` = ``WrapDistribution`` over ``tfp.distributions.TruncatedNormal``
+    (``src/zfit/models/dist_tfp.py:357-417``; value ``distribution.prob``, :108-110; integral ``cdf(upper) - cdf(lower)``,
+    :113-120).
+
+    Third-party arithmetic (tensorflow-probability >=0.24,<1.0; not vendored) restated from its published source
+    (``truncated_normal.py``): ``log_prob = -(0.5*((x-loc)/scale)**2 + 0.5*log(2*pi) + log(scale) + log Z)`` with
+    ``Z = ndtr(std_high) - ndtr(std_low)``, ``-inf`` outside ``[low, high]``; ``cdf = clip((ndtr((x-loc)/scale) -
+    ndtr(std_low)) / Z, 0, 1)``.  (Newer releases form ``log Z`` from ``log_ndtr`` differences; same value.)
+    """
+
+    def __init__(self, mu, sigma, low, high, obs, limits, yield_=None):
+        super().__init__(obs, limits, yield_)
+        self.mu, self.sigma, self.low, self.high = mu, sigma, low, high
+
+    def param_names(self):
+        return _names(self.mu) + _names(self.sigma) + _names(self.low) + _names(self.high)
+
+    def _parts(self, B, P):
+        mu, sigma = _val(B, P, self.mu), _val(B, P, self.sigma)
+        low, high = _val(B, P, self.low), _val(B, P, self.high)
+        z = Gauss.ndtr(B, (high - mu) / sigma) - Gauss.ndtr(B, (low - mu) / sigma)
+        return mu, sigma, low, high, z
+
+    def unnorm(self, B, x, P, norm):
+        mu, sigma, low, high, z = self._parts(B, P)
+        t = (x - mu) / sigma
+        log_prob = -(B.const(0.5) * B.square(t) + B.const(0.5 * math.log(2.0 * math.pi)) + B.log(sigma) + B.log(z))
+        prob = B.exp(log_prob)
+        return B.where((x > high) | (x < low), B.zeros_like(prob), prob)
+
+    def integral(self, B, P, lo, hi, norm):
+        mu, sigma, low, high, z = self._parts(B, P)
+
+        def cdf(v):
+            c = (Gauss.ndtr(B, (B.const(v) - mu) / sigma) - Gauss.ndtr(B, (low - mu) / sigma)) / z
+            one, zero = B.const(1.0), B.const(0.0)
+            return B.where(c < zero, zero * c, B.where(c > one, one + zero * c, c))
+
+        return cdf(hi) - cdf(lo)
+
+
 class GeneralizedCB(_Leaf):
     """``zfit.pdf.GeneralizedCB`` (``src/zfit/models/physics.py:47-80,186-232``); ``DoubleCB`` = ``sigmal is sigmar``."""
 
@@ -567,7 +656,8 @@ def leaf_get_yield(pdf, B, P):
     return _val(B, P, pdf.yield_)
 
 
-for _cls in (Gauss, Exponential, CrystalBall, Chebyshev, Legendre, Chebyshev2, GeneralizedCB, GaussExpTail, GeneralizedGaussExpTail):
+for _cls in (Gauss, Exponential, CrystalBall, Chebyshev, Legendre, Chebyshev2, Bernstein, TruncatedGauss, GeneralizedCB,
+             GaussExpTail, GeneralizedGaussExpTail):
     _cls.get_yield = lambda self, B, P: _val(B, P, self.yield_)
 
 

@@ -244,6 +244,40 @@ def get_exp_case(generalized, n=100_000, seed=13):
                 [x], m, ["x"], kernel=f"Sum<{kern},Expo<0>>")
 
 
+def bernstein_case(n=100_000, seed=15):
+    """Gauss + Bernstein background (degree 3: in the catalogue)."""
+    rng = np.random.default_rng(seed)
+    lo, hi = -6.0, 8.0
+    x = _trunc(rng, lambda k: np.concatenate([rng.normal(1, 1.2, k // 3), rng.uniform(lo, hi, k - k // 3)]), lo, hi, n)
+    nodes = [
+        Z.Node(Z.SUM, 2, 0, 0, 0, 0, 0, 0, 0),
+        Z.Node(Z.GAUSS, 0, 0, 0, lo, hi, 0, 0, 0),
+        Z.Node(Z.BERNSTEIN, 0, 0, 3, lo, hi, lo, hi, 0),
+    ]
+    cn = ["b0", "b1", "b2", "b3"]
+    m = O.SumPDF([O.Gauss("mu", "sigma", "x", (lo, hi)), O.Bernstein(cn, "x", (lo, hi))], fracs=["f0", "f1"])
+    return Case("gauss_bernstein", nodes, ["f0", "f1", "mu", "sigma", *cn], [0.3, 0.7, 0.8, 1.3, 0.9, 1.2, 0.7, 1.05], [x], m, ["x"],
+                kernel="Sum<Gauss<0>,Bern<0,3>>")
+
+
+def tgauss_case(n=100_000, seed=16):
+    """TruncatedGauss + exponential: a third of the events lie outside [low, high], where only the background contributes."""
+    rng = np.random.default_rng(seed)
+    lo, hi = -6.0, 8.0
+    sig = _trunc(rng, lambda k: rng.normal(1.0, 1.5, k), -1.0, 3.5, int(0.4 * n))
+    bkg = _trunc(rng, lambda k: lo + rng.exponential(1 / 0.15, k), lo, hi, n - sig.size)
+    x = rng.permutation(np.concatenate([sig, bkg]))
+    nodes = [
+        Z.Node(Z.SUM, 2, 0, 0, 0, 0, 0, 0, 0),
+        Z.Node(Z.TGAUSS, 0, 0, 0, lo, hi, 0, 0, 0),
+        Z.Node(Z.EXP, 0, 0, 0, lo, hi, 0, 0, 0.5 * (lo + hi)),
+    ]
+    tg = O.TruncatedGauss("mu", "sigma", "low", "high", "x", (lo, hi))
+    m = O.SumPDF([tg, O.Exponential("lam", "x", (lo, hi))], fracs=["f0", "f1"])
+    return Case("tgauss_exp", nodes, ["f0", "f1", "mu", "sigma", "low", "high", "lam"], [0.35, 0.65, 0.8, 1.7, -1.0, 3.5, -0.12],
+                [x], m, ["x"], kernel="Sum<TGauss<0>,Expo<0>>")
+
+
 class _SumOfProducts:
     """SumPDF over N-D ProductPDFs (functor.py:197-206: sum_i frac_i * pdf_i.pdf(x))."""
 
@@ -271,4 +305,6 @@ ALL_CASES = {
     "cheb2": lambda **kw: poly_case("cheb2", **kw),
     "get_exp": lambda **kw: get_exp_case(False, **kw),
     "gget_exp": lambda **kw: get_exp_case(True, **kw),
+    "bernstein": bernstein_case,
+    "tgauss": tgauss_case,
 }

@@ -47,6 +47,11 @@ def _translate(nodes, obs, i, slot, in_prod):
         names = [f"s{slot + k}" for k in range(nd.degree + 1)]
         cls = {Z.CHEB: O.Chebyshev, Z.LEGENDRE: O.Legendre, Z.CHEB2: O.Chebyshev2}[nd.kind]
         return cls(names[1:], o, lim, coeff0=names[0]), i + 1, slot + nd.degree + 1
+    if nd.kind == Z.BERNSTEIN:
+        assert (nd.space_lo, nd.space_hi) == lim, "oracle translation needs norm == space for polynomials"
+        return O.Bernstein([f"s{slot + k}" for k in range(nd.degree + 1)], o, lim), i + 1, slot + nd.degree + 1
+    if nd.kind == Z.TGAUSS:
+        return O.TruncatedGauss(*[f"s{slot + k}" for k in range(4)], o, lim), i + 1, slot + 4
     if nd.kind == Z.GET:
         return O.GaussExpTail(f"s{slot}", f"s{slot + 1}", f"s{slot + 2}", o, lim), i + 1, slot + 3
     if nd.kind == Z.GGET:

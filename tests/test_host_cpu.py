@@ -117,6 +117,41 @@ def test_host_prologue_gaussexptail_family():
     assert abs(float(pdf.integrate((-8, 7))[0]) - 1.0) < 1e-13 and pdf._lower()[0][0].kind == Z.GGET
 
 
+def test_host_prologue_bernstein_and_truncated_gauss():
+    """SURVEY section 8f row 3, last two leaves: integrals + derivatives vs the oracle tape, lowering, validation."""
+    cn, cv = ["c0", "c1", "c2", "c3"], [0.8, 1.3, 0.4, 1.1]
+    for lo, hi in [(-10, 10), (-3, 7), (2.5, 9.0)]:
+        I, dI = Z.leaf_integral(Z.Node(Z.BERNSTEIN, 0, 0, 3, lo, hi, -10, 10, 0), cv)
+        rI, rdI = _autograd_integral(O.Bernstein(cn, "x", (-10, 10)), cn, cv, lo, hi, (lo, hi))
+        assert abs(I - rI) <= 1e-14 * abs(rI) and np.allclose(dI, rdI, rtol=1e-13)
+    tn = ["mu", "sigma", "low", "high"]
+    for vals, lo, hi in [([0.3, 1.2, -1.0, 2.0], -2, 3), ([0.3, 1.2, -5.0, 2.0], -2, 3), ([0.3, 1.2, -1.0, 8.0], -2, 3),
+                         ([0.3, 1.2, -5.0, 8.0], -2, 3), ([5280.0, 20.0, 5100.0, 5500.0], 5000, 5600)]:
+        I, dI = Z.leaf_integral(Z.Node(Z.TGAUSS, 0, 0, 0, lo, hi, 0, 0, 0), vals)
+        # the oracle's integral carries the truncation's own normaliser Z, which cancels in pdf = prob / integral:
+        # compare I / Z and the derivatives of ln(I / Z)... i.e. differentiate the oracle's  integral * Z
+        tg = O.TruncatedGauss(*tn, "x", (lo, hi))
+
+        class _TimesZ:
+            limits = (lo, hi)
+
+            def integral(self, B, P, a, b, norm):
+                return tg.integral(B, P, a, b, norm) * tg._parts(B, P)[4]
+
+        rI, rdI = _autograd_integral(_TimesZ(), tn, vals, lo, hi, (lo, hi))
+        assert abs(I - rI) <= 1e-14 * abs(rI)
+        np.testing.assert_allclose(dI, rdI, rtol=1e-11, atol=1e-14)
+    obs = zfit.Space("x", -2, 3)
+    tgp = zfit.pdf.TruncatedGauss(0.3, 1.2, -1.0, 2.0, obs)
+    assert abs(float(tgp.integrate((-2, 3))[0]) - 1.0) < 1e-13 and tgp._lower()[0][0].kind == Z.TGAUSS
+    bern = zfit.pdf.Bernstein(obs, cv)
+    nodes, slots = bern._lower()
+    assert nodes[0].kind == Z.BERNSTEIN and nodes[0].degree == 3 and len(slots) == 4 and bern.degree == 3
+    assert abs(float(bern.integrate((-2, 3))[0]) - 1.0) < 1e-13
+    with pytest.raises(ValueError, match="at least one coefficient"):
+        zfit.pdf.Bernstein(obs, [])
+
+
 def test_double_cb_shares_sigma_slot():
     obs = zfit.Space("m", 5000, 5600)
     mu, sigma = zfit.Parameter("mu_dcb", 5280.0), zfit.Parameter("sigma_dcb", 20.0)

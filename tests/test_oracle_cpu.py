@@ -199,3 +199,28 @@ def test_torch_and_numpy_backends_agree():
         idx, names, theta = c.free()
         b, _ = ON.value_and_gradient([c.oracle_model], [c.data], theta, names, weights=w)
         assert abs(a - b) < 1e-9 * abs(a)
+
+
+def test_bernstein_and_truncated_gauss_against_scipy():
+    """Known answers for the last two leaves of SURVEY section 8f row 3: scipy.interpolate.BPoly (the Bernstein basis) and
+    scipy.stats.truncnorm (the reference compares its TruncatedGauss with a Gauss x Uniform product, tests/test_pdfs.py)."""
+    from scipy import integrate, interpolate, stats
+
+    from oracle.backend import NumpyBackend
+
+    B = NumpyBackend()
+    x = np.linspace(-1.9, 2.9, 41)
+    c = {"c0": 0.8, "c1": 1.3, "c2": 0.4, "c3": 1.1}
+    bn = O.Bernstein(list(c), "x", (-2, 3))
+    bp = interpolate.BPoly(np.array(list(c.values()))[:, None], [-2, 3])
+    assert np.abs(bn.unnorm(B, x, c, None) - bp(x)).max() < 1e-15
+    assert abs(bn.integral(B, c, -1.0, 2.5, None) - integrate.quad(bp, -1.0, 2.5)[0]) < 1e-13
+    assert np.abs(bn.pdf(B, {"x": x}, c) - bp(x) / integrate.quad(bp, -2, 3)[0]).max() < 1e-14
+    P = {"mu": 0.3, "sigma": 1.2, "low": -1.0, "high": 2.0}
+    tg = O.TruncatedGauss("mu", "sigma", "low", "high", "x", (-2, 3))
+    ref = stats.truncnorm.pdf(x, (P["low"] - P["mu"]) / P["sigma"], (P["high"] - P["mu"]) / P["sigma"], loc=P["mu"], scale=P["sigma"])
+    assert np.abs(tg.pdf(B, {"x": x}, P) - ref).max() < 1e-15
+    inner = O.TruncatedGauss("mu", "sigma", "low", "high", "x", (-0.5, 1.5))  # norm range inside the truncation: plain Gauss
+    xs = np.array([0.0, 1.0])
+    gauss = stats.norm.pdf(xs, 0.3, 1.2) / (stats.norm.cdf(1.5, 0.3, 1.2) - stats.norm.cdf(-0.5, 0.3, 1.2))
+    assert np.abs(inner.pdf(B, {"x": xs}, P) - gauss).max() < 1e-15

@@ -29,8 +29,8 @@ class _Builder:
         sp = zfit.Space(obs, lo, hi)
         r = self.rng
         mid, wid = 0.5 * (lo + hi), hi - lo
-        kind = r.choice(["gauss", "expo", "cb", "cheb", "legendre", "get", "gcb"])
-        if kind in ("expo", "cheb", "legendre"):
+        kind = r.choice(["gauss", "expo", "cb", "cheb", "legendre", "get", "gcb", "bernstein", "tgauss"])
+        if kind in ("expo", "cheb", "legendre", "bernstein"):
             mu = sg = None
         else:
             mu = self.par(mid + 0.2 * wid * r.uniform(-1, 1), lo, hi)
@@ -45,6 +45,10 @@ class _Builder:
             deg = int(r.integers(1, 4))
             cs = [self.par(r.uniform(-0.15, 0.15), -1, 1) for _ in range(deg)]
             return (zfit.pdf.Chebyshev if kind == "cheb" else zfit.pdf.Legendre)(sp, cs)
+        if kind == "bernstein":
+            return zfit.pdf.Bernstein(sp, [self.par(r.uniform(0.5, 1.5), 0.01, 5) for _ in range(int(r.integers(2, 5)))])
+        if kind == "tgauss":  # the truncation keeps most of the range, so part of the events fall outside it
+            return zfit.pdf.TruncatedGauss(mu, sg, self.par(lo + 0.15 * wid, lo, mid), self.par(hi - 0.1 * wid, mid, hi), sp)
         if kind == "get":
             return zfit.pdf.GaussExpTail(mu, sg, self.par(r.uniform(0.5, 2.0), 0.1, 5), sp)
         return zfit.pdf.GeneralizedCB(
@@ -68,7 +72,7 @@ class _Builder:
         return zfit.pdf.SumPDF(kids, fracs=fracs)
 
 
-@pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106, 107, 108])
+@pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112])
 def test_random_tree_value_gradient_parity(seed):
     b = _Builder(seed)
     obs = list(OBS)[: 1 + seed % 3]

@@ -32,6 +32,8 @@ pdf = _types.SimpleNamespace(
     Chebyshev=_pdf_mod.Chebyshev,
     Legendre=_pdf_mod.Legendre,
     Chebyshev2=_pdf_mod.Chebyshev2,
+    Bernstein=_pdf_mod.Bernstein,
+    TruncatedGauss=_pdf_mod.TruncatedGauss,
     DoubleCB=_pdf_mod.DoubleCB,
     GeneralizedCB=_pdf_mod.GeneralizedCB,
     GaussExpTail=_pdf_mod.GaussExpTail,

@@ -15,6 +15,8 @@ static const ZnllCatalogEntry kEntries[] = {
     ZNLL_ENTRY(Sum<Gauss<0>,Chb2<0,2>>),
     ZNLL_ENTRY(Sum<GETail<0>,Expo<0>>),
     ZNLL_ENTRY(Sum<GGETail<0>,Expo<0>>),
+    ZNLL_ENTRY(Sum<Gauss<0>,Bern<0,3>>),
+    ZNLL_ENTRY(Sum<TGauss<0>,Expo<0>>),
 };
 static Registrar reg_c(kEntries, sizeof(kEntries) / sizeof(kEntries[0]));
 

@@ -330,6 +330,49 @@ struct Gauss {
   using Node = GaussN<COL, V>;
 };
 
+// TruncatedGauss (models/dist_tfp.py:357-417, tfp TruncatedNormal): the Gauss shape, zero outside [low, high]; the
+// truncation's own normaliser cancels against the integral over the norm range, which the host takes over the
+// intersection of the two intervals.  consts [1/sigma, -mu/sigma, -(0.5*ln(2pi)+ln sigma) - ln I, low, high];
+// slots [mu, sigma, low, high] (low / high only move the normalisation: no per-event derivative).
+template <int COL, class V>
+struct TGaussN {
+  typedef typename Lanes<V>::Mask Mask;
+  V t, P;
+  Mask out;
+
+  template <int CO>
+  ZNLL_DEV V fwd_log(const Ctx&, const double* __restrict__ c, const V* x, Mask&) {
+    t = zfma(x[COL], c[CO + 0], c[CO + 1]);
+    const double low = c[CO + 3], high = c[CO + 4];
+    out = Lanes<V>::mask(la(x[COL]) < low || la(x[COL]) > high, lb(x[COL]) < low || lb(x[COL]) > high);
+    // a huge negative log stands for "probability zero": exp() gives 0, sums and differences stay finite
+    return zsel(out, zbc<V>(-1e300), zfma(zmul(t, -0.5), t, c[CO + 2]));
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
+    Mask neg;
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    return P;
+  }
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
+    const V gi = zsel(out, zbc<V>(0.0), zmul(g, c[CO + 0]));
+    zacc(acc[AO + 0], gi, t);
+    zacc(acc[AO + 1], gi, zfma(t, t, -1.0));
+  }
+  template <int CO, int AO, class A>
+  ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
+    bwd_log<CO, AO>(zmul(a, P), c, acc);
+  }
+};
+template <int COL>
+struct TGauss {
+  static constexpr int NS = 4, NC = 5, COLMASK = 1 << COL;
+  static constexpr bool LOGNAT = true;
+  template <class V>
+  using Node = TGaussN<COL, V>;
+};
+
 // Exponential: consts [lambda, shift, -ln I];  slots [lambda]
 template <int COL, class V>
 struct ExpoN {
@@ -525,6 +568,7 @@ struct GGETail {
 
 // Orthogonal-polynomial sums of degree DEG (models/polynomials.py:46-175): slots [c_0 .. c_DEG]
 // consts [0 2/(hi-lo), 1 -(lo+hi)/(hi-lo), 2 1/I, 3.. c_k/I]
+// KIND 3: Bernstein basis B_{k,DEG}(t), t = (x - lo)/(hi - lo) (rescale_zero_one + de_casteljau, :872-905).
 // KIND 0: Chebyshev T_n (T_{n+1} = 2zT_n - T_{n-1}, polynomials.py:338-343); 1: Legendre
 // ((n+1)P_{n+1} = (2n+1)zP_n - nP_{n-1}, :181-190); 2: Chebyshev of the second kind U_n (U_1 = 2z, :487-560)
 template <int COL, int DEG, int KIND, class V>
@@ -536,6 +580,26 @@ struct PolyN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx&, const double* __restrict__ c, const V* x) {
     const V z = zfma(x[COL], c[CO + 0], c[CO + 1]);
+    if constexpr (KIND == 3) {  // Bernstein basis on t = z in [0, 1]: B_k = C(DEG, k) t^k (1 - t)^(DEG - k)
+      const V u = zfma(z, -1.0, 1.0);
+      V tp[DEG + 1], up[DEG + 1];
+      tp[0] = up[0] = zbc<V>(1.0);
+#pragma unroll
+      for (int k = 1; k <= DEG; ++k) {
+        tp[k] = zmul(tp[k - 1], z);
+        up[k] = zmul(up[k - 1], u);
+      }
+      V p = zbc<V>(0.0);
+      double binom = 1.0;
+#pragma unroll
+      for (int k = 0; k <= DEG; ++k) {
+        T[k] = zmul(zmul(tp[k], up[DEG - k]), binom);
+        p = zfma(T[k], c[CO + 3 + k], p);
+        binom = binom * (double)(DEG - k) / (double)(k + 1);
+      }
+      P = p;
+      return p;
+    }
     T[0] = zbc<V>(1.0);
     V p = zbc<V>(c[CO + 3]);
     const V z2 = zadd(z, z);
@@ -565,7 +629,10 @@ struct PolyN {
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     const V ai = zmul(a, c[CO + 2]);
-    zacc1(acc[AO + 0], ai);
+    if constexpr (KIND == 3)
+      zacc(acc[AO + 0], ai, T[0]);
+    else
+      zacc1(acc[AO + 0], ai);
 #pragma unroll
     for (int k = 1; k <= DEG; ++k) zacc(acc[AO + k], ai, T[k]);
   }
@@ -587,6 +654,8 @@ template <int COL, int DEG>
 using Legd = Poly<COL, DEG, 1>;
 template <int COL, int DEG>
 using Chb2 = Poly<COL, DEG, 2>;
+template <int COL, int DEG>
+using Bern = Poly<COL, DEG, 3>;  // Bernstein (models/polynomials.py:872-1028); consts [0], [1] map x to t in [0, 1]
 
 // Generalized (two-sided) CrystalBall (models/physics.py:47-80, 186-232): x < mu -> CrystalBall(mu, sigmal, alphal, nl),
 // else CrystalBall(mu, sigmar, -alphar, nr); DoubleCB is the same node with sigmal = sigmar = sigma.

@@ -94,6 +94,17 @@ static void gauss_integral(double mu, double sigma, double lo, double hi, double
   dI[1] = (zphi(zl, 1) - zphi(zh, 1)) / sigma;
 }
 
+// TruncatedGauss (dist_tfp.py:357-417 over tfp TruncatedNormal): the integral over [lo, hi] of the shape that is zero
+// outside [low, high] -- the truncation's own normaliser cancels in pdf/integral.  slots [mu, sigma, low, high]
+static void tgauss_integral(const double* s, double lo, double hi, double* I, double* dI) {
+  const double mu = s[0], sigma = s[1], low = s[2], high = s[3];
+  const bool cut_lo = low > lo, cut_hi = high < hi;
+  const double a = cut_lo ? low : lo, b = cut_hi ? high : hi;
+  gauss_integral(mu, sigma, a, b, I, dI);
+  dI[2] = cut_lo ? -zphi((a - mu) / sigma, 0) / sigma : 0.0;
+  dI[3] = cut_hi ? zphi((b - mu) / sigma, 0) / sigma : 0.0;
+}
+
 // src/zfit/models/basic.py:211-229 (shifted raw integral)
 static void exp_integral(double lam, double lo, double hi, double s, double* I, double* dI) {
   const double eh = exp(lam * (hi - s)), el = exp(lam * (lo - s));
@@ -202,6 +213,29 @@ static void cb_integral(double mu, double sigma, double alpha, double n, double 
 static void poly_integral(int kind, const double* c, int deg, double lo, double hi, double slo, double shi, double* I,
                           double* dI) {
   if (kind == ZNLL_CHEB) return cheb_integral(c, deg, lo, hi, slo, shi, I, dI);
+  if (kind == ZNLL_BERNSTEIN) {
+    // polynomials.py:1000-1025: int_0^t B_{k,m} = (1/(m+1)) sum_{j>k} B_{j,m+1}(t); times the volume of the space
+    const int m1 = deg + 1;
+    auto basis = [&](double t, double* B) {  // B_{j,m1}(t), j = 0..m1
+      double binom = 1.0;
+      for (int j = 0; j <= m1; ++j) {
+        B[j] = binom * pow(t, j) * pow(1.0 - t, m1 - j);
+        binom = binom * (double)(m1 - j) / (double)(j + 1);
+      }
+    };
+    std::vector<double> Bu(m1 + 1), Bl(m1 + 1);
+    basis((hi - slo) / (shi - slo), Bu.data());
+    basis((lo - slo) / (shi - slo), Bl.data());
+    double integral = 0.0;
+    for (int k = 0; k <= deg; ++k) {
+      double j = 0.0;
+      for (int q = k + 1; q <= m1; ++q) j += Bu[q] - Bl[q];
+      dI[k] = j / (double)m1 * (shi - slo);
+      integral += c[k] * dI[k];
+    }
+    *I = integral;
+    return;
+  }
   const double zl = (2.0 * lo - slo - shi) / (shi - slo), zu = (2.0 * hi - slo - shi) / (shi - slo);
   std::vector<double> Pu(deg + 3), Pl(deg + 3), J(deg + 1);
   if (kind == ZNLL_LEGENDRE) {
@@ -321,7 +355,9 @@ static int leaf_n_slots(const znll_node& nd) {
     case ZNLL_CB: return 4;
     case ZNLL_CHEB:
     case ZNLL_LEGENDRE:
-    case ZNLL_CHEB2: return nd.degree + 1;
+    case ZNLL_CHEB2:
+    case ZNLL_BERNSTEIN: return nd.degree + 1;
+    case ZNLL_TGAUSS: return 4;
     case ZNLL_GCB: return 7;
     case ZNLL_GET: return 3;
     case ZNLL_GGET: return 5;
@@ -335,7 +371,9 @@ static int leaf_n_consts(const znll_node& nd) {
     case ZNLL_CB: return 13;
     case ZNLL_CHEB:
     case ZNLL_LEGENDRE:
-    case ZNLL_CHEB2: return 3 + nd.degree + 1;
+    case ZNLL_CHEB2:
+    case ZNLL_BERNSTEIN: return 3 + nd.degree + 1;
+    case ZNLL_TGAUSS: return 5;
     case ZNLL_GCB: return 24;
     case ZNLL_GET: return 7;
     case ZNLL_GGET: return 12;
@@ -350,7 +388,9 @@ static int leaf_integral(const znll_node& nd, const double* s, double* I, double
     case ZNLL_CB: cb_integral(s[0], s[1], s[2], s[3], nd.norm_lo, nd.norm_hi, I, dI); return 0;
     case ZNLL_CHEB:
     case ZNLL_LEGENDRE:
-    case ZNLL_CHEB2: poly_integral(nd.kind, s, nd.degree, nd.norm_lo, nd.norm_hi, nd.space_lo, nd.space_hi, I, dI); return 0;
+    case ZNLL_CHEB2:
+    case ZNLL_BERNSTEIN: poly_integral(nd.kind, s, nd.degree, nd.norm_lo, nd.norm_hi, nd.space_lo, nd.space_hi, I, dI); return 0;
+    case ZNLL_TGAUSS: tgauss_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
     case ZNLL_GCB: gcb_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
     case ZNLL_GET: get_integral(s[0], s[1], s[2], nd.norm_lo, nd.norm_hi, I, dI); return 0;
     case ZNLL_GGET: gget_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
@@ -460,7 +500,9 @@ static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int par
   const int ns = leaf_n_slots(nd), nc = leaf_n_consts(nd);
   if (ns < 0 || nd.n_children != 0) return -1;
   if (nd.column < 0 || nd.column >= ZNLL_MAX_COLS) return -1;
-  if ((nd.kind == ZNLL_CHEB || nd.kind == ZNLL_LEGENDRE || nd.kind == ZNLL_CHEB2) && (nd.degree < 0 || nd.degree > 16)) return -1;
+  if ((nd.kind == ZNLL_CHEB || nd.kind == ZNLL_LEGENDRE || nd.kind == ZNLL_CHEB2 || nd.kind == ZNLL_BERNSTEIN) &&
+      (nd.degree < 0 || nd.degree > 16))
+    return -1;
   c.n_slots += ns;
   c.n_consts += nc;
   c.nodes.push_back(ni);
@@ -473,6 +515,8 @@ static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int par
     case ZNLL_GGET: snprintf(buf, sizeof buf, "GGETail<%d>", nd.column); break;
     case ZNLL_LEGENDRE: snprintf(buf, sizeof buf, "Legd<%d,%d>", nd.column, nd.degree); break;
     case ZNLL_CHEB2: snprintf(buf, sizeof buf, "Chb2<%d,%d>", nd.column, nd.degree); break;
+    case ZNLL_BERNSTEIN: snprintf(buf, sizeof buf, "Bern<%d,%d>", nd.column, nd.degree); break;
+    case ZNLL_TGAUSS: snprintf(buf, sizeof buf, "TGauss<%d>", nd.column); break;
     default: snprintf(buf, sizeof buf, "Cheb<%d,%d>", nd.column, nd.degree); break;
   }
   name += buf;
@@ -574,6 +618,22 @@ static void fill_consts(Channel& c, const double* slots) {
           q[9] = n / (a * a) + 1.0;
           q[10] = alpha > 0 ? 1.0 : (alpha < 0 ? -1.0 : 0.0);
         }
+        break;
+      }
+      case ZNLL_TGAUSS: {
+        const double mu = s[0], sigma = s[1];
+        k[0] = 1.0 / sigma;
+        k[1] = -(mu / sigma);
+        k[2] = -(kHalfLog2Pi + log(sigma)) - lnI;
+        k[3] = s[2];
+        k[4] = s[3];
+        break;
+      }
+      case ZNLL_BERNSTEIN: {
+        k[0] = 1.0 / (nd.space_hi - nd.space_lo);
+        k[1] = -nd.space_lo / (nd.space_hi - nd.space_lo);
+        k[2] = 1.0 / I;
+        for (int i = 0; i <= nd.degree; ++i) k[3 + i] = s[i] / I;
         break;
       }
       case ZNLL_CHEB:
@@ -686,7 +746,9 @@ static std::mutex g_mu;
 static std::map<std::string, Kernel> g_cache;
 
 // compile nll_kernel<Model, W, G> for the four (W, G) variants
-static int build(const std::string& model, Kernel* out) {
+// n_slots decides whether the covariance-pass kernels are instantiated: with 2 + NS + (NS+1)(NS+2)/2 > 256 accumulators
+// they would not fit the reduction's shared memory (znll_eval_cov refuses such trees), and must not break the build.
+static int build(const std::string& model, int n_slots, Kernel* out) {
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_cache.find(model);
   if (it != g_cache.end()) {
@@ -725,8 +787,11 @@ static int build(const std::string& model, Kernel* out) {
   const std::string pdf_expr = "znll::pdf_kernel<" + q + ">";
   a.addname(prog, pdf_expr.c_str());
   const std::string cov_expr[2] = {"znll::cov_kernel<" + q + ",false>", "znll::cov_kernel<" + q + ",true>"};
-  a.addname(prog, cov_expr[0].c_str());
-  a.addname(prog, cov_expr[1].c_str());
+  const bool with_cov = 2 + n_slots + (n_slots + 1) * (n_slots + 2) / 2 <= 256;
+  if (with_cov) {
+    a.addname(prog, cov_expr[0].c_str());
+    a.addname(prog, cov_expr[1].c_str());
+  }
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const int rc = a.compile(prog, 3, opts);
   if (rc) {
@@ -767,7 +832,7 @@ static int build(const std::string& model, Kernel* out) {
       return fail("cuModuleGetFunction failed for '%s'", pdf_expr.c_str());
     }
   }
-  for (int w = 0; w < 2; ++w) {
+  for (int w = 0; w < 2 && with_cov; ++w) {
     const char* low = nullptr;
     a.lowered(prog, cov_expr[w].c_str(), &low);
     if (!low || a.getfn(&k.cufunc_cov[w], mod, low)) {
@@ -874,7 +939,7 @@ int znll_plan_set_model(znll_plan* p, int ch, const znll_node* nodes, int n_node
     k.origin = 1;
     k.aot = e;
   } else {
-    if (rtc::build(name, &k)) return 1;
+    if (rtc::build(name, c.n_slots, &k)) return 1;
   }
   c.kernel = k;
   if (c.d_partials) cudaFree(c.d_partials), c.d_partials = nullptr;

@@ -339,6 +339,18 @@ class Gauss(_Leaf1D):
         super().__init__(obs, params, extended=extended, norm=norm, name=name, label=label)
 
 
+class TruncatedGauss(_Leaf1D):
+    """``zfit.pdf.TruncatedGauss(mu, sigma, low, high, obs, ...)`` (``models/dist_tfp.py:357-417``): the Gauss shape,
+    zero outside ``[low, high]``."""
+
+    _KIND = Z.TGAUSS
+
+    def __init__(self, mu, sigma, low, high, obs, *, extended=None, norm=None, name="TruncatedGauss", label=None):
+        params = {"mu": convert_to_parameter(mu), "sigma": convert_to_parameter(sigma),
+                  "low": convert_to_parameter(low), "high": convert_to_parameter(high)}
+        super().__init__(obs, params, extended=extended, norm=norm, name=name, label=label)
+
+
 class Exponential(_Leaf1D):
     """``zfit.pdf.Exponential(lam=None, obs=None, *, extended, norm, name, lambda_=None, label)``
     (``models/basic.py:34-243``)."""
@@ -432,6 +444,41 @@ class Chebyshev2(_RecursivePolynomial):
     """``zfit.pdf.Chebyshev2`` -- second kind, ``U_1 = 2x`` (``models/polynomials.py:487-600``)."""
 
     _KIND = Z.CHEB2
+
+
+class Bernstein(_Leaf1D):
+    """``zfit.pdf.Bernstein(obs, coeffs, apply_scaling=True, *, extended, norm, name, label)``
+    (``models/polynomials.py:872-1028``): ``sum_k c_k B_{k,n}(t)`` with ``t`` the observable rescaled to ``(0, 1)``; every
+    coefficient is a parameter (there is no implicit ``c_0 = 1``)."""
+
+    _KIND = Z.BERNSTEIN
+
+    def __init__(self, obs, coeffs, apply_scaling=True, *, extended=None, norm=None, name="Bernstein", label=None):
+        if not apply_scaling:
+            msg = "Bernstein without rescaling is not lowered to the fused kernel"
+            raise ModelNotOnDeviceError(msg)
+        space = obs if isinstance(obs, Space) else Space(obs)
+        if not space.has_limits:
+            msg = "obs need to be a Space with exactly one limit if rescaling is requested."
+            raise ValueError(msg)
+        coeffs = [coeffs] if isinstance(coeffs, (ZfitParameter, int, float)) else list(coeffs)
+        if len(coeffs) < 1:
+            msg = "Need at least one coefficient in de_casteljau of Bernstein."
+            raise ValueError(msg)
+        if len(coeffs) - 1 > 16:
+            msg = "polynomial degree > 16 is not supported by the fused kernel"
+            raise ModelNotOnDeviceError(msg)
+        self._degree = len(coeffs) - 1
+        super().__init__(space, {f"c_{i}": convert_to_parameter(c) for i, c in enumerate(coeffs)}, extended=extended,
+                         norm=norm, name=name, label=label)
+
+    @property
+    def degree(self):
+        return self._degree
+
+    def _node(self, column, lo, hi, shift):
+        slo, shi = self._space.limit1d
+        return Z.Node(self._KIND, 0, column, self._degree, lo, hi, slo, shi, 0.0)
 
 
 class GeneralizedCB(_Leaf1D):
