@@ -103,6 +103,36 @@ def test_ragged_sizes(n):
         assert abs(g[i] - og[j]) <= 1e-9 * max(1.0, np.abs(og).max())
 
 
+@pytest.mark.parametrize("n", [1, 2, 511, 512, 513, 10_001])
+def test_no_value_outside_the_bound_range_is_consumed(n):
+    """Canary check (compute-sanitizer is not available on the pool): the bound columns sit inside larger buffers whose
+    surroundings are NaN; a read past either end that reached the arithmetic would poison value, gradient or the
+    covariance pass.  Results must equal those of tightly allocated copies bit for bit."""
+    import torch
+
+    case = ALL_CASES["product"](n=12_000)  # three columns: exercises the two-buffer loop
+    pad = 64
+    tight, padded, keep = [], [], []
+    for c in case.cols:
+        buf = torch.full((n + 2 * pad,), float("nan"), dtype=torch.float64, device="cuda:0")
+        buf[pad : pad + n] = torch.from_numpy(np.ascontiguousarray(c[:n])).cuda()
+        keep.append(buf)
+        padded.append(buf[pad : pad + n])
+        tight.append(buf[pad : pad + n].clone())
+    out = []
+    for cols in (tight, padded):
+        plan = Z.Plan(1)
+        plan.set_model(0, case.nodes)
+        torch.cuda.synchronize()
+        plan.bind_device_ptrs(0, [c.data_ptr() for c in cols], 0, n)
+        v, g = plan.eval(case.slots, grad=True)
+        _, _, mats = plan.eval_cov(case.slots)
+        out.append((float(v[0]), np.array(g), np.array(mats[0])))
+        plan.close()
+    assert np.isfinite(out[1][0]) and np.all(np.isfinite(out[1][1])) and np.all(np.isfinite(out[1][2]))
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
 def test_nan_propagates_not_raises():
     # negative Chebyshev pdf -> log of a negative number -> NaN must reach the caller (evaluation.py:212-227)
     case = ALL_CASES["gauss_cheb"](n=5000)
