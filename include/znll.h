@@ -170,6 +170,10 @@ size_t znll_plan_exchange_bytes(const znll_plan* plan, int world);
 /* Per-event normalised pdf values of channel ch on its bound events: out_host[n_events].
  * Replaces BasePDF.pdf (core/basepdf.py:398-429) for plotting / diagnostics; not on the fit's hot path. */
 int znll_pdf(znll_plan* plan, int ch, const double* slots, double* out_host, void* stream);
+/* Same values into a caller-owned DEVICE buffer of n_events doubles, launched on `stream` without synchronising: the
+ * accept-reject step of on-device toy generation (replaces the pdf evaluation inside accept_reject_sample,
+ * core/sample.py:148-566, for SamplerData.resample, core/data.py:1563-1599). */
+int znll_pdf_device(znll_plan* plan, int ch, const double* slots, double* out_dev, void* stream);
 
 /* Host-only helpers (no GPU needed): normalisation integral of one leaf and d I / d slot, exactly
  * as the per-call prologue computes them.  Replaces the registered analytic integrals

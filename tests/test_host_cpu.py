@@ -641,3 +641,29 @@ def test_constraints_values_and_partials():
             assert abs(ana[leaf] - num[leaf]) < 1e-6 * max(1.0, abs(num[leaf]))
     with pytest.raises(ValueError):
         zfit.constraint.GaussianConstraint([a], observation=[1.0], sigma=[0.1], cov=[0.01])
+
+
+def test_update_data_in_place_invalidates_binding_and_offset():
+    """``Data.update_data`` (what ``SamplerData.resample`` calls, data.py:1031-1060, 1563-1599): a loss holding the Data
+    sees the new events, and its automatic offset is recomputed (``is_precompiled``, loss.py:247-262)."""
+    rng = np.random.default_rng(5)
+    obs = zfit.Space("x", -5, 5)
+    mu, sigma = zfit.Parameter("mu_upd", 0.2, -2, 2), zfit.Parameter("sigma_upd", 1.1, 0.2, 4)
+    model = zfit.pdf.Gauss(mu, sigma, obs)
+    data = zfit.Data(rng.normal(0.0, 1.0, 3000), obs=obs)
+    nll = use_oracle(zfit.loss.UnbinnedNLL(model, data))
+    h0 = data.hashint
+    v0 = nll.value(full=False)
+    off0 = nll.options["subtr_const_value"]
+    assert abs(v0 - 10000.0) < 1e-6
+    x2 = rng.normal(0.5, 1.3, 2500)
+    data.update_data(x2)
+    assert data.hashint != h0 and data.num_entries == np.sum(np.abs(x2) <= 5)
+    v1 = nll.value(full=False)
+    assert abs(v1 - 10000.0) < 1e-6 and nll.options["subtr_const_value"] != off0  # offset recomputed for the new sample
+    fresh = use_oracle(zfit.loss.UnbinnedNLL(model, zfit.Data(x2, obs=obs)))
+    assert abs(nll.value(full=True) - fresh.value(full=True)) < 1e-9
+    g1, g2 = nll.gradient(), fresh.gradient()
+    np.testing.assert_allclose(g1, g2, rtol=1e-12)
+    with pytest.raises(ValueError, match="same length"):
+        data.update_data(x2, weights=np.ones(3))

@@ -17,7 +17,7 @@ from . import minimize as _min_mod
 from . import parameter as _param_mod
 from . import pdf as _pdf_mod
 from .constraint import GaussianConstraint, LogNormalConstraint, PoissonConstraint, SimpleConstraint
-from .data import Data, convert_to_data
+from .data import Data, SamplerData, convert_to_data
 from .parameter import ComposedParameter, ConstantParameter, Parameter, convert_to_parameter
 from .settings import run, ztypes
 from .space import Space, combine_spaces, convert_to_space
@@ -66,7 +66,7 @@ param = _types.SimpleNamespace(
     set_values=_param_mod.set_values,
     assign_values=_param_mod.assign_values,
 )
-data = _types.SimpleNamespace(Data=Data, concat=_data_mod.concat, convert_to_data=convert_to_data)
+data = _types.SimpleNamespace(Data=Data, SamplerData=SamplerData, concat=_data_mod.concat, convert_to_data=convert_to_data)
 constraint = _types.SimpleNamespace(
     GaussianConstraint=GaussianConstraint,
     PoissonConstraint=PoissonConstraint,

@@ -72,6 +72,7 @@ SYMBOLS = {
     "znll_plan_exchange_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "znll_eval_cov": (C.c_int, [C.c_void_p, _DP, C.c_double, _DP, _DP, _DP, C.c_void_p]),
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
+    "znll_pdf_device": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_void_p, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
     "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
     "znll_fp64_peak": (C.c_int, [C.c_int, C.c_double, _DP]),
@@ -232,6 +233,11 @@ class Plan:
         out = np.empty(n, dtype=np.float64)
         _check(lib().znll_pdf(self._h, ch, _dptr(slots), _dptr(out), C.c_void_p(stream)))
         return out
+
+    def pdf_values_device(self, ch: int, slots, out_ptr: int, stream=0):
+        """Per-event pdf values into a caller-owned device buffer (asynchronous on ``stream``)."""
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        _check(lib().znll_pdf_device(self._h, ch, _dptr(slots), C.c_void_p(out_ptr), C.c_void_p(stream)))
 
     def launch(self, slots, *, grad=True, log_offset=0.0, stream=0):
         slots = np.ascontiguousarray(slots, dtype=np.float64)

@@ -1280,17 +1280,11 @@ int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* 
   return 0;
 }
 
-int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* stream) {
-  if (!p || ch < 0 || ch >= (int)p->ch.size() || !slots || !out_host) return fail("znll_pdf: bad arguments");
-  CUDA_OK(cudaSetDevice(p->device));
+// launches pdf_kernel of channel ch into a device buffer of c.n doubles (no synchronisation)
+static int pdf_launch(znll_plan* p, int ch, const double* slots, double* d_out, cudaStream_t st) {
   Channel& c = p->ch[ch];
-  if (c.nodes.empty() || !c.bound) return fail("znll_pdf: channel without model or data");
-  if (c.n == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;  // NULL is the (legacy) default stream
   c.slots.assign(slots, slots + c.n_slots);
   fill_consts(c, c.slots.data());
-  double* d_out = nullptr;
-  CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (size_t)c.n));
   ZnllLaunchArgs la;
   for (int i = 0; i < ZNLL_MAX_COLS; ++i) la.cols[i] = c.cols[i];
   la.w = c.w;
@@ -1310,6 +1304,19 @@ int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* 
     rc = rtc::launch_fn(c.kernel.cufunc_pdf, c.kernel.name.c_str(), la, c.consts.data(), c.n_consts, (int)g, st);
   }
   p->launches++;
+  return rc;
+}
+
+int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* stream) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size() || !slots || !out_host) return fail("znll_pdf: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  Channel& c = p->ch[ch];
+  if (c.nodes.empty() || !c.bound) return fail("znll_pdf: channel without model or data");
+  if (c.n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the (legacy) default stream
+  double* d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (size_t)c.n));
+  const int rc = pdf_launch(p, ch, slots, d_out, st);
   cudaError_t e = cudaSuccess;
   if (!rc) e = cudaMemcpyAsync(out_host, d_out, sizeof(double) * (size_t)c.n, cudaMemcpyDeviceToHost, st);
   if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1317,6 +1324,15 @@ int znll_pdf(znll_plan* p, int ch, const double* slots, double* out_host, void* 
   if (rc) return rc;
   if (e != cudaSuccess) return fail("znll_pdf: %s", cudaGetErrorString(e));
   return 0;
+}
+
+int znll_pdf_device(znll_plan* p, int ch, const double* slots, double* out_dev, void* stream) {
+  if (!p || ch < 0 || ch >= (int)p->ch.size() || !slots || !out_dev) return fail("znll_pdf_device: bad arguments");
+  CUDA_OK(cudaSetDevice(p->device));
+  Channel& c = p->ch[ch];
+  if (c.nodes.empty() || !c.bound) return fail("znll_pdf_device: channel without model or data");
+  if (c.n == 0) return 0;
+  return pdf_launch(p, ch, slots, out_dev, (cudaStream_t)stream);
 }
 
 int znll_leaf_integral(const znll_node* leaf, const double* slots, double* integral, double* dintegral) {

@@ -5,7 +5,8 @@ optional 1-D weight column -- the layout the fused kernel reads with coalesced `
 Columns live either on the host (numpy) or already on the GPU (torch CUDA tensors; torch is used
 for device memory only).  Events outside the limits of ``obs`` are dropped once, at construction,
 inclusive on both ends (``check_cut_data_weights``, ``data.py:1203-1244``; ``space.py:229-230``).
-``SamplerData``, ``from_root``, binning are out of scope.
+``SamplerData`` (``data.py:1247-1606``) is the in-place resampled dataset of toy studies; its events are generated on the
+GPU (``sampler.py``).  ``from_root`` and binning are out of scope.
 """
 
 from __future__ import annotations
@@ -57,6 +58,7 @@ class Data:
         self.name = name or "Data"
         self.label = label or self.name
         self._dev_cache = None
+        self._version = 0
 
     # ------------------------------------------------------------------ ingestion
     @staticmethod
@@ -180,7 +182,25 @@ class Data:
 
     @property
     def hashint(self):
-        return id(self)
+        """Changes whenever the events change (``update_data``): losses re-bind and recompute their offset
+        (``loss.py:247-262``)."""
+        return hash((id(self), self._version))
+
+    def update_data(self, sample, weights=None, *, guarantee_limits=False):
+        """Replace the events in place (``data.py:1031-1060``); objects holding this Data see the new sample."""
+        cols, weights = self._ingest(sample, self._space, weights)
+        if len(cols) != self._space.n_obs:
+            msg = f"data has {len(cols)} columns but obs {self._space.obs} has {self._space.n_obs}"
+            raise ShapeIncompatibleError(msg)
+        n = int(cols[0].shape[0]) if cols else 0
+        if weights is not None and int(weights.shape[0]) != n:
+            msg = f"Weights have to have the same length as the data, not {int(weights.shape[0])} != {n}."
+            raise ValueError(msg)
+        if self._space.has_limits and not guarantee_limits and n > 0:
+            cols, weights = _cut(cols, weights, self._space)
+        self._cols, self._weights = cols, weights
+        self._dev_cache = None
+        self._version += 1
 
     def __len__(self):
         return self.num_entries
@@ -236,6 +256,7 @@ class Data:
         new._space = space
         new.name, new.label = self.name, self.label
         new._dev_cache = None
+        new._version = 0
         if isinstance(obs, Space) and obs.has_limits and obs != self._space.with_obs(names) and not guarantee_limits:
             new._cols, new._weights = _cut(new._cols, new._weights, obs)
         return new
@@ -248,6 +269,7 @@ class Data:
             msg = "Weights have to have the same length as the data"
             raise ValueError(msg)
         new._dev_cache = None
+        new._version = 0
         return new
 
     def to_pandas(self, obs=None, weightsname=None):
@@ -334,6 +356,36 @@ def _upload_numpy(a, dev):
         if want != prev:
             torch.set_num_threads(prev)
     return out
+
+
+class SamplerData(Data):
+    """``SamplerData`` (``data.py:1247-1606``): a Data whose events are drawn from a pdf and re-drawn in place by
+    ``resample``.  The parameter values used for sampling are those at creation (``fixed_params``) unless overridden per
+    call.  Events are generated, accepted and kept on the GPU; a loss built on it re-binds without any host copy."""
+
+    def __init__(self, sampler, n, *, fixed_params, obs, name=None, label=None):
+        self._sampler = sampler
+        self._n = n
+        self.params = dict(fixed_params)
+        super().__init__(sampler.draw(n, self.params), obs=obs, name=name or "SamplerData", label=label, guarantee_limits=True)
+
+    @property
+    def n(self):
+        return self._n
+
+    def resample(self, params=None, *, n=None, param_values=None):
+        if param_values is not None:
+            if params is not None:
+                msg = "Cannot specify both `fixed_params` and `params`."
+                raise ValueError(msg)
+            params = param_values
+        values = dict(self.params)
+        if params is not None:
+            byname = {p.name: p for p in values}
+            for k, v in dict(params).items():
+                key = byname.get(k, k) if isinstance(k, str) else k
+                values[key] = float(v.value() if hasattr(v, "value") and callable(v.value) else v)
+        self.update_data(self._sampler.draw(self._n if n is None else n, values), guarantee_limits=True)
 
 
 def _as_col(x):

@@ -63,6 +63,7 @@ def shard(data, r: int | None = None, world: int | None = None):
     new._weights = None if data._weights is None else data._weights[start:stop]
     new._space, new.name, new.label = data._space, data.name, data.label
     new._dev_cache = None
+    new._version = 0
     return new
 
 

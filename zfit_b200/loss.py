@@ -90,6 +90,7 @@ class CudaEngine:
             self.n_local.append(n)
         self.samplesize = [self.plan.sumw(k) for k in range(len(models))]
         self.n_entries = list(self.n_local)
+        self._bind_args = (list(models), list(fit_ranges), sort_events)
         if self.distributed:
             t = torch.tensor(self.samplesize + [float(n) for n in self.n_local], dtype=torch.float64, device=f"cuda:{device}")
             _dist.all_reduce_sum_(t, deterministic=True)
@@ -109,6 +110,29 @@ class CudaEngine:
             if self.reduce_mode == "nccl":
                 self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
         self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
+
+    def rebind(self, datas):
+        """The events of the bound ``Data`` objects changed in place (``SamplerData.resample``): bind the new columns to
+        the existing plan -- same compiled kernels, no host copy when the data was born on the device."""
+        if self.distributed:
+            msg = "in-place resampling of a sharded loss is not supported"
+            raise NotImplementedError(msg)
+        models, fit_ranges, sort_events = self._bind_args
+        torch = self.torch
+        self._keep = []
+        for k, (model, data, rng) in enumerate(zip(models, datas, fit_ranges)):
+            if rng is not None:
+                data = data.with_obs(rng, guarantee_limits=False)
+            cols, w = data.device_columns(self.device)
+            n = data.num_entries
+            if sort_events and n > 1:
+                cols, w = self._sort_for_coherence(model, data, cols, w)
+            self._keep.append((cols, w))
+            torch.cuda.synchronize(self.device)
+            self.plan.bind_device_ptrs(k, [c.data_ptr() for c in cols], 0 if w is None else w.data_ptr(), n)
+            self.n_local[k] = n
+        self.samplesize = [self.plan.sumw(k) for k in range(len(models))]
+        self.n_entries = list(self.n_local)
 
     def _sort_for_coherence(self, model, data, cols, w):
         """Events are static for the whole fit and the NLL is a sum, so they may be reordered once at bind
@@ -219,6 +243,7 @@ class BaseLoss:
         self._errordef = None
         self._engine = None
         self._engine_factory = None
+        self._data_hashes = None
         self._all_params = None
         self._slot_plan = None
         self._assert_params_unique()
@@ -360,7 +385,22 @@ class BaseLoss:
         return params
 
     # ------------------------------------------------------------------ engine
+    def _check_data_changed(self):
+        """The events of a bound Data changed in place (``SamplerData.resample``): re-bind them, and the automatic offset
+        is stale (``is_precompiled``, ``loss.py:247-262``)."""
+        hashes = [d.hashint for d in self.data]
+        if self._engine is not None and hashes != self._data_hashes:
+            if hasattr(self._engine, "rebind"):
+                self._engine.rebind(self.data)
+            else:
+                self._engine = None
+            if self._options.get("subtr_const") is True:
+                self._options["subtr_const_value"] = None
+            self._options["_precompiled"] = False
+        self._data_hashes = hashes
+
     def _get_engine(self):
+        self._check_data_changed()
         if self._engine is None:
             if self._engine_factory is not None:
                 self._engine = self._engine_factory(self.model, self.data, self.fit_range)
@@ -479,6 +519,7 @@ class BaseLoss:
 
     # ------------------------------------------------------------------ offsets (loss.py:383-411)
     def check_precompile(self, *, params=None, force=False):
+        self._check_data_changed()
         if self._options.get("_precompiled") and not force:
             return params, False
         with self._check_set_input_params(params):

@@ -262,6 +262,30 @@ class BasePDF:
                 out = np.concatenate([out, cand[rng.uniform(0, pmax, size=p.shape) < p]])
         return Data(out[:n], obs=limits, guarantee_limits=True)
 
+    def create_sampler(self, n=None, limits=None, *, fixed_params=True, params=None):
+        """``BasePDF.create_sampler`` (``core/basepdf.py``, ``core/data.py:1247-1606``): a ``SamplerData`` drawn from this
+        pdf that ``resample()`` re-draws in place -- on the GPU, with the tree's own ``pdf_kernel`` as the density.
+        ``fixed_params=True`` freezes the current parameter values for all later resamples (the reference's default)."""
+        from .data import SamplerData
+        from .sampler import DeviceSampler
+
+        limits = self._space if limits is None else (limits if isinstance(limits, Space) else self._space.with_limits(limits))
+        if n is None and not self.is_extended:
+            msg = "n has to be given for a non-extended pdf"
+            raise ValueError(msg)
+        allp = list(self.get_params(floating=None, is_yield=None))
+        if fixed_params is True:
+            fixed = {p: p.value() for p in allp}
+        elif fixed_params is False or fixed_params is None:
+            fixed = {}
+        else:
+            fixed = {p: p.value() for p in fixed_params}
+        if params is not None:
+            byname = {p.name: p for p in allp}
+            for k, v in dict(params).items():
+                fixed[byname[k] if isinstance(k, str) else k] = float(v)
+        return SamplerData(DeviceSampler(self, limits), n, fixed_params=fixed, obs=limits)
+
     def __repr__(self):
         return f"<zfit.pdf.{type(self).__name__} name={self.name} obs={self.obs} params={[p.name for p in self._params.values()]}>"
 

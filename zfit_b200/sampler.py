@@ -1,0 +1,93 @@
+"""On-device toy generation (reference: ``accept_reject_sample`` / ``UniformSampleAndWeights``,
+``src/zfit/core/sample.py:148-566``, driven by ``BasePDF.create_sampler`` / ``SamplerData.resample``,
+``core/basepdf.py`` / ``core/data.py:1563-1599``).
+
+Accept-reject with uniform proposals, entirely on the GPU: torch's generator fills a fixed proposal buffer per observable,
+the model tree's ``pdf_kernel`` (the same compiled tree the likelihood uses) writes the densities into a device buffer
+(``znll_pdf_device``), and the accepted events are compacted with a boolean mask.  The only host traffic per batch is the
+accepted count.  The envelope starts at 1.2 x the largest density seen and is raised -- and the sample restarted -- if a
+proposal ever exceeds it, so the result is an unbiased sample (the reference re-weights instead, ``sample.py:440-505``).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _znll as Z
+
+
+class DeviceSampler:
+    def __init__(self, pdf, limits, *, device=None, batch=1 << 20):
+        import torch
+
+        from . import distributed as _dist
+
+        self.torch = torch
+        self.pdf = pdf
+        self.limits = limits
+        self.device = _dist.local_device() if device is None else device
+        self.batch = int(batch)
+        dev = torch.device("cuda", self.device)
+        self.lower = [float(v) for v in np.atleast_1d(limits._lower).ravel()]
+        self.upper = [float(v) for v in np.atleast_1d(limits._upper).ravel()]
+        nodes, self.slot_params = pdf._lower(limits.obs, None)
+        self.plan = Z.Plan(1, device=self.device)
+        self.plan.set_model(0, nodes)
+        self.cols = [torch.empty(self.batch, dtype=torch.float64, device=dev) for _ in limits.obs]
+        self.pvals = torch.empty(self.batch, dtype=torch.float64, device=dev)
+        self.unif = torch.empty(self.batch, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(self.device)
+        self.plan.bind_device_ptrs(0, [c.data_ptr() for c in self.cols], 0, self.batch, keepalive=self.cols)
+        self.generator = torch.Generator(device=dev)
+        self.generator.manual_seed(int(np.random.randint(0, 2**31 - 1)))
+        self.pmax = None
+
+    def seed(self, seed):
+        self.generator.manual_seed(int(seed))
+
+    def _slots(self, values):
+        from .pdf import _maybe_set
+
+        with _maybe_set(dict(values), self.pdf):
+            return np.array([p.value() for p in self.slot_params], dtype=np.float64)
+
+    def draw(self, n, values):
+        """-> dict obs -> device column with exactly n events drawn at the parameter values ``values``."""
+        torch = self.torch
+        if n is None:
+            if not self.pdf.is_extended:
+                msg = "n has to be given for a non-extended pdf"
+                raise ValueError(msg)
+            from .pdf import _maybe_set
+
+            with _maybe_set(dict(values), self.pdf):
+                n = int(np.random.poisson(self.pdf.get_yield().value()))
+        n = int(n)
+        slots = self._slots(values)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        pmax = self.pmax
+        while True:  # restarted only if the envelope turned out too low
+            kept = [[] for _ in self.cols]
+            have, restart = 0, False
+            while have < n:
+                for c, lo, up in zip(self.cols, self.lower, self.upper):
+                    c.uniform_(lo, up, generator=self.generator)
+                self.plan.pdf_values_device(0, slots, self.pvals.data_ptr(), stream=stream)
+                batch_max = float(self.pvals.max())
+                if pmax is None:
+                    pmax = 1.2 * batch_max
+                elif batch_max > pmax:
+                    pmax, restart = 1.2 * batch_max, True
+                    break
+                self.unif.uniform_(0.0, pmax, generator=self.generator)
+                mask = self.unif < self.pvals
+                for k, c in enumerate(self.cols):
+                    kept[k].append(c[mask])
+                have += int(mask.sum())
+            if not restart:
+                break
+        self.pmax = pmax
+        return {o: torch.cat(parts)[:n].contiguous() for o, parts in zip(self.limits.obs, kept)}
+
+    def close(self):
+        self.plan.close()
