@@ -16,7 +16,10 @@ it is not installed in this image and cannot be.  This module implements the sam
 * when the loss can supply its information matrix (summed outer product of the per-event scores, ONE fused pass), that
   seeds the metric instead of Minuit's diagonal seed (P passes, no correlations) and refreshes it once when the
   inflated EDM first drops below 1 (about one sigma from the minimum, where the information matrix is the Hessian up
-  to O(1/sqrt(N))) -- a B200-side addition: the pass is cheap here and removes most DFP iterations,
+  to O(1/sqrt(N))).  The refreshed metric is credited with ``Dcovar = 0.05``, the threshold of the strategy-1 rule: if
+  the DFP updates that follow are small (relative size <= 0.05, i.e. the metric was right) the fit ends without HESSE,
+  exactly as Minuit2 ends a fit whose metric it trusts; larger updates push ``Dcovar`` back over the threshold and HESSE
+  verifies as usual.  A B200-side addition: the pass is cheap here and removes most DFP iterations and the P HESSE passes,
 * ``grad=None`` -> the driver's own finite-difference gradient of ``value`` (Minuit's default, :139-141).
 
 The driver only sees ``value(x)`` and ``gradient(x)`` callbacks of a ``LossEval``.
@@ -31,6 +34,7 @@ import numpy as np
 
 FAR = 0.5  # a second line-search probe only when the secant puts the line minimum this far from the unit step
 REFRESH_EDM = 1.0  # refresh the metric from the information matrix once the inflated EDM drops below this
+REFRESH_DCOVAR = 0.05  # relative uncertainty credited to the refreshed metric (the HESSE threshold of strategy 1)
 
 
 class _Transform:
@@ -345,7 +349,7 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             refreshed = True
             Vi = information_metric(y)
             if Vi is not None and float(g @ Vi @ g) > 0:
-                V, dcovar = Vi, 0.5
+                V, dcovar = Vi, REFRESH_DCOVAR
                 edm = 0.5 * float(g @ V @ g)
         step = -V @ g
         gdel = float(step @ g)
