@@ -9,8 +9,6 @@ from __future__ import annotations
 
 import math
 
-import numpy as np
-
 from . import distributed as D
 
 FULL_SIZES = {1: 10_000, 2: 100_000_000, 3: 50_000_000, 4: 100_000_000, 5: 125_000_000}
