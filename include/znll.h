@@ -175,6 +175,37 @@ int znll_pdf(znll_plan* plan, int ch, const double* slots, double* out_host, voi
  * core/sample.py:148-566, for SamplerData.resample, core/data.py:1563-1599). */
 int znll_pdf_device(znll_plan* plan, int ch, const double* slots, double* out_dev, void* stream);
 
+/* ---- native MIGRAD-protocol driver (host only; no GPU, no CUDA types) --------------------------------------------
+ * Stands in for iminuit's C++ Minuit2 behind zfit.minimize.Minuit (src/zfit/minimizers/minimizer_minuit.py:175-319):
+ * Minuit's parameter transformations, DFP metric update, line search, EDM stop rule with the Dcovar bookkeeping,
+ * HESSE from gradient differences, the driver's own numerical gradient when has_gradient = 0, and optionally a metric
+ * seeded / refreshed from the objective's information matrix.  The objective is seen only through the callbacks; they
+ * return 0 on success, non-zero aborts the minimisation (znll_migrad then returns 2). */
+#define ZNLL_FCN_VALUE 1
+#define ZNLL_FCN_GRADIENT 2
+/* what: bit mask of ZNLL_FCN_*; value is written when VALUE is set, grad[n] when GRADIENT is set (x is external). */
+typedef int (*znll_fcn_t)(void* user, const double* x, int what, double* value, double* grad);
+/* info[n*n] (row-major): approximate Hessian of the objective at x, e.g. the summed score outer product of a likelihood;
+ * non-zero return = not available (the driver then uses Minuit's diagonal seed). */
+typedef int (*znll_info_t)(void* user, const double* x, double* info);
+typedef struct znll_migrad_options {
+  double edm_goal;        /* stop when EDM (1 + 3 Dcovar) < edm_goal (zfit passes its tol, minimizer_minuit.py:313-315) */
+  int32_t maxfcn;         /* limit on value + gradient calls; <= 0: 10000 */
+  int32_t hesse;          /* 1: strategy-1 HESSE verification while Dcovar > 0.05; 0: never */
+  int32_t has_gradient;   /* 0: finite differences of the value inside the driver (Minuit's default) */
+  int32_t has_value_gradient; /* 1: a VALUE|GRADIENT call costs one pass (line-search probes then ask for both) */
+} znll_migrad_options;
+typedef struct znll_migrad_result {
+  double fval, edm;
+  int32_t niter, nfcn, ngrad, converged, valid;
+  char message[96];
+} znll_migrad_result;
+/* lower / upper: per-parameter limits, NaN or +-inf = none (either pointer may be NULL); cov_out[n*n] = inverse Hessian
+ * estimate in external coordinates, grad_out[n] = external gradient at the result (both may be NULL). */
+int znll_migrad(znll_fcn_t fcn, znll_info_t info, void* user, int n, const double* x0, const double* steps,
+                const double* lower, const double* upper, const znll_migrad_options* options, double* x_out,
+                double* cov_out, double* grad_out, znll_migrad_result* result);
+
 /* Host-only helpers (no GPU needed): normalisation integral of one leaf and d I / d slot, exactly
  * as the per-call prologue computes them.  Replaces the registered analytic integrals
  * (dist_tfp.py:113-120, basic.py:211-229, physics.py:83-142, polynomials.py:443-478). */

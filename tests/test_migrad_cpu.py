@@ -5,7 +5,19 @@ information-matrix seed with its fall-backs (reference driver: iminuit behind ``
 import numpy as np
 import pytest
 
-from zfit_b200 import _migrad
+from zfit_b200 import _migrad as _migrad_py
+from zfit_b200 import _migrad_native
+
+
+@pytest.fixture(params=["native", "python"], autouse=True)
+def _driver(request, monkeypatch):
+    """Every test runs on the C++ driver and on its Python statement."""
+    global _migrad
+    _migrad = _migrad_native if request.param == "native" else _migrad_py
+    return request.param
+
+
+_migrad = _migrad_native
 
 
 def _quadratic(A, x0):
@@ -120,3 +132,30 @@ def test_call_limit_and_nonfinite_value_are_reported_not_raised():
     bad = _migrad.minimize(lambda x: float("nan"), lambda x: np.full(3, np.nan), [0.0] * 3, [0.1] * 3, [None] * 3, [None] * 3,
                            edm_goal=1e-6)
     assert not bad.valid and "non-finite" in bad.message
+
+
+def test_native_and_python_drivers_walk_the_same_path():
+    f, g, fg, c1 = _quadratic(A3, X3)
+    a = _migrad_native.minimize(f, g, [0.0] * 3, [0.1] * 3, [-5, None, None], [5, None, 9], edm_goal=1e-6, value_gradient=fg)
+    n1 = dict(c1)
+    f, g, fg, c2 = _quadratic(A3, X3)
+    b = _migrad_py.minimize(f, g, [0.0] * 3, [0.1] * 3, [-5, None, None], [5, None, 9], edm_goal=1e-6, value_gradient=fg)
+    assert n1 == dict(c2) and a.niter == b.niter and a.nfcn == b.nfcn and a.ngrad == b.ngrad
+    assert np.allclose(a.x, b.x, rtol=0, atol=1e-9) and abs(a.fval - b.fval) < 1e-12 and np.allclose(a.covariance, b.covariance, rtol=1e-6)
+    assert a.message == b.message == "converged"
+
+
+def test_exception_in_the_objective_crosses_the_native_driver():
+    class Boom(RuntimeError):
+        pass
+
+    calls = {"n": 0}
+
+    def f(x):
+        calls["n"] += 1
+        if calls["n"] > 3:
+            raise Boom("stop")
+        return float(np.sum(np.asarray(x) ** 2))
+
+    with pytest.raises(Boom):
+        _migrad_native.minimize(f, None, [1.0, 2.0], [0.1, 0.1], [None] * 2, [None] * 2, edm_goal=1e-6)

@@ -1,0 +1,100 @@
+"""ctypes front end of the native MIGRAD driver (``csrc/znll_migrad.cpp``, ``znll_migrad`` in ``include/znll.h``).
+
+Same call signature and result object as ``_migrad.minimize`` (the Python statement of the algorithm, kept as the
+cross-check): the C++ driver owns the iteration, this module only adapts the three Python callbacks.  An exception raised
+inside a callback (``MaximumIterationReached``, a NaN strategy giving up ...) aborts the C++ loop and is re-raised here.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _znll as Z
+from ._migrad import MigradResult
+
+_DP = C.POINTER(C.c_double)
+FCN_T = C.CFUNCTYPE(C.c_int, C.c_void_p, _DP, C.c_int, _DP, _DP)
+INFO_T = C.CFUNCTYPE(C.c_int, C.c_void_p, _DP, _DP)
+VALUE, GRADIENT = 1, 2
+
+
+class Options(C.Structure):
+    _fields_ = [("edm_goal", C.c_double), ("maxfcn", C.c_int32), ("hesse", C.c_int32), ("has_gradient", C.c_int32),
+                ("has_value_gradient", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("fval", C.c_double), ("edm", C.c_double), ("niter", C.c_int32), ("nfcn", C.c_int32), ("ngrad", C.c_int32),
+                ("converged", C.c_int32), ("valid", C.c_int32), ("message", C.c_char * 96)]
+
+
+def _bound(v, inf):
+    return inf if v is None else float(v)
+
+
+def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000, hesse=True, verbose=False,
+             value_gradient=None, information=None):
+    lib = Z.lib()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = x0.size
+    steps = np.ascontiguousarray(steps, dtype=np.float64)
+    lo = np.array([_bound(v, -np.inf) for v in lower], dtype=np.float64)
+    up = np.array([_bound(v, np.inf) for v in upper], dtype=np.float64)
+    error = []
+
+    def fcn(_user, xp, what, vp, gp):
+        try:
+            x = np.ctypeslib.as_array(xp, (n,)).copy()
+            if what == VALUE | GRADIENT and value_gradient is not None:
+                v, g = value_gradient(x)
+                vp[0] = float(v)
+                np.ctypeslib.as_array(gp, (n,))[:] = g
+            elif what & GRADIENT:
+                np.ctypeslib.as_array(gp, (n,))[:] = gradient(x)
+                if what & VALUE:
+                    vp[0] = float(value(x))
+            else:
+                vp[0] = float(value(x))
+            return 0
+        except BaseException as exc:  # noqa: BLE001 -- carried across the C frame and re-raised below
+            error.append(exc)
+            return 1
+
+    def info(_user, xp, hp):
+        try:
+            H = information(np.ctypeslib.as_array(xp, (n,)).copy())
+            if H is None:
+                return 1
+            H = np.asarray(H, dtype=np.float64)
+            if H.shape != (n, n):
+                return 1
+            np.ctypeslib.as_array(hp, (n * n,))[:] = H.ravel()
+            return 0
+        except Exception:  # the seed is an optimisation; any trouble falls back to Minuit's own seed
+            return 1
+
+    opts = Options(float(edm_goal), int(min(maxfcn, 2**31 - 1)), int(bool(hesse)), int(gradient is not None),
+                   int(gradient is not None and value_gradient is not None))
+    out = Result()
+    x = np.zeros(n)
+    cov = np.zeros((n, n))
+    grad = np.zeros(n)
+    cb = FCN_T(fcn)
+    icb = INFO_T(info) if information is not None else C.cast(None, INFO_T)
+    rc = lib.znll_migrad(cb, icb, None, n, x0.ctypes.data_as(_DP), steps.ctypes.data_as(_DP), lo.ctypes.data_as(_DP),
+                         up.ctypes.data_as(_DP), C.byref(opts), x.ctypes.data_as(_DP), cov.ctypes.data_as(_DP),
+                         grad.ctypes.data_as(_DP), C.byref(out))
+    if error:
+        raise error[0]
+    if rc:
+        msg = f"znll_migrad failed (rc={rc}): {out.message.decode(errors='replace')}"
+        raise RuntimeError(msg)
+    res = MigradResult()
+    res.x, res.fval, res.edm = x, out.fval, out.edm
+    res.covariance, res.grad = cov, grad
+    res.valid, res.converged = bool(out.valid), bool(out.converged)
+    res.nfcn, res.ngrad, res.niter = out.nfcn, out.ngrad, out.niter
+    res.message = out.message.decode(errors="replace")
+    return res

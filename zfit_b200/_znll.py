@@ -74,6 +74,7 @@ SYMBOLS = {
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_pdf_device": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_void_p, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
+    "znll_migrad": (C.c_int, None),  # callback pointers and structs: see _migrad_native.py
     "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
     "znll_fp64_peak": (C.c_int, [C.c_int, C.c_double, _DP]),
 }

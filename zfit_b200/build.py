@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 BPS = os.environ.get("ZNLL_BPS", "2")  # resident CTAs (256 threads) per SM the kernels are tuned for
 CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", f"-DZNLL_MIN_BLOCKS={BPS}", f"-DZNLL_BLOCKS_PER_SM={BPS}"]
 
-SOURCES = ["znll_host.cu", "znll_catalog_a.cu", "znll_catalog_b.cu", "znll_catalog_c.cu"]
+SOURCES = ["znll_host.cu", "znll_catalog_a.cu", "znll_catalog_b.cu", "znll_catalog_c.cu", "znll_migrad.cpp"]
 
 
 def _nvcc() -> str:

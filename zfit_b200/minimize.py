@@ -15,7 +15,7 @@ from collections.abc import Mapping
 
 import numpy as np
 
-from . import _migrad
+from . import _migrad, _migrad_native
 from .exception import DerivativeCalculationError, FailMinimizeNaN, MaximumIterationReached
 from .parameter import ZfitParameter, assign_values, set_values
 
@@ -638,8 +638,9 @@ class Minuit(BaseMinimizer):
 
     ``gradient=None/True`` -> the driver's own numerical gradient (Minuit's default, :139-141);
     ``gradient="zfit"/False`` -> ``loss.gradient`` (the fused kernel's analytic gradient).
-    Uses iminuit when it is importable; this image has no iminuit, so the native MIGRAD-protocol driver in
-    ``_migrad.py`` runs instead and ``result.info["driver"]`` says which one ran.
+    Uses iminuit when it is importable; this image has no iminuit, so the native MIGRAD-protocol driver runs instead
+    (C++: ``csrc/znll_migrad.cpp`` through ``_migrad_native.py``; ``options={"driver": "python"}`` selects the Python
+    statement of the same algorithm in ``_migrad.py``) and ``result.info["driver"]`` says which one ran.
     """
 
     def __init__(self, tol=None, mode=None, gradient=None, verbosity=None, options=None, maxiter=None, criterion=None,
@@ -728,7 +729,10 @@ class Minuit(BaseMinimizer):
         for i, p in enumerate(params):
             if p.has_limits and p.lower is not None and p.upper is not None and not p.has_stepsize:
                 steps[i] = min(steps[i], 0.1 * (p.upper - p.lower))
-        res = _migrad.minimize(
+        # the C++ driver runs unless the Python statement of the same algorithm is asked for (or its per-iteration trace)
+        use_python = self.minimizer_options.get("driver") == "python" or self.verbosity > 6
+        driver = _migrad if use_python else _migrad_native
+        res = driver.minimize(
             evaluator.value, grad, [p.value() for p in params], steps, [p.lower for p in params],
             [p.upper for p in params], edm_goal=self.tol, maxfcn=evaluator.maxiter or 100000, hesse=self.mode >= 1,
             verbose=self.verbosity > 6, value_gradient=None if self.minuit_grad else evaluator.value_gradient,
@@ -741,7 +745,8 @@ class Minuit(BaseMinimizer):
             edm=res.edm, fminopt=res.fval, message=res.message, criterion=criterion,
             approx={"inv_hessian": res.covariance * (2.0 * loss.errordef), "gradient": res.grad}, evaluator=evaluator,
             info={"n_eval": evaluator.niter, "n_value": evaluator.nfunc_eval, "n_gradient": evaluator.ngrad_eval,
-                  "n_pass": evaluator.npass, "n_iter": res.niter, "driver": "native-migrad (iminuit not installed)"},
+                  "n_pass": evaluator.npass, "n_iter": res.niter,
+                  "driver": ("python-migrad" if driver is _migrad else "native-migrad (C++)") + " (iminuit not installed)"},
         )
 
 
