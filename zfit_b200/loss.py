@@ -399,8 +399,9 @@ class BaseLoss:
             self._options["_precompiled"] = False
         self._data_hashes = hashes
 
-    def _get_engine(self):
-        self._check_data_changed()
+    def _get_engine(self, check=True):
+        if check:  # the evaluation entry points have already checked (check_precompile): their inner calls skip it
+            self._check_data_changed()
         if self._engine is None:
             if self._engine_factory is not None:
                 self._engine = self._engine_factory(self.model, self.data, self.fit_range)
@@ -423,7 +424,7 @@ class BaseLoss:
 
     # ------------------------------------------------------------------ core evaluation
     def _nll_channels(self, want_grad, log_offset):
-        eng = self._get_engine()
+        eng = self._get_engine(check=False)
         if self._slot_plan is None or self._slot_plan[0] is not eng:
             sp = eng.slot_params
             direct = [(j, p) for j, p in enumerate(sp) if p.independent]
@@ -809,7 +810,7 @@ class ExtendedUnbinnedNLL(UnbinnedNLL):
         return True
 
     def _extra_terms(self, want_grad, log_offset):
-        eng = self._get_engine()
+        eng = self._get_engine(check=False)
         total = 0.0
         grad = {}
         for k, mod in enumerate(self.model):
