@@ -390,9 +390,14 @@ def run_product(args):
         barrier()
         t0 = time.perf_counter()
         minimizer = zfit.minimize.Minuit(gradient="zfit")
-        result = minimizer.minimize(loss)
+        try:
+            result = minimizer.minimize(loss)
+        except Exception as exc:  # a failed fit must not cost the evaluation numbers of this line
+            result = None
+            line["fit"] = {"error": repr(exc)}
         barrier()
         fit_s = time.perf_counter() - t0
+    if not args.no_fit and result is not None:
         line["fit"] = {
             "wall_s": fit_s,
             "n_eval": int(result.info.get("n_eval", -1)),
