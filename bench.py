@@ -387,19 +387,24 @@ def run_product(args):
         # ---- end-to-end fit wall time (all ranks run the same minimizer in lock-step) ---------------------------
         for p, v in zip(params, theta0):
             p.assign(v)
-        barrier()
-        t0 = time.perf_counter()
         minimizer = zfit.minimize.Minuit(gradient="zfit")
+        fit_times = []
         try:
-            result = minimizer.minimize(loss)
+            for _ in range(2):  # the first fit pays one-time costs (lazy load of the covariance-pass kernel, callbacks)
+                for p, v in zip(params, theta0):
+                    p.assign(v)
+                barrier()
+                t0 = time.perf_counter()
+                result = minimizer.minimize(loss)
+                barrier()
+                fit_times.append(time.perf_counter() - t0)
         except Exception as exc:  # a failed fit must not cost the evaluation numbers of this line
             result = None
             line["fit"] = {"error": repr(exc)}
-        barrier()
-        fit_s = time.perf_counter() - t0
     if not args.no_fit and result is not None:
         line["fit"] = {
-            "wall_s": fit_s,
+            "wall_s": fit_times[-1],
+            "cold_wall_s": fit_times[0],
             "n_eval": int(result.info.get("n_eval", -1)),
             "n_pass": int(result.info.get("n_pass", -1)),
             "valid": bool(result.valid),
