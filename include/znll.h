@@ -211,6 +211,16 @@ int znll_migrad(znll_fcn_t fcn, znll_info_t info, void* user, int n, const doubl
  * (dist_tfp.py:113-120, basic.py:211-229, physics.py:83-142, polynomials.py:443-478). */
 int znll_leaf_integral(const znll_node* leaf, const double* slots, double* integral, double* dintegral);
 
+/* Test hooks, host only (no GPU): the per-call prologue (slots -> the kernel's constant block, in the layout
+ * znll_device.cuh documents) and epilogue (raw accumulators [sum, Kahan compensation, slot sums...] -> channel value and
+ * d value / d slot) that znll_eval runs around the kernel.  tests/hostsim compiles the device header for the host and
+ * uses these two to check the kernels' per-event arithmetic against the oracle on a CPU; the product never runs a
+ * kernel on the host.  kernel_name receives the tree's instantiation name, e.g. "Sum<CBall<0>,Expo<0>>". */
+int znll_test_prologue(const znll_node* nodes, int n_nodes, const double* slots, double* consts, int max_consts,
+                       int* n_consts, int* n_slots, char* kernel_name, int name_len);
+int znll_test_epilogue(const znll_node* nodes, int n_nodes, const double* slots, const double* acc, double sumw,
+                       double* value, double* grad_slots /* nullable */);
+
 /* Test hook: out[i] = f(in[i]) on the device for the kernel's own fp64 elementary functions
  * (kind 0: exp, 1: log, 2: reciprocal), so their accuracy can be checked against libm. */
 int znll_test_math(int kind, int64_t n, const double* in_host, double* out_host);

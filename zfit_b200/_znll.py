@@ -74,6 +74,9 @@ SYMBOLS = {
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_pdf_device": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_void_p, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
+    "znll_test_prologue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.c_char_p, C.c_int]),
+    "znll_test_epilogue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_double, _DP, _DP]),
     "znll_migrad": (C.c_int, None),  # callback pointers and structs: see _migrad_native.py
     "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
     "znll_fp64_peak": (C.c_int, [C.c_int, C.c_double, _DP]),
@@ -266,3 +269,31 @@ def test_math(kind: int, x):
     out = np.empty_like(x)
     _check(lib().znll_test_math(kind, x.size, _dptr(x), _dptr(out)))
     return out
+
+
+def test_prologue(nodes, slots):
+    """Host only: (kernel name, constant block) the prologue builds for a tree at these slots -- test hook."""
+    arr = (Node * len(nodes))(*nodes)
+    slots = np.ascontiguousarray(slots, dtype=np.float64)
+    consts = np.zeros(1024)
+    nc, ns = C.c_int(0), C.c_int(0)
+    name = C.create_string_buffer(512)
+    _check(lib().znll_test_prologue(arr, len(nodes), _dptr(slots), _dptr(consts), consts.size, C.byref(nc), C.byref(ns), name, 512))
+    if ns.value != slots.size:
+        msg = f"expected {ns.value} slots, got {slots.size}"
+        raise ValueError(msg)
+    return name.value.decode(), consts[: nc.value].copy()
+
+
+def test_epilogue(nodes, slots, acc, sumw, grad=True):
+    """Host only: raw accumulators -> (channel value, d value / d slot | None) -- test hook."""
+    arr = (Node * len(nodes))(*nodes)
+    slots = np.ascontiguousarray(slots, dtype=np.float64)
+    acc = np.ascontiguousarray(acc, dtype=np.float64)
+    if acc.size != 2 + slots.size:
+        msg = f"expected {2 + slots.size} accumulators, got {acc.size}"
+        raise ValueError(msg)
+    value = np.zeros(1)
+    g = np.zeros(max(slots.size, 1))
+    _check(lib().znll_test_epilogue(arr, len(nodes), _dptr(slots), _dptr(acc), float(sumw), _dptr(value), _dptr(g) if grad else None))
+    return float(value[0]), (g[: slots.size].copy() if grad else None)

@@ -1341,6 +1341,42 @@ int znll_leaf_integral(const znll_node* leaf, const double* slots, double* integ
   return leaf_integral(*leaf, slots, integral, dintegral);
 }
 
+// host-only test hooks: the prologue and the epilogue that znll_eval runs around the kernel, reachable without a device
+static int test_parse(Channel& c, const znll_node* nodes, int n_nodes, const double* slots, std::string* name) {
+  std::string nm;
+  const int end = parse(c, nodes, n_nodes, 0, -1, nm, 0);
+  if (end != n_nodes) return fail("malformed tree (parsed %d of %d nodes)", end, n_nodes);
+  c.n_acc = 2 + c.n_slots;
+  c.slots.assign(slots, slots + c.n_slots);
+  fill_consts(c, c.slots.data());
+  if (name) *name = nm;
+  return 0;
+}
+
+int znll_test_prologue(const znll_node* nodes, int n_nodes, const double* slots, double* consts, int max_consts,
+                       int* n_consts, int* n_slots, char* kernel_name, int name_len) {
+  if (!nodes || n_nodes < 1 || !slots || !consts || !n_consts || !n_slots) return fail("znll_test_prologue: bad arguments");
+  Channel c;
+  std::string name;
+  if (test_parse(c, nodes, n_nodes, slots, &name)) return 1;
+  if (c.n_consts > max_consts) return fail("znll_test_prologue: %d consts do not fit %d", c.n_consts, max_consts);
+  for (int i = 0; i < c.n_consts; ++i) consts[i] = c.consts[i];
+  *n_consts = c.n_consts;
+  *n_slots = c.n_slots;
+  if (kernel_name && name_len > 0) snprintf(kernel_name, (size_t)name_len, "%s", name.c_str());
+  return 0;
+}
+
+int znll_test_epilogue(const znll_node* nodes, int n_nodes, const double* slots, const double* acc, double sumw,
+                       double* value, double* grad_slots) {
+  if (!nodes || n_nodes < 1 || !slots || !acc || !value) return fail("znll_test_epilogue: bad arguments");
+  Channel c;
+  if (test_parse(c, nodes, n_nodes, slots, nullptr)) return 1;
+  c.sumw = sumw;
+  finish(c, acc, grad_slots ? ZNLL_WANT_GRAD : 0u, value, grad_slots);
+  return 0;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
