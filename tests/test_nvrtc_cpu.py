@@ -1,0 +1,64 @@
+"""The run-time instantiation path compiles: the device source embedded in ``libznll.so`` goes through NVRTC for sm_100a
+with the exact name expressions and options ``znll_host.cu::rtc::build`` uses.  NVRTC needs no GPU to compile; loading the
+cubin and launching it is covered by the ``-m gpu`` tests (``tests/test_random_trees_gpu.py``)."""
+
+import ctypes as C
+
+import pytest
+
+from zfit_b200 import _znll as Z
+
+
+def _nvrtc():
+    for name in ("libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"):
+        try:
+            return C.CDLL(name)
+        except OSError:
+            continue
+    pytest.skip("libnvrtc not found")
+
+
+def _compile(tree, n_slots):
+    nv = _nvrtc()
+    lib = C.CDLL(str(Z.LIB_PATH))
+    src = C.string_at(C.addressof(C.c_char.in_dll(lib, "znll_device_src")))
+    prog = C.c_void_p()
+    assert nv.nvrtcCreateProgram(C.byref(prog), src + b"\n", b"znll_rtc.cu", 0, None, None) == 0
+    import re
+
+    q = re.sub(r"[A-Za-z_][A-Za-z_0-9]*", lambda m: "znll::" + m.group(0), tree)
+    names = [f"znll::nll_kernel<{q},{w},{g}>" for w in ("false", "true") for g in ("false", "true")]
+    names.append(f"znll::pdf_kernel<{q}>")
+    if 2 + n_slots + (n_slots + 1) * (n_slots + 2) // 2 <= 256:
+        names += [f"znll::cov_kernel<{q},false>", f"znll::cov_kernel<{q},true>"]
+    for n in names:
+        assert nv.nvrtcAddNameExpression(prog, n.encode()) == 0
+    opts = (C.c_char_p * 3)(b"--gpu-architecture=sm_100a", b"--std=c++17", b"-lineinfo")
+    rc = nv.nvrtcCompileProgram(prog, 3, opts)
+    size = C.c_size_t()
+    nv.nvrtcGetProgramLogSize(prog, C.byref(size))
+    log = C.create_string_buffer(size.value + 1)
+    nv.nvrtcGetProgramLog(prog, log)
+    assert rc == 0, log.value.decode(errors="replace")[-3000:]
+    lowered = []
+    for n in names:
+        low = C.c_char_p()
+        assert nv.nvrtcGetLoweredName(prog, n.encode(), C.byref(low)) == 0 and low.value
+        lowered.append(low.value)
+    nv.nvrtcGetCUBINSize(prog, C.byref(size))
+    nv.nvrtcDestroyProgram(C.byref(prog))
+    return size.value, lowered
+
+
+@pytest.mark.parametrize(
+    "tree,n_slots",
+    [
+        ("Sum<Gauss<0>,Gauss<0>,Cheb<0,2>>", 10),  # the `rtc` parity case of tests/_cases.py
+        ("Prod<Sum<CBall<0>,Expo<0>>,Sum<Gauss<1>,Legd<1,3>>>", 7 + 8),  # sums under a product: log-native and not
+        ("Sum<GCBall<0>,GGETail<0>,TGauss<0>,Bern<0,2>>", 4 + 7 + 5 + 4 + 3),
+    ],
+)
+def test_embedded_source_compiles_with_nvrtc(tree, n_slots):
+    cubin_bytes, lowered = _compile(tree, n_slots)
+    assert cubin_bytes > 10_000
+    assert all(name.startswith(b"_ZN4znll") for name in lowered)

@@ -81,12 +81,77 @@ def stats(instrs, lo, hi):
             "hist": hist}
 
 
+# operands that only occur in libdevice's special-case handling (inf / NaN results, subnormal rescaling): blocks holding
+# them are rare paths, however short -- the walker must not take them as shortcuts
+RARE_MARKS = ("+INF", "-INF", "QNAN", "e+16", "CALL")
+
+
+def cost(op, text):
+    if any(m in text for m in RARE_MARKS):
+        return 100000
+    base = op.split(".")[0]
+    if base in DP_OPS:
+        return 3 if base == "DFMA" and distinct_regs(text) >= 3 else 2
+    return 1
+
+
+def hot_path(instrs, lo, hi):
+    """Cheapest path (in issue cycles) from the loop head to its back edge through the control-flow graph of the body:
+    every range test of the event code is a hammock whose fast side is the cheaper one, so this is the instruction
+    stream of an iteration that takes no rare path (for a CrystalBall: a pair on the Gaussian core).
+    -> (path as a list of instruction indices, its cost)"""
+    import heapq
+
+    body = [(a, op, t) for a, op, t in instrs if lo <= a <= hi]
+    index = {a: i for i, (a, _, _) in enumerate(body)}
+    n = len(body)
+    dist = [None] * n
+    prev = [None] * n
+    heap = [(cost(body[0][1], body[0][2]), 0, None)]
+    while heap:
+        d, i, p = heapq.heappop(heap)
+        if dist[i] is not None:
+            continue
+        dist[i], prev[i] = d, p
+        a, op, text = body[i]
+        if a == hi:
+            break
+        succ = []
+        base = op.split(".")[0]
+        if base == "BRA":
+            m = re.search(r"0x([0-9a-f]+)", text)
+            tgt = int(m.group(1), 16) if m else None
+            if tgt in index:
+                succ.append(index[tgt])
+            if text.startswith("@") and i + 1 < n:  # predicated: may fall through
+                succ.append(i + 1)
+        elif base in ("EXIT", "RET", "BRX", "JMP"):
+            if text.startswith("@") and i + 1 < n:
+                succ.append(i + 1)
+        elif i + 1 < n:
+            succ.append(i + 1)
+        for j in succ:
+            if dist[j] is None:
+                heapq.heappush(heap, (d + cost(body[j][1], body[j][2]), j, i))
+    end = index[hi]
+    if dist[end] is None:
+        return [], None
+    path, i = [], end
+    while i is not None:
+        path.append(i)
+        i = prev[i]
+    path.reverse()
+    return [body[i] for i in path], dist[end]
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("kernel", help="substring of the demangled kernel name (spaces ignored)")
     ap.add_argument("--object", action="append", help="object file(s); default: every zfit_b200/_build/znll_catalog_*.o")
     ap.add_argument("--min-body", type=int, default=40, help="ignore loops shorter than this many instructions")
     ap.add_argument("--top", type=int, default=12, help="opcodes to list")
+    ap.add_argument("--hot", action="store_true", help="also walk the cheapest path through each loop body (no rare path taken)")
+    ap.add_argument("--dump-hot", action="store_true", help="print that path")
     args = ap.parse_args()
     objs = [Path(o) for o in args.object] if args.object else sorted((ROOT / "zfit_b200" / "_build").glob("znll_catalog_*.o"))
     want = args.kernel.replace(" ", "")
@@ -108,6 +173,16 @@ def main():
                 print(f"  loop 0x{lo:04x}-0x{hi:04x}: {s['n']} instr, DP {s['dp']} (3-register DFMA {s['dp3']}), "
                       f"non-DP {s['non_dp']}, issue cycles/iteration ~ {s['cycles']}")
                 print(f"    {top}")
+                if args.hot or args.dump_hot:
+                    path, c = hot_path(instrs, lo, hi)
+                    if c is not None:
+                        dp = sum(1 for _, op, _ in path if op.split(".")[0] in DP_OPS)
+                        hist = collections.Counter(op.split(".")[0] for _, op, _ in path)
+                        print(f"    cheapest path: {len(path)} instr, DP {dp}, non-DP {len(path) - dp}, issue cycles ~ {c}")
+                        print("      " + ", ".join(f"{k} {v}" for k, v in hist.most_common(args.top)))
+                        if args.dump_hot:
+                            for a, _, t in path:
+                                print(f"        {a:05x}  {t}")
     if not found:
         sys.exit(f"no kernel matching {args.kernel!r}")
 

@@ -137,7 +137,7 @@ ZNLL_DEV typename Lanes<V>::Mask zlt(V x, double y) {
 }
 template <class M>
 ZNLL_DEV bool zany(M m) {
-  return la(m) || lb(m);
+  return la(m) | lb(m);  // not ||: both lanes are known, a second branch would cost more than the OR
 }
 template <class M>
 ZNLL_DEV bool zall(M m) {
@@ -215,6 +215,8 @@ struct Ctx {
 
 ZNLL_DEV bool exp_in_range(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x4085E000; }  // |x| < 700
 ZNLL_DEV bool log_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u; }
+// x < -690 read off the high word (the sign bit set and the magnitude above 690; -inf and negative NaNs included)
+ZNLL_DEV bool below_m690(double x) { return (unsigned)__double2hiint(x) > 0xC0859000u; }
 ZNLL_DEV bool rcp_in_range(double x) { return (((unsigned)__double2hiint(x) >> 20) & 0x7ffu) - 1u < 0x7fdu; }
 ZNLL_DEV double scale2n(double p, int n) { return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p)); }
 ZNLL_DEV double rcp_seed(double x) {
@@ -224,8 +226,7 @@ ZNLL_DEV double rcp_seed(double x) {
 }
 
 template <class V>
-ZNLL_DEV V fast_exp(V x) {
-  if (!(exp_in_range(la(x)) && exp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
+ZNLL_DEV V exp_core(V x) {  // |x| < 700
   const V t = zfma(x, kMathC[0], kMathC[1]);
   const V nd = zsub(t, kMathC[1]);
   V r = zfma(nd, kMathC[2], x);
@@ -237,16 +238,32 @@ ZNLL_DEV V fast_exp(V x) {
   p = zfma(p, r, 1.0);
   return Lanes<V>::make(scale2n(la(p), __double2loint(la(t))), scale2n(lb(p), __double2loint(lb(t))));
 }
+template <class V>
+ZNLL_DEV V fast_exp(V x) {
+  if (!(exp_in_range(la(x)) && exp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
+  return exp_core(x);
+}
+// the same for an argument whose sign bit is known to be set (-|d|): the range test is one integer compare
+ZNLL_DEV bool negexp_in_range(double x) { return (unsigned)__double2hiint(x) < 0xC085E000u; }  // -700 < x <= -0
+template <class V>
+ZNLL_DEV V fast_exp_neg(V x) {
+  if (!(negexp_in_range(la(x)) && negexp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
+  return exp_core(x);
+}
 
 template <class V>
-ZNLL_DEV V fast_rcp(V x) {
-  if (!(rcp_in_range(la(x)) && rcp_in_range(lb(x)))) return Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));  // rare
+ZNLL_DEV V rcp_core(V x) {  // x normal, 1/x normal
   V y = Lanes<V>::make(rcp_seed(la(x)), rcp_seed(lb(x)));
   const V nx = zneg(x);
   V e = zfma(nx, y, 1.0);
   y = zfma(y, e, y);
   e = zfma(nx, y, 1.0);
   return zfma(y, e, y);
+}
+template <class V>
+ZNLL_DEV V fast_rcp(V x) {
+  if (!(rcp_in_range(la(x)) && rcp_in_range(lb(x)))) return Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));  // rare
+  return rcp_core(x);
 }
 
 struct LogSplit {
@@ -264,8 +281,7 @@ ZNLL_DEV LogSplit log_split(double x, const Ctx& cx) {
 }
 
 template <class V>
-ZNLL_DEV V fast_log(V x, const Ctx& cx) {
-  if (!(log_in_range(la(x)) && log_in_range(lb(x)))) return Lanes<V>::make(log(la(x)), log(lb(x)));  // rare
+ZNLL_DEV V log_core(V x, const Ctx& cx) {  // x positive, normal, finite
   const LogSplit sa = log_split(la(x), cx), sb = log_split(lb(x), cx);
   const V z = Lanes<V>::make(sa.z, sb.z), invc = Lanes<V>::make(sa.tc.x, sb.tc.x), logc = Lanes<V>::make(sa.tc.y, sb.tc.y);
   const V kd = zsub(Lanes<V>::make(sa.kd, sb.kd), kMathC[6]);
@@ -276,6 +292,41 @@ ZNLL_DEV V fast_log(V x, const Ctx& cx) {
   const V w = zfma(kd, kMathC[4], logc);
   const V t2 = zfma(zmul(r, r), s, zmul(kd, kMathC[5]));
   return zadd(w, zadd(r, t2));
+}
+template <class V>
+ZNLL_DEV V fast_log(V x, const Ctx& cx) {
+  if (!(log_in_range(la(x)) && log_in_range(lb(x)))) return Lanes<V>::make(log(la(x)), log(lb(x)));  // rare
+  return log_core(x, cx);
+}
+
+// log and reciprocal of the SAME argument behind ONE range test (the step kernels are issue-bound: a test is ~4 integer
+// instructions per lane plus a branch and its convergence barrier).  Fast path: x positive and normal with a normal
+// reciprocal (biased exponent 1..2045); everything else -- zero, negative, subnormal, huge, inf, NaN -- is answered by
+// libdevice once per pair, so the IEEE results (log of a negative number is NaN, 1/0 is inf) are unchanged.
+ZNLL_DEV bool pos_normal(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fd00000u; }
+template <class V>
+ZNLL_DEV void fast_log_rcp(V x, const Ctx& cx, V& lg, V& rc) {
+  if (!(pos_normal(la(x)) && pos_normal(lb(x)))) {  // rare
+    lg = Lanes<V>::make(log(la(x)), log(lb(x)));
+    rc = Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));
+    return;
+  }
+  lg = log_core(x, cx);
+  rc = rcp_core(x);
+}
+// lg = log|x|, rc = 1/x, neg = (x < 0): for values that are positive in every sane fit (a polynomial pdf, a sum of
+// fractions times pdfs) but whose sign must be tracked when they are not
+template <class V>
+ZNLL_DEV void fast_logabs_rcp(V x, const Ctx& cx, V& lg, V& rc, typename Lanes<V>::Mask& neg) {
+  if (!(pos_normal(la(x)) && pos_normal(lb(x)))) {  // rare
+    lg = Lanes<V>::make(log(fabs(la(x))), log(fabs(lb(x))));
+    rc = Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));
+    neg = zlt(x, 0.0);
+    return;
+  }
+  lg = log_core(x, cx);
+  rc = rcp_core(x);
+  neg = Lanes<V>::mask(false, false);
 }
 
 // one entry per thread < 128, then __syncthreads() by the caller
@@ -431,8 +482,9 @@ struct CBallN {
     }
     // A*(B-t)^-n == exp(ln A - n*ln(B-t)); a lane on the core gets the safe value u = 2 (z.safe_where)
     const V u = zsel(tail, zsub(c[CO + 5], t), zbc<V>(2.0));
-    lu = fast_log(u, cx);
-    const V dtt = zmul(fast_rcp(u), c[CO + 4]);
+    V ru;
+    fast_log_rcp(u, cx, lu, ru);  // one range test for both
+    const V dtt = zmul(ru, c[CO + 4]);
     const V lp_tail = zfma(lu, -c[CO + 4], c[CO + 6]);
     dt = zsel(tail, dtt, zneg(t));
     return zsel(tail, lp_tail, lp_core);
@@ -575,7 +627,7 @@ template <int COL, int DEG, int KIND, class V>
 struct PolyN {
   typedef typename Lanes<V>::Mask Mask;
   V T[DEG + 1];
-  V P;
+  V P, rP;  // rP = 1/P, produced together with log|P| by fwd_log
 
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx&, const double* __restrict__ c, const V* x) {
@@ -623,8 +675,11 @@ struct PolyN {
   template <int CO>
   ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
     const V p = fwd_val<CO>(cx, c, x);
-    neg = mxor(neg, zlt(p, 0.0));
-    return fast_log(zabs(p), cx);
+    V lg;
+    Mask ng;
+    fast_logabs_rcp(p, cx, lg, rP, ng);
+    neg = mxor(neg, ng);
+    return lg;
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
@@ -638,7 +693,7 @@ struct PolyN {
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
-    bwd_val<CO, AO>(zmul(g, fast_rcp(P)), c, acc);
+    bwd_val<CO, AO>(zmul(g, rP), c, acc);
   }
 };
 template <int COL, int DEG, int KIND>
@@ -690,9 +745,10 @@ struct GCBallN {
       return lp_core;
     }
     const V u = zsel(tail, zsub(side<4>(cc), t), zbc<V>(2.0));
-    lu = fast_log(u, cx);
+    V ru;
+    fast_log_rcp(u, cx, lu, ru);
     const V n = side<3>(cc);
-    const V dtt = zmul(fast_rcp(u), n);
+    const V dtt = zmul(ru, n);
     const V lp_tail = zfma(lu, zneg(n), side<5>(cc));
     dt = zsel(tail, dtt, zneg(t));
     return zsel(tail, lp_tail, lp_core);
@@ -772,7 +828,7 @@ struct SumN {
   static constexpr int K = sizeof...(Cs);
   Kids<V, Cs...> kids;
   V p[K];
-  V P;
+  V P, rP;  // rP = 1/P, produced together with log|P| by fwd_log
 
   template <int CO, int I, int CK, class KD>
   ZNLL_DEV void fwd_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const V* x, V& tot) {
@@ -800,8 +856,11 @@ struct SumN {
   template <int CO>
   ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
     const V v = fwd_val<CO>(cx, c, x);
-    neg = mxor(neg, zlt(v, 0.0));
-    return fast_log(zabs(v), cx);
+    V lg;
+    Mask ng;
+    fast_logabs_rcp(v, cx, lg, rP, ng);
+    neg = mxor(neg, ng);
+    return lg;
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
@@ -809,7 +868,7 @@ struct SumN {
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
-    bwd_val<CO, AO>(zmul(g, fast_rcp(P)), c, acc);
+    bwd_val<CO, AO>(zmul(g, rP), c, acc);
   }
 };
 // SumPDF of exactly two log-native children (the signal + background case), in log-sum-exp form:
@@ -832,17 +891,19 @@ struct SumLseN {
     const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
     const V d = zsub(l0, l1);
     const Mask lt = zlt(d, 0.0);  // l0 < l1
-    const V e = fast_exp(zneg(zabs(d)));
+    const V e = fast_exp_neg(zneg(zabs(d)));
     const V one = zbc<V>(1.0);
     V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
     e0 = zsel(n0, zneg(e0), e0);  // children that are themselves products with a negative factor
     e1 = zsel(n1, zneg(e1), e1);
     const V S = zfma(e0, c[CO + 0], zmul(e1, c[CO + 1]));
-    neg = mxor(neg, zlt(S, 0.0));
-    const V rS = fast_rcp(S);
+    V lS, rS;
+    Mask ng;
+    fast_logabs_rcp(S, cx, lS, rS, ng);  // one range test for both; S < 0 (a negative fraction) is the rare path
+    neg = mxor(neg, ng);
     q0 = zmul(e0, rS);
     q1 = zmul(e1, rS);
-    return zadd(zsel(lt, l1, l0), fast_log(zabs(S), cx));
+    return zadd(zsel(lt, l1, l0), lS);
   }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
@@ -1042,8 +1103,7 @@ ZNLL_DEV V event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, d
     Mask neg = Lanes<V>::mask(false, false);
     const V lp = m.template fwd_log<0>(cx, c, x, neg);
     l = lp;
-    V g = zbc<V>(1.0);
-    if (zany(zlt(lp, -690.0)) || zany(neg)) {  // p + 1e-307 matters only here (loss.py:117); rare
+    if (below_m690(la(lp)) | below_m690(lb(lp)) | zany(neg)) {  // p + 1e-307 matters only here (loss.py:117); rare
       double ll[2] = {la(lp), lb(lp)}, gg[2] = {1.0, 1.0};
       const bool ng[2] = {la(neg), lb(neg)};
 #pragma unroll
@@ -1056,18 +1116,28 @@ ZNLL_DEV V event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, d
         }
       }
       l = Lanes<V>::make(ll[0], ll[1]);
-      g = Lanes<V>::make(gg[0], gg[1]);
+      if constexpr (GRAD) {
+        V g = Lanes<V>::make(gg[0], gg[1]);
+        if constexpr (WEIGHTED) g = zmul(g, w);
+        m.template bwd_log<0, 2>(g, c, acc);
+      }
+    } else if constexpr (GRAD) {
+      // the adjoint of ln P is exactly 1 (or the weight): a compile-time constant the reverse sweep folds away
+      if constexpr (WEIGHTED)
+        m.template bwd_log<0, 2>(w, c, acc);
+      else
+        m.template bwd_log<0, 2>(zbc<V>(1.0), c, acc);
     }
-    if constexpr (WEIGHTED) g = zmul(g, w);
-    if constexpr (GRAD) m.template bwd_log<0, 2>(g, c, acc);
   } else {
     const V P = m.template fwd_val<0>(cx, c, x);
     const V pp = zadd(P, ZNLL_LOG_EPS);
-    l = fast_log(pp, cx);
     if constexpr (GRAD) {
-      V g = fast_rcp(pp);
+      V g;
+      fast_log_rcp(pp, cx, l, g);  // one range test for both
       if constexpr (WEIGHTED) g = zmul(g, w);
       m.template bwd_val<0, 2>(g, c, acc);
+    } else {
+      l = fast_log(pp, cx);
     }
   }
   if constexpr (WEIGHTED)
