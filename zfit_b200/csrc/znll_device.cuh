@@ -135,6 +135,15 @@ template <class V>
 ZNLL_DEV typename Lanes<V>::Mask zlt(V x, double y) {
   return Lanes<V>::mask(la(x) < y, lb(x) < y);
 }
+// x < 0 read off the sign bit (true for -0.0 and negative NaNs as well): one integer compare instead of a DSETP
+template <class V>
+ZNLL_DEV typename Lanes<V>::Mask zsignbit(V x) {
+  return Lanes<V>::mask(__double2hiint(la(x)) < 0, __double2hiint(lb(x)) < 0);
+}
+template <class V>
+ZNLL_DEV bool zany_signbit(V x) {
+  return (__double2hiint(la(x)) | __double2hiint(lb(x))) < 0;
+}
 template <class M>
 ZNLL_DEV bool zany(M m) {
   return la(m) | lb(m);  // not ||: both lanes are known, a second branch would cost more than the OR
@@ -243,12 +252,12 @@ ZNLL_DEV V fast_exp(V x) {
   if (!(exp_in_range(la(x)) && exp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
   return exp_core(x);
 }
-// the same for an argument whose sign bit is known to be set (-|d|): the range test is one integer compare
-ZNLL_DEV bool negexp_in_range(double x) { return (unsigned)__double2hiint(x) < 0xC085E000u; }  // -700 < x <= -0
+// exp(-|d|): the range test reads d itself, so -|d| never has to exist in a register (the DFMAs of the core take it
+// through their operand modifiers)
 template <class V>
-ZNLL_DEV V fast_exp_neg(V x) {
-  if (!(negexp_in_range(la(x)) && negexp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
-  return exp_core(x);
+ZNLL_DEV V fast_exp_negabs(V d) {
+  if (!(exp_in_range(la(d)) && exp_in_range(lb(d)))) return Lanes<V>::make(exp(-fabs(la(d))), exp(-fabs(lb(d))));  // rare
+  return exp_core(zneg(zabs(d)));
 }
 
 template <class V>
@@ -472,8 +481,11 @@ struct CBallN {
   template <int CO>
   ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask&) {
     t = zmul(zsub(x[COL], c[CO + 0]), c[CO + 1]);
-    tail = zlt(t, -c[CO + 3]);
-    any_tail = zany(tail);
+    // t < -|alpha|  <=>  t + |alpha| < 0, and that sum has the exact sign (it is exact when the two are within a factor
+    // of two of each other, far from zero otherwise; t == -|alpha| gives +0): integer sign tests replace three DSETPs
+    const V ta = zadd(t, c[CO + 3]);
+    tail = zsignbit(ta);
+    any_tail = zany_signbit(ta);
     const V lp_core = zfma(zmul(t, -0.5), t, c[CO + 7]);  // exp(-t^2/2)
     if (!any_tail) {                                       // whole pair on the Gaussian core (events are sorted)
       dt = zneg(t);
@@ -891,7 +903,7 @@ struct SumLseN {
     const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
     const V d = zsub(l0, l1);
     const Mask lt = zlt(d, 0.0);  // l0 < l1
-    const V e = fast_exp_neg(zneg(zabs(d)));
+    const V e = fast_exp_negabs(d);
     const V one = zbc<V>(1.0);
     V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
     e0 = zsel(n0, zneg(e0), e0);  // children that are themselves products with a negative factor
