@@ -37,6 +37,7 @@ _DRIVER = r"""
 #include <cstring>
 using namespace znll;
 namespace {
+#ifdef HOSTSIM_OLD_TABLES  // headers before the shared MathTabs block (kept for old-versus-new comparisons)
 double2 g_logtab[128];
 bool g_ready = false;
 Ctx make_ctx() {
@@ -52,6 +53,23 @@ Ctx make_ctx() {
   cx.logtab = g_logtab;
   return cx;
 }
+#define HOSTSIM_EXP(x, cx) fast_exp(x)
+#else
+MathTabs g_tabs;
+bool g_ready = false;
+Ctx make_ctx() {
+  if (!g_ready) {
+    for (unsigned t = 0; t < 128; ++t) {  // what the 128 filling threads of a block do
+      threadIdx.x = t;
+      init_tabs(g_tabs);
+    }
+    threadIdx.x = 0;
+    g_ready = true;
+  }
+  return ctx_of(g_tabs);
+}
+#define HOSTSIM_EXP(x, cx) fast_exp(x, cx)
+#endif
 template <class M>
 void load_pair(const double* const* cols, long long i, D2* x) {
   for (int k = 0; k < ZNLL_MAXCOL; ++k)
@@ -160,11 +178,11 @@ void hostsim_math(int kind, int pairs, long long n, const double* in, double* ou
       D2 x;
       x.a = in[i];
       x.b = in[i + 1];
-      const D2 r = kind == 0 ? fast_exp(x) : (kind == 1 ? fast_log(x, cx) : fast_rcp(x));
+      const D2 r = kind == 0 ? HOSTSIM_EXP(x, cx) : (kind == 1 ? fast_log(x, cx) : fast_rcp(x));
       out[i] = r.a;
       out[i + 1] = r.b;
     }
-  for (; i < n; ++i) out[i] = kind == 0 ? fast_exp(in[i]) : (kind == 1 ? fast_log(in[i], cx) : fast_rcp(in[i]));
+  for (; i < n; ++i) out[i] = kind == 0 ? HOSTSIM_EXP(in[i], cx) : (kind == 1 ? fast_log(in[i], cx) : fast_rcp(in[i]));
 }
 }
 """
@@ -187,6 +205,9 @@ class HostSim:
         entries = ",\n".join(f"    HOSTSIM_ENTRY({t})" for t in self.trees)
         driver = _DRIVER.replace("@ENTRIES@", entries)
         shim = (SHIM_DIR / "cuda_shim.h").read_text()
+        defines = list(defines)
+        if "struct MathTabs" not in text:
+            defines.append("HOSTSIM_OLD_TABLES")
         flags = ["-std=c++17", "-O1", "-fPIC", "-shared", "-march=native", *[f"-D{d}" for d in defines]]
         key = hashlib.sha256("\0".join([header, driver, shim, *flags]).encode()).hexdigest()[:16]
         work = BUILD_DIR / key

@@ -158,3 +158,17 @@ def test_fast_rcp(sim, pairs):
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     ok = ~np.isnan(ref)
     np.testing.assert_allclose(got[ok], ref[ok], rtol=4e-16)
+
+
+def test_table_driven_exp_option(cases):
+    """ZNLL_EXP_TABLE=1 (off by default, znll_device.cuh): same accuracy bound, same parity."""
+    case = cases["gauss_cheb"]
+    tab = HostSim([case.kernel], defines=("ZNLL_EXP_TABLE=1",))
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-699, 699, 100_000), rng.uniform(-40, 5, 100_000), rng.normal(0, 1e-3, 50_000), [0.0, -0.0, 1.0, -1.0]])
+    for pairs in (False, True):
+        assert _ulp_err(tab.math(0, x, pairs), np.exp(x)).max() <= 2.0
+    v, g, _ = tab.eval(case.nodes, case.slots, case.cols, case.weights)
+    ov, idx, og = _oracle(case)
+    assert abs(v - ov) <= 1e-12 * abs(ov)
+    np.testing.assert_allclose(g[idx], og, rtol=0, atol=GRAD_RTOL * np.abs(og).max())

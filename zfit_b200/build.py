@@ -16,12 +16,15 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-OBJ = HERE / "_build"
+# ZNLL_LIB_OUT / ZNLL_OBJ_DIR / ZNLL_EXTRA_CFLAGS: tuning experiments only (a variant library next to the product one,
+# selected at run time with ZNLL_LIB, e.g. ZNLL_EXTRA_CFLAGS=-DZNLL_EXP_TABLE=1)
+OBJ = Path(os.environ.get("ZNLL_OBJ_DIR", HERE / "_build"))
 LIB = Path(os.environ.get("ZNLL_LIB_OUT", HERE / "libznll.so"))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 BPS = os.environ.get("ZNLL_BPS", "2")  # resident CTAs (256 threads) per SM the kernels are tuned for
-CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", f"-DZNLL_MIN_BLOCKS={BPS}", f"-DZNLL_BLOCKS_PER_SM={BPS}"]
+CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", f"-DZNLL_MIN_BLOCKS={BPS}", f"-DZNLL_BLOCKS_PER_SM={BPS}",
+          *os.environ.get("ZNLL_EXTRA_CFLAGS", "").split()]
 
 SOURCES = ["znll_host.cu", "znll_catalog_a.cu", "znll_catalog_b.cu", "znll_catalog_c.cu", "znll_migrad.cpp"]
 
@@ -53,7 +56,7 @@ def _digest(paths) -> str:
 
 
 def build(verbose: bool = False, force: bool = False) -> Path:
-    OBJ.mkdir(exist_ok=True)
+    OBJ.mkdir(parents=True, exist_ok=True)
     deps = [CSRC / f for f in os.listdir(CSRC) if (CSRC / f).is_file()] + [HERE.parent / "include" / "znll.h", Path(__file__)]
     stamp = OBJ / "stamp"
     digest = _digest(deps)

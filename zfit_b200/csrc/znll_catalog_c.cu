@@ -28,14 +28,13 @@ cudaError_t znll_launch_sumw(const double* w, long long n, double* partials, uns
 }
 
 __global__ void test_math_kernel(int kind, const double* __restrict__ in, double* __restrict__ out, long long n) {
-  __shared__ double2 logtab[128];
-  init_logtab(logtab);
+  __shared__ MathTabs tabs;
+  init_tabs(tabs);
   __syncthreads();
-  Ctx cx;
-  cx.logtab = logtab;
+  const Ctx cx = ctx_of(tabs);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double x = in[i];
-    out[i] = kind == 0 ? fast_exp(x) : (kind == 1 ? fast_log(x, cx) : fast_rcp(x));
+    out[i] = kind == 0 ? fast_exp(x, cx) : (kind == 1 ? fast_log(x, cx) : fast_rcp(x));
   }
 }
 cudaError_t znll_launch_test_math(int kind, const double* in, double* out, long long n, cudaStream_t stream) {

@@ -218,8 +218,69 @@ static __constant__ double kMathC[8] = {
     4503601774854144.0,           // 6 2^52 + 2^31
     0.0};
 
+// ZNLL_EXP_TABLE = 1 selects a table-driven exp (see exp_core); 0 the table-free degree-11 polynomial.  The modelled gain
+// of the table is under 2 % of an event pair's issue cycles and it adds a shared-memory look-up with data-dependent
+// bank conflicts, so it stays off until a GPU measurement says otherwise.
+#ifndef ZNLL_EXP_TABLE
+#define ZNLL_EXP_TABLE 0
+#endif
+#if ZNLL_EXP_TABLE
+// 2^(j/128), j = 0..127, correctly rounded (generated with mpmath); copied into shared memory by init_tabs
+static __constant__ double kExp2Tab[128] = {
+    0x1.0000000000000p+0, 0x1.0163da9fb3335p+0, 0x1.02c9a3e778061p+0, 0x1.04315e86e7f85p+0,
+    0x1.059b0d3158574p+0, 0x1.0706b29ddf6dep+0, 0x1.0874518759bc8p+0, 0x1.09e3ecac6f383p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0cc922b7247f7p+0, 0x1.0e3ec32d3d1a2p+0, 0x1.0fb66affed31bp+0,
+    0x1.11301d0125b51p+0, 0x1.12abdc06c31ccp+0, 0x1.1429aaea92de0p+0, 0x1.15a98c8a58e51p+0,
+    0x1.172b83c7d517bp+0, 0x1.18af9388c8deap+0, 0x1.1a35beb6fcb75p+0, 0x1.1bbe084045cd4p+0,
+    0x1.1d4873168b9aap+0, 0x1.1ed5022fcd91dp+0, 0x1.2063b88628cd6p+0, 0x1.21f49917ddc96p+0,
+    0x1.2387a6e756238p+0, 0x1.251ce4fb2a63fp+0, 0x1.26b4565e27cddp+0, 0x1.284dfe1f56381p+0,
+    0x1.29e9df51fdee1p+0, 0x1.2b87fd0dad990p+0, 0x1.2d285a6e4030bp+0, 0x1.2ecafa93e2f56p+0,
+    0x1.306fe0a31b715p+0, 0x1.32170fc4cd831p+0, 0x1.33c08b26416ffp+0, 0x1.356c55f929ff1p+0,
+    0x1.371a7373aa9cbp+0, 0x1.38cae6d05d866p+0, 0x1.3a7db34e59ff7p+0, 0x1.3c32dc313a8e5p+0,
+    0x1.3dea64c123422p+0, 0x1.3fa4504ac801cp+0, 0x1.4160a21f72e2ap+0, 0x1.431f5d950a897p+0,
+    0x1.44e086061892dp+0, 0x1.46a41ed1d0057p+0, 0x1.486a2b5c13cd0p+0, 0x1.4a32af0d7d3dep+0,
+    0x1.4bfdad5362a27p+0, 0x1.4dcb299fddd0dp+0, 0x1.4f9b2769d2ca7p+0, 0x1.516daa2cf6642p+0,
+    0x1.5342b569d4f82p+0, 0x1.551a4ca5d920fp+0, 0x1.56f4736b527dap+0, 0x1.58d12d497c7fdp+0,
+    0x1.5ab07dd485429p+0, 0x1.5c9268a5946b7p+0, 0x1.5e76f15ad2148p+0, 0x1.605e1b976dc09p+0,
+    0x1.6247eb03a5585p+0, 0x1.6434634ccc320p+0, 0x1.6623882552225p+0, 0x1.68155d44ca973p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6c012750bdabfp+0, 0x1.6dfb23c651a2fp+0, 0x1.6ff7df9519484p+0,
+    0x1.71f75e8ec5f74p+0, 0x1.73f9a48a58174p+0, 0x1.75feb564267c9p+0, 0x1.780694fde5d3fp+0,
+    0x1.7a11473eb0187p+0, 0x1.7c1ed0130c132p+0, 0x1.7e2f336cf4e62p+0, 0x1.80427543e1a12p+0,
+    0x1.82589994cce13p+0, 0x1.8471a4623c7adp+0, 0x1.868d99b4492edp+0, 0x1.88ac7d98a6699p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8cf3216b5448cp+0, 0x1.8f1ae99157736p+0, 0x1.9145b0b91ffc6p+0,
+    0x1.93737b0cdc5e5p+0, 0x1.95a44cbc8520fp+0, 0x1.97d829fde4e50p+0, 0x1.9a0f170ca07bap+0,
+    0x1.9c49182a3f090p+0, 0x1.9e86319e32323p+0, 0x1.a0c667b5de565p+0, 0x1.a309bec4a2d33p+0,
+    0x1.a5503b23e255dp+0, 0x1.a799e1330b358p+0, 0x1.a9e6b5579fdbfp+0, 0x1.ac36bbfd3f37ap+0,
+    0x1.ae89f995ad3adp+0, 0x1.b0e07298db666p+0, 0x1.b33a2b84f15fbp+0, 0x1.b59728de5593ap+0,
+    0x1.b7f76f2fb5e47p+0, 0x1.ba5b030a1064ap+0, 0x1.bcc1e904bc1d2p+0, 0x1.bf2c25bd71e09p+0,
+    0x1.c199bdd85529cp+0, 0x1.c40ab5fffd07ap+0, 0x1.c67f12e57d14bp+0, 0x1.c8f6d9406e7b5p+0,
+    0x1.cb720dcef9069p+0, 0x1.cdf0b555dc3fap+0, 0x1.d072d4a07897cp+0, 0x1.d2f87080d89f2p+0,
+    0x1.d5818dcfba487p+0, 0x1.d80e316c98398p+0, 0x1.da9e603db3285p+0, 0x1.dd321f301b460p+0,
+    0x1.dfc97337b9b5fp+0, 0x1.e264614f5a129p+0, 0x1.e502ee78b3ff6p+0, 0x1.e7a51fbc74c83p+0,
+    0x1.ea4afa2a490dap+0, 0x1.ecf482d8e67f1p+0, 0x1.efa1bee615a27p+0, 0x1.f252b376bba97p+0,
+    0x1.f50765b6e4540p+0, 0x1.f7bfdad9cbe14p+0, 0x1.fa7c1819e90d8p+0, 0x1.fd3c22b8f71f1p+0,
+};
+static __constant__ double kExpT[8] = {
+    0x1.71547652b82fep+7,    // 0 128/ln2
+    6755399441055744.0,      // 1 1.5 * 2^52
+    -0x1.62e42fef80000p-8,   // 2 -(ln2/128)_hi: 35 significant bits, n * hi is exact for |n| < 2^18
+    -0x1.1cf79abc9e3b4p-43,  // 3 -(ln2/128)_lo
+    0x1.1111111111111p-7,    // 4 1/120
+    0x1.5555555555555p-5,    // 5 1/24
+    0x1.5555555555555p-3,    // 6 1/6
+    0.0};
+#endif
+
+// per-block tables of the elementary functions, in shared memory
+struct MathTabs {
+  double2 log[128];  // (1/c_i, log c_i) for 128 intervals of [0.6875, 1.375)
+#if ZNLL_EXP_TABLE
+  double exp2[128];  // 2^(j/128)
+#endif
+};
 struct Ctx {
-  const double2* logtab;  // shared memory: (1/c_i, log c_i) for 128 intervals of [0.6875, 1.375)
+  const double2* logtab;
+  const double* exptab;
 };
 
 ZNLL_DEV bool exp_in_range(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x4085E000; }  // |x| < 700
@@ -234,8 +295,29 @@ ZNLL_DEV double rcp_seed(double x) {
   return y;
 }
 
+#if ZNLL_EXP_TABLE
+// exp(x) = 2^k * 2^(j/128) * e^r with n = 128 k + j = nearest(x * 128/ln2) and |r| <= ln2/256: a table look-up in shared
+// memory and a degree-5 Taylor polynomial (truncation 6e-19) -- 10 DP instructions instead of the 17 of the table-free
+// version, for one LDS and three integer instructions more.  Total error about 1 ulp (table 0.5 + final FMA 0.5).
+ZNLL_DEV double exp_tab(int n, const Ctx& cx) { return cx.exptab[n & 127]; }
 template <class V>
-ZNLL_DEV V exp_core(V x) {  // |x| < 700
+ZNLL_DEV V exp_core(V x, const Ctx& cx) {  // |x| < 700
+  const V t = zfma(x, kExpT[0], kExpT[1]);
+  const int na = __double2loint(la(t)), nb = __double2loint(lb(t));
+  const V T = Lanes<V>::make(exp_tab(na, cx), exp_tab(nb, cx));
+  const V nd = zsub(t, kExpT[1]);
+  V r = zfma(nd, kExpT[2], x);
+  r = zfma(nd, kExpT[3], r);
+  V q = zfma(r, kExpT[4], kExpT[5]);
+  q = zfma(q, r, kExpT[6]);
+  q = zfma(q, r, 0.5);
+  const V p = zfma(zmul(r, r), q, r);  // e^r - 1
+  const V v = zfma(T, p, T);
+  return Lanes<V>::make(scale2n(la(v), na >> 7), scale2n(lb(v), nb >> 7));
+}
+#else
+template <class V>
+ZNLL_DEV V exp_core(V x, const Ctx&) {  // |x| < 700
   const V t = zfma(x, kMathC[0], kMathC[1]);
   const V nd = zsub(t, kMathC[1]);
   V r = zfma(nd, kMathC[2], x);
@@ -247,17 +329,18 @@ ZNLL_DEV V exp_core(V x) {  // |x| < 700
   p = zfma(p, r, 1.0);
   return Lanes<V>::make(scale2n(la(p), __double2loint(la(t))), scale2n(lb(p), __double2loint(lb(t))));
 }
+#endif
 template <class V>
-ZNLL_DEV V fast_exp(V x) {
+ZNLL_DEV V fast_exp(V x, const Ctx& cx) {
   if (!(exp_in_range(la(x)) && exp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
-  return exp_core(x);
+  return exp_core(x, cx);
 }
 // exp(-|d|): the range test reads d itself, so -|d| never has to exist in a register (the DFMAs of the core take it
 // through their operand modifiers)
 template <class V>
-ZNLL_DEV V fast_exp_negabs(V d) {
+ZNLL_DEV V fast_exp_negabs(V d, const Ctx& cx) {
   if (!(exp_in_range(la(d)) && exp_in_range(lb(d)))) return Lanes<V>::make(exp(-fabs(la(d))), exp(-fabs(lb(d))));  // rare
-  return exp_core(zneg(zabs(d)));
+  return exp_core(zneg(zabs(d)), cx);
 }
 
 template <class V>
@@ -339,13 +422,26 @@ ZNLL_DEV void fast_logabs_rcp(V x, const Ctx& cx, V& lg, V& rc, typename Lanes<V
 }
 
 // one entry per thread < 128, then __syncthreads() by the caller
-ZNLL_DEV void init_logtab(double2* tab) {
+ZNLL_DEV void init_tabs(MathTabs& tabs) {
   if (threadIdx.x < 128) {
     const int ha = 0x3fe60000 + ((int)threadIdx.x << 13);
     const double a = __hiloint2double(ha, 0), b = __hiloint2double(ha + (1 << 13), 0);
     const double invc = 1.0 / (0.5 * (a + b));
-    tab[threadIdx.x] = make_double2(invc, -log(invc));
+    tabs.log[threadIdx.x] = make_double2(invc, -log(invc));
+#if ZNLL_EXP_TABLE
+    tabs.exp2[threadIdx.x] = kExp2Tab[threadIdx.x];
+#endif
   }
+}
+ZNLL_DEV Ctx ctx_of(const MathTabs& tabs) {
+  Ctx cx;
+  cx.logtab = tabs.log;
+#if ZNLL_EXP_TABLE
+  cx.exptab = tabs.exp2;
+#else
+  cx.exptab = nullptr;
+#endif
+  return cx;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -368,7 +464,7 @@ struct GaussN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     return P;
   }
   template <int CO, int AO, class A>
@@ -411,7 +507,7 @@ struct TGaussN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     return P;
   }
   template <int CO, int AO, class A>
@@ -447,7 +543,7 @@ struct ExpoN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     return P;
   }
   template <int CO, int AO, class A>
@@ -504,7 +600,7 @@ struct CBallN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     return P;
   }
   template <int CO, int AO, class A>
@@ -550,7 +646,7 @@ struct GETailN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     return P;
   }
   template <int CO, int AO, class A>
@@ -601,7 +697,7 @@ struct GGETailN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     return P;
   }
   template <int CO, int AO, class A>
@@ -768,7 +864,7 @@ struct GCBallN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
-    P = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    P = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     return P;
   }
   template <int CO, int AO, class A>
@@ -903,7 +999,7 @@ struct SumLseN {
     const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
     const V d = zsub(l0, l1);
     const Mask lt = zlt(d, 0.0);  // l0 < l1
-    const V e = fast_exp_negabs(d);
+    const V e = fast_exp_negabs(d, cx);
     const V one = zbc<V>(1.0);
     V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
     e0 = zsel(n0, zneg(e0), e0);  // children that are themselves products with a negative factor
@@ -920,7 +1016,7 @@ struct SumLseN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg = Lanes<V>::mask(false, false);
-    const V e = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    const V e = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     P = zsel(neg, zneg(e), e);
     return P;
   }
@@ -1003,7 +1099,7 @@ struct ProdN {
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg = Lanes<V>::mask(false, false);
-    const V e = fast_exp(fwd_log<CO>(cx, c, x, neg));
+    const V e = fast_exp(fwd_log<CO>(cx, c, x, neg), cx);
     P = zsel(neg, zneg(e), e);
     return P;
   }
@@ -1287,11 +1383,10 @@ __host__ __device__ constexpr int zpopc(unsigned m) {
 template <class M, bool WEIGHTED, bool GRAD>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NACC = 2 + M::NS;
-  __shared__ double2 logtab[128];
-  init_logtab(logtab);
+  __shared__ MathTabs tabs;
+  init_tabs(tabs);
   __syncthreads();
-  Ctx cx;
-  cx.logtab = logtab;
+  const Ctx cx = ctx_of(tabs);
   double acc[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
@@ -1353,11 +1448,10 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
 template <class M, bool WEIGHTED>
 __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NS = M::NS, NE = NS + 1, NQ = NE * (NE + 1) / 2, NACC = 2 + NS + NQ;
-  __shared__ double2 logtab[128];
-  init_logtab(logtab);
+  __shared__ MathTabs tabs;
+  init_tabs(tabs);
   __syncthreads();
-  Ctx cx;
-  cx.logtab = logtab;
+  const Ctx cx = ctx_of(tabs);
   double acc[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
@@ -1418,11 +1512,10 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constan
 // per-event normalised pdf values (BasePDF.pdf, core/basepdf.py:398-429): out[i] = P(x_i); args.partials = out
 template <class M>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) pdf_kernel(const __grid_constant__ KArgs<M::NC> args) {
-  __shared__ double2 logtab[128];
-  init_logtab(logtab);
+  __shared__ MathTabs tabs;
+  init_tabs(tabs);
   __syncthreads();
-  Ctx cx;
-  cx.logtab = logtab;
+  const Ctx cx = ctx_of(tabs);
   const double* __restrict__ c = args.c;
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
   for (long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x; i < args.n; i += stride) {
