@@ -59,7 +59,7 @@ MathTabs g_tabs;
 bool g_ready = false;
 Ctx make_ctx() {
   if (!g_ready) {
-    for (unsigned t = 0; t < 128; ++t) {  // what the 128 filling threads of a block do
+    for (unsigned t = 0; t < ZNLL_BLOCK; ++t) {  // what the threads of a block do
       threadIdx.x = t;
       init_tabs(g_tabs);
     }

@@ -160,15 +160,18 @@ def test_fast_rcp(sim, pairs):
     np.testing.assert_allclose(got[ok], ref[ok], rtol=4e-16)
 
 
-def test_table_driven_exp_option(cases):
-    """ZNLL_EXP_TABLE=1 (off by default, znll_device.cuh): same accuracy bound, same parity."""
+def test_small_table_option(cases):
+    """ZNLL_TAB_BITS=7 (128-entry tables with the longer polynomials, znll_device.cuh): same accuracy bounds, same parity."""
     case = cases["gauss_cheb"]
-    tab = HostSim([case.kernel], defines=("ZNLL_EXP_TABLE=1",))
+    small = HostSim([case.kernel], defines=("ZNLL_TAB_BITS=7",))
     rng = np.random.default_rng(3)
     x = np.concatenate([rng.uniform(-699, 699, 100_000), rng.uniform(-40, 5, 100_000), rng.normal(0, 1e-3, 50_000), [0.0, -0.0, 1.0, -1.0]])
+    y = np.concatenate([np.exp(rng.uniform(-700, 700, 100_000)), rng.uniform(0.5, 2.0, 100_000)])
     for pairs in (False, True):
-        assert _ulp_err(tab.math(0, x, pairs), np.exp(x)).max() <= 2.0
-    v, g, _ = tab.eval(case.nodes, case.slots, case.cols, case.weights)
+        assert _ulp_err(small.math(0, x, pairs), np.exp(x)).max() <= 2.0
+        got, ref = small.math(1, y, pairs), np.log(y)
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-2)) <= 4e-16
+    v, g, _ = small.eval(case.nodes, case.slots, case.cols, case.weights)
     ov, idx, og = _oracle(case)
     assert abs(v - ov) <= 1e-12 * abs(ov)
     np.testing.assert_allclose(g[idx], og, rtol=0, atol=GRAD_RTOL * np.abs(og).max())
