@@ -54,7 +54,9 @@ Ctx make_ctx() {
   return cx;
 }
 #define HOSTSIM_EXP(x, cx) fast_exp(x)
+#define HOSTSIM_PAIR_OFFSET(off) (off)
 #else
+#define HOSTSIM_PAIR_OFFSET(off) (2.0 * (off))  // event() takes the offset of the whole pair
 MathTabs g_tabs;
 bool g_ready = false;
 Ctx make_ctx() {
@@ -70,6 +72,9 @@ Ctx make_ctx() {
 }
 #define HOSTSIM_EXP(x, cx) fast_exp(x, cx)
 #endif
+// event() returns the pair's summed term; headers before that change returned the two lanes
+inline double pair_term(double t) { return t; }
+inline double pair_term(D2 t) { return t.a + t.b; }
 template <class M>
 void load_pair(const double* const* cols, long long i, D2* x) {
   for (int k = 0; k < ZNLL_MAXCOL; ++k)
@@ -93,8 +98,7 @@ void run_nll(const double* const* cols, const double* w, long long n, const doub
       wv.a = w[2 * i];
       wv.b = w[2 * i + 1];
     }
-    const D2 t = event<M, D2, W, G>(cx, c, x, wv, off, acc);
-    kahan_add(acc, t.a + t.b);
+    kahan_add(acc, pair_term(event<M, D2, W, G>(cx, c, x, wv, HOSTSIM_PAIR_OFFSET(off), acc)));
   }
   if (n & 1) {
     double xa[ZNLL_MAXCOL];

@@ -171,6 +171,11 @@ ZNLL_DEV V zbc(double x) {
 ZNLL_DEV void zacc(double& acc, double g, double d) { acc = fma(g, d, acc); }
 ZNLL_DEV void zacc(double& acc, D2 g, D2 d) { acc = fma(g.b, d.b, fma(g.a, d.a, acc)); }
 ZNLL_DEV void zacc(double& acc, D2 g, double d) { acc = fma(g.a + g.b, d, acc); }
+// sum over lanes of l (or w*l) minus the pair's offset
+ZNLL_DEV double zsum_minus(double l, double o) { return l - o; }
+ZNLL_DEV double zsum_minus(D2 l, double o) { return (l.a + l.b) - o; }
+ZNLL_DEV double zdot_minus(double w, double l, double o) { return fma(w, l, -o); }
+ZNLL_DEV double zdot_minus(D2 w, D2 l, double o) { return fma(w.b, l.b, fma(w.a, l.a, -o)); }
 // per-lane accumulators (covariance pass: the two events of a pair keep separate score vectors)
 ZNLL_DEV void zacc(D2& acc, D2 g, D2 d) {
   acc.a = fma(g.a, d.a, acc.a);
@@ -371,8 +376,8 @@ static __constant__ double kLogC[6] = {-0.5,
 #error "ZNLL_TAB_BITS must be 7 or 9"
 #endif
 static __constant__ double kMathC[4] = {
-    0x1.62e42fefa3800p-1,  // 0 ln2_hi (42 significant bits: k*ln2_hi is exact)
-    0x1.ef35793c76730p-45, // 1 ln2_lo
+    0x1.62e42fefa39efp-1,  // 0 ln2 (its rounding error, 5.5e-17 relative, is relative to k ln2 and so to the result)
+    0.0,
     4503601774854144.0,    // 2 2^52 + 2^31
     0.0};
 
@@ -477,8 +482,7 @@ ZNLL_DEV V log_core(V x, const Ctx& cx) {  // x positive, normal, finite
   for (int j = 3; j >= 0; --j) s = zfma(s, r, kLogC[j]);
 #endif
   const V w = zfma(kd, kMathC[0], logc);
-  const V t2 = zfma(zmul(r, r), s, zmul(kd, kMathC[1]));
-  return zadd(w, zadd(r, t2));
+  return zadd(w, zfma(zmul(r, r), s, r));
 }
 template <class V>
 ZNLL_DEV V fast_log(V x, const Ctx& cx) {
@@ -546,6 +550,12 @@ ZNLL_DEV Ctx ctx_of(const MathTabs& tabs) {
   cx.exptab = tabs.exp2;
   return cx;
 }
+// A tree that is evaluated in log space from leaves that need neither exp nor log (a Gauss, an Exponential, products of
+// them: cfg 1) never touches the tables; its kernels skip filling them (the rare p + 1e-307 path uses libdevice).
+template <class M>
+struct NeedTabs {
+  static constexpr bool value = !M::LOGNAT || M::TABS;
+};
 
 // ----------------------------------------------------------------------------------------------
 // leaves.  c = const block, x = this event's (pair's) column values, acc = per-thread accumulators.
@@ -585,6 +595,7 @@ template <int COL>
 struct Gauss {
   static constexpr int NS = 2, NC = 3, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = false;  // does log-space evaluation look up the exp / log tables?
   template <class V>
   using Node = GaussN<COL, V>;
 };
@@ -628,6 +639,7 @@ template <int COL>
 struct TGauss {
   static constexpr int NS = 4, NC = 5, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = false;
   template <class V>
   using Node = TGaussN<COL, V>;
 };
@@ -662,6 +674,7 @@ template <int COL>
 struct Expo {
   static constexpr int NS = 1, NC = 3, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = false;
   template <class V>
   using Node = ExpoN<COL, V>;
 };
@@ -673,7 +686,7 @@ struct Expo {
 template <int COL, class V>
 struct CBallN {
   typedef typename Lanes<V>::Mask Mask;
-  V t, dt, lu, P;  // dt = d ln v / d t ; lu = ln(B-t) on the tail
+  V t, mdt, lu, P;  // mdt = -d ln v / d t (t itself on the Gaussian core); lu = ln(B-t) on the tail
   Mask tail;
   bool any_tail;
 
@@ -687,7 +700,7 @@ struct CBallN {
     any_tail = zany_signbit(ta);
     const V lp_core = zfma(zmul(t, -0.5), t, c[CO + 7]);  // exp(-t^2/2)
     if (!any_tail) {                                       // whole pair on the Gaussian core (events are sorted)
-      dt = zneg(t);
+      mdt = t;
       lu = zbc<V>(0.0);
       return lp_core;
     }
@@ -695,9 +708,9 @@ struct CBallN {
     const V u = zsel(tail, zsub(c[CO + 5], t), zbc<V>(2.0));
     V ru;
     fast_log_rcp(u, cx, lu, ru);  // one range test for both
-    const V dtt = zmul(ru, c[CO + 4]);
+    const V mdtt = zmul(ru, -c[CO + 4]);  // -n/u
     const V lp_tail = zfma(lu, -c[CO + 4], c[CO + 6]);
-    dt = zsel(tail, dtt, zneg(t));
+    mdt = zsel(tail, mdtt, t);
     return zsel(tail, lp_tail, lp_core);
   }
   template <int CO>
@@ -708,14 +721,14 @@ struct CBallN {
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
-    const V gd = zmul(g, dt);
-    zacc(acc[AO + 0], zneg(gd), c[CO + 1]);             // dt/dmu    = -sign/sigma
-    zacc(acc[AO + 1], zmul(zneg(gd), t), c[CO + 2]);    // dt/dsigma = -t/sigma
+    const V gm = zmul(g, mdt);                   // -g * d ln v/dt
+    zacc(acc[AO + 0], gm, c[CO + 1]);            // dt/dmu    = -sign/sigma
+    zacc(acc[AO + 1], zmul(gm, t), c[CO + 2]);   // dt/dsigma = -t/sigma
     if (any_tail) {
       // d ln v/d|alpha| = -n/a - a + (n/u)(n/a^2+1) ; d ln v/dn = ln(n/a)+1 - ln u - (n/u)/a ; 0 on the core
       const V gt = zsel(tail, g, zbc<V>(0.0));
-      zacc(acc[AO + 2], zmul(gt, c[CO + 12]), zfma(dt, c[CO + 11], c[CO + 10]));
-      zacc(acc[AO + 3], gt, zsub(zsub(c[CO + 8], lu), zmul(dt, c[CO + 9])));
+      zacc(acc[AO + 2], zmul(gt, c[CO + 12]), zfma(mdt, -c[CO + 11], c[CO + 10]));
+      zacc(acc[AO + 3], gt, zfma(mdt, c[CO + 9], zsub(c[CO + 8], lu)));
     }
   }
   template <int CO, int AO, class A>
@@ -727,6 +740,7 @@ template <int COL>
 struct CBall {
   static constexpr int NS = 4, NC = 13, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = true;
   template <class V>
   using Node = CBallN<COL, V>;
 };
@@ -768,6 +782,7 @@ template <int COL>
 struct GETail {
   static constexpr int NS = 3, NC = 7, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = false;
   template <class V>
   using Node = GETailN<COL, V>;
 };
@@ -825,6 +840,7 @@ template <int COL>
 struct GGETail {
   static constexpr int NS = 5, NC = 12, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = false;
   template <class V>
   using Node = GGETailN<COL, V>;
 };
@@ -911,6 +927,7 @@ template <int COL, int DEG, int KIND>
 struct Poly {
   static constexpr int NS = DEG + 1, NC = 3 + DEG + 1, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = false;
+  static constexpr bool TABS = true;
   template <class V>
   using Node = PolyN<COL, DEG, KIND, V>;
 };
@@ -998,6 +1015,7 @@ template <int COL>
 struct GCBall {
   static constexpr int NS = 7, NC = 24, COLMASK = 1 << COL;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = true;
   template <class V>
   using Node = GCBallN<COL, V>;
 };
@@ -1010,12 +1028,14 @@ struct Meta;
 template <>
 struct Meta<> {
   static constexpr int NS = 0, NC = 0, COLMASK = 0;
+  static constexpr bool TABS = false;
 };
 template <class H, class... T>
 struct Meta<H, T...> {
   static constexpr int NS = H::NS + Meta<T...>::NS;
   static constexpr int NC = H::NC + Meta<T...>::NC;
   static constexpr int COLMASK = H::COLMASK | Meta<T...>::COLMASK;
+  static constexpr bool TABS = H::TABS || Meta<T...>::TABS;
 };
 
 template <class V, class... Cs>
@@ -1101,7 +1121,7 @@ struct SumLseN {
     const V l0 = k0.template fwd_log<CO + 2>(cx, c, x, n0);
     const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
     const V d = zsub(l0, l1);
-    const Mask lt = zlt(d, 0.0);  // l0 < l1
+    const Mask lt = zsignbit(d);  // l0 < l1 (a -0.0 or NaN difference may land on either side: same result)
     const V e = fast_exp_negabs(d, cx);
     const V one = zbc<V>(1.0);
     V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
@@ -1168,6 +1188,7 @@ struct Sum {
   static constexpr int NS = K + Meta<Cs...>::NS, NC = K + Meta<Cs...>::NC;
   static constexpr int COLMASK = Meta<Cs...>::COLMASK;
   static constexpr bool LOGNAT = AllLog<Cs...>::value;
+  static constexpr bool TABS = true;
   template <class V>
   using Node = typename SumPick<V, Cs...>::type;
 };
@@ -1195,8 +1216,8 @@ struct ProdN {
   }
   template <int CO>
   ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
-    V tot = zbc<V>(0.0);
-    fwd_rec<CO>(kids, cx, c, x, tot, neg);
+    V tot = kids.h.template fwd_log<CO>(cx, c, x, neg);  // at least one factor
+    fwd_rec<CO + Kids<V, Cs...>::Head::NC>(kids.t, cx, c, x, tot, neg);
     return tot;
   }
   template <int CO>
@@ -1220,6 +1241,7 @@ struct Prod {
   static constexpr int NS = Meta<Cs...>::NS, NC = Meta<Cs...>::NC;
   static constexpr int COLMASK = Meta<Cs...>::COLMASK;
   static constexpr bool LOGNAT = true;
+  static constexpr bool TABS = Meta<Cs...>::TABS;
   template <class V>
   using Node = ProdN<V, Cs...>;
 };
@@ -1304,9 +1326,10 @@ struct KArgs {
 };
 
 // accumulators: [0] running sum of w*l - offset, [1] its Kahan compensation, [2..] slots.
-// Returns the term(s)  w*l - offset  of this event (pair).
+// Returns this event's (this pair's) contribution to [0]:  sum over lanes of w*l, minus `off` -- the log offset times
+// the number of lanes, prepared by the caller.
 template <class M, class V, bool WEIGHTED, bool GRAD, class A>
-ZNLL_DEV V event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, double off, A* acc) {
+ZNLL_DEV double event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, double off, A* acc) {
   typedef typename Lanes<V>::Mask Mask;
   typename M::template Node<V> m;
   V l;
@@ -1348,10 +1371,11 @@ ZNLL_DEV V event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, d
       m.template bwd_val<0, 2>(g, c, acc);
     }
   }
+  // weights multiply first, then the unweighted offset is subtracted per event (loss.py:134-137)
   if constexpr (WEIGHTED)
-    return zfma(w, l, -off);  // weights multiply first, then the unweighted offset (loss.py:134-137)
+    return zdot_minus(w, l, off);
   else
-    return zsub(l, off);
+    return zsum_minus(l, off);
 }
 
 ZNLL_DEV void kahan_add(double* acc, double term) {
@@ -1484,14 +1508,16 @@ template <class M, bool WEIGHTED, bool GRAD>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NACC = 2 + M::NS;
   __shared__ MathTabs tabs;
-  init_tabs(tabs);
-  __syncthreads();
+  if constexpr (NeedTabs<M>::value) {
+    init_tabs(tabs);
+    __syncthreads();
+  }
   const Ctx cx = ctx_of(tabs);
   double acc[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
   const double* __restrict__ c = args.c;
-  const double off = args.log_offset;
+  const double off = args.log_offset, off2 = 2.0 * args.log_offset;
   const long long nvec = args.n >> 1;
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
   long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x;
@@ -1504,17 +1530,11 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
     while (i < nvec) {
       i += stride;
       if (i < nvec) b1.load(args, i);
-      {
-        const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, b0.x, b0.w, off, acc);
-        kahan_add(acc, t.a + t.b);
-      }
+      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, b0.x, b0.w, off2, acc));
       if (i >= nvec) break;
       i += stride;
       if (i < nvec) b0.load(args, i);
-      {
-        const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, b1.x, b1.w, off, acc);
-        kahan_add(acc, t.a + t.b);
-      }
+      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, b1.x, b1.w, off2, acc));
     }
   } else {
     EventPair<M, WEIGHTED> cur, nxt;
@@ -1523,8 +1543,7 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
       cur = nxt;
       i += stride;
       if (i < nvec) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
-      const D2 t = event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, off, acc);
-      kahan_add(acc, t.a + t.b);
+      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, off2, acc));
     }
   }
   if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event: scalar instantiation
@@ -1549,8 +1568,10 @@ template <class M, bool WEIGHTED>
 __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NS = M::NS, NE = NS + 1, NQ = NE * (NE + 1) / 2, NACC = 2 + NS + NQ;
   __shared__ MathTabs tabs;
-  init_tabs(tabs);
-  __syncthreads();
+  if constexpr (NeedTabs<M>::value) {
+    init_tabs(tabs);
+    __syncthreads();
+  }
   const Ctx cx = ctx_of(tabs);
   double acc[NACC];
 #pragma unroll
@@ -1569,8 +1590,7 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constan
     D2 e[2 + NE];
 #pragma unroll
     for (int j = 0; j < 2 + NE; ++j) e[j] = zbc<D2>(0.0);
-    const D2 t = event<M, D2, WEIGHTED, true>(cx, c, cur.x, cur.w, args.log_offset, e);
-    kahan_add(acc, t.a + t.b);
+    kahan_add(acc, event<M, D2, WEIGHTED, true>(cx, c, cur.x, cur.w, 2.0 * args.log_offset, e));
     e[2 + NS] = cur.w;
 #pragma unroll
     for (int j = 0; j < NS; ++j) acc[2 + j] += e[2 + j].a + e[2 + j].b;
@@ -1613,8 +1633,10 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constan
 template <class M>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) pdf_kernel(const __grid_constant__ KArgs<M::NC> args) {
   __shared__ MathTabs tabs;
-  init_tabs(tabs);
-  __syncthreads();
+  if constexpr (NeedTabs<M>::value) {
+    init_tabs(tabs);
+    __syncthreads();
+  }
   const Ctx cx = ctx_of(tabs);
   const double* __restrict__ c = args.c;
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
