@@ -350,13 +350,18 @@ def run_product(args):
     t_fp64 = flops / (fp64_peak * 1e12)
     t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
     bound = "fp64" if t_fp64 >= t_hbm else "hbm"
-    traffic = None
+    traffic, dp_per_event = None, None
     tr = ROOT / "profiles" / "traffic.json"
     if tr.exists():
         try:
-            traffic = json.loads(tr.read_text()).get(f"cfg{cfg}")
+            captured = json.loads(tr.read_text())
+            traffic = captured.get(f"cfg{cfg}")
+            dp_per_event = captured.get("dp_instr_per_event", {}).get(f"cfg{cfg}")
         except Exception:
-            traffic = None
+            traffic, dp_per_event = None, None
+    # executed FP64 instructions (ncu capture) over the pipe's measured issue peak (one DFMA = 2 flop): the hardware-side
+    # utilisation next to the convention-side "frac"
+    pipe_frac = None if dp_per_event is None else dp_per_event * n_events / (kern_ms * 1e-3) / (fp64_peak * 1e12 / 2.0)
     line["roofline"] = {
         "bound": bound,
         "achieved": achieved_tf if bound == "fp64" else achieved_gbs,
@@ -374,8 +379,13 @@ def run_product(args):
         "hbm_achieved_gbs": achieved_gbs,
         "hbm_peak_gbs": peaks["hbm_gbs"],
         "hbm_peak_source": peak_src,
+        "executed_dp_instr_per_event": dp_per_event,
+        "fp64_pipe_frac": pipe_frac,
         "note": "roofline = slower of (bytes at HBM bandwidth, algorithmic fp64 flops at the DFMA peak), per north_star; "
-                "no tensor cores: elementwise transcendental map-reduce",
+                "no tensor cores: elementwise transcendental map-reduce.  The algorithmic flop count is SURVEY.md 8d's "
+                "frozen convention, which prices EXP / LOG / RCP at libdevice cost (30 / 45 / 14); the kernels' table-driven "
+                "functions execute fewer instructions, so frac can exceed 1 -- fp64_pipe_frac is the executed DP "
+                "instruction rate (ncu capture under profiles/) over the measured DFMA issue peak",
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
