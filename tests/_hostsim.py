@@ -291,3 +291,42 @@ class HostSim:
         dp = C.POINTER(C.c_double)
         self.lib.hostsim_math(kind, int(pairs), x.size, x.ctypes.data_as(dp), out.ctypes.data_as(dp))
         return out
+
+
+class HostSimEngine:
+    """Test double with the ``CudaEngine`` interface (``loss._set_engine_factory``): model lowering, prologue and epilogue
+    are the product's own, the kernel's event loop is the host-compiled device header.  Lets API-level cases (random
+    trees, composed parameters, shared parameters) exercise the device arithmetic on a CPU box."""
+
+    def __init__(self, models, datas, fit_ranges):
+        self.slot_params, self.channel_slots, self.channels = [], [], []
+        datas = [d if r is None else d.with_obs(r, guarantee_limits=False) for d, r in zip(datas, fit_ranges)]
+        for model, data, rng in zip(models, datas, fit_ranges):
+            nodes, slots = model._lower(data.obs, rng)
+            start = len(self.slot_params)
+            self.slot_params.extend(slots)
+            self.channel_slots.append((start, len(self.slot_params)))
+            cols = [np.ascontiguousarray(data.value(o), dtype=np.float64) for o in data.obs]
+            name, _ = Z.test_prologue(nodes, [p.value() for p in slots])
+            self.channels.append((nodes, name, cols, data.weights))
+        self.sim = HostSim([name for _, name, _, _ in self.channels])
+        self.n_local = [d.num_entries for d in datas]
+        self.n_entries = list(self.n_local)
+        self.samplesize = [d.samplesize for d in datas]
+        self.kernel_names = [name for _, name, _, _ in self.channels]
+        self.distributed = False
+
+    def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
+        values, gs = [], np.zeros(len(self.slot_params))
+        for (nodes, _, cols, w), (lo, hi) in zip(self.channels, self.channel_slots):
+            v, g, _ = self.sim.eval(nodes, np.asarray(slots[lo:hi], dtype=np.float64), cols, w, grad=grad, log_offset=log_offset)
+            values.append(v)
+            if grad:
+                gs[lo:hi] = g
+        return np.asarray(values), (gs if grad else None)
+
+    def launch_count(self):
+        return 0
+
+    def close(self):
+        pass
