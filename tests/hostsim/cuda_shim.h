@@ -68,3 +68,4 @@ void __threadfence();
 void __threadfence_system();
 unsigned atomicAdd(unsigned*, unsigned);
 long long clock64();
+size_t __cvta_generic_to_shared(const void*);

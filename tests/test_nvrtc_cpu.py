@@ -18,7 +18,7 @@ def _nvrtc():
     pytest.skip("libnvrtc not found")
 
 
-def _compile(tree, n_slots):
+def _compile(tree, n_slots, extra=()):
     nv = _nvrtc()
     lib = C.CDLL(str(Z.LIB_PATH))
     src = C.string_at(C.addressof(C.c_char.in_dll(lib, "znll_device_src")))
@@ -33,8 +33,9 @@ def _compile(tree, n_slots):
         names += [f"znll::cov_kernel<{q},false>", f"znll::cov_kernel<{q},true>"]
     for n in names:
         assert nv.nvrtcAddNameExpression(prog, n.encode()) == 0
-    opts = (C.c_char_p * 3)(b"--gpu-architecture=sm_100a", b"--std=c++17", b"-lineinfo")
-    rc = nv.nvrtcCompileProgram(prog, 3, opts)
+    flags = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-lineinfo", *extra]
+    opts = (C.c_char_p * len(flags))(*flags)
+    rc = nv.nvrtcCompileProgram(prog, len(flags), opts)
     size = C.c_size_t()
     nv.nvrtcGetProgramLogSize(prog, C.byref(size))
     log = C.create_string_buffer(size.value + 1)
@@ -62,3 +63,9 @@ def test_embedded_source_compiles_with_nvrtc(tree, n_slots):
     cubin_bytes, lowered = _compile(tree, n_slots)
     assert cubin_bytes > 10_000
     assert all(name.startswith(b"_ZN4znll") for name in lowered)
+
+
+def test_ring_experiment_compiles_with_nvrtc():
+    """ZNLL_RING=1 (off by default): the cp.async staging loop for three- and four-stream trees."""
+    cubin_bytes, _ = _compile("Prod<Sum<Gauss<0>,Expo<0>>,Gauss<1>,Cheb<2,3>>", 4 + 1 + 2 + 4, extra=(b"-DZNLL_RING=1",))
+    assert cubin_bytes > 10_000

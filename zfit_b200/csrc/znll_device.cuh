@@ -1504,6 +1504,55 @@ __host__ __device__ constexpr int zpopc(unsigned m) {
   }
   return n;
 }
+// ZNLL_RING = 1 (experiment, off by default): trees that read three or four 8-byte streams per event stage them through a
+// two-deep cp.async ring in shared memory, so that TWO pairs per thread are in flight instead of one.  Motivation: with
+// the instruction stream of the end of round 1, cfg 4 (75.7 instructions per event) saturates no unit and runs at the
+// one-pair-in-flight streaming ceiling (5.2 of 5.37 TB/s, stream_skeleton_bench.py; 6.38 TB/s with two pairs).  Every
+// thread touches only its own 16-byte slots, so there are no bank conflicts and no block barrier in the loop.
+// First measurement (one 100-step run on the B200, cfg 4): kernel 0.456 -> 0.445 ms back to back, 0.485 -> 0.420 ms per
+// step; the product-tree parity and out-of-range canary tests pass with it.  It stays off until the whole GPU suite (four
+// streams, NVRTC trees) has run with it.
+#ifndef ZNLL_RING
+#define ZNLL_RING 0
+#endif
+ZNLL_DEV void cp_async16(void* smem, const void* gmem) {  // LDGSTS, L2 only
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+ZNLL_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+ZNLL_DEV void cp_async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+ZNLL_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <class M, bool WEIGHTED>
+struct Ring {
+  static constexpr int NSTREAM = zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0);
+  double2 slot[2][NSTREAM][ZNLL_BLOCK];  // [stage][stream][thread]
+  template <int NC>
+  ZNLL_DEV void issue(int stage, const KArgs<NC>& args, long long i) {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < ZNLL_MAXCOL; ++k)
+      if ((M::COLMASK >> k) & 1) cp_async16(&slot[stage][s++][threadIdx.x], reinterpret_cast<const double2*>(args.cols[k]) + i);
+    if constexpr (WEIGHTED) cp_async16(&slot[stage][s][threadIdx.x], reinterpret_cast<const double2*>(args.w) + i);
+  }
+  ZNLL_DEV void fetch(int stage, EventPair<M, WEIGHTED>& p) const {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < ZNLL_MAXCOL; ++k)
+      if ((M::COLMASK >> k) & 1) {
+        const double2 v = slot[stage][s++][threadIdx.x];
+        p.x[k].a = v.x;
+        p.x[k].b = v.y;
+      }
+    p.w.a = p.w.b = 1.0;
+    if constexpr (WEIGHTED) {
+      const double2 v = slot[stage][s][threadIdx.x];
+      p.w.a = v.x;
+      p.w.b = v.y;
+    }
+  }
+};
+
 template <class M, bool WEIGHTED, bool GRAD>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NACC = 2 + M::NS;
@@ -1521,7 +1570,34 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
   const long long nvec = args.n >> 1;
   const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
   long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x;
-  if constexpr ((ZNLL_PINGPONG != 0) && (zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0) >= 3)) {
+  constexpr int NSTREAM = zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0);
+  // the ring, the tables and the reduction scratch must fit the 48 KB of static shared memory
+  constexpr bool RING_FITS = 2 * NSTREAM * ZNLL_BLOCK * 16 + sizeof(MathTabs) + (ZNLL_BLOCK / 32) * NACC * 8 + 256 <= 48 * 1024;
+  if constexpr ((ZNLL_RING != 0) && (NSTREAM == 3 || NSTREAM == 4) && RING_FITS) {
+    __shared__ Ring<M, WEIGHTED> ring;
+    EventPair<M, WEIGHTED> p;
+    // groups are committed unconditionally (an empty group is legal), so "all but the newest" is always the stage read next
+    if (i < nvec) ring.issue(0, args, i);
+    cp_async_commit();
+    if (i + stride < nvec) ring.issue(1, args, i + stride);
+    cp_async_commit();
+    while (i < nvec) {
+      cp_async_wait_all_but_one();
+      ring.fetch(0, p);
+      if (i + 2 * stride < nvec) ring.issue(0, args, i + 2 * stride);  // refill the stage just read (same thread: program order)
+      cp_async_commit();
+      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, off2, acc));
+      i += stride;
+      if (i >= nvec) break;
+      cp_async_wait_all_but_one();
+      ring.fetch(1, p);
+      if (i + 2 * stride < nvec) ring.issue(1, args, i + 2 * stride);
+      cp_async_commit();
+      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, off2, acc));
+      i += stride;
+    }
+    cp_async_wait_all();
+  } else if constexpr ((ZNLL_PINGPONG != 0) && (NSTREAM >= 3)) {
     // three or more 8-byte streams per event: two register buffers used alternately -- the loop body exists twice and no
     // buffer is ever copied (the copy is 12+ moves per pair there; measured -10 % on cfg 4, while one- and two-stream
     // trees lose 1 % to the doubled loop body and keep the copying loop below)
