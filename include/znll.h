@@ -29,6 +29,7 @@
  *       ZNLL_GGET   mu, sigmal, alphal, sigmar, alphar   (GeneralizedGaussExpTail, physics.py:625-634,689-724,819-923)
  *       ZNLL_BERNSTEIN  c_0 .. c_degree       (Bernstein, polynomials.py:872-1028; every coefficient is a slot)
  *       ZNLL_TGAUSS mu, sigma, low, high      (TruncatedGauss, dist_tfp.py:357-417: zero outside [low, high])
+ *       ZNLL_HERMITE, ZNLL_LAGUERRE  c_0 .. c_degree   (Hermite, polynomials.py:752-869; Laguerre, :600-750)
  *       ZNLL_SUM    frac_0 .. frac_{k-1}      (src/zfit/models/functor.py:74-313; ALL k fractions)
  *       ZNLL_PROD   (none)                    (src/zfit/models/functor.py:331-483)
  *   The library differentiates with respect to slots; the host applies d(slot)/d(theta)
@@ -59,6 +60,8 @@ enum znll_kind {
   ZNLL_GGET = 9,
   ZNLL_BERNSTEIN = 10,
   ZNLL_TGAUSS = 11,
+  ZNLL_HERMITE = 12,
+  ZNLL_LAGUERRE = 13,
   ZNLL_SUM = 16,
   ZNLL_PROD = 17
 };

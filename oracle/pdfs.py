@@ -342,6 +342,66 @@ class Chebyshev2(Chebyshev):
         return integral * (B.const(0.5) * B.const(self.limits[1] - self.limits[0]))
 
 
+class Hermite(Chebyshev):
+    """``zfit.pdf.Hermite`` (``src/zfit/models/polynomials.py:752-869``): physicists' H_0 = 1, H_1 = 2x,
+    H_{n+1} = 2 (x H_n - n H_{n-1})."""
+
+    @staticmethod
+    def _recurrence(B, x, degree):  # hermite_polys + hermite_recurrence, polynomials.py:752-760
+        polys = [B.ones_like(x), x * B.const(2.0)]
+        for n in range(1, degree):
+            polys.append(B.const(2.0) * (x * polys[-1] - B.const(float(n)) * polys[-2]))
+        return polys
+
+    def integral(self, B, P, lo, hi, norm):  # func_integral_hermite, polynomials.py:841-866
+        coeffs = [_val(B, P, c) for c in self.coeffs]
+        lower = self._rescale(B, B.const(lo))
+        upper = self._rescale(B, B.const(hi))
+
+        def indefinite(lim):  # the integral of H_n is H_{n+1} / (2 (n+1)): a Hermite sum with shifted coefficients, c_0 = 0
+            polys = self._recurrence(B, lim, self.degree + 1)
+            tot = None
+            for n, c in enumerate(coeffs):
+                term = (c / B.const((n + 1) * 2.0)) * polys[n + 1]
+                tot = term if tot is None else tot + term
+            return tot
+
+        integral = indefinite(upper) - indefinite(lower)
+        return integral * (B.const(0.5) * B.const(self.limits[1] - self.limits[0]))
+
+
+class Laguerre(Chebyshev):
+    """``zfit.pdf.Laguerre`` (``src/zfit/models/polynomials.py:600-750``): L_0 = 1, L_1 = 1 - x,
+    (n+1) L_{n+1} = (2n + 1 - x) L_n - n L_{n-1}."""
+
+    @staticmethod
+    def _general(B, x, degree, alpha):  # generalized_laguerre_polys_factory / _recurrence_factory, polynomials.py:600-619
+        polys = [B.ones_like(x), B.const(1.0 + alpha) - x]
+        for n in range(1, degree):
+            polys.append(((B.const(2.0 * n + 1.0 + alpha) - x) * polys[-1] - B.const(n + alpha) * polys[-2]) / B.const(n + 1.0))
+        return polys
+
+    @classmethod
+    def _recurrence(cls, B, x, degree):
+        return cls._general(B, x, degree, 0.0)
+
+    def integral(self, B, P, lo, hi, norm):  # func_integral_laguerre, polynomials.py:711-746
+        coeffs = [_val(B, P, c) for c in self.coeffs]
+        lower = self._rescale(B, B.const(lo))
+        upper = self._rescale(B, B.const(hi))
+
+        def indefinite(lim):  # the integral of L_n is -L^(-1)_{n+1}: a generalised (alpha = -1) sum with c_0 = 0
+            polys = self._general(B, lim, self.degree + 1, -1.0)
+            tot = None
+            for n, c in enumerate(coeffs):
+                term = c * polys[n + 1]
+                tot = term if tot is None else tot + term
+            return B.const(-1.0) * tot
+
+        integral = indefinite(upper) - indefinite(lower)
+        return integral * (B.const(0.5) * B.const(self.limits[1] - self.limits[0]))
+
+
 class Bernstein(_Leaf):
     """``zfit.pdf.Bernstein`` (``src/zfit/models/polynomials.py:872-1028``): De Casteljau's algorithm on the observable
     rescaled to (0, 1) with the pdf's *space* limits; every coefficient is a parameter."""
@@ -656,7 +716,7 @@ def leaf_get_yield(pdf, B, P):
     return _val(B, P, pdf.yield_)
 
 
-for _cls in (Gauss, Exponential, CrystalBall, Chebyshev, Legendre, Chebyshev2, Bernstein, TruncatedGauss, GeneralizedCB,
+for _cls in (Gauss, Exponential, CrystalBall, Chebyshev, Legendre, Chebyshev2, Hermite, Laguerre, Bernstein, TruncatedGauss, GeneralizedCB,
              GaussExpTail, GeneralizedGaussExpTail):
     _cls.get_yield = lambda self, B, P: _val(B, P, self.yield_)
 

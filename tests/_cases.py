@@ -206,11 +206,13 @@ def gcb_exp_case(n=100_000, seed=9):
 
 
 def poly_case(kind, n=100_000, seed=10):
-    """Gauss + Legendre / Chebyshev2 background (degree 3: outside the catalogue -> NVRTC; degree 2: catalogue)."""
+    """Gauss + Legendre / Chebyshev2 / Hermite / Laguerre background (degree 3: outside the catalogue -> NVRTC; degree 2:
+    catalogue)."""
     rng = np.random.default_rng(seed)
     lo, hi = -6.0, 8.0
     x = _trunc(rng, lambda k: np.concatenate([rng.normal(1, 1.2, k // 3), rng.uniform(lo, hi, k - k // 3)]), lo, hi, n)
-    zk, ocls, tname, deg = {"legendre": (Z.LEGENDRE, O.Legendre, "Legd", 3), "cheb2": (Z.CHEB2, O.Chebyshev2, "Chb2", 2)}[kind]
+    zk, ocls, tname, deg = {"legendre": (Z.LEGENDRE, O.Legendre, "Legd", 3), "cheb2": (Z.CHEB2, O.Chebyshev2, "Chb2", 2),
+                            "hermite": (Z.HERMITE, O.Hermite, "Herm", 3), "laguerre": (Z.LAGUERRE, O.Laguerre, "Lagr", 3)}[kind]
     nodes = [
         Z.Node(Z.SUM, 2, 0, 0, 0, 0, 0, 0, 0),
         Z.Node(Z.GAUSS, 0, 0, 0, lo, hi, 0, 0, 0),
@@ -303,6 +305,8 @@ ALL_CASES = {
     "gcb_exp": gcb_exp_case,
     "legendre": lambda **kw: poly_case("legendre", **kw),
     "cheb2": lambda **kw: poly_case("cheb2", **kw),
+    "hermite": lambda **kw: poly_case("hermite", **kw),
+    "laguerre": lambda **kw: poly_case("laguerre", **kw),
     "get_exp": lambda **kw: get_exp_case(False, **kw),
     "gget_exp": lambda **kw: get_exp_case(True, **kw),
     "bernstein": bernstein_case,

@@ -42,10 +42,11 @@ def _translate(nodes, obs, i, slot, in_prod):
         return O.Exponential(f"s{slot}", o, lim), i + 1, slot + 1
     if nd.kind == Z.CB:
         return O.CrystalBall(f"s{slot}", f"s{slot + 1}", f"s{slot + 2}", f"s{slot + 3}", o, lim), i + 1, slot + 4
-    if nd.kind in (Z.CHEB, Z.LEGENDRE, Z.CHEB2):
+    if nd.kind in (Z.CHEB, Z.LEGENDRE, Z.CHEB2, Z.HERMITE, Z.LAGUERRE):
         assert (nd.space_lo, nd.space_hi) == lim, "oracle translation needs norm == space for polynomials"
         names = [f"s{slot + k}" for k in range(nd.degree + 1)]
-        cls = {Z.CHEB: O.Chebyshev, Z.LEGENDRE: O.Legendre, Z.CHEB2: O.Chebyshev2}[nd.kind]
+        cls = {Z.CHEB: O.Chebyshev, Z.LEGENDRE: O.Legendre, Z.CHEB2: O.Chebyshev2, Z.HERMITE: O.Hermite,
+               Z.LAGUERRE: O.Laguerre}[nd.kind]
         return cls(names[1:], o, lim, coeff0=names[0]), i + 1, slot + nd.degree + 1
     if nd.kind == Z.BERNSTEIN:
         assert (nd.space_lo, nd.space_hi) == lim, "oracle translation needs norm == space for polynomials"

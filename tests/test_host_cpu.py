@@ -85,9 +85,10 @@ def test_host_prologue_other_leaf_integrals():
 
 
 def test_host_prologue_next_row_leaves():
-    """Legendre / Chebyshev2 / GeneralizedCB integrals + derivatives vs the oracle tape."""
+    """Legendre / Chebyshev2 / Hermite / Laguerre / GeneralizedCB integrals + derivatives vs the
+    oracle tape."""
     cn, cv = ["c0", "c1", "c2", "c3"], [1.0, 0.3, -0.2, 0.1]
-    for kind, cls in ((Z.LEGENDRE, O.Legendre), (Z.CHEB2, O.Chebyshev2)):
+    for kind, cls in ((Z.LEGENDRE, O.Legendre), (Z.CHEB2, O.Chebyshev2), (Z.HERMITE, O.Hermite), (Z.LAGUERRE, O.Laguerre)):
         I, dI = Z.leaf_integral(Z.Node(kind, 0, 0, 3, -3, 7, -10, 10, 0), cv)
         rI, rdI = _autograd_integral(cls(cn[1:], "x", (-10, 10), coeff0="c0"), cn, cv, -3, 7, (-3, 7))
         assert abs(I - rI) <= 1e-14 * abs(rI) and np.allclose(dI, rdI, rtol=1e-13)

@@ -57,6 +57,7 @@ def _compile(tree, n_slots, extra=()):
         ("Sum<Gauss<0>,Gauss<0>,Cheb<0,2>>", 10),  # the `rtc` parity case of tests/_cases.py
         ("Prod<Sum<CBall<0>,Expo<0>>,Sum<Gauss<1>,Legd<1,3>>>", 7 + 8),  # sums under a product: log-native and not
         ("Sum<GCBall<0>,GGETail<0>,TGauss<0>,Bern<0,2>>", 4 + 7 + 5 + 4 + 3),
+        ("Sum<Gauss<0>,Herm<0,3>,Lagr<0,2>>", 3 + 2 + 4 + 3),
     ],
 )
 def test_embedded_source_compiles_with_nvrtc(tree, n_slots):

@@ -28,3 +28,39 @@ def test_random_tree_device_code_matches_oracle(seed):
     assert abs(v - r) <= 1e-12 * max(abs(r), n), (v, r, names)
     scale = max(np.abs(rg).max(), 1.0)
     assert np.all(np.abs(g - rg) <= 1e-10 * np.maximum(np.abs(rg), scale)), (g, rg, names)
+
+
+@pytest.mark.parametrize("name", ["Hermite", "Laguerre"])
+def test_hermite_laguerre_through_the_api(name):
+    """``zfit.pdf.Hermite`` / ``Laguerre`` (models/polynomials.py:600-869): lowering, normalisation integral and its
+    derivative, device arithmetic (host-compiled) against the oracle restatement, and ``integrate`` against quadrature."""
+    import zfit_b200 as zfit
+    from scipy import integrate as si
+
+    rng = np.random.default_rng(7)
+    obs = zfit.Space("x", -6.0, 8.0)
+    tag = name.lower()
+    mu, sg = zfit.Parameter(f"mu_{tag}", 0.8, -5, 5), zfit.Parameter(f"sg_{tag}", 1.3, 0.3, 5)
+    cs = [zfit.Parameter(f"c{k}_{tag}", v, -1, 1) for k, v in enumerate([0.12, -0.07, 0.05], start=1)]
+    fr = zfit.Parameter(f"fr_{tag}", 0.3, 0, 1)
+    poly = getattr(zfit.pdf, name)(obs, cs)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu, sg, obs), poly], fracs=fr)
+    data = zfit.Data(np.concatenate([rng.normal(1, 1.2, 1500), rng.uniform(-6, 8, 3501)]), obs=obs)
+    loss = zfit.loss.UnbinnedNLL(model, data)
+    ref = loss.create_new()
+    ref._set_engine_factory(OracleEngine)
+    loss._set_engine_factory(HostSimEngine)
+    params = list(loss.get_params())
+    v, g = loss.value_gradient(params, full=True)
+    r, rg = ref.value_gradient(params, full=True)
+    assert abs(v - r) <= 1e-12 * abs(r)
+    np.testing.assert_allclose(g, rg, rtol=0, atol=1e-10 * np.abs(rg).max())
+    # the registered analytic integral (host prologue) against numerical quadrature of the shape
+    z = lambda x: (2 * x + 6 - 8) / 14.0
+    c = [1.0, 0.12, -0.07, 0.05]
+    if name == "Hermite":
+        shape = lambda x: np.polynomial.hermite.hermval(z(x), c)
+    else:
+        shape = lambda x: np.polynomial.laguerre.lagval(z(x), c)
+    num = si.quad(shape, -2.0, 5.0)[0] / si.quad(shape, -6.0, 8.0)[0]
+    assert abs(float(poly.integrate((-2.0, 5.0))[0]) - num) <= 1e-12

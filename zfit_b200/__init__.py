@@ -32,6 +32,8 @@ pdf = _types.SimpleNamespace(
     Chebyshev=_pdf_mod.Chebyshev,
     Legendre=_pdf_mod.Legendre,
     Chebyshev2=_pdf_mod.Chebyshev2,
+    Hermite=_pdf_mod.Hermite,
+    Laguerre=_pdf_mod.Laguerre,
     Bernstein=_pdf_mod.Bernstein,
     TruncatedGauss=_pdf_mod.TruncatedGauss,
     DoubleCB=_pdf_mod.DoubleCB,

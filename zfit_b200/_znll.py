@@ -16,7 +16,8 @@ import os as _os
 
 LIB_PATH = Path(_os.environ.get("ZNLL_LIB", _HERE / "libznll.so"))  # ZNLL_LIB: tuning experiments only
 
-GAUSS, EXP, CB, CHEB, LEGENDRE, CHEB2, GCB, GET, GGET, BERNSTEIN, TGAUSS, SUM, PROD = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 16, 17
+GAUSS, EXP, CB, CHEB, LEGENDRE, CHEB2, GCB, GET, GGET, BERNSTEIN, TGAUSS, HERMITE, LAGUERRE, SUM, PROD = (
+    1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17)
 WANT_GRAD, KAHAN = 1, 2
 MAX_COLS = 8
 

@@ -849,7 +849,9 @@ struct GGETail {
 // consts [0 2/(hi-lo), 1 -(lo+hi)/(hi-lo), 2 1/I, 3.. c_k/I]
 // KIND 3: Bernstein basis B_{k,DEG}(t), t = (x - lo)/(hi - lo) (rescale_zero_one + de_casteljau, :872-905).
 // KIND 0: Chebyshev T_n (T_{n+1} = 2zT_n - T_{n-1}, polynomials.py:338-343); 1: Legendre
-// ((n+1)P_{n+1} = (2n+1)zP_n - nP_{n-1}, :181-190); 2: Chebyshev of the second kind U_n (U_1 = 2z, :487-560)
+// ((n+1)P_{n+1} = (2n+1)zP_n - nP_{n-1}, :181-190); 2: Chebyshev of the second kind U_n (U_1 = 2z, :487-560);
+// 4: Hermite, physicists' (H_1 = 2z, H_{n+1} = 2(zH_n - nH_{n-1}), :752-764); 5: Laguerre (L_1 = 1 - z,
+// (n+1)L_{n+1} = (2n+1-z)L_n - nL_{n-1}, :600-633)
 template <int COL, int DEG, int KIND, class V>
 struct PolyN {
   typedef typename Lanes<V>::Mask Mask;
@@ -883,7 +885,10 @@ struct PolyN {
     V p = zbc<V>(c[CO + 3]);
     const V z2 = zadd(z, z);
     if constexpr (DEG >= 1) {
-      T[1] = KIND == 2 ? z2 : z;
+      if constexpr (KIND == 5)
+        T[1] = zfma(z, -1.0, 1.0);
+      else
+        T[1] = (KIND == 2 || KIND == 4) ? z2 : z;
       p = zfma(T[1], c[CO + 4], p);
     }
 #pragma unroll
@@ -891,6 +896,11 @@ struct PolyN {
       if constexpr (KIND == 1) {
         const double n = (double)(k - 1);
         T[k] = zsub(zmul(zmul(z, T[k - 1]), (2.0 * n + 1.0) / (n + 1.0)), zmul(T[k - 2], n / (n + 1.0)));
+      } else if constexpr (KIND == 4) {
+        T[k] = zfma(z2, T[k - 1], zmul(T[k - 2], -2.0 * (double)(k - 1)));
+      } else if constexpr (KIND == 5) {
+        const double n = (double)(k - 1);
+        T[k] = zfma(zfma(z, -1.0 / (n + 1.0), (2.0 * n + 1.0) / (n + 1.0)), T[k - 1], zmul(T[k - 2], -n / (n + 1.0)));
       } else {
         T[k] = zfma(z2, T[k - 1], zneg(T[k - 2]));
       }
@@ -937,6 +947,10 @@ template <int COL, int DEG>
 using Legd = Poly<COL, DEG, 1>;
 template <int COL, int DEG>
 using Chb2 = Poly<COL, DEG, 2>;
+template <int COL, int DEG>
+using Herm = Poly<COL, DEG, 4>;
+template <int COL, int DEG>
+using Lagr = Poly<COL, DEG, 5>;
 template <int COL, int DEG>
 using Bern = Poly<COL, DEG, 3>;  // Bernstein (models/polynomials.py:872-1028); consts [0], [1] map x to t in [0, 1]
 

@@ -248,6 +248,24 @@ static void poly_integral(int kind, const double* c, int deg, double lo, double 
     rec(zl, Pl.data());
     J[0] = zu - zl;
     for (int k = 1; k <= deg; ++k) J[k] = (Pu[k + 1] - Pu[k - 1]) / (2.0 * k + 1.0) - (Pl[k + 1] - Pl[k - 1]) / (2.0 * k + 1.0);
+  } else if (kind == ZNLL_HERMITE) {  // func_integral_hermite, polynomials.py:841-866: int H_k = H_{k+1} / (2 (k+1))
+    auto rec = [&](double z, double* P) {
+      P[0] = 1.0;
+      P[1] = 2.0 * z;
+      for (int n = 1; n <= deg; ++n) P[n + 1] = 2.0 * (z * P[n] - n * P[n - 1]);
+    };
+    rec(zu, Pu.data());
+    rec(zl, Pl.data());
+    for (int k = 0; k <= deg; ++k) J[k] = (Pu[k + 1] - Pl[k + 1]) / (2.0 * (k + 1.0));
+  } else if (kind == ZNLL_LAGUERRE) {  // func_integral_laguerre, polynomials.py:711-746: int L_k = -L^(-1)_{k+1}
+    auto rec = [&](double z, double* P) {  // generalised Laguerre, alpha = -1: (n+1) P_{n+1} = (2n - z) P_n - (n-1) P_{n-1}
+      P[0] = 1.0;
+      P[1] = -z;
+      for (int n = 1; n <= deg; ++n) P[n + 1] = ((2.0 * n - z) * P[n] - (n - 1.0) * P[n - 1]) / (n + 1.0);
+    };
+    rec(zu, Pu.data());
+    rec(zl, Pl.data());
+    for (int k = 0; k <= deg; ++k) J[k] = -(Pu[k + 1] - Pl[k + 1]);
   } else {  // Chebyshev2
     cheb_T(zu, deg + 1, Pu.data());
     cheb_T(zl, deg + 1, Pl.data());
@@ -356,6 +374,8 @@ static int leaf_n_slots(const znll_node& nd) {
     case ZNLL_CHEB:
     case ZNLL_LEGENDRE:
     case ZNLL_CHEB2:
+    case ZNLL_HERMITE:
+    case ZNLL_LAGUERRE:
     case ZNLL_BERNSTEIN: return nd.degree + 1;
     case ZNLL_TGAUSS: return 4;
     case ZNLL_GCB: return 7;
@@ -372,6 +392,8 @@ static int leaf_n_consts(const znll_node& nd) {
     case ZNLL_CHEB:
     case ZNLL_LEGENDRE:
     case ZNLL_CHEB2:
+    case ZNLL_HERMITE:
+    case ZNLL_LAGUERRE:
     case ZNLL_BERNSTEIN: return 3 + nd.degree + 1;
     case ZNLL_TGAUSS: return 5;
     case ZNLL_GCB: return 24;
@@ -389,6 +411,8 @@ static int leaf_integral(const znll_node& nd, const double* s, double* I, double
     case ZNLL_CHEB:
     case ZNLL_LEGENDRE:
     case ZNLL_CHEB2:
+    case ZNLL_HERMITE:
+    case ZNLL_LAGUERRE:
     case ZNLL_BERNSTEIN: poly_integral(nd.kind, s, nd.degree, nd.norm_lo, nd.norm_hi, nd.space_lo, nd.space_hi, I, dI); return 0;
     case ZNLL_TGAUSS: tgauss_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
     case ZNLL_GCB: gcb_integral(s, nd.norm_lo, nd.norm_hi, I, dI); return 0;
@@ -500,7 +524,8 @@ static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int par
   const int ns = leaf_n_slots(nd), nc = leaf_n_consts(nd);
   if (ns < 0 || nd.n_children != 0) return -1;
   if (nd.column < 0 || nd.column >= ZNLL_MAX_COLS) return -1;
-  if ((nd.kind == ZNLL_CHEB || nd.kind == ZNLL_LEGENDRE || nd.kind == ZNLL_CHEB2 || nd.kind == ZNLL_BERNSTEIN) &&
+  if ((nd.kind == ZNLL_CHEB || nd.kind == ZNLL_LEGENDRE || nd.kind == ZNLL_CHEB2 || nd.kind == ZNLL_BERNSTEIN ||
+       nd.kind == ZNLL_HERMITE || nd.kind == ZNLL_LAGUERRE) &&
       (nd.degree < 0 || nd.degree > 16))
     return -1;
   c.n_slots += ns;
@@ -515,6 +540,8 @@ static int parse(Channel& c, const znll_node* nodes, int n_nodes, int i, int par
     case ZNLL_GGET: snprintf(buf, sizeof buf, "GGETail<%d>", nd.column); break;
     case ZNLL_LEGENDRE: snprintf(buf, sizeof buf, "Legd<%d,%d>", nd.column, nd.degree); break;
     case ZNLL_CHEB2: snprintf(buf, sizeof buf, "Chb2<%d,%d>", nd.column, nd.degree); break;
+    case ZNLL_HERMITE: snprintf(buf, sizeof buf, "Herm<%d,%d>", nd.column, nd.degree); break;
+    case ZNLL_LAGUERRE: snprintf(buf, sizeof buf, "Lagr<%d,%d>", nd.column, nd.degree); break;
     case ZNLL_BERNSTEIN: snprintf(buf, sizeof buf, "Bern<%d,%d>", nd.column, nd.degree); break;
     case ZNLL_TGAUSS: snprintf(buf, sizeof buf, "TGauss<%d>", nd.column); break;
     default: snprintf(buf, sizeof buf, "Cheb<%d,%d>", nd.column, nd.degree); break;
@@ -638,7 +665,9 @@ static void fill_consts(Channel& c, const double* slots) {
       }
       case ZNLL_CHEB:
       case ZNLL_LEGENDRE:
-      case ZNLL_CHEB2: {
+      case ZNLL_CHEB2:
+      case ZNLL_HERMITE:
+      case ZNLL_LAGUERRE: {
         k[0] = 2.0 / (nd.space_hi - nd.space_lo);
         k[1] = -(nd.space_lo + nd.space_hi) / (nd.space_hi - nd.space_lo);
         k[2] = 1.0 / I;

@@ -470,6 +470,18 @@ class Chebyshev2(_RecursivePolynomial):
     _KIND = Z.CHEB2
 
 
+class Hermite(_RecursivePolynomial):
+    """``zfit.pdf.Hermite`` -- physicists' ``H_n``, ``H_1 = 2x`` (``models/polynomials.py:752-869``)."""
+
+    _KIND = Z.HERMITE
+
+
+class Laguerre(_RecursivePolynomial):
+    """``zfit.pdf.Laguerre`` -- ``L_1 = 1 - x`` (``models/polynomials.py:600-750``)."""
+
+    _KIND = Z.LAGUERRE
+
+
 class Bernstein(_Leaf1D):
     """``zfit.pdf.Bernstein(obs, coeffs, apply_scaling=True, *, extended, norm, name, label)``
     (``models/polynomials.py:872-1028``): ``sum_k c_k B_{k,n}(t)`` with ``t`` the observable rescaled to ``(0, 1)``; every
