@@ -22,7 +22,8 @@ network).  The oracle is therefore pinned against
   ``_unbinned_nll_tf`` / ``_nll_calc_unbinned_tf`` (``core/loss.py``), ``SumPDF._pdf``
   / ``ProductPDF._pdf`` (``models/functor.py``) and ``z.safe_where`` out of
   ``/root/reference`` with ``ast`` and runs it over numpy stand-ins of ``znp`` /
-  ``tf`` (58 definitions); the vectors are committed as
+  ``tf`` (60 definitions, the two loss bodies ``UnbinnedNLL._loss_func_watched`` and
+  ``ExtendedUnbinnedNLL._loss_func`` included); the vectors are committed as
   ``tests/golden/reference_formulas.npz`` and ``tests/test_reference_formulas_cpu.py``
   holds the oracle (<= 2e-14), the product's host prologue (<= 1e-13) and the
   host-compiled device code (<= 2e-13) to them;

@@ -66,7 +66,7 @@ def _t(x):
 znp = types.SimpleNamespace(
     exp=np.exp, log=np.log, abs=np.abs, square=np.square, power=np.power, sqrt=np.sqrt, where=np.where,
     zeros_like=np.zeros_like, ones_like=np.ones_like, multiply=np.multiply, maximum=np.maximum, minimum=np.minimum,
-    sum=np.sum, asarray=lambda x, dtype=None: _t(x), reshape=lambda x, newshape=None, **kw: _t(np.reshape(x, newshape)),
+    sum=np.sum, atleast_1d=np.atleast_1d, concatenate=np.concatenate, stack=np.stack, asarray=lambda x, dtype=None: _t(x), reshape=lambda x, newshape=None, **kw: _t(np.reshape(x, newshape)),
     float64=np.float64, pi=np.pi,
 )
 
@@ -79,6 +79,7 @@ tf = types.SimpleNamespace(
     where=_tf_where, less=np.less, greater=np.greater, less_equal=np.less_equal, greater_equal=np.greater_equal,
     ones_like=np.ones_like, sign=np.sign, square=np.square, Tensor=object, float64=np.float64,
     constant=lambda v, dtype=None: _f64(v), math=types.SimpleNamespace(erf=scipy.special.erf),
+    nn=types.SimpleNamespace(log_poisson_loss=lambda *a, **k: _log_poisson_loss(*a, **k)),
 )
 
 
@@ -133,6 +134,18 @@ def _methods(path: Path, class_name: str, names, namespace: dict):
     return out
 
 
+def _log_poisson_loss(targets, log_input, compute_full_loss=False):
+    """tf.nn.log_poisson_loss by its published definition (third party, NOT pinned by this script): exp(c) - c*z, plus
+    Stirling's z*log(z) - z + 0.5*log(2*pi*z) where z is outside [0, 1] when compute_full_loss."""
+    targets, log_input = _f64(targets), _f64(log_input)
+    result = np.exp(log_input) - log_input * targets
+    if compute_full_loss:
+        with np.errstate(all="ignore"):
+            stirling = targets * np.log(targets) - targets + 0.5 * np.log(2.0 * np.pi * targets)
+        result = result + np.where((targets >= 0.0) & (targets <= 1.0), 0.0, stirling)
+    return _t(result)
+
+
 def _kahan_sum(input_tensor, axis=0):  # stand-in for tfp.math.reduce_kahan_sum (third party, NOT pinned by this script)
     s = c = 0.0
     for v in np.asarray(input_tensor, dtype=np.float64):
@@ -149,7 +162,7 @@ def load_reference():
           "operator": __import__("operator"), "supports": lambda *a, **k: (lambda f: f),
           "is_container": lambda obj: isinstance(obj, (list, tuple)),
           "tfp": types.SimpleNamespace(math=types.SimpleNamespace(reduce_kahan_sum=_kahan_sum)),
-          "SpecificFunctionNotImplemented": RuntimeError}
+          "SpecificFunctionNotImplemented": RuntimeError, "NotExtendedPDFError": RuntimeError}
     _top_level(REF / "z" / "zextension.py", ns, only_functions={"safe_where"})
     z.safe_where = ns["safe_where"]
     got = _top_level(REF / "models" / "physics.py", ns) + _top_level(REF / "models" / "polynomials.py", ns)
@@ -161,7 +174,10 @@ def load_reference():
     # SumPDF / ProductPDF value (models/functor.py)
     ns["sum_methods"] = _methods(REF / "models" / "functor.py", "SumPDF", {"_pdf"}, ns)
     ns["prod_methods"] = _methods(REF / "models" / "functor.py", "ProductPDF", {"_pdf"}, ns)
-    got += ["Exponential._unnormalized_pdf", "Exponential._shift_x", "SumPDF._pdf", "ProductPDF._pdf"]
+    ns["nll_methods"] = _methods(REF / "core" / "loss.py", "UnbinnedNLL", {"_loss_func_watched"}, ns)
+    ns["extnll_methods"] = _methods(REF / "core" / "loss.py", "ExtendedUnbinnedNLL", {"_loss_func"}, ns)
+    got += ["Exponential._unnormalized_pdf", "Exponential._shift_x", "SumPDF._pdf", "ProductPDF._pdf",
+            "UnbinnedNLL._loss_func_watched", "ExtendedUnbinnedNLL._loss_func"]
     return ns, got
 
 
@@ -323,6 +339,39 @@ def main():
                 cases.append([0.0 if weights is None else 1.0, np.nan if log_offset is False else log_offset, float(kahan),
                               float(nll), float(corr)])
     out["nll_cases"] = np.array(cases)  # weighted?, log_offset (NaN = False), kahan?, nll, corr
+
+    # the loss bodies around it: UnbinnedNLL._loss_func_watched (constraints, nll - corr) and
+    # ExtendedUnbinnedNLL._loss_func (per-channel Poisson term from samplesize and yield, offset per channel)
+    class _Ext(_Model):
+        def __init__(self, probs, yield_):
+            super().__init__(probs)
+            self.is_extended, self._y = True, yield_
+
+        def get_yield(self):
+            return _t(self._y)
+
+    class _ExtData(_Data):
+        def __init__(self, n, weights=None):
+            super().__init__(weights)
+            self.samplesize = float(n) if weights is None else float(np.sum(weights))
+
+    yields = np.array([3900.0, 2600.5])
+    out["ext_yields"] = yields
+    constraint_values = np.array([0.37, 1.25])
+    out["ext_constraints"] = constraint_values
+    cons = [types.SimpleNamespace(value=lambda v=v: _t(v)) for v in constraint_values]
+    cases = []
+    for weights in (None, w1):
+        for log_offset in (False, -1.75):
+            for with_cons in (False, True):
+                mods = [_Ext(p1, yields[0]), _Ext(p2, yields[1])]
+                dats = [_ExtData(n1, weights), _ExtData(n2)]
+                ext = ns["extnll_methods"]["_loss_func"](None, mods, dats, [None, None], cons if with_cons else [], log_offset)
+                plain = ns["nll_methods"]["_loss_func_watched"](None, dats, mods, [None, None], cons if with_cons else [], log_offset,
+                                                               sumtype=None)
+                cases.append([0.0 if weights is None else 1.0, np.nan if log_offset is False else log_offset, float(with_cons),
+                              float(ext), float(plain)])
+    out["loss_cases"] = np.array(cases)  # weighted?, log_offset (NaN = False), constraints?, extended NLL, plain NLL
 
     # ---- models/functor.py: SumPDF._pdf and ProductPDF._pdf from given daughter values
     d1, d2, d3 = p1[:2000] + 1e-3, np.exp(rng.normal(-1.0, 0.5, 2000)), rng.uniform(0.1, 2.0, 2000)

@@ -171,3 +171,34 @@ def test_functor_values_from_given_daughters():
     P = {f"f{i}": np.float64(f) for i, f in enumerate(fr)}
     _close(s.pdf(B, {"x": np.zeros(d.shape[1])}, P), G["sum_pdf"], rtol=4e-16)
     _close(d[0] * d[1] * d[2], G["prod_pdf"], rtol=4e-16)  # ProductPDF of normalised daughters: the plain product, in order
+
+
+class _GivenProbsExt(_GivenProbs):
+    def __init__(self, probs, yield_):
+        super().__init__(probs)
+        self._y = yield_
+
+    def get_yield(self, B_, P):
+        return B_.const(self._y)
+
+
+def test_loss_bodies_extended_term_and_constraints():
+    """``UnbinnedNLL._loss_func_watched`` and ``ExtendedUnbinnedNLL._loss_func`` (core/loss.py:1134-1158, 1291-1318): the
+    Poisson term per channel from samplesize (sum of weights) and yield, the offset added once per channel, Stirling only
+    without an offset, the constraints' sum.  ``tf.nn.log_poisson_loss`` itself is the published formula on both sides."""
+    from oracle import nll as ON
+
+    p1, p2, w1 = G["nll_p1"], G["nll_p2"], G["nll_w1"]
+    y = G["ext_yields"]
+    models = [_GivenProbsExt(p1, y[0]), _GivenProbsExt(p2, y[1])]
+    datas = [{"x": np.zeros(len(p1))}, {"x": np.zeros(len(p2))}]
+    csum = float(np.sum(G["ext_constraints"]))
+    for weighted, off, with_cons, ext, plain in G["loss_cases"]:
+        weights = [w1, None] if weighted else None
+        log_offset = False if np.isnan(off) else float(off)
+        add = csum if with_cons else 0.0
+        scale = float(np.sum(np.abs(np.log(p1 + 1e-307)) * (np.abs(w1) if weighted else 1.0)) + np.sum(np.abs(np.log(p2 + 1e-307))))
+        got_plain = float(ON.unbinned_nll(models, datas, {}, weights=weights, log_offset=log_offset)) + add
+        got_ext = float(ON.unbinned_nll(models, datas, {}, weights=weights, log_offset=log_offset, extended=True)) + add
+        assert abs(got_plain - plain) <= 2e-14 * scale
+        assert abs(got_ext - ext) <= 2e-14 * scale, (weighted, off, with_cons, got_ext, ext)
