@@ -300,6 +300,7 @@ class HostSimEngine:
 
     def __init__(self, models, datas, fit_ranges):
         self.slot_params, self.channel_slots, self.channels = [], [], []
+        self._args, self._oracle = (list(models), list(datas), list(fit_ranges)), None
         datas = [d if r is None else d.with_obs(r, guarantee_limits=False) for d, r in zip(datas, fit_ranges)]
         for model, data, rng in zip(models, datas, fit_ranges):
             nodes, slots = model._lower(data.obs, rng)
@@ -324,6 +325,15 @@ class HostSimEngine:
             if grad:
                 gs[lo:hi] = g
         return np.asarray(values), (gs if grad else None)
+
+    def eval_cov(self, slots):
+        """The covariance pass only seeds the MIGRAD metric here: taken from the oracle engine (the kernel's own
+        covariance pass is covered by the GPU tests)."""
+        if self._oracle is None:
+            from tests._oracle_engine import OracleEngine
+
+            self._oracle = OracleEngine(*self._args)
+        return self._oracle.eval_cov(slots)
 
     def launch_count(self):
         return 0
