@@ -668,3 +668,64 @@ def test_update_data_in_place_invalidates_binding_and_offset():
     np.testing.assert_allclose(g1, g2, rtol=1e-12)
     with pytest.raises(ValueError, match="same length"):
         data.update_data(x2, weights=np.ones(3))
+
+
+def test_plan_step_path_marshalling(tmp_path, monkeypatch):
+    """``Plan.eval / launch / collect`` keep persistent argument buffers and cached ctypes pointers (step-path overhead);
+    checked here without a GPU against a C stub with the signatures of ``znll_eval`` / ``znll_launch`` / ``znll_collect``
+    (``include/znll.h``) that echoes what it received."""
+    import ctypes as C
+    import subprocess
+
+    src = tmp_path / "stub.c"
+    src.write_text(
+        """
+        static double seen[16]; static unsigned seen_flags; static double seen_off; static void* seen_stream; static int nslots = 3;
+        int stub_eval(void* p, const double* s, unsigned f, double off, double* v, double* g, void* st) {
+          if (p != (void*)0x1234) return 1;
+          for (int i = 0; i < nslots; ++i) g[i] = 10.0 * s[i];
+          v[0] = off + f; v[1] = (double)(long)st; return 0; }
+        int stub_launch(void* p, const double* s, unsigned f, double off, void* st) {
+          for (int i = 0; i < nslots; ++i) seen[i] = s[i];
+          seen_flags = f; seen_off = off; seen_stream = st; return 0; }
+        int stub_collect(void* p, unsigned f, double* v, double* g, void* st) {
+          if (f != seen_flags || st != seen_stream) return 1;
+          for (int i = 0; i < nslots; ++i) g[i] = -seen[i];
+          v[0] = seen_off; v[1] = 7.0; return 0; }
+        int stub_fail(void* p, const double* s, unsigned f, double off, double* v, double* g, void* st) { return 1; }
+        """
+    )
+    so = tmp_path / "libstub.so"
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+    stub = C.CDLL(str(so))
+    L = Z.lib()
+    for name, sym in (("stub_eval", "znll_eval"), ("stub_launch", "znll_launch"), ("stub_collect", "znll_collect"),
+                      ("stub_fail", "znll_eval")):
+        fn = getattr(stub, name)
+        fn.restype, fn.argtypes = Z.SYMBOLS[sym]
+    monkeypatch.setattr(L, "znll_eval", stub.stub_eval, raising=False)
+    monkeypatch.setattr(L, "znll_launch", stub.stub_launch, raising=False)
+    monkeypatch.setattr(L, "znll_collect", stub.stub_collect, raising=False)
+    monkeypatch.setattr(L, "znll_plan_total_slots", lambda h: 3, raising=False)
+    plan = Z.Plan.__new__(Z.Plan)  # no device: only the argument path is under test
+    plan._h, plan.n_channels, plan._keep = C.c_void_p(0x1234), 2, []
+    try:
+        plan._buffers()
+        for slots in (np.array([1.0, 2.0, 3.0]), [1.0, 2.0, 3.0], np.array([1, 2, 3]), np.arange(6.0)[::2] * 1.0 + 1 - np.arange(3.0)):
+            v, g = plan.eval(slots, grad=True, log_offset=0.25, stream=77)
+            assert v.tolist() == [0.25 + Z.WANT_GRAD, 77.0]
+            assert g.tolist() == [10.0, 20.0, 30.0]
+        v0, g0 = plan.eval([4.0, 5.0, 6.0], grad=False, log_offset=np.float64(1.5), kahan=True)
+        assert g0 is None and v0.tolist() == [1.5 + Z.KAHAN, 0.0]
+        assert v.tolist() == [0.25 + Z.WANT_GRAD, 77.0]  # results handed out earlier are copies
+        plan.launch(np.array([7.0, 8.0, 9.0]), grad=True, log_offset=2.0, stream=5)
+        v, g = plan.collect(grad=True, stream=5)
+        assert v.tolist() == [2.0, 7.0] and g.tolist() == [-7.0, -8.0, -9.0]
+        with pytest.raises(ValueError, match="expected 3 slots"):
+            plan.eval([1.0, 2.0])
+        monkeypatch.setattr(L, "znll_eval", stub.stub_fail, raising=False)
+        plan._buffers()
+        with pytest.raises(Z.ZnllError):
+            plan.eval([1.0, 2.0, 3.0])
+    finally:
+        plan._h = C.c_void_p()  # nothing to destroy

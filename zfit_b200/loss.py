@@ -110,6 +110,24 @@ class CudaEngine:
             if self.reduce_mode == "nccl":
                 self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
         self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
+        self._raw_stream = self._pick_stream_getter()
+
+    def _pick_stream_getter(self):
+        """torch's current stream on this device as a raw ``cudaStream_t``.  ``torch.cuda.current_stream(d).cuda_stream``
+        builds a Stream object per call (~2 us on the step path); torch's own raw getter (the one its compiled graphs
+        use) returns the handle directly.  It is used only if it exists and agrees with the public API right now."""
+        torch, dev = self.torch, self.device
+
+        def public():
+            return torch.cuda.current_stream(dev).cuda_stream
+
+        raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        try:
+            if raw is not None and int(raw(dev)) == int(public()):
+                return lambda: raw(dev)
+        except Exception:
+            pass
+        return public
 
     def rebind(self, datas):
         """The events of the bound ``Data`` objects changed in place (``SamplerData.resample``): bind the new columns to
@@ -173,7 +191,7 @@ class CudaEngine:
 
     def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
         # kernels go to torch's current stream, so torch ops (NCCL all-reduce, data preparation) order with them
-        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._raw_stream()
         if not self.distributed or self.reduce_mode == "fused-nvlink":
             return self.plan.eval(slots, grad=grad, log_offset=log_offset, kahan=kahan, stream=stream)
         self.plan.launch(slots, grad=grad, log_offset=log_offset, stream=stream)
