@@ -70,3 +70,38 @@ def test_ring_experiment_compiles_with_nvrtc():
     """ZNLL_RING=1 (off by default): the cp.async staging loop for three- and four-stream trees."""
     cubin_bytes, _ = _compile("Prod<Sum<Gauss<0>,Expo<0>>,Gauss<1>,Cheb<2,3>>", 4 + 1 + 2 + 4, extra=(b"-DZNLL_RING=1",))
     assert cubin_bytes > 10_000
+
+
+def test_compiled_images_are_cached_on_disk(tmp_path, monkeypatch):
+    """``rtc::obtain_image`` (what ``znll_plan_set_model`` uses for trees outside the catalogue): first call compiles and
+    writes ``$ZNLL_CACHE_DIR/rtc-<key>.cubin``, the second reads it back; a damaged, truncated or foreign file is ignored
+    (recompiled and replaced); ``ZNLL_CACHE_DIR=off`` never touches the disk."""
+    import time
+
+    _nvrtc()
+    tree, n_slots = "Sum<Gauss<0>,Expo<0>,Cheb<0,1>>", 3 + 2 + 1 + 2
+    cache = tmp_path / "nested" / "cache"
+    monkeypatch.setenv("ZNLL_CACHE_DIR", str(cache))
+    t0 = time.perf_counter()
+    size, names, cached = Z.test_rtc_image(tree, n_slots)
+    t_compile = time.perf_counter() - t0
+    assert size > 10_000 and names == 7 and not cached
+    files = list(cache.glob("rtc-*.cubin"))
+    assert len(files) == 1 and files[0].stat().st_size > size and not list(cache.glob("*.tmp.*"))
+    t0 = time.perf_counter()
+    assert Z.test_rtc_image(tree, n_slots) == (size, names, True)
+    t_hit = time.perf_counter() - t0
+    assert t_hit < 0.25 * t_compile, (t_hit, t_compile)
+    # a different tree is a different key
+    assert Z.test_rtc_image("Sum<Gauss<0>,Expo<0>,Cheb<0,2>>", n_slots + 1)[2] is False
+    assert len(list(cache.glob("rtc-*.cubin"))) == 2
+    good = files[0].read_bytes()
+    for bad in (good[: len(good) // 2], good[:-1] + bytes([good[-1] ^ 1]), b"ZNLLRTC1" + b"\0" * 64, b""):
+        files[0].write_bytes(bad)
+        assert Z.test_rtc_image(tree, n_slots)[1:] == (names, False)  # not trusted: compiled again ...
+        assert Z.test_rtc_image(tree, n_slots)[1:] == (names, True)  # ... and replaced by a valid file
+    monkeypatch.setenv("ZNLL_CACHE_DIR", "off")
+    assert Z.test_rtc_image(tree, n_slots)[1:] == (names, False)
+    # an unwritable cache location is not an error
+    monkeypatch.setenv("ZNLL_CACHE_DIR", "/proc/znll-cannot-exist")
+    assert Z.test_rtc_image(tree, n_slots)[1:] == (names, False)

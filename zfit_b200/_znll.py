@@ -77,6 +77,7 @@ SYMBOLS = {
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
     "znll_test_prologue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.c_char_p, C.c_int]),
+    "znll_test_rtc_image": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "znll_test_epilogue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_double, _DP, _DP]),
     "znll_migrad": (C.c_int, None),  # callback pointers and structs: see _migrad_native.py
     "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
@@ -291,6 +292,13 @@ def test_prologue(nodes, slots):
         msg = f"expected {ns.value} slots, got {slots.size}"
         raise ValueError(msg)
     return name.value.decode(), consts[: nc.value].copy()
+
+
+def test_rtc_image(model: str, n_slots: int, use_cache: bool = True):
+    """Host only: (cubin bytes, number of kernels, came from the on-disk cache) for a tree outside the catalogue -- test hook."""
+    size, names, cached = C.c_size_t(0), C.c_int(0), C.c_int(0)
+    _check(lib().znll_test_rtc_image(model.encode(), n_slots, int(use_cache), C.byref(size), C.byref(names), C.byref(cached)))
+    return size.value, names.value, bool(cached.value)
 
 
 def test_epilogue(nodes, slots, acc, sumw, grad=True):

@@ -14,7 +14,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <map>
@@ -718,8 +722,9 @@ typedef int (*cuModuleLoadData_t)(void**, const void*);
 typedef int (*cuModuleGetFunction_t)(void**, void*, const char*);
 typedef int (*cuLaunchKernel_t)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*,
                                 void**, void**);
+typedef int (*nvrtcVersion_t)(int*, int*);
 struct Api {
-  bool ok = false;
+  bool nvrtc_ok = false, ok = false;  // ok: NVRTC and the driver API (module load + launch)
   std::string why;
   nvrtcCreateProgram_t create;
   nvrtcCompileProgram_t compile;
@@ -730,6 +735,7 @@ struct Api {
   nvrtcGetProgramLogSize_t logsize;
   nvrtcGetProgramLog_t log;
   nvrtcDestroyProgram_t destroy;
+  nvrtcVersion_t version;
   cuModuleLoadData_t modload;
   cuModuleGetFunction_t getfn;
   cuLaunchKernel_t launch;
@@ -742,9 +748,8 @@ static Api& api() {
     const char* nv[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
     for (auto n : nv)
       if ((hn = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
-    void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-    if (!hn || !hc) {
-      a.why = !hn ? "libnvrtc.so.12 not found" : "libcuda.so.1 not found";
+    if (!hn) {
+      a.why = "libnvrtc.so.12 not found";
       return;
     }
 #define L(h, field, sym)                                   \
@@ -762,6 +767,13 @@ static Api& api() {
     L(hn, logsize, "nvrtcGetProgramLogSize")
     L(hn, log, "nvrtcGetProgramLog")
     L(hn, destroy, "nvrtcDestroyProgram")
+    L(hn, version, "nvrtcVersion")
+    a.nvrtc_ok = true;  // compiling needs no driver (the CPU test suite compiles for sm_100a without a GPU)
+    void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!hc) {
+      a.why = "libcuda.so.1 not found";
+      return;
+    }
     L(hc, modload, "cuModuleLoadData")
     L(hc, getfn, "cuModuleGetFunction")
     L(hc, launch, "cuLaunchKernel")
@@ -774,23 +786,25 @@ static Api& api() {
 static std::mutex g_mu;
 static std::map<std::string, Kernel> g_cache;
 
-// compile nll_kernel<Model, W, G> for the four (W, G) variants
-// n_slots decides whether the covariance-pass kernels are instantiated: with 2 + NS + (NS+1)(NS+2)/2 > 256 accumulators
-// they would not fit the reduction's shared memory (znll_eval_cov refuses such trees), and must not break the build.
-static int build(const std::string& model, int n_slots, Kernel* out) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_cache.find(model);
-  if (it != g_cache.end()) {
-    *out = it->second;
-    return 0;
-  }
+// What one NVRTC compilation yields: the cubin and the lowered (mangled) names of the instantiations, in the fixed order
+// nll<false,false>, nll<false,true>, nll<true,false>, nll<true,true>, pdf, [cov<false>, cov<true>].
+struct Image {
+  std::vector<std::string> lowered;
+  std::vector<char> cubin;
+};
+
+static const char* const kOpts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+
+// compile nll_kernel<Model, W, G> for the four (W, G) variants, pdf_kernel<Model> and -- n_slots permitting -- cov_kernel:
+// with 2 + NS + (NS+1)(NS+2)/2 > 256 accumulators the covariance pass would not fit the reduction's shared memory
+// (znll_eval_cov refuses such trees), and must not break the build.
+static int compile_image(const std::string& model, int n_slots, Image* img) {
   Api& a = api();
-  if (!a.ok) return fail("model '%s' is not in the ahead-of-time catalogue and NVRTC is unavailable (%s)",
-                         model.c_str(), a.why.c_str());
+  if (!a.nvrtc_ok) return fail("model '%s' is not in the ahead-of-time catalogue and NVRTC is unavailable (%s)",
+                               model.c_str(), a.why.c_str());
   std::string src = std::string(znll_device_src) + "\n";
   void* prog = nullptr;
   if (a.create(&prog, src.c_str(), "znll_rtc.cu", 0, nullptr, nullptr)) return fail("nvrtcCreateProgram failed");
-  std::string exprs[2][2];
   // qualify nested names: insert "znll::" before every identifier that starts a template name
   auto qualify = [](const std::string& m) {
     std::string o;
@@ -808,21 +822,17 @@ static int build(const std::string& model, int n_slots, Kernel* out) {
     return o;
   };
   const std::string q = qualify(model);
+  std::vector<std::string> exprs;
   for (int w = 0; w < 2; ++w)
-    for (int g = 0; g < 2; ++g) {
-      exprs[w][g] = "znll::nll_kernel<" + q + "," + (w ? "true" : "false") + "," + (g ? "true" : "false") + ">";
-      a.addname(prog, exprs[w][g].c_str());
-    }
-  const std::string pdf_expr = "znll::pdf_kernel<" + q + ">";
-  a.addname(prog, pdf_expr.c_str());
-  const std::string cov_expr[2] = {"znll::cov_kernel<" + q + ",false>", "znll::cov_kernel<" + q + ",true>"};
-  const bool with_cov = 2 + n_slots + (n_slots + 1) * (n_slots + 2) / 2 <= 256;
-  if (with_cov) {
-    a.addname(prog, cov_expr[0].c_str());
-    a.addname(prog, cov_expr[1].c_str());
+    for (int g = 0; g < 2; ++g)
+      exprs.push_back("znll::nll_kernel<" + q + "," + (w ? "true" : "false") + "," + (g ? "true" : "false") + ">");
+  exprs.push_back("znll::pdf_kernel<" + q + ">");
+  if (2 + n_slots + (n_slots + 1) * (n_slots + 2) / 2 <= 256) {
+    exprs.push_back("znll::cov_kernel<" + q + ",false>");
+    exprs.push_back("znll::cov_kernel<" + q + ",true>");
   }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
-  const int rc = a.compile(prog, 3, opts);
+  for (auto& e : exprs) a.addname(prog, e.c_str());
+  const int rc = a.compile(prog, (int)(sizeof(kOpts) / sizeof(kOpts[0])), kOpts);
   if (rc) {
     size_t n = 0;
     a.logsize(prog, &n);
@@ -831,45 +841,183 @@ static int build(const std::string& model, int n_slots, Kernel* out) {
     a.destroy(&prog);
     return fail("NVRTC compile of '%s' failed: %.800s", model.c_str(), log.c_str());
   }
+  img->lowered.clear();
+  for (auto& e : exprs) {
+    const char* low = nullptr;
+    a.lowered(prog, e.c_str(), &low);
+    if (!low) {
+      a.destroy(&prog);
+      return fail("nvrtcGetLoweredName failed for '%s'", e.c_str());
+    }
+    img->lowered.push_back(low);
+  }
   size_t sz = 0;
   a.cubinsize(prog, &sz);
-  std::vector<char> cubin(sz);
-  a.cubin(prog, cubin.data());
+  img->cubin.resize(sz);
+  a.cubin(prog, img->cubin.data());
+  a.destroy(&prog);
+  return 0;
+}
+
+// ---- on-disk cache of compiled images --------------------------------------------------------------------------------
+// A tree outside the catalogue costs 3-8 s of NVRTC per process; the result depends only on the embedded source, the
+// tree's name, the options and the NVRTC version, so it is kept under $ZNLL_CACHE_DIR (default $XDG_CACHE_HOME/zfit_b200
+// or ~/.cache/zfit_b200; "" or "off" disables).  Any problem with a cache file -- absent, truncated, wrong key or checksum,
+// a cubin the driver refuses -- falls back to compiling; files are written to a temporary name and renamed.
+static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+
+static std::string cache_dir() {
+  const char* e = getenv("ZNLL_CACHE_DIR");
+  if (e) return (!*e || !strcmp(e, "off") || !strcmp(e, "0")) ? std::string() : std::string(e);
+  if (const char* x = getenv("XDG_CACHE_HOME"); x && *x) return std::string(x) + "/zfit_b200";
+  if (const char* h = getenv("HOME"); h && *h) return std::string(h) + "/.cache/zfit_b200";
+  return std::string();
+}
+
+static uint64_t image_key(const std::string& model, int n_slots) {
+  int major = 0, minor = 0;
+  Api& a = api();
+  if (a.nvrtc_ok) a.version(&major, &minor);
+  uint64_t h = fnv1a(znll_device_src, strlen(znll_device_src));
+  h = fnv1a(model.data(), model.size(), h);
+  for (auto o : kOpts) h = fnv1a(o, strlen(o) + 1, h);
+  const int tail[4] = {n_slots, major, minor, 1 /* file format */};
+  return fnv1a(tail, sizeof(tail), h);
+}
+
+static std::string cache_file(uint64_t key) {
+  const std::string dir = cache_dir();
+  if (dir.empty()) return dir;
+  char name[64];
+  snprintf(name, sizeof(name), "/rtc-%016llx.cubin", (unsigned long long)key);
+  return dir + name;
+}
+
+static const char kMagic[8] = {'Z', 'N', 'L', 'L', 'R', 'T', 'C', '1'};
+
+static bool cache_load(const std::string& path, uint64_t key, Image* img) {
+  if (path.empty()) return false;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::vector<char> buf;
+  char chunk[1 << 16];
+  size_t n;
+  while ((n = fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + n);
+  fclose(f);
+  uint64_t head[3];  // key, payload bytes, payload checksum
+  if (buf.size() < sizeof(kMagic) + sizeof(head) || memcmp(buf.data(), kMagic, sizeof(kMagic))) return false;
+  memcpy(head, buf.data() + sizeof(kMagic), sizeof(head));
+  const char* pay = buf.data() + sizeof(kMagic) + sizeof(head);
+  const size_t len = buf.size() - sizeof(kMagic) - sizeof(head);
+  if (head[0] != key || head[1] != len || head[2] != fnv1a(pay, len)) return false;
+  size_t off = 0;
+  auto take = [&](void* dst, size_t k) {
+    if (off + k > len) return false;
+    memcpy(dst, pay + off, k);
+    off += k;
+    return true;
+  };
+  uint32_t n_names = 0;
+  if (!take(&n_names, 4) || (n_names != 5 && n_names != 7)) return false;
+  img->lowered.clear();
+  for (uint32_t i = 0; i < n_names; ++i) {
+    uint32_t l = 0;
+    if (!take(&l, 4) || l == 0 || l > 4096 || off + l > len) return false;
+    img->lowered.emplace_back(pay + off, l);
+    off += l;
+  }
+  uint64_t sz = 0;
+  if (!take(&sz, 8) || sz == 0 || sz != len - off) return false;
+  img->cubin.assign(pay + off, pay + off + sz);
+  return true;
+}
+
+static void mkdirs(const std::string& dir) {
+  for (size_t i = 1; i <= dir.size(); ++i)
+    if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);  // EEXIST is fine
+}
+
+static void cache_store(const std::string& path, uint64_t key, const Image& img) {
+  if (path.empty()) return;
+  std::vector<char> pay;
+  auto put = [&](const void* src, size_t k) { pay.insert(pay.end(), (const char*)src, (const char*)src + k); };
+  const uint32_t n_names = (uint32_t)img.lowered.size();
+  put(&n_names, 4);
+  for (auto& s : img.lowered) {
+    const uint32_t l = (uint32_t)s.size();
+    put(&l, 4);
+    put(s.data(), l);
+  }
+  const uint64_t sz = img.cubin.size();
+  put(&sz, 8);
+  put(img.cubin.data(), sz);
+  const uint64_t head[3] = {key, (uint64_t)pay.size(), fnv1a(pay.data(), pay.size())};
+  mkdirs(path.substr(0, path.rfind('/')));
+  char suffix[48];
+  snprintf(suffix, sizeof(suffix), ".tmp.%ld", (long)getpid());
+  const std::string tmp = path + suffix;
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;  // read-only or missing cache directory: the cache is an optimisation only
+  bool ok = fwrite(kMagic, 1, sizeof(kMagic), f) == sizeof(kMagic) && fwrite(head, 1, sizeof(head), f) == sizeof(head) &&
+            fwrite(pay.data(), 1, pay.size(), f) == pay.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path.c_str())) remove(tmp.c_str());
+}
+
+// from_cache (nullable): 1 when the image came from disk
+static int obtain_image(const std::string& model, int n_slots, Image* img, int* from_cache, bool use_cache = true) {
+  const uint64_t key = image_key(model, n_slots);
+  const std::string path = use_cache ? cache_file(key) : std::string();
+  if (from_cache) *from_cache = 0;
+  if (cache_load(path, key, img)) {
+    if (from_cache) *from_cache = 1;
+    return 0;
+  }
+  if (compile_image(model, n_slots, img)) return 1;
+  cache_store(path, key, *img);
+  return 0;
+}
+
+static int load_image(const Image& img, const std::string& model, Kernel* k) {
+  Api& a = api();
   void* mod = nullptr;
   cudaFree(0);  // make sure the primary context is current
-  if (a.modload(&mod, cubin.data())) {
-    a.destroy(&prog);
-    return fail("cuModuleLoadData failed for '%s'", model.c_str());
+  if (a.modload(&mod, img.cubin.data())) return fail("cuModuleLoadData failed for '%s'", model.c_str());
+  k->name = model;
+  k->origin = 2;
+  void** dst[7] = {&k->cufunc[0][0], &k->cufunc[0][1], &k->cufunc[1][0], &k->cufunc[1][1], &k->cufunc_pdf,
+                   &k->cufunc_cov[0], &k->cufunc_cov[1]};
+  for (size_t i = 0; i < img.lowered.size() && i < 7; ++i)
+    if (a.getfn(dst[i], mod, img.lowered[i].c_str())) return fail("cuModuleGetFunction failed for '%s'", img.lowered[i].c_str());
+  return 0;
+}
+
+static int build(const std::string& model, int n_slots, Kernel* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_cache.find(model);
+  if (it != g_cache.end()) {
+    *out = it->second;
+    return 0;
   }
+  Api& a = api();
+  if (!a.ok) return fail("model '%s' is not in the ahead-of-time catalogue and NVRTC is unavailable (%s)",
+                         model.c_str(), a.why.c_str());
+  Image img;
+  int from_cache = 0;
+  if (obtain_image(model, n_slots, &img, &from_cache)) return 1;
   Kernel k;
-  k.name = model;
-  k.origin = 2;
-  for (int w = 0; w < 2; ++w)
-    for (int g = 0; g < 2; ++g) {
-      const char* low = nullptr;
-      a.lowered(prog, exprs[w][g].c_str(), &low);
-      if (!low || a.getfn(&k.cufunc[w][g], mod, low)) {
-        a.destroy(&prog);
-        return fail("cuModuleGetFunction failed for '%s'", exprs[w][g].c_str());
-      }
-    }
-  {
-    const char* low = nullptr;
-    a.lowered(prog, pdf_expr.c_str(), &low);
-    if (!low || a.getfn(&k.cufunc_pdf, mod, low)) {
-      a.destroy(&prog);
-      return fail("cuModuleGetFunction failed for '%s'", pdf_expr.c_str());
-    }
+  if (load_image(img, model, &k)) {
+    if (!from_cache) return 1;
+    // a cached image the driver refuses (e.g. written by another toolkit): drop it and compile
+    remove(cache_file(image_key(model, n_slots)).c_str());
+    k = Kernel();
+    if (obtain_image(model, n_slots, &img, nullptr, /*use_cache=*/false) || load_image(img, model, &k)) return 1;
+    cache_store(cache_file(image_key(model, n_slots)), image_key(model, n_slots), img);
   }
-  for (int w = 0; w < 2 && with_cov; ++w) {
-    const char* low = nullptr;
-    a.lowered(prog, cov_expr[w].c_str(), &low);
-    if (!low || a.getfn(&k.cufunc_cov[w], mod, low)) {
-      a.destroy(&prog);
-      return fail("cuModuleGetFunction failed for '%s'", cov_expr[w].c_str());
-    }
-  }
-  a.destroy(&prog);
   g_cache[model] = k;
   *out = k;
   return 0;
@@ -1112,7 +1260,8 @@ int znll_plan_set_peers(znll_plan* p, int rank, int world, void* const* peer_buf
   }
   p->x_rank = rank;
   p->x_world = world;
-  p->x_seq = 0;
+  p->x_seq = 0;  // every rank restarts its sequence with the freshly zeroed exchange buffers ...
+  if (p->h_flag) *p->h_flag = 0ull;  // ... so the host flag of evaluations made before this call must not match again
   return 0;
 }
 
@@ -1393,6 +1542,15 @@ int znll_test_prologue(const znll_node* nodes, int n_nodes, const double* slots,
   *n_consts = c.n_consts;
   *n_slots = c.n_slots;
   if (kernel_name && name_len > 0) snprintf(kernel_name, (size_t)name_len, "%s", name.c_str());
+  return 0;
+}
+
+int znll_test_rtc_image(const char* model, int n_slots, int use_cache, size_t* cubin_bytes, int* n_names, int* from_cache) {
+  if (!model || !*model || n_slots < 0 || !cubin_bytes || !n_names || !from_cache) return fail("znll_test_rtc_image: bad arguments");
+  rtc::Image img;
+  if (rtc::obtain_image(model, n_slots, &img, from_cache, use_cache != 0)) return 1;
+  *cubin_bytes = img.cubin.size();
+  *n_names = (int)img.lowered.size();
   return 0;
 }
 
