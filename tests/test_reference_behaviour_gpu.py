@@ -263,3 +263,92 @@ def test_product_pdf_values_are_product_of_factors():  # tests/test_pdfs.py:204-
     np.testing.assert_allclose(prod.pdf(data), expected, rtol=1e-12)
     np.testing.assert_allclose(prod.pdf(data.with_obs(["z", "x", "y"])), expected, rtol=1e-12)  # obs are matched by name
     assert abs(float(prod.integrate(ox * oy * oz)[0]) - 1.0) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# the flows of the reference's example scripts (examples/*.py), on seeded data, checked against the truth
+# ------------------------------------------------------------------------------------------------
+def test_example_flow_extended_fit_with_param_update_disabled():  # examples/signal_bkg_mass_extended_fit.py
+    t = _tag()
+    r = np.random.default_rng(11)
+    obs = zfit.Space("x", -10, 10)
+    mu = zfit.Parameter("mu" + t, 1.0, -4, 6)
+    sigma = zfit.Parameter("sigma" + t, 1.0, 0.1, 10)
+    lambd = zfit.Parameter("lambda" + t, -0.06, -1, -0.01)
+    n_bkg = zfit.Parameter("n_bkg" + t, 20000, 0, 50000)
+    n_sig = zfit.Parameter("n_sig" + t, 1000, 0, 30000)
+    model = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu=mu, sigma=sigma, obs=obs, extended=n_sig),
+                             zfit.pdf.Exponential(lambd, obs=obs, extended=n_bkg)])
+    bkg = -10.0 - np.log1p(-r.uniform(size=20000) * (1.0 - np.exp(-0.06 * 20.0))) / 0.06  # exp(-0.06 x) on (-10, 10)
+    sample = np.concatenate([r.normal(1.0, 1.0, size=1200), bkg])
+    sample = sample[(sample > -10) & (sample < 10)]
+    data = zfit.Data.from_numpy(obs=obs, array=sample)
+    start = {mu: 0.5, sigma: 1.2, lambd: -0.05}
+    zfit.param.set_values(start)
+    nll = zfit.loss.ExtendedUnbinnedNLL(model=model, data=data)
+    with zfit.run.experimental_disable_param_update(True):
+        result = Minuit(gradient="zfit").minimize(nll)
+        assert [p.value() for p in start] == list(start.values())  # the fit left the parameters alone
+        assert result.valid
+        assert result.update_params() is result
+    assert zfit.settings.options["auto_update_params"] is True
+    assert mu.value() == result.params[mu]["value"]
+    hesse = result.hesse()
+    errors, _ = result.errors()
+    n = len(sample)
+    assert n_sig.value() + n_bkg.value() == pytest.approx(n, abs=0.6)  # extended fit: yields sum to the sample size
+    for p, truth in ((mu, 1.0), (sigma, 1.0), (lambd, -0.06), (n_sig, 1200.0), (n_bkg, n - 1200.0)):
+        err = hesse[p]["error"]
+        assert abs(p.value() - truth) < 4.5 * err, (p.name, p.value(), truth, err)
+        assert errors[p]["lower"] < 0 < errors[p]["upper"]
+        assert 0.5 * (errors[p]["upper"] - errors[p]["lower"]) == pytest.approx(err, rel=0.15)
+    zfit.param.set_values(model.get_params(), result)  # set_values accepts a FitResult
+    assert sigma.value() == result.params[sigma]["value"]
+
+
+def test_example_flow_simultaneous_fit_by_loss_addition():  # examples/simultaneous_fit.py
+    t = _tag()
+    r = np.random.default_rng(12)
+    obs = zfit.Space("x", -10, 10)
+    mu_shared = zfit.Parameter("mu_shared" + t, 1.0, -4, 6)
+    sigma1 = zfit.Parameter("sigma_one" + t, 1.0, 0.1, 10)
+    sigma2 = zfit.Parameter("sigma_two" + t, 1.0, 0.1, 10)
+    gauss1 = zfit.pdf.Gauss(mu=mu_shared, sigma=sigma1, obs=obs)
+    gauss2 = zfit.pdf.Gauss(mu=mu_shared, sigma=sigma2, obs=obs)
+    data1 = zfit.Data.from_numpy(obs=obs, array=r.normal(2.0, 3.0, size=10000))
+    data2 = zfit.Data.from_numpy(obs=obs, array=r.normal(2.0, 4.0, size=10000))
+    together = zfit.loss.UnbinnedNLL(model=[gauss1, gauss2], data=[data1, data2])
+    added = zfit.loss.UnbinnedNLL(model=gauss1, data=data1) + zfit.loss.UnbinnedNLL(model=gauss2, data=data2)
+    assert list(added.get_params()) == [mu_shared, sigma1, sigma2]
+    assert added.value() == pytest.approx(together.value(), rel=1e-13)
+    result = Minuit().minimize(added).update_params()
+    result.hesse()
+    result.errors()
+    assert result.valid
+    for p, truth in ((mu_shared, 2.0), (sigma1, 3.0), (sigma2, 4.0)):
+        assert abs(p.value() - truth) < 4.5 * result.params[p]["hesse"]["error"]
+        assert result.params[p]["errors"]["upper"] == pytest.approx(result.params[p]["hesse"]["error"], rel=0.1)
+    assert "mu_shared" in str(result)
+
+
+def test_example_flow_multidim_product_from_dataframe():  # examples/multidim_preprocess_fit.py
+    pd = pytest.importorskip("pandas")
+    t = _tag()
+    r = np.random.default_rng(13)
+    xobs, yobs, zobs = zfit.Space("xobs", -4, 4), zfit.Space("yobs", -3, 5), zfit.Space("z", -2, 4)
+    obs = xobs * yobs * zobs
+    mu1 = zfit.Parameter("mu1" + t, 1.0, -4, 6)
+    mu23 = zfit.Parameter("mu_shared" + t, 1.0, -4, 6)
+    sigma12 = zfit.Parameter("sigma_shared" + t, 1.0, 0.1, 10)
+    sigma3 = zfit.Parameter("sigma3" + t, 1.0, 0.1, 10)
+    product = zfit.pdf.ProductPDF([zfit.pdf.Gauss(mu=mu1, sigma=sigma12, obs=xobs), zfit.pdf.Gauss(mu=mu23, sigma=sigma12, obs=yobs),
+                                   zfit.pdf.Gauss(mu=mu23, sigma=sigma3, obs=zobs)])
+    raw = zfit.Data(r.normal(loc=[2.0, 2.5, 2.5], scale=[3.0, 3.0, 1.5], size=(10000, 3)), obs=obs)  # cut to the space
+    df = raw.to_pandas()
+    assert isinstance(df, pd.DataFrame) and list(df.columns) == ["xobs", "yobs", "z"] and len(df) == raw.num_entries < 10000
+    nll = zfit.loss.UnbinnedNLL(model=product, data=df)  # a dataframe is taken directly
+    result = Minuit().minimize(nll).update_params()
+    errors, _ = result.errors()
+    assert result.valid
+    for p, truth in ((mu1, 2.0), (mu23, 2.5), (sigma12, 3.0), (sigma3, 1.5)):
+        assert abs(p.value() - truth) < 4.5 * 0.5 * (errors[p]["upper"] - errors[p]["lower"]), (p.name, p.value())

@@ -64,6 +64,22 @@ class RunManager:
 
         return self._n_cpu if isinstance(self._n_cpu, int) else len(os.sched_getaffinity(0))
 
+    def experimental_disable_param_update(self, value: bool = True):
+        """``util/execution.py:165-181``: minimizers stop writing the fitted values into the parameters (call
+        ``result.update_params()`` instead); applied at once, usable as a context manager that restores the old setting."""
+        old = options["auto_update_params"]
+        options["auto_update_params"] = not value
+
+        class _Restore:
+            def __enter__(self):
+                return self
+
+            def __exit__(self, *exc):
+                options["auto_update_params"] = old
+                return False
+
+        return _Restore()
+
     def get_graph_mode(self):
         return False
 
