@@ -729,3 +729,49 @@ def test_plan_step_path_marshalling(tmp_path, monkeypatch):
             plan.eval([1.0, 2.0, 3.0])
     finally:
         plan._h = C.c_void_p()  # nothing to destroy
+
+
+def test_data_from_root_reads_branches_through_uproot(monkeypatch):
+    """``Data.from_root`` (``core/data.py:612-698``): obs / obs_alias -> branches, weights by branch name, inclusive cut;
+    ``uproot`` is optional and absent here, so a stand-in module records what is asked of it."""
+    import sys
+    import types
+
+    r = np.random.default_rng(5)
+    branches = {"B_M": r.uniform(5000, 5600, 50), "pt": r.uniform(0, 10, 50), "sw": r.normal(1, 0.3, 50)}
+    asked = {}
+
+    class _Tree:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def arrays(self, expressions, library):
+            asked["expressions"], asked["library"] = tuple(expressions), library
+            return {k: branches[k] for k in expressions}
+
+    class _File(dict):
+        pass
+
+    def _open(path, **options):
+        asked["path"], asked["options"] = path, options
+        return _File({"DecayTree": _Tree()})
+
+    with pytest.raises(ImportError, match="uproot"):
+        zfit.Data.from_root("f.root", "DecayTree", obs="B_M")
+    monkeypatch.setitem(sys.modules, "uproot", types.SimpleNamespace(open=_open))
+    obs = zfit.Space("mass", 5100, 5500) * zfit.Space("pt", 0, 10)
+    d = zfit.Data.from_root("f.root", "DecayTree", obs=obs, weights="sw", obs_alias={"mass": "B_M"}, root_dir_options={"timeout": 3})
+    assert asked == {"path": "f.root", "options": {"timeout": 3}, "expressions": ("B_M", "pt", "sw"), "library": "np"}
+    keep = (branches["B_M"] >= 5100) & (branches["B_M"] <= 5500)
+    assert d.obs == ("mass", "pt") and d.num_entries == keep.sum() and d.has_weights
+    np.testing.assert_array_equal(d["mass"], branches["B_M"][keep])
+    np.testing.assert_array_equal(d.weights, branches["sw"][keep])
+    d2 = zfit.Data.from_root("f.root", "DecayTree", obs=["pt"])
+    assert d2.obs == ("pt",) and d2.num_entries == 50 and not d2.has_weights
+    with pytest.raises(ValueError):
+        zfit.Data.from_root("f.root", "DecayTree")
+    with pytest.raises(zexc.BreakingAPIChangeError):
+        zfit.Data.from_root("f.root", "DecayTree", obs="pt", branches=["pt"])

@@ -132,6 +132,41 @@ class Data:
             obs = [k for k in mapping if k != weights]
         return cls(mapping, obs=obs, weights=weights, name=name, label=label, **kw)
 
+    @classmethod
+    def from_root(cls, path, treepath, obs=None, *, weights=None, obs_alias=None, name=None, label=None,
+                  root_dir_options=None, branches=None, branches_alias=None, **kw):
+        """``Data.from_root`` (``core/data.py:612-698``): the branches named by ``obs`` (or ``obs_alias[obs]``) of one
+        tree, read with ``uproot`` straight into per-observable columns; ``weights`` may name a branch.  ``uproot`` is an
+        optional dependency, imported here."""
+        from .exception import BreakingAPIChangeError
+
+        if branches:
+            msg = "Use `obs` instead of `branches`."
+            raise BreakingAPIChangeError(msg)
+        if branches_alias is not None:
+            msg = "Use `obs_alias` instead of `branches_alias`."
+            raise BreakingAPIChangeError(msg)
+        if obs is None and obs_alias is None:
+            msg = "Either branches or branches_alias has to be specified."
+            raise ValueError(msg)
+        obs_alias = {} if obs_alias is None else dict(obs_alias)
+        if obs is None:
+            obs = list(obs_alias.values())
+        space = obs if isinstance(obs, Space) else Space(obs)
+        wanted = [obs_alias.get(o, o) for o in space.obs]
+        weight_branch = weights if isinstance(weights, str) else None
+        try:
+            import uproot
+        except ImportError as error:
+            msg = "Data.from_root needs the optional dependency `uproot`, which is not installed"
+            raise ImportError(msg) from error
+        with uproot.open(path, **(root_dir_options or {}))[treepath] as tree:
+            arrays = tree.arrays(expressions=tuple([*wanted, weight_branch] if weight_branch else wanted), library="np")
+        columns = {o: np.asarray(arrays[b], dtype=np.float64) for o, b in zip(space.obs, wanted)}
+        if weight_branch:
+            weights = np.asarray(arrays[weight_branch], dtype=np.float64)
+        return cls(columns, obs=space, weights=weights, name=name, label=label, **kw)
+
     # ------------------------------------------------------------------ properties
     @property
     def space(self) -> Space:
