@@ -43,20 +43,28 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
     lo = np.array([_bound(v, -np.inf) for v in lower], dtype=np.float64)
     up = np.array([_bound(v, np.inf) for v in upper], dtype=np.float64)
     error = []
+    # the driver's x / gradient buffers are copied to and from two persistent arrays with memmove: wrapping the raw
+    # pointers in numpy arrays on every callback costs more than a small fit's kernel
+    xbuf, gbuf = np.zeros(n), np.zeros(n)
+    x_addr, g_addr, nbytes = xbuf.ctypes.data, gbuf.ctypes.data, 8 * n
+    memmove = C.memmove
 
     def fcn(_user, xp, what, vp, gp):
         try:
-            x = np.ctypeslib.as_array(xp, (n,)).copy()
+            memmove(x_addr, xp, nbytes)
+            x = xbuf.copy()
             if what == VALUE | GRADIENT and value_gradient is not None:
                 v, g = value_gradient(x)
-                vp[0] = float(v)
-                np.ctypeslib.as_array(gp, (n,))[:] = g
+                vp[0] = v
+                gbuf[:] = g
+                memmove(gp, g_addr, nbytes)
             elif what & GRADIENT:
-                np.ctypeslib.as_array(gp, (n,))[:] = gradient(x)
+                gbuf[:] = gradient(x)
+                memmove(gp, g_addr, nbytes)
                 if what & VALUE:
-                    vp[0] = float(value(x))
+                    vp[0] = value(x)
             else:
-                vp[0] = float(value(x))
+                vp[0] = value(x)
             return 0
         except BaseException as exc:  # noqa: BLE001 -- carried across the C frame and re-raised below
             error.append(exc)
@@ -64,13 +72,14 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
 
     def info(_user, xp, hp):
         try:
-            H = information(np.ctypeslib.as_array(xp, (n,)).copy())
+            memmove(x_addr, xp, nbytes)
+            H = information(xbuf.copy())
             if H is None:
                 return 1
-            H = np.asarray(H, dtype=np.float64)
+            H = np.ascontiguousarray(H, dtype=np.float64)
             if H.shape != (n, n):
                 return 1
-            np.ctypeslib.as_array(hp, (n * n,))[:] = H.ravel()
+            memmove(hp, H.ctypes.data, 8 * n * n)
             return 0
         except Exception:  # the seed is an optimisation; any trouble falls back to Minuit's own seed
             return 1

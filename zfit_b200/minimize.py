@@ -82,6 +82,8 @@ DefaultStrategy = PushbackStrategy
 # LossEval (evaluation.py:51-406)
 # ------------------------------------------------------------------------------------------------
 def check_derivative_none_raise(values, params):
+    if isinstance(values, np.ndarray) and values.dtype != object:  # a float array holds no None
+        return
     if values is None or any(v is None for v in values):
         none = [p for p, v in zip(params, values or [None] * len(params)) if v is None]
         msg = f"The derivative of the following parameters is None: {none}."
@@ -172,7 +174,7 @@ class LossEval:
         if self.do_print:
             print_gradient(params, values, gradient, loss_value)
         check_derivative_none_raise(gradient, params)
-        if np.any(np.isnan(gradient)) or np.isnan(loss_value):
+        if loss_value != loss_value or np.isnan(gradient).any():
             loss_value, gradient = self._nan(loss_value, gradient, "vg")
         else:
             self.nan_counter = 0
@@ -632,6 +634,23 @@ class BaseMinimizer:
         return f"<{type(self).__name__} {self.name} tol={self.tol}>"
 
 
+_IMINUIT = None
+
+
+def _have_iminuit() -> bool:
+    """Probed once per process: a failing ``import`` is not cached by Python and costs a file-system search every time
+    (~0.3 ms of a 1.4 ms host budget for a small fit)."""
+    global _IMINUIT
+    if _IMINUIT is None:
+        try:
+            import iminuit  # noqa: F401
+
+            _IMINUIT = True
+        except ImportError:
+            _IMINUIT = False
+    return _IMINUIT
+
+
 class Minuit(BaseMinimizer):
     """``zfit.minimize.Minuit(tol=None, mode=None, gradient=None, verbosity=None, options=None, maxiter=None,
     criterion=None, strategy=None, name=None)`` (``minimizer_minuit.py:35-165``).
@@ -663,12 +682,9 @@ class Minuit(BaseMinimizer):
                          minimizer_options=options, maxiter=maxiter, name=name or "Minuit")
 
     def _minimize(self, loss, params, init):
-        try:
-            import iminuit  # noqa: F401
-
+        if _have_iminuit():
             return self._minimize_iminuit(loss, params, init)
-        except ImportError:
-            return self._minimize_native(loss, params, init)
+        return self._minimize_native(loss, params, init)
 
     # -- the reference's route, used whenever iminuit exists (minimizer_minuit.py:175-319)
     def _minimize_iminuit(self, loss, params, init):

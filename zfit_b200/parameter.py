@@ -506,8 +506,8 @@ def assign_values(params, values, **_):
         return
     if isinstance(params, ZfitParameter):
         params, values = [params], [values]
-    for p, v in zip(params, np.asarray(values, dtype=np.float64).reshape(-1)):
-        p.assign(float(v))
+    for p, v in zip(params, np.asarray(values, dtype=np.float64).reshape(-1).tolist()):
+        p.assign(v)
 
 
 assign_values_jit = assign_values
