@@ -55,16 +55,16 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
             x = xbuf.copy()
             if what == VALUE | GRADIENT and value_gradient is not None:
                 v, g = value_gradient(x)
-                vp[0] = v
+                vp[0] = float(v)
                 gbuf[:] = g
                 memmove(gp, g_addr, nbytes)
             elif what & GRADIENT:
                 gbuf[:] = gradient(x)
                 memmove(gp, g_addr, nbytes)
                 if what & VALUE:
-                    vp[0] = value(x)
+                    vp[0] = float(value(x))
             else:
-                vp[0] = value(x)
+                vp[0] = float(value(x))
             return 0
         except BaseException as exc:  # noqa: BLE001 -- carried across the C frame and re-raised below
             error.append(exc)
