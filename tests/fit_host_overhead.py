@@ -2,11 +2,11 @@
 infrastructure) behind a memo keyed by the slot values, so from the second fit on every engine call is a dictionary
 lookup and what remains is the Python / ctypes / C++-driver layer.  CPU only.
 
-    python tools/fit_host_overhead.py [cfg]
+    python tests/fit_host_overhead.py [cfg]
 """
 import sys, time, numpy as np, cProfile, pstats, io
 import os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import zfit_b200 as zfit
 from zfit_b200 import workloads as W
 from tests._hostsim import HostSimEngine
