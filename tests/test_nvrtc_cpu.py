@@ -105,3 +105,31 @@ def test_compiled_images_are_cached_on_disk(tmp_path, monkeypatch):
     # an unwritable cache location is not an error
     monkeypatch.setenv("ZNLL_CACHE_DIR", "/proc/znll-cannot-exist")
     assert Z.test_rtc_image(tree, n_slots)[1:] == (names, False)
+
+
+def test_built_step_kernels_fit_two_blocks_per_sm_without_spills():
+    """Resource usage of every kernel in the built ``libznll.so`` (``cuobjdump --dump-resource-usage``, no GPU needed): the
+    step kernels are tuned for two resident 256-thread blocks per SM, i.e. at most 128 registers,
+    and none of them -- nor the pdf / covariance kernels -- may touch local memory (spills) or a stack frame; static shared
+    memory has to leave room for two blocks within the 227 KB an SM offers."""
+    import re
+    import shutil
+    import subprocess
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([tool, "--dump-resource-usage", str(Z.LIB_PATH)], capture_output=True, text=True)
+    if out.returncode:
+        pytest.skip("cuobjdump not usable: " + out.stderr[-200:])
+    rows = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out.stdout)
+    kinds = {"nll": [], "pdf": [], "cov": []}
+    for name, reg, stack, shared, local in rows:
+        for kind in kinds:
+            if f"znll{len(kind) + 7}{kind}_kernel" in name:  # _ZN4znll10nll_kernelI...
+                kinds[kind].append((name, int(reg), int(stack), int(shared), int(local)))
+    assert len(kinds["nll"]) >= 4 * 25 and len(kinds["pdf"]) >= 25 and len(kinds["cov"]) >= 2 * 25  # the whole catalogue was seen
+    for kind, found in kinds.items():
+        for name, reg, stack, shared, local in found:
+            assert stack == 0 and local == 0, (name, stack, local)
+            assert shared <= 48 * 1024, (name, shared)
+            if kind == "nll":
+                assert reg <= 128, (name, reg)
