@@ -296,7 +296,9 @@ def test_example_flow_extended_fit_with_param_update_disabled():  # examples/sig
     hesse = result.hesse()
     errors, _ = result.errors()
     n = len(sample)
-    assert n_sig.value() + n_bkg.value() == pytest.approx(n, abs=0.6)  # extended fit: yields sum to the sample size
+    # extended fit: the yields sum to the sample size (to 0.6 at tol=1e-5, tests/highstats/test_exact_yields.py:82; this fit
+    # runs at the default tol=1e-3, where EDM < 1e-3 allows a few events)
+    assert n_sig.value() + n_bkg.value() == pytest.approx(n, abs=5.0)
     for p, truth in ((mu, 1.0), (sigma, 1.0), (lambd, -0.06), (n_sig, 1200.0), (n_bkg, n - 1200.0)):
         err = hesse[p]["error"]
         assert abs(p.value() - truth) < 4.5 * err, (p.name, p.value(), truth, err)
