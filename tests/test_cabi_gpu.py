@@ -66,6 +66,43 @@ def test_rtc_origin_and_catalogue_origin():
     assert origin == 1
 
 
+def test_rtc_image_cache_across_processes(tmp_path):
+    """A tree outside the catalogue in two fresh processes sharing one ``ZNLL_CACHE_DIR``: the first compiles with NVRTC and
+    stores the image, the second loads the stored cubin (no compilation) -- same kernel, bit-identical results."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import json, sys, time\n"
+        f"sys.path.insert(0, {str(root)!r})\n"
+        "from tests._cases import ALL_CASES\n"
+        "from zfit_b200 import _znll as Z\n"
+        "c = ALL_CASES['rtc'](n=3000)\n"
+        "plan = Z.Plan(1)\n"
+        "t0 = time.perf_counter(); plan.set_model(0, c.nodes); dt = time.perf_counter() - t0\n"
+        "plan.bind_host(0, c.cols, c.weights)\n"
+        "v, g = plan.eval(c.slots, grad=True)\n"
+        "_, _, mats = plan.eval_cov(c.slots)\n"
+        "print(json.dumps({'origin': plan.kernel_origin(0), 'v': float(v[0]).hex(), 'g': [float(x).hex() for x in g],"
+        " 'cov': float(mats[0].sum()).hex(), 'set_model_s': dt}))\n"
+    )
+    env = dict(os.environ, ZNLL_CACHE_DIR=str(tmp_path / "rtc"))
+    runs = []
+    for _ in range(2):
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+        assert len(list((tmp_path / "rtc").glob("rtc-*.cubin"))) == 1
+    first, second = runs
+    assert first["origin"] == second["origin"] == 2
+    assert (first["v"], first["g"], first["cov"]) == (second["v"], second["g"], second["cov"])
+    assert second["set_model_s"] < 0.5 * first["set_model_s"], (first["set_model_s"], second["set_model_s"])
+
+
 @pytest.mark.parametrize("key", ["cb_exp", "gauss_cheb_weighted"])
 def test_log_offset_is_subtracted_per_event_unweighted(key):
     case = ALL_CASES[key](n=20_000)
