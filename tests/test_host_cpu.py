@@ -775,3 +775,45 @@ def test_data_from_root_reads_branches_through_uproot(monkeypatch):
         zfit.Data.from_root("f.root", "DecayTree")
     with pytest.raises(zexc.BreakingAPIChangeError):
         zfit.Data.from_root("f.root", "DecayTree", obs="pt", branches=["pt"])
+
+
+def test_host_prologue_crystalball_integral_fuzz():
+    """Seeded sweep over the CrystalBall integral's whole case structure (limits left of / right of / across the tail
+    boundary, either sign of alpha, n near 1 where the reference switches to its log form, physics.py:83-142): the host
+    prologue's closed form and its four analytic derivatives against the oracle's tape, and the integral itself against
+    adaptive quadrature of the oracle's shape."""
+    from scipy.integrate import quad
+
+    r = np.random.default_rng(20261020)
+    B = TorchBackend()
+    import torch
+
+    checked_branches = set()
+    for _ in range(120):
+        mu, s = r.uniform(-2, 2), r.uniform(0.3, 3.0)
+        a = r.uniform(0.2, 3.0) * r.choice([-1.0, 1.0])
+        n = 1.0 + r.choice([3e-6, -4e-6, 1e-3]) if r.uniform() < 0.25 else r.uniform(1.05, 8.0)
+        edge = mu - abs(a) * s if a > 0 else mu + abs(a) * s  # where core and tail meet
+        kind = r.integers(3)
+        if kind == 0:  # across the boundary
+            lo, hi = edge - r.uniform(0.5, 6) * s, edge + r.uniform(0.5, 6) * s
+        elif (kind == 1) == (a > 0):  # tail only
+            lo, hi = sorted([edge - np.sign(a) * r.uniform(0.1, 3) * s, edge - np.sign(a) * r.uniform(3.5, 8) * s])
+        else:  # core only
+            lo, hi = sorted([edge + np.sign(a) * r.uniform(0.1, 2) * s, edge + np.sign(a) * r.uniform(2.5, 7) * s])
+        checked_branches.add((int(kind), bool(a > 0), bool(abs(n - 1) < 1e-5)))
+        I, dI = Z.leaf_integral(Z.Node(Z.CB, 0, 0, 0, lo, hi, 0, 0, 0), [mu, s, a, n])
+        opdf = O.CrystalBall("mu", "s", "a", "n", "x", (lo, hi))
+        rI, rdI = _autograd_integral(opdf, ["mu", "s", "a", "n"], [mu, s, a, n], lo, hi, (lo, hi))
+        assert abs(I - rI) <= 2e-13 * abs(rI), (mu, s, a, n, lo, hi)
+        if abs(n - 1) >= 1e-5:  # the log form's tape differentiates a different expression: compared by value only
+            np.testing.assert_allclose(dI, rdI, rtol=2e-9, atol=1e-12 * abs(rI), err_msg=str((mu, s, a, n, lo, hi)))
+        P = {k: torch.tensor(v, dtype=torch.float64) for k, v in zip(["mu", "s", "a", "n"], [mu, s, a, n])}
+        shape = lambda x: float(opdf.unnorm(B, torch.tensor([x], dtype=torch.float64), P, (lo, hi))[0])
+        pts = [edge] if lo < edge < hi else None
+        q, _ = quad(shape, lo, hi, points=pts, epsabs=0, epsrel=1e-11, limit=200)
+        # inside |n - 1| < 1e-5 the reference integrates the tail as if n were exactly 1 (its `use_log` switch,
+        # physics.py:106-112): mirrored on purpose, so there the closed form is off the true integral by O(|n - 1|)
+        tol = 2e-9 if abs(n - 1) >= 1e-5 else 4.0 * abs(n - 1)
+        assert abs(I - q) <= tol * abs(q), (mu, s, a, n, lo, hi, I, q)
+    assert len(checked_branches) >= 10
