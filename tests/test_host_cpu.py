@@ -813,7 +813,7 @@ def test_host_prologue_crystalball_integral_fuzz():
         pts = [edge] if lo < edge < hi else None
         q, _ = quad(shape, lo, hi, points=pts, epsabs=0, epsrel=1e-11, limit=200)
         # inside |n - 1| < 1e-5 the reference integrates the tail as if n were exactly 1 (its `use_log` switch,
-        # physics.py:106-112): mirrored on purpose, so there the closed form is off the true integral by O(|n - 1|)
+        # physics.py:88,123,132): mirrored on purpose, so there the closed form is off the true integral by O(|n - 1|)
         tol = 2e-9 if abs(n - 1) >= 1e-5 else 4.0 * abs(n - 1)
         assert abs(I - q) <= tol * abs(q), (mu, s, a, n, lo, hi, I, q)
     assert len(checked_branches) >= 10
