@@ -202,3 +202,25 @@ def test_loss_bodies_extended_term_and_constraints():
         got_ext = float(ON.unbinned_nll(models, datas, {}, weights=weights, log_offset=log_offset, extended=True)) + add
         assert abs(got_plain - plain) <= 2e-14 * scale
         assert abs(got_ext - ext) <= 2e-14 * scale, (weighted, off, with_cons, got_ext, ext)
+
+
+def test_committed_fixture_is_what_the_generator_produces_from_the_reference(tmp_path, capsys):
+    """Provenance of ``tests/golden/reference_formulas.npz``: where the reference tree is present (the build container --
+    never the GPU box), running the committed generator again on the reference's source gives the committed arrays bit
+    for bit."""
+    import importlib.util
+    from pathlib import Path
+
+    gen = Path(__file__).resolve().parent / "golden" / "make_reference_formulas.py"
+    spec = importlib.util.spec_from_file_location("make_reference_formulas", gen)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not mod.REF.exists():
+        pytest.skip("the reference source tree is not on this machine")
+    mod.OUT = tmp_path / "regenerated.npz"
+    mod.main()
+    capsys.readouterr()
+    new, old = np.load(mod.OUT), np.load(gen.parent / "reference_formulas.npz")
+    assert sorted(new.files) == sorted(old.files) and len(new.files) > 100
+    for key in new.files:
+        assert new[key].shape == old[key].shape and np.array_equal(new[key], old[key], equal_nan=True), key
