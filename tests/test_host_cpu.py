@@ -817,3 +817,28 @@ def test_host_prologue_crystalball_integral_fuzz():
         tol = 2e-9 if abs(n - 1) >= 1e-5 else 4.0 * abs(n - 1)
         assert abs(I - q) <= tol * abs(q), (mu, s, a, n, lo, hi, I, q)
     assert len(checked_branches) >= 10
+
+
+def test_lazy_sort_countdown_of_the_engine():
+    """``options={"sort_events": "lazy"}`` (experimental): the engine binds unsorted and sorts exactly once, after
+    ``LAZY_SORT_AFTER`` evaluations; the default mode never takes that path.  Device work is stubbed out."""
+    import importlib
+
+    CudaEngine = importlib.import_module("zfit_b200.loss").CudaEngine
+
+    class _Plan:
+        def eval(self, slots, **kw):
+            return np.zeros(1), np.zeros(len(slots))
+
+    for mode, expect in (("lazy", 1), (None, 0)):
+        eng = CudaEngine.__new__(CudaEngine)
+        eng.plan, eng.distributed, eng.reduce_mode = _Plan(), False, "none"
+        eng._raw_stream = lambda: 0
+        eng._lazy_sort_in = CudaEngine.LAZY_SORT_AFTER if mode == "lazy" else None
+        calls = []
+        eng._sort_now = lambda: calls.append(eng._lazy_sort_in)
+        for _ in range(CudaEngine.LAZY_SORT_AFTER + 30):
+            eng.eval(np.zeros(3))
+            if not calls:
+                assert mode is None or eng._lazy_sort_in >= 0
+        assert len(calls) == expect and eng._lazy_sort_in is None

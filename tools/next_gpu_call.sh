@@ -43,7 +43,7 @@ import zfit_b200 as zfit
 from zfit_b200 import workloads as W
 w = W.build(2, device="cuda:0")
 params = list(w["loss"].get_params()); th = [p.value() for p in params]
-for sort in (True, False):
+for sort in (True, False, "lazy"):
     loss = type(w["loss"])(model=w["model"], data=w["data"], options={"sort_events": sort})
     torch.cuda.synchronize(); t0 = time.perf_counter()
     loss.value_gradient(params, full=False)

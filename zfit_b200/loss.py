@@ -56,6 +56,7 @@ class CudaEngine:
         from . import _znll as Z
 
         self.Z = Z
+        sort_events = "lazy" if sort_events == "lazy" else bool(sort_events)
         self.distributed = _dist.is_distributed() if distributed is None else bool(distributed)
         self.reduce_mode = "none"
         self.deterministic_reduce = deterministic_reduce
@@ -80,7 +81,7 @@ class CudaEngine:
             self.channel_slots.append((start, len(self.slot_params)))
             cols, w = data.device_columns(device)
             n = data.num_entries
-            if sort_events and n > 1:
+            if sort_events is True and n > 1:
                 cols, w = self._sort_for_coherence(model, data, cols, w)
             self._keep.append((cols, w))
             # the columns were produced by torch kernels on torch's stream (upload, cut, sort); the plan launches
@@ -88,9 +89,14 @@ class CudaEngine:
             torch.cuda.synchronize(device)
             self.plan.bind_device_ptrs(k, [c.data_ptr() for c in cols], 0 if w is None else w.data_ptr(), n)
             self.n_local.append(n)
+        # sort_events="lazy" (experimental, not the default): bind unsorted and sort only once the loss has been evaluated
+        # LAZY_SORT_AFTER times -- a bind-time sort of 1e8 events costs about as much as a whole fit's kernel time, so a
+        # loss that is fitted once should not pay it, one that is profiled or refitted should (ski-rental rule)
+        self._lazy_sort_in = self.LAZY_SORT_AFTER if sort_events == "lazy" else None
         self.samplesize = [self.plan.sumw(k) for k in range(len(models))]
         self.n_entries = list(self.n_local)
         self._bind_args = (list(models), list(fit_ranges), sort_events)
+        self._bound_datas = list(datas)
         if self.distributed:
             t = torch.tensor(self.samplesize + [float(n) for n in self.n_local], dtype=torch.float64, device=f"cuda:{device}")
             _dist.all_reduce_sum_(t, deterministic=True)
@@ -129,6 +135,25 @@ class CudaEngine:
             pass
         return public
 
+    LAZY_SORT_AFTER = 48
+
+    def _sort_now(self):
+        """Deferred bind-time sort: reorder the resident columns and bind them again (same kernels, same plan)."""
+        models, fit_ranges, _ = self._bind_args
+        torch = self.torch
+        for k, (model, data, rng) in enumerate(zip(models, self._bound_datas, fit_ranges)):
+            cols, w = self._keep[k]
+            n = self.n_local[k]
+            if n > 1:
+                if rng is not None:
+                    data = data.with_obs(rng, guarantee_limits=False)
+                cols, w = self._sort_for_coherence(model, data, cols, w)
+                self._keep[k] = (cols, w)
+                torch.cuda.synchronize(self.device)
+                self.plan.bind_device_ptrs(k, [c.data_ptr() for c in cols], 0 if w is None else w.data_ptr(), n)
+                if self.distributed:
+                    self.plan.set_sumw(k, self.samplesize[k])  # binding recomputed the local sum; the global one holds
+
     def rebind(self, datas):
         """The events of the bound ``Data`` objects changed in place (``SamplerData.resample``): bind the new columns to
         the existing plan -- same compiled kernels, no host copy when the data was born on the device."""
@@ -143,7 +168,7 @@ class CudaEngine:
                 data = data.with_obs(rng, guarantee_limits=False)
             cols, w = data.device_columns(self.device)
             n = data.num_entries
-            if sort_events and n > 1:
+            if sort_events is True and n > 1:
                 cols, w = self._sort_for_coherence(model, data, cols, w)
             self._keep.append((cols, w))
             torch.cuda.synchronize(self.device)
@@ -151,6 +176,8 @@ class CudaEngine:
             self.n_local[k] = n
         self.samplesize = [self.plan.sumw(k) for k in range(len(models))]
         self.n_entries = list(self.n_local)
+        self._bound_datas = list(datas)
+        self._lazy_sort_in = self.LAZY_SORT_AFTER if sort_events == "lazy" else None
 
     def _sort_for_coherence(self, model, data, cols, w):
         """Events are static for the whole fit and the NLL is a sum, so they may be reordered once at bind
@@ -192,6 +219,11 @@ class CudaEngine:
     def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
         # kernels go to torch's current stream, so torch ops (NCCL all-reduce, data preparation) order with them
         stream = self._raw_stream()
+        if self._lazy_sort_in is not None:
+            self._lazy_sort_in -= 1
+            if self._lazy_sort_in < 0:
+                self._lazy_sort_in = None
+                self._sort_now()
         if not self.distributed or self.reduce_mode == "fused-nvlink":
             return self.plan.eval(slots, grad=grad, log_offset=log_offset, kahan=kahan, stream=stream)
         self.plan.launch(slots, grad=grad, log_offset=log_offset, stream=stream)
