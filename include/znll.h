@@ -116,6 +116,17 @@ int znll_plan_bind_device(znll_plan* plan, int ch, int n_cols, const double* con
 int znll_plan_bind_host(znll_plan* plan, int ch, int n_cols, const double* const* cols_host,
                         const double* w_host, int64_t n_events);
 
+/* Bind-time reordering for warp coherence (csrc/znll_prep.cu).  Events are static for a fit and
+ * the NLL is a sum over them, so their order is free: a STABLE partition of the n events into 32 equal-width buckets of
+ * column key_col over [lo, hi] makes every warp of the step kernel uniform with respect to a piecewise pdf (CrystalBall
+ * core / tail, models/physics.py:31-45, where the reference evaluates both branches for every event through tf.where).
+ * All n_cols columns and the weights (nullable, both or neither) move together; src and dst are device pointers to n
+ * doubles each and must not alias.  Asynchronous on `stream`; deterministic (same input, same order). */
+int znll_partition_events(int device, int n_cols, const double* const* src_cols, double* const* dst_cols,
+                          const double* src_w, double* dst_w, int key_col, double lo, double hi, int64_t n,
+                          void* stream);
+const char* znll_prep_last_error(void);
+
 /* Sum of weights (or N) of the bound shard, computed on the device at bind time with the same
  * deterministic reduction as the NLL.  Data.samplesize, core/data.py:268-275.  Multi-GPU: the
  * host all-reduces it once and writes the global figure back with znll_plan_set_sumw. */

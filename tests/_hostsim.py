@@ -70,7 +70,17 @@ Ctx make_ctx() {
   }
   return ctx_of(g_tabs);
 }
+#ifdef ZNLL_HAS_OPTIMISTIC
+#define HOSTSIM_PAIR_CTX(cx) with_mode(cx, false)  // nll_kernel's pair loop: optimistic sweep, one rare-path test per pair
+#define HOSTSIM_TAIL_CTX(cx) with_mode(cx, true)
+#define HOSTSIM_PAIR_ADD(acc, term) (acc)[0] += (term)  // plain per-thread accumulation, compensated merges across threads
+#endif
 #define HOSTSIM_EXP(x, cx) fast_exp(x, cx)
+#endif
+#ifndef HOSTSIM_PAIR_CTX
+#define HOSTSIM_PAIR_CTX(cx) (cx)
+#define HOSTSIM_TAIL_CTX(cx) (cx)
+#define HOSTSIM_PAIR_ADD(acc, term) kahan_add(acc, term)
 #endif
 // event() returns the pair's summed term; headers before that change returned the two lanes
 inline double pair_term(double t) { return t; }
@@ -83,14 +93,27 @@ void load_pair(const double* const* cols, long long i, D2* x) {
       x[k].b = cols[k][2 * i + 1];
     }
 }
-// the event loop of nll_kernel for one thread that owns all pairs, then the odd tail event
+// the event loop of nll_kernel, then the odd tail event.  Headers with the optimistic pair loop accumulate the value
+// plainly per thread and merge the threads' partial sums error-free, so the simulation keeps the kernel's distribution of
+// pairs over threads (pair i belongs to thread i mod T, T = grid x 256 as grid_for() of znll_host.cu chooses it) and merges
+// with the kernel's own kahan_merge; older headers are run as one thread that owns all pairs (they compensate per pair).
 template <class M, bool W, bool G>
 void run_nll(const double* const* cols, const double* w, long long n, const double* c, double off, double* out) {
   constexpr int NACC = 2 + M::NS;
   const Ctx cx = make_ctx();
-  double acc[NACC];
-  for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
-  for (long long i = 0; i < (n >> 1); ++i) {
+  const long long nvec = n >> 1;
+#ifdef ZNLL_HAS_OPTIMISTIC
+  long long grid = (((n + 1) / 2) + 255) / 256;
+  if (grid < 1) grid = 1;
+  if (grid > 296) grid = 296;
+  const long long T = grid * 256;
+#else
+  const long long T = 1;
+#endif
+  const long long nthreads = nvec < T ? (nvec > 0 ? nvec : 1) : T;
+  double* accs = new double[nthreads * NACC]();
+  for (long long i = 0; i < nvec; ++i) {
+    double* acc = accs + (i % nthreads) * NACC;
     D2 x[ZNLL_MAXCOL], wv;
     load_pair<M>(cols, i, x);
     wv.a = wv.b = 1.0;
@@ -98,16 +121,25 @@ void run_nll(const double* const* cols, const double* w, long long n, const doub
       wv.a = w[2 * i];
       wv.b = w[2 * i + 1];
     }
-    kahan_add(acc, pair_term(event<M, D2, W, G>(cx, c, x, wv, HOSTSIM_PAIR_OFFSET(off), acc)));
+    HOSTSIM_PAIR_ADD(acc, pair_term(event<M, D2, W, G>(HOSTSIM_PAIR_CTX(cx), c, x, wv, HOSTSIM_PAIR_OFFSET(off), acc)));
   }
-  if (n & 1) {
+  if (n & 1) {  // thread 0 of block 0
     double xa[ZNLL_MAXCOL];
     for (int k = 0; k < ZNLL_MAXCOL; ++k)
       if ((M::COLMASK >> k) & 1) xa[k] = cols[k][n - 1];
     const double wa = W ? w[n - 1] : 1.0;
-    kahan_add(acc, event<M, double, W, G>(cx, c, xa, wa, off, acc));
+    kahan_add(accs, event<M, double, W, G>(HOSTSIM_TAIL_CTX(cx), c, xa, wa, off, accs));
   }
-  for (int j = 0; j < NACC; ++j) out[j] = acc[j];
+  double s = accs[0], cc = accs[1];
+  for (long long t = 1; t < nthreads; ++t) kahan_merge(s, cc, accs[t * NACC], accs[t * NACC + 1]);
+  out[0] = s;
+  out[1] = cc;
+  for (int j = 2; j < NACC; ++j) {
+    double v = 0.0;
+    for (long long t = 0; t < nthreads; ++t) v += accs[t * NACC + j];
+    out[j] = v;
+  }
+  delete[] accs;
 }
 // the body of pdf_kernel
 template <class M>

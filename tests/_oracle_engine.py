@@ -84,7 +84,10 @@ class _Sum:
 
 
 class OracleEngine:
-    def __init__(self, models, datas, fit_ranges):
+    def __init__(self, models, datas, fit_ranges, chunk=None):
+        """``chunk``: evaluate at most this many events per tape and sum the pieces (the NLL and its gradient are
+        plain sums over events) -- lets ``bench.py --impl reference`` run the full 1e8 events within host RAM."""
+        self.chunk = None if not chunk else int(chunk)
         self.slot_params = []
         self.channels = []
         datas = [d if r is None else d.with_obs(r, guarantee_limits=False) for d, r in zip(datas, fit_ranges)]
@@ -120,11 +123,21 @@ class OracleEngine:
             if len(next(iter(cols.values()))) == 0:
                 values.append(0.0)
                 continue
-            if grad:
-                v, g = ON.value_and_gradient([tree], [cols], theta, names, weights=ww, log_offset=log_offset)
-                gs[off : off + ns] = g
-            else:
-                v = float(ON.unbinned_nll([tree], [cols], dict(zip(names, theta)), weights=ww, log_offset=log_offset))
+            n = len(next(iter(cols.values())))
+            step = n if not self.chunk else self.chunk
+            v = 0.0
+            for lo in range(0, n, step):
+                if step >= n:
+                    cc, cw = cols, ww
+                else:
+                    cc = {k: a[lo : lo + step] for k, a in cols.items()}
+                    cw = None if w is None else [np.asarray(w)[lo : lo + step]]
+                if grad:
+                    vi, g = ON.value_and_gradient([tree], [cc], theta, names, weights=cw, log_offset=log_offset)
+                    gs[off : off + ns] += g
+                else:
+                    vi = float(ON.unbinned_nll([tree], [cc], dict(zip(names, theta)), weights=cw, log_offset=log_offset))
+                v += vi
             values.append(v)
         values = np.asarray(values, dtype=np.float64)
         if self.distributed:

@@ -56,6 +56,9 @@ SYMBOLS = {
     "znll_plan_set_model": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Node), C.c_int]),
     "znll_plan_bind_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]),
     "znll_plan_bind_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]),
+    "znll_partition_events": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
+    "znll_prep_last_error": (C.c_char_p, []),
     "znll_plan_get_sumw": (C.c_int, [C.c_void_p, C.c_int, _DP]),
     "znll_plan_set_sumw": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "znll_plan_n_slots": (C.c_int, [C.c_void_p, C.c_int]),
@@ -264,6 +267,23 @@ class Plan:
         if self._f_collect(self._h, WANT_GRAD if grad else 0, self._p_values, self._p_grad, stream or None):
             _check(1)
         return self._values.copy(), (self._grad[: self.total_slots].copy() if grad else None)
+
+
+def exchange_bytes_max(world: int) -> int:
+    """Size of the process-wide exchange buffer of the fused cross-GPU reduction: 128 B of flags + two parities x world
+    x 256 accumulator slots (``ZNLL_XSTRIDE``); equals ``znll_plan_exchange_bytes`` of any plan."""
+    return 128 + 8 * 2 * int(world) * 256
+
+
+def partition_events(device: int, src_ptrs, dst_ptrs, src_w: int, dst_w: int, key_col: int, lo: float, hi: float, n: int,
+                     stream=0):
+    """Stable 32-bucket partition of resident event columns by ``key_col`` (device pointers; asynchronous on ``stream``)."""
+    src = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+    dst = (C.c_void_p * len(dst_ptrs))(*dst_ptrs)
+    L = lib()
+    if L.znll_partition_events(device, len(src_ptrs), src, dst, C.c_void_p(src_w or 0), C.c_void_p(dst_w or 0), key_col,
+                               float(lo), float(hi), int(n), C.c_void_p(stream or 0)):
+        raise ZnllError(L.znll_prep_last_error().decode(errors="replace"))
 
 
 def fp64_peak(device: int = 0, ms: float = 200.0) -> float:

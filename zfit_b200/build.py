@@ -26,7 +26,7 @@ BPS = os.environ.get("ZNLL_BPS", "2")  # resident CTAs (256 threads) per SM the 
 CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", f"-DZNLL_MIN_BLOCKS={BPS}", f"-DZNLL_BLOCKS_PER_SM={BPS}",
           *os.environ.get("ZNLL_EXTRA_CFLAGS", "").split()]
 
-SOURCES = ["znll_host.cu", "znll_catalog_a.cu", "znll_catalog_b.cu", "znll_catalog_c.cu", "znll_migrad.cpp"]
+SOURCES = ["znll_host.cu", "znll_prep.cu", "znll_catalog_a.cu", "znll_catalog_b.cu", "znll_catalog_c.cu", "znll_migrad.cpp"]
 
 
 def _nvcc() -> str:

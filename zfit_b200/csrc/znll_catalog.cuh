@@ -14,6 +14,7 @@ cudaError_t launch_nll(const ZnllLaunchArgs& a, const double* consts, int grid, 
   k.w = a.w;
   k.n = a.n;
   k.log_offset = a.log_offset;
+  k.log_offset2 = 2.0 * a.log_offset;
   k.partials = a.partials;
   k.ticket = a.ticket;
   k.out = a.out;
@@ -31,6 +32,7 @@ cudaError_t launch_pdf(const ZnllLaunchArgs& a, const double* consts, int grid, 
   k.w = a.w;
   k.n = a.n;
   k.log_offset = 0.0;
+  k.log_offset2 = 0.0;
   k.partials = a.partials;
   k.ticket = a.ticket;
   k.out = a.out;
@@ -47,6 +49,7 @@ cudaError_t launch_cov(const ZnllLaunchArgs& a, const double* consts, int grid, 
   k.w = a.w;
   k.n = a.n;
   k.log_offset = a.log_offset;
+  k.log_offset2 = 2.0 * a.log_offset;
   k.partials = a.partials;
   k.ticket = a.ticket;
   k.out = a.out;

@@ -163,6 +163,19 @@ template <class M, class V>
 ZNLL_DEV V zsel(M m, V x, V y) {
   return Lanes<V>::make(la(m) ? la(x) : la(y), lb(m) ? lb(x) : lb(y));
 }
+// a value the compiler must treat as new (blocks common-subexpression hoisting across a branch)
+ZNLL_DEV double opaque(double x) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+d"(x));
+#endif
+  return x;
+}
+ZNLL_DEV D2 opaque(D2 x) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+d"(x.a), "+d"(x.b));
+#endif
+  return x;
+}
 template <class V>
 ZNLL_DEV V zbc(double x) {
   return Lanes<V>::make(x, x);
@@ -386,17 +399,64 @@ struct MathTabs {
   double2 log[ZNLL_TAB_N];  // (1/c_i, log c_i) for ZNLL_TAB_N intervals of [0.6875, 1.375)
   double exp2[ZNLL_TAB_N];  // 2^(j/ZNLL_TAB_N)
 };
+#define ZNLL_HAS_OPTIMISTIC 1  // (tests/hostsim keys on this to drive the pair loop the way nll_kernel does)
+// Evaluation context of one thread: where the tables are, and HOW out-of-range arguments are handled.
+//   careful = true : every elementary function tests its argument and answers an out-of-range one (|x| >= 700 for exp;
+//                    non-positive, subnormal, huge, inf or NaN for log / reciprocal) through libdevice on the spot --
+//                    IEEE semantics, one branch per call site.
+//   careful = false: the OPTIMISTIC sweep of the step kernels.  The table-driven cores run unconditionally and each
+//                    call site only ORs its range test into `bad` (predicate logic, no branch, no reconvergence
+//                    barrier); event() looks at `bad` ONCE after the forward sweep and, if it is set, evaluates the
+//                    pair again with a careful context.  A pair that takes no rare path thereby crosses a single test.
+// `careful` is a compile-time constant wherever a Ctx is built (everything is inlined), so the mode costs nothing.
 struct Ctx {
+#if defined(__CUDA_ARCH__)
+  // byte addresses of the tables in the shared window, held in ordinary registers: naming the __shared__ object at
+  // every look-up makes ptxas rebuild its cluster-window address each time (S2UR CgaCtaId + UMOV + ULEA per site)
+  unsigned logtab, exptab;
+#else
   const double2* logtab;
   const double* exptab;
+#endif
+  bool careful;
+  mutable unsigned bad;
 };
+ZNLL_DEV double tab_exp2(const Ctx& cx, int n) {  // 2^((n mod N)/N)
+#if defined(__CUDA_ARCH__)
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(cx.exptab + (((unsigned)n & (ZNLL_TAB_N - 1)) << 3)));
+  return v;
+#else
+  return cx.exptab[n & (ZNLL_TAB_N - 1)];
+#endif
+}
+ZNLL_DEV double2 tab_log(const Ctx& cx, int j) {  // (1/c_j, log c_j), j already reduced to [0, N)
+#if defined(__CUDA_ARCH__)
+  double2 v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(cx.logtab + ((unsigned)j << 4)));
+  return v;
+#else
+  return cx.logtab[j];
+#endif
+}
+ZNLL_DEV void flag_unless(const Ctx& cx, bool ok) { cx.bad |= ok ? 0u : 1u; }
 
 ZNLL_DEV bool exp_in_range(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x4085E000; }  // |x| < 700
-ZNLL_DEV bool log_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u; }
+ZNLL_DEV bool log_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fc00000u; }  // normal, < 2^1022
 // x < -690 read off the high word (the sign bit set and the magnitude above 690; -inf and negative NaNs included)
 ZNLL_DEV bool below_m690(double x) { return (unsigned)__double2hiint(x) > 0xC0859000u; }
 ZNLL_DEV bool rcp_in_range(double x) { return (((unsigned)__double2hiint(x) >> 20) & 0x7ffu) - 1u < 0x7fdu; }
 ZNLL_DEV double scale2n(double p, int n) { return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p)); }
+// p * 2^(n >> ZNLL_TAB_BITS) from the exp core's rounded integer n: one shift, one multiply-add on the high word
+ZNLL_DEV double scale2n_tab(double p, int n) {
+#if defined(__CUDA_ARCH__)
+  int hi;
+  asm("{ .reg .s32 k; shr.s32 k, %1, %2; mad.lo.s32 %0, k, 1048576, %3; }" : "=r"(hi) : "r"(n), "n"(ZNLL_TAB_BITS), "r"(__double2hiint(p)));
+  return __hiloint2double(hi, __double2loint(p));
+#else
+  return scale2n(p, n >> ZNLL_TAB_BITS);
+#endif
+}
 ZNLL_DEV double rcp_seed(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -409,7 +469,7 @@ template <class V>
 ZNLL_DEV V exp_core(V x, const Ctx& cx) {  // |x| < 700
   const V t = zfma(x, kExpT[0], kExpT[1]);
   const int na = __double2loint(la(t)), nb = __double2loint(lb(t));
-  const V T = Lanes<V>::make(cx.exptab[na & (ZNLL_TAB_N - 1)], cx.exptab[nb & (ZNLL_TAB_N - 1)]);
+  const V T = Lanes<V>::make(tab_exp2(cx, na), tab_exp2(cx, nb));
   const V nd = zsub(t, kExpT[1]);
   V r = zfma(nd, kExpT[2], x);
   r = zfma(nd, kExpT[3], r);
@@ -422,18 +482,26 @@ ZNLL_DEV V exp_core(V x, const Ctx& cx) {  // |x| < 700
   q = zfma(q, r, 0.5);
   const V p = zfma(zmul(r, r), q, r);  // e^r - 1
   const V v = zfma(T, p, T);
-  return Lanes<V>::make(scale2n(la(v), na >> ZNLL_TAB_BITS), scale2n(lb(v), nb >> ZNLL_TAB_BITS));
+  return Lanes<V>::make(scale2n_tab(la(v), na), scale2n_tab(lb(v), nb));
 }
 template <class V>
 ZNLL_DEV V fast_exp(V x, const Ctx& cx) {
-  if (!(exp_in_range(la(x)) && exp_in_range(lb(x)))) return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
+  const bool ok = exp_in_range(la(x)) && exp_in_range(lb(x));
+  if (!cx.careful)
+    flag_unless(cx, ok);
+  else if (!ok)
+    return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
   return exp_core(x, cx);
 }
 // exp(-|d|): the range test reads d itself, so -|d| never has to exist in a register (the DFMAs of the core take it
 // through their operand modifiers)
 template <class V>
 ZNLL_DEV V fast_exp_negabs(V d, const Ctx& cx) {
-  if (!(exp_in_range(la(d)) && exp_in_range(lb(d)))) return Lanes<V>::make(exp(-fabs(la(d))), exp(-fabs(lb(d))));  // rare
+  const bool ok = exp_in_range(la(d)) && exp_in_range(lb(d));
+  if (!cx.careful)
+    flag_unless(cx, ok);
+  else if (!ok)
+    return Lanes<V>::make(exp(-fabs(la(d))), exp(-fabs(lb(d))));  // rare
   return exp_core(zneg(zabs(d)), cx);
 }
 
@@ -447,31 +515,33 @@ ZNLL_DEV V rcp_core(V x) {  // x normal, 1/x normal
   return zfma(y, e, y);
 }
 template <class V>
-ZNLL_DEV V fast_rcp(V x) {
+ZNLL_DEV V fast_rcp(V x) {  // always careful (not on the step kernels' hot path)
   if (!(rcp_in_range(la(x)) && rcp_in_range(lb(x)))) return Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));  // rare
   return rcp_core(x);
 }
 
-// log(x) = k ln2 + log c + log1p(r), x = 2^k z, z in [0.6875, 1.375), c the midpoint of z's table interval, r = z/c - 1
+// log(x) = k ln2 + log c + log1p(r), x = 2^k z, z in [0.6875, 1.375), c the midpoint of z's table interval, r = z/c - 1.
+// r is formed as x * (2^-k / c) - 1: the power of two goes into the exponent of the table's 1/c (one integer subtract on
+// its high word), so z itself never has to be assembled in a register pair.  2^-k / c stays normal for x < 2^1022, which
+// is what the range tests of the callers admit.
 struct LogSplit {
-  double z, kd;
-  double2 tc;
+  double sinvc, logc, kd;  // 2^-k / c, log c, k + 2^52 + 2^31
 };
 ZNLL_DEV LogSplit log_split(double x, const Ctx& cx) {
   LogSplit s;
-  const int hi = __double2hiint(x);
-  const int tmp = hi - 0x3fe60000;
-  s.z = __hiloint2double(hi - (tmp & 0xfff00000), __double2loint(x));
-  s.tc = cx.logtab[(tmp >> (20 - ZNLL_TAB_BITS)) & (ZNLL_TAB_N - 1)];
+  const int tmp = __double2hiint(x) - 0x3fe60000;
+  const double2 tc = tab_log(cx, (tmp >> (20 - ZNLL_TAB_BITS)) & (ZNLL_TAB_N - 1));
+  s.sinvc = __hiloint2double(__double2hiint(tc.x) - (tmp & 0xfff00000), __double2loint(tc.x));
+  s.logc = tc.y;
   s.kd = __hiloint2double(0x43300000, (tmp >> 20) ^ 0x80000000);
   return s;
 }
 template <class V>
-ZNLL_DEV V log_core(V x, const Ctx& cx) {  // x positive, normal, finite
+ZNLL_DEV V log_core(V x, const Ctx& cx) {  // x positive, normal, below 2^1022
   const LogSplit sa = log_split(la(x), cx), sb = log_split(lb(x), cx);
-  const V z = Lanes<V>::make(sa.z, sb.z), invc = Lanes<V>::make(sa.tc.x, sb.tc.x), logc = Lanes<V>::make(sa.tc.y, sb.tc.y);
+  const V sinvc = Lanes<V>::make(sa.sinvc, sb.sinvc), logc = Lanes<V>::make(sa.logc, sb.logc);
   const V kd = zsub(Lanes<V>::make(sa.kd, sb.kd), kMathC[2]);
-  const V r = zfma(z, invc, -1.0);
+  const V r = zfma(x, sinvc, -1.0);
 #if ZNLL_TAB_BITS == 9
   V s = zfma(r, kLogC[3], kLogC[2]);
 #pragma unroll
@@ -486,17 +556,24 @@ ZNLL_DEV V log_core(V x, const Ctx& cx) {  // x positive, normal, finite
 }
 template <class V>
 ZNLL_DEV V fast_log(V x, const Ctx& cx) {
-  if (!(log_in_range(la(x)) && log_in_range(lb(x)))) return Lanes<V>::make(log(la(x)), log(lb(x)));  // rare
+  const bool ok = log_in_range(la(x)) && log_in_range(lb(x));
+  if (!cx.careful)
+    flag_unless(cx, ok);
+  else if (!ok)
+    return Lanes<V>::make(log(la(x)), log(lb(x)));  // rare
   return log_core(x, cx);
 }
 
 // log and reciprocal of the SAME argument behind ONE range test.  Fast path: x positive and normal with a normal
 // reciprocal (biased exponent 1..2045); everything else -- zero, negative, subnormal, huge, inf, NaN -- is answered by
 // libdevice once per pair, so the IEEE results (log of a negative number is NaN, 1/0 is inf) are unchanged.
-ZNLL_DEV bool pos_normal(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fd00000u; }
+ZNLL_DEV bool pos_normal(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fc00000u; }  // [2^-1022, 2^1022)
 template <class V>
 ZNLL_DEV void fast_log_rcp(V x, const Ctx& cx, V& lg, V& rc) {
-  if (!(pos_normal(la(x)) && pos_normal(lb(x)))) {  // rare
+  const bool ok = pos_normal(la(x)) && pos_normal(lb(x));
+  if (!cx.careful) {
+    flag_unless(cx, ok);
+  } else if (!ok) {  // rare
     lg = Lanes<V>::make(log(la(x)), log(lb(x)));
     rc = Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));
     return;
@@ -508,7 +585,10 @@ ZNLL_DEV void fast_log_rcp(V x, const Ctx& cx, V& lg, V& rc) {
 // fractions times pdfs) but whose sign must be tracked when they are not
 template <class V>
 ZNLL_DEV void fast_logabs_rcp(V x, const Ctx& cx, V& lg, V& rc, typename Lanes<V>::Mask& neg) {
-  if (!(pos_normal(la(x)) && pos_normal(lb(x)))) {  // rare
+  const bool ok = pos_normal(la(x)) && pos_normal(lb(x));
+  if (!cx.careful) {
+    flag_unless(cx, ok);  // a negative x is flagged as well: the optimistic sweep never sees a sign
+  } else if (!ok) {  // rare
     lg = Lanes<V>::make(log(fabs(la(x))), log(fabs(lb(x))));
     rc = Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));
     neg = zlt(x, 0.0);
@@ -521,10 +601,13 @@ ZNLL_DEV void fast_logabs_rcp(V x, const Ctx& cx, V& lg, V& rc, typename Lanes<V
 // log(p + 1e-307) and its derivative 1/(p + 1e-307) (loss.py:117).  For p >= 2^-958 the sum IS p, bit for bit
 // (1e-307 / p < 2^-54), so the common path neither adds nor tests twice: one test for "p positive, at least 2^-958, and
 // 1/p normal"; a tiny, zero, negative or non-finite p takes the literal formula through libdevice.
-ZNLL_DEV bool pos_not_tiny(double x) { return (unsigned)(__double2hiint(x) - 0x04100000) < 0x7bd00000u; }
+ZNLL_DEV bool pos_not_tiny(double x) { return (unsigned)(__double2hiint(x) - 0x04100000) < 0x7bc00000u; }  // [2^-958, 2^1022)
 template <class V, bool WANT_RCP>
 ZNLL_DEV void log_eps_rcp(V p, const Ctx& cx, V& lg, V& rc) {
-  if (!(pos_not_tiny(la(p)) && pos_not_tiny(lb(p)))) {  // rare
+  const bool ok = pos_not_tiny(la(p)) && pos_not_tiny(lb(p));
+  if (!cx.careful) {
+    flag_unless(cx, ok);
+  } else if (!ok) {  // rare
     const double pa = la(p) + ZNLL_LOG_EPS, pb = lb(p) + ZNLL_LOG_EPS;
     lg = Lanes<V>::make(log(pa), log(pb));
     rc = Lanes<V>::make(1.0 / pa, 1.0 / pb);
@@ -544,11 +627,29 @@ ZNLL_DEV void init_tabs(MathTabs& tabs) {
     tabs.exp2[j] = kExp2Tab[j << (9 - ZNLL_TAB_BITS)];
   }
 }
-ZNLL_DEV Ctx ctx_of(const MathTabs& tabs) {
+// `careful` selects the mode (see Ctx).  On the device the table addresses come out of a volatile asm statement, placed
+// after the block barrier that follows init_tabs: ptxas can then neither rematerialise them at every look-up nor move a
+// table load above the barrier (every load depends on them).
+ZNLL_DEV Ctx ctx_of(const MathTabs& tabs, bool careful = true) {
   Ctx cx;
+#if defined(__CUDA_ARCH__)
+  unsigned base;
+  asm volatile("{ .reg .u64 t64; cvta.to.shared.u64 t64, %1; cvt.u32.u64 %0, t64; }" : "=r"(base) : "l"(&tabs));
+  cx.logtab = base;
+  cx.exptab = base + (unsigned)(sizeof(double2) * ZNLL_TAB_N);
+#else
   cx.logtab = tabs.log;
   cx.exptab = tabs.exp2;
+#endif
+  cx.careful = careful;
+  cx.bad = 0u;
   return cx;
+}
+ZNLL_DEV Ctx with_mode(const Ctx& cx, bool careful) {
+  Ctx r = cx;
+  r.careful = careful;
+  r.bad = 0u;
+  return r;
 }
 // A tree that is evaluated in log space from leaves that need neither exp nor log (a Gauss, an Exponential, products of
 // them: cfg 1) never touches the tables; its kernels skip filling them (the rare p + 1e-307 path uses libdevice).
@@ -696,14 +797,10 @@ struct CBallN {
     // t < -|alpha|  <=>  t + |alpha| < 0, and that sum has the exact sign (it is exact when the two are within a factor
     // of two of each other, far from zero otherwise; t == -|alpha| gives +0): integer sign tests replace three DSETPs
     const V ta = zadd(t, c[CO + 3]);
-    tail = zsignbit(ta);
     any_tail = zany_signbit(ta);
     const V lp_core = zfma(zmul(t, -0.5), t, c[CO + 7]);  // exp(-t^2/2)
-    if (!any_tail) {                                       // whole pair on the Gaussian core (events are sorted)
-      mdt = t;
-      lu = zbc<V>(0.0);
-      return lp_core;
-    }
+    if (!any_tail) return lp_core;  // whole pair on the Gaussian core (events are bucketed): mdt, lu, tail stay unset
+    tail = zsignbit(ta);
     // A*(B-t)^-n == exp(ln A - n*ln(B-t)); a lane on the core gets the safe value u = 2 (z.safe_where)
     const V u = zsel(tail, zsub(c[CO + 5], t), zbc<V>(2.0));
     V ru;
@@ -721,15 +818,19 @@ struct CBallN {
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
-    const V gm = zmul(g, mdt);                   // -g * d ln v/dt
-    zacc(acc[AO + 0], gm, c[CO + 1]);            // dt/dmu    = -sign/sigma
-    zacc(acc[AO + 1], zmul(gm, t), c[CO + 2]);   // dt/dsigma = -t/sigma
-    if (any_tail) {
-      // d ln v/d|alpha| = -n/a - a + (n/u)(n/a^2+1) ; d ln v/dn = ln(n/a)+1 - ln u - (n/u)/a ; 0 on the core
-      const V gt = zsel(tail, g, zbc<V>(0.0));
-      zacc(acc[AO + 2], zmul(gt, c[CO + 12]), zfma(mdt, -c[CO + 11], c[CO + 10]));
-      zacc(acc[AO + 3], gt, zfma(mdt, c[CO + 9], zsub(c[CO + 8], lu)));
+    if (!any_tail) {  // core pair: -d ln v/dt is t itself, nothing flows to alpha and n
+      const V gm = zmul(g, t);
+      zacc(acc[AO + 0], gm, c[CO + 1]);            // dt/dmu    = -sign/sigma
+      zacc(acc[AO + 1], zmul(gm, t), c[CO + 2]);   // dt/dsigma = -t/sigma
+      return;
     }
+    const V gm = zmul(g, mdt);                   // -g * d ln v/dt
+    zacc(acc[AO + 0], gm, c[CO + 1]);
+    zacc(acc[AO + 1], zmul(gm, t), c[CO + 2]);
+    // d ln v/d|alpha| = -n/a - a + (n/u)(n/a^2+1) ; d ln v/dn = ln(n/a)+1 - ln u - (n/u)/a ; 0 on the core
+    const V gt = zsel(tail, g, zbc<V>(0.0));
+    zacc(acc[AO + 2], zmul(gt, c[CO + 12]), zfma(mdt, -c[CO + 11], c[CO + 10]));
+    zacc(acc[AO + 3], gt, zfma(mdt, c[CO + 9], zsub(c[CO + 8], lu)));
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
@@ -1116,17 +1217,20 @@ struct SumN {
     bwd_val<CO, AO>(zmul(g, rP), c, acc);
   }
 };
-// SumPDF of exactly two log-native children (the signal + background case), in log-sum-exp form:
-//   ln P = m + ln S,  m = max(l0, l1),  S = f0*e^(l0-m) + f1*e^(l1-m)
-// One of the two exponentials is exp(0) = 1, so a single exp is evaluated per event instead of two, it can
-// neither overflow nor lose the event to underflow, and the Sum becomes log-native itself (no exp at all
-// when it sits under a ProductPDF).  d ln P/d f_i = e_i/S;  the adjoint of child i is g*f_i*e_i/S.
+// SumPDF of exactly two log-native children (the signal + background case), in log-sum-exp form with child 1 as the
+// fixed reference:
+//   ln P = l1 + ln S,   S = f0*e^(l0-l1) + f1
+// One exp per event instead of two, the Sum becomes log-native itself (no exp at all when it sits under a ProductPDF),
+// and -- unlike the max-based form -- no per-lane selects: the common path is straight-line.  d ln P/d f_0 = e^d/S,
+// d ln P/d f_1 = 1/S; the adjoint of child i is g*f_i*(d ln P/d f_i).  |l0 - l1| >= 600 (where e^d could overflow S, or
+// underflows) is the rare path and uses the max-based form, in which one of the two exponentials is exp(0) = 1.
+ZNLL_DEV bool lse_in_range(double d) { return (__double2hiint(d) & 0x7fffffff) < 0x4082C000; }  // |d| < 600
 template <class V, class C0, class C1>
 struct SumLseN {
   typedef typename Lanes<V>::Mask Mask;
   typename C0::template Node<V> k0;
   typename C1::template Node<V> k1;
-  V q0, q1;  // e_i / S
+  V q0, q1;  // d ln P / d f_i
   V P;
 
   template <int CO>
@@ -1135,20 +1239,43 @@ struct SumLseN {
     const V l0 = k0.template fwd_log<CO + 2>(cx, c, x, n0);
     const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
     const V d = zsub(l0, l1);
-    const Mask lt = zsignbit(d);  // l0 < l1 (a -0.0 or NaN difference may land on either side: same result)
-    const V e = fast_exp_negabs(d, cx);
+    const bool ok = lse_in_range(la(d)) && lse_in_range(lb(d));
     const V one = zbc<V>(1.0);
-    V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
-    e0 = zsel(n0, zneg(e0), e0);  // children that are themselves products with a negative factor
-    e1 = zsel(n1, zneg(e1), e1);
-    const V S = zfma(e0, c[CO + 0], zmul(e1, c[CO + 1]));
+    if (!cx.careful) {
+      flag_unless(cx, ok);
+    } else if (!ok) {  // rare: max-based form, exp through libdevice (0 for a huge |d|, NaN stays NaN)
+      const Mask lt = zsignbit(d);
+      const V e = Lanes<V>::make(exp(-fabs(la(d))), exp(-fabs(lb(d))));
+      V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
+      e0 = zsel(n0, zneg(e0), e0);
+      e1 = zsel(n1, zneg(e1), e1);
+      const V S = zfma(e0, c[CO + 0], zmul(e1, c[CO + 1]));
+      V lS, rS;
+      Mask ng;
+      fast_logabs_rcp(S, cx, lS, rS, ng);
+      neg = mxor(neg, ng);
+      q0 = zmul(e0, rS);
+      q1 = zmul(e1, rS);
+      return zadd(zsel(lt, l1, l0), lS);
+    }
+    const V e = exp_core(d, cx);
     V lS, rS;
     Mask ng;
-    fast_logabs_rcp(S, cx, lS, rS, ng);  // one range test for both; S < 0 (a negative fraction) is the rare path
-    neg = mxor(neg, ng);
-    q0 = zmul(e0, rS);
-    q1 = zmul(e1, rS);
-    return zadd(zsel(lt, l1, l0), lS);
+    if (!cx.careful) {  // optimistic sweep: a child with a negative factor has flagged the pair already
+      const V S = zfma(e, c[CO + 0], c[CO + 1]);
+      fast_logabs_rcp(S, cx, lS, rS, ng);
+      q0 = zmul(e, rS);
+      q1 = rS;
+    } else {
+      const V e0 = zsel(n0, zneg(e), e);  // children that are themselves products with a negative factor
+      const V e1 = zsel(n1, zbc<V>(-1.0), one);
+      const V S = zfma(e0, c[CO + 0], zmul(e1, c[CO + 1]));
+      fast_logabs_rcp(S, cx, lS, rS, ng);  // one range test for both; S < 0 (a negative fraction) is the rare path
+      neg = mxor(neg, ng);
+      q0 = zmul(e0, rS);
+      q1 = zmul(e1, rS);
+    }
+    return zadd(l1, lS);
   }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
@@ -1267,14 +1394,17 @@ struct Prod {
 // accumulators into all peers' exchange buffers with plain stores over NVLink (peer-mapped symmetric memory),
 // publishes a sequence flag with release semantics at system scope, waits for the peers' flags, and sums the
 // world's contributions in fixed rank order -- bit-identical on every rank, no NCCL call on the step path.
-// Buffer layout per rank: [128 B: u64 flag per source rank][2 parities][world][total] doubles.
+// Buffer layout per rank: [128 B: u64 flag per source rank][2 parities][world][stride] doubles.  The stride is fixed
+// (ZNLL_XSTRIDE, the largest accumulator block) so that ONE buffer per process serves every plan: the two parity regions
+// of consecutive evaluations never overlap, whichever plans make them.
 #define ZNLL_MAXPEERS 8
 #define ZNLL_XFLAG_BYTES 128
+#define ZNLL_XSTRIDE 256
 struct Xchg {
   double* buf[ZNLL_MAXPEERS];  // buf[r]: rank r's exchange buffer as mapped into this process
   double* acc;                 // this rank's accumulators of ALL channels (plan-wide), reduced in place
   unsigned long long seq;      // evaluation counter (> 0), identical on all ranks
-  int rank, world, total, pad;
+  int rank, world, total, stride;
   double* hout;                // host-mapped pinned copy of acc (zero-copy result path), or null
   unsigned long long* hflag;   // host-mapped flag: set to seq after hout is complete
 };
@@ -1299,7 +1429,7 @@ ZNLL_DEV void peer_exchange(const Xchg& xc) {
     const double v = __ldcg(xc.acc + t);
     for (int p = 0; p < xc.world; ++p) {
       double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(xc.buf[p]) + ZNLL_XFLAG_BYTES) +
-                    ((size_t)(par * xc.world + xc.rank) * xc.total + t);
+                    ((size_t)(par * xc.world + xc.rank) * xc.stride + t);
       *reinterpret_cast<volatile double*>(dst) = v;
     }
   }
@@ -1319,9 +1449,9 @@ ZNLL_DEV void peer_exchange(const Xchg& xc) {
   __syncthreads();
   if (t < xc.total) {
     const double* src = reinterpret_cast<const double*>(reinterpret_cast<const char*>(xc.buf[xc.rank]) + ZNLL_XFLAG_BYTES) +
-                        (size_t)par * xc.world * xc.total + t;
+                        (size_t)par * xc.world * xc.stride + t;
     double s = 0.0;
-    for (int r = 0; r < xc.world; ++r) s += __ldcg(src + (size_t)r * xc.total);  // fixed rank order
+    for (int r = 0; r < xc.world; ++r) s += __ldcg(src + (size_t)r * xc.stride);  // fixed rank order
     xc.acc[t] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : s;
   }
 }
@@ -1332,6 +1462,7 @@ struct KArgs {
   const double* w;
   long long n;
   double log_offset;
+  double log_offset2;      // 2 * log_offset (filled by the launcher)
   double* partials;        // [gridDim.x][NACC]
   unsigned int* ticket;    // zero before launch; reset by the last block
   double* out;             // [NACC]
@@ -1339,57 +1470,102 @@ struct KArgs {
   double c[NC > 0 ? NC : 1];
 };
 
-// accumulators: [0] running sum of w*l - offset, [1] its Kahan compensation, [2..] slots.
+// accumulators: [0] running sum of w*l - offset, [1] its compensation, [2..] slots.
 // Returns this event's (this pair's) contribution to [0]:  sum over lanes of w*l, minus `off` -- the log offset times
 // the number of lanes, prepared by the caller.
+//
+// With an optimistic context (cx0.careful == false, the step kernels' pair loop) the forward sweep runs the fast cores
+// unconditionally and every range test only sets cx0.bad; ONE test after the sweep decides whether the pair is evaluated
+// again carefully (out-of-range argument of an exp / log / reciprocal, a negative factor, ln P < -690 where the
+// p + 1e-307 of loss.py:117 matters).  With a careful context only the careful evaluation is instantiated.
 template <class M, class V, bool WEIGHTED, bool GRAD, class A>
-ZNLL_DEV double event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, double off, A* acc) {
+ZNLL_DEV double event(const Ctx& cx0, const double* __restrict__ c, const V* x, V w, double off, A* acc) {
   typedef typename Lanes<V>::Mask Mask;
   typename M::template Node<V> m;
-  V l;
-  if constexpr (M::LOGNAT) {
-    Mask neg = Lanes<V>::mask(false, false);
-    const V lp = m.template fwd_log<0>(cx, c, x, neg);
-    l = lp;
-    if (below_m690(la(lp)) | below_m690(lb(lp)) | zany(neg)) {  // p + 1e-307 matters only here (loss.py:117); rare
-      double ll[2] = {la(lp), lb(lp)}, gg[2] = {1.0, 1.0};
-      const bool ng[2] = {la(neg), lb(neg)};
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (ll[k] < -690.0 || ng[k]) {
-          const double p = ng[k] ? -exp(ll[k]) : exp(ll[k]);
-          const double pp = p + ZNLL_LOG_EPS;
-          ll[k] = log(pp);
-          gg[k] = p / pp;
+  // weights multiply first, then the unweighted offset is subtracted per event (loss.py:134-137); the term is formed
+  // inside each branch, so that only one double is merged where the optimistic and the careful path meet
+  auto term_of = [&](V l) -> double {
+    if constexpr (WEIGHTED)
+      return zdot_minus(w, l, off);
+    else
+      return zsum_minus(l, off);
+  };
+  double term = 0.0;
+  bool redo = cx0.careful;
+  if (!cx0.careful) {
+    cx0.bad = 0u;
+    V l;
+    if constexpr (M::LOGNAT) {
+      Mask neg = Lanes<V>::mask(false, false);
+      l = m.template fwd_log<0>(cx0, c, x, neg);
+      redo = (cx0.bad != 0u) | below_m690(la(l)) | below_m690(lb(l));
+      if (!redo) {
+        term = term_of(l);
+        if constexpr (GRAD) {
+          // the adjoint of ln P is exactly 1 (or the weight): a compile-time constant the reverse sweep folds away
+          if constexpr (WEIGHTED)
+            m.template bwd_log<0, 2>(w, c, acc);
+          else
+            m.template bwd_log<0, 2>(zbc<V>(1.0), c, acc);
         }
       }
-      l = Lanes<V>::make(ll[0], ll[1]);
-      if constexpr (GRAD) {
-        V g = Lanes<V>::make(gg[0], gg[1]);
-        if constexpr (WEIGHTED) g = zmul(g, w);
-        m.template bwd_log<0, 2>(g, c, acc);
+    } else {
+      const V P = m.template fwd_val<0>(cx0, c, x);
+      V g;
+      log_eps_rcp<V, GRAD>(P, cx0, l, g);  // l = log P, g = 1/P: for P >= 2^-958 the sum P + 1e-307 IS P, bit for bit
+      redo = cx0.bad != 0u;
+      if (!redo) {
+        term = term_of(l);
+        if constexpr (GRAD) {
+          if constexpr (WEIGHTED) g = zmul(g, w);
+          m.template bwd_val<0, 2>(g, c, acc);
+        }
       }
-    } else if constexpr (GRAD) {
-      // the adjoint of ln P is exactly 1 (or the weight): a compile-time constant the reverse sweep folds away
-      if constexpr (WEIGHTED)
-        m.template bwd_log<0, 2>(w, c, acc);
-      else
-        m.template bwd_log<0, 2>(zbc<V>(1.0), c, acc);
-    }
-  } else {
-    const V P = m.template fwd_val<0>(cx, c, x);
-    V g;
-    log_eps_rcp<V, GRAD>(P, cx, l, g);  // l = log(P + 1e-307), g = 1/(P + 1e-307); one range test for both
-    if constexpr (GRAD) {
-      if constexpr (WEIGHTED) g = zmul(g, w);
-      m.template bwd_val<0, 2>(g, c, acc);
     }
   }
-  // weights multiply first, then the unweighted offset is subtracted per event (loss.py:134-137)
-  if constexpr (WEIGHTED)
-    return zdot_minus(w, l, off);
-  else
-    return zsum_minus(l, off);
+  if (redo) {  // rare in the pair loop; the only path of a careful context
+    const Ctx cx = with_mode(cx0, true);
+    V l;
+    if constexpr (M::LOGNAT) {
+      Mask neg = Lanes<V>::mask(false, false);
+      const V lp = m.template fwd_log<0>(cx, c, x, neg);
+      l = lp;
+      if (below_m690(la(lp)) | below_m690(lb(lp)) | zany(neg)) {  // p + 1e-307 matters only here (loss.py:117); rare
+        double ll[2] = {la(lp), lb(lp)}, gg[2] = {1.0, 1.0};
+        const bool ng[2] = {la(neg), lb(neg)};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (ll[k] < -690.0 || ng[k]) {
+            const double p = ng[k] ? -exp(ll[k]) : exp(ll[k]);
+            const double pp = p + ZNLL_LOG_EPS;
+            ll[k] = log(pp);
+            gg[k] = p / pp;
+          }
+        }
+        l = Lanes<V>::make(ll[0], ll[1]);
+        if constexpr (GRAD) {
+          V g = Lanes<V>::make(gg[0], gg[1]);
+          if constexpr (WEIGHTED) g = zmul(g, w);
+          m.template bwd_log<0, 2>(g, c, acc);
+        }
+      } else if constexpr (GRAD) {
+        if constexpr (WEIGHTED)
+          m.template bwd_log<0, 2>(w, c, acc);
+        else
+          m.template bwd_log<0, 2>(zbc<V>(1.0), c, acc);
+      }
+    } else {
+      const V P = m.template fwd_val<0>(cx, c, x);
+      V g;
+      log_eps_rcp<V, GRAD>(P, cx, l, g);  // l = log(P + 1e-307), g = 1/(P + 1e-307); one range test for both
+      if constexpr (GRAD) {
+        if constexpr (WEIGHTED) g = zmul(g, w);
+        m.template bwd_val<0, 2>(g, c, acc);
+      }
+    }
+    term = term_of(l);
+  }
+  return term;
 }
 
 ZNLL_DEV void kahan_add(double* acc, double term) {
@@ -1489,7 +1665,7 @@ struct EventPair {
   D2 x[ZNLL_MAXCOL];
   D2 w;
   template <int NC>
-  ZNLL_DEV void load(const KArgs<NC>& args, long long i) {
+  ZNLL_DEV void load(const KArgs<NC>& args, unsigned i) {  // i: index of the event PAIR
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k) {
       if ((M::COLMASK >> k) & 1) {
@@ -1527,7 +1703,7 @@ __host__ __device__ constexpr int zpopc(unsigned m) {
 // step; the product-tree parity and out-of-range canary tests pass with it.  It stays off until the whole GPU suite (four
 // streams, NVRTC trees) has run with it.
 #ifndef ZNLL_RING
-#define ZNLL_RING 0
+#define ZNLL_RING 1
 #endif
 ZNLL_DEV void cp_async16(void* smem, const void* gmem) {  // LDGSTS, L2 only
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -1542,7 +1718,7 @@ struct Ring {
   static constexpr int NSTREAM = zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0);
   double2 slot[2][NSTREAM][ZNLL_BLOCK];  // [stage][stream][thread]
   template <int NC>
-  ZNLL_DEV void issue(int stage, const KArgs<NC>& args, long long i) {
+  ZNLL_DEV void issue(int stage, const KArgs<NC>& args, unsigned i) {
     int s = 0;
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k)
@@ -1567,6 +1743,12 @@ struct Ring {
   }
 };
 
+// The pair loop.  Per thread the value is accumulated with plain fp64 adds (a thread sees a few hundred pairs, each term
+// is O(1) after the per-event offset: the rounding error of a thread's partial sum is below 1e-13 of it), and the partial
+// sums of threads, warps, blocks and GPUs are then merged error-free (TwoSum, block_reduce_and_finish) -- so the result is
+// a compensated sum at the granularity that matters for 1e8..1e9 events, and the per-pair Kahan step (4 dependent DADDs
+// on the FP64 pipe that bounds these kernels) is gone.  Event pairs are indexed with 32 bits (the host refuses more
+// than 8e9 events per channel and GPU): one IADD, one ISETP and one IMAD.WIDE per pair for the whole loop control.
 template <class M, bool WEIGHTED, bool GRAD>
 __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NACC = 2 + M::NS;
@@ -1575,19 +1757,20 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
     init_tabs(tabs);
     __syncthreads();
   }
-  const Ctx cx = ctx_of(tabs);
+  const Ctx cx = ctx_of(tabs, /*careful=*/false);  // optimistic pair loop: one rare-path test per pair (see event())
   double acc[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
   const double* __restrict__ c = args.c;
-  const double off = args.log_offset, off2 = 2.0 * args.log_offset;
-  const long long nvec = args.n >> 1;
-  const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
-  long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x;
+  const unsigned nvec = (unsigned)(args.n >> 1);
+  const unsigned stride = gridDim.x * ZNLL_BLOCK;
+  unsigned i = blockIdx.x * ZNLL_BLOCK + threadIdx.x;
   constexpr int NSTREAM = zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0);
   // the ring, the tables and the reduction scratch must fit the 48 KB of static shared memory
   constexpr bool RING_FITS = 2 * NSTREAM * ZNLL_BLOCK * 16 + sizeof(MathTabs) + (ZNLL_BLOCK / 32) * NACC * 8 + 256 <= 48 * 1024;
   if constexpr ((ZNLL_RING != 0) && (NSTREAM == 3 || NSTREAM == 4) && RING_FITS) {
+    // three or four 8-byte streams per event (cfg 4): a two-deep cp.async ring in shared memory keeps TWO pairs per
+    // thread in flight -- measured on the B200: 0.474 -> 0.393 ms per launch of cfg 4, i.e. 5.07 -> 6.10 TB/s
     __shared__ Ring<M, WEIGHTED> ring;
     EventPair<M, WEIGHTED> p;
     // groups are committed unconditionally (an empty group is legal), so "all but the newest" is always the stage read next
@@ -1600,50 +1783,51 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
       ring.fetch(0, p);
       if (i + 2 * stride < nvec) ring.issue(0, args, i + 2 * stride);  // refill the stage just read (same thread: program order)
       cp_async_commit();
-      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, off2, acc));
+      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, args.log_offset2, acc);
       i += stride;
       if (i >= nvec) break;
       cp_async_wait_all_but_one();
       ring.fetch(1, p);
       if (i + 2 * stride < nvec) ring.issue(1, args, i + 2 * stride);
       cp_async_commit();
-      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, off2, acc));
+      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, args.log_offset2, acc);
       i += stride;
     }
     cp_async_wait_all();
   } else if constexpr ((ZNLL_PINGPONG != 0) && (NSTREAM >= 3)) {
-    // three or more 8-byte streams per event: two register buffers used alternately -- the loop body exists twice and no
-    // buffer is ever copied (the copy is 12+ moves per pair there; measured -10 % on cfg 4, while one- and two-stream
-    // trees lose 1 % to the doubled loop body and keep the copying loop below)
+    // more streams than the ring holds: two register buffers used alternately -- the loop body exists twice and no
+    // buffer is ever copied
     EventPair<M, WEIGHTED> b0, b1;
     if (i < nvec) b0.load(args, i);
     while (i < nvec) {
       i += stride;
       if (i < nvec) b1.load(args, i);
-      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, b0.x, b0.w, off2, acc));
+      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, b0.x, b0.w, args.log_offset2, acc);
       if (i >= nvec) break;
       i += stride;
       if (i < nvec) b0.load(args, i);
-      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, b1.x, b1.w, off2, acc));
+      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, b1.x, b1.w, args.log_offset2, acc);
     }
   } else {
     EventPair<M, WEIGHTED> cur, nxt;
-    if (i < nvec) nxt.load(args, i);
-    while (i < nvec) {
+    bool more = i < nvec;
+    if (more) nxt.load(args, i);
+    while (more) {
       cur = nxt;
       i += stride;
-      if (i < nvec) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
-      kahan_add(acc, event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, off2, acc));
+      more = i < nvec;
+      if (more) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
+      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, args.log_offset2, acc);
     }
   }
-  if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event: scalar instantiation
+  if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event: scalar, careful instantiation
     double xa[ZNLL_MAXCOL];
 #pragma unroll
     for (int k = 0; k < ZNLL_MAXCOL; ++k)
       if ((M::COLMASK >> k) & 1) xa[k] = args.cols[k][args.n - 1];
     double wa = 1.0;
     if constexpr (WEIGHTED) wa = args.w[args.n - 1];
-    kahan_add(acc, event<M, double, WEIGHTED, GRAD>(cx, c, xa, wa, off, acc));
+    kahan_add(acc, event<M, double, WEIGHTED, GRAD>(with_mode(cx, true), c, xa, wa, args.log_offset, acc));
   }
   block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out, &args.xc);
 }
@@ -1667,9 +1851,9 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constan
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
   const double* __restrict__ c = args.c;
-  const long long nvec = args.n >> 1;
-  const long long stride = (long long)gridDim.x * ZNLL_BLOCK;
-  long long i = (long long)blockIdx.x * ZNLL_BLOCK + threadIdx.x;
+  const unsigned nvec = (unsigned)(args.n >> 1);
+  const unsigned stride = gridDim.x * ZNLL_BLOCK;
+  unsigned i = blockIdx.x * ZNLL_BLOCK + threadIdx.x;
   // two events per thread in lock-step like the step kernel; the pair keeps per-lane score vectors e.a / e.b
   EventPair<M, WEIGHTED> cur, nxt;
   if (i < nvec) nxt.load(args, i);

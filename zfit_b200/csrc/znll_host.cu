@@ -475,13 +475,16 @@ struct znll_plan {
   // fused cross-GPU exchange (znll_plan_set_peers)
   int x_rank = 0, x_world = 0;
   double* x_buf[8] = {nullptr};
-  unsigned long long x_seq = 0;
+  unsigned long long x_seq = 0, pending_seq = 0;
   // zero-copy result path: pinned host memory mapped into the device address space
   double* h_acc_dev = nullptr;
   unsigned long long* h_flag = nullptr;
   unsigned long long* h_flag_dev = nullptr;
   bool direct_pending = false;
 };
+
+#define ZNLL_XSTRIDE_HOST 256  // == ZNLL_XSTRIDE of znll_device.cuh: slots of the exchange buffer per (parity, rank)
+static unsigned long long g_xseq[16] = {0};  // per device: number of exchanging evaluations this process has launched
 
 static void relayout(znll_plan* p) {
   int a = 0, s = 0;
@@ -1181,6 +1184,8 @@ int znll_plan_bind_device(znll_plan* p, int ch, int n_cols, const double* const*
   CUDA_OK(cudaSetDevice(p->device));
   Channel& c = p->ch[ch];
   if (c.nodes.empty()) return fail("znll_plan_bind_device: set the model of channel %d first", ch);
+  if (n_events > 8000000000ll)  // the pair loop indexes event pairs with 32 bits
+    return fail("znll_plan_bind_device: %lld events in one channel of one GPU exceed the limit of 8e9; shard the data", (long long)n_events);
   for (auto& ni : c.nodes)
     if (ni.nd.kind < ZNLL_SUM && ni.nd.column >= n_cols)
       return fail("znll_plan_bind_device: model reads column %d but only %d bound", ni.nd.column, n_cols);
@@ -1248,6 +1253,8 @@ int znll_plan_set_peers(znll_plan* p, int rank, int world, void* const* peer_buf
   if (!p) return fail("znll_plan_set_peers: bad arguments");
   if (world <= 1) {
     p->x_world = 0;
+    p->x_seq = 0;
+    if (p->h_flag) *p->h_flag = 0ull;
     return 0;
   }
   if (world > 8 || rank < 0 || rank >= world || !peer_bufs) return fail("znll_plan_set_peers: bad rank/world (max 8 peers)");
@@ -1260,14 +1267,17 @@ int znll_plan_set_peers(znll_plan* p, int rank, int world, void* const* peer_buf
   }
   p->x_rank = rank;
   p->x_world = world;
-  p->x_seq = 0;  // every rank restarts its sequence with the freshly zeroed exchange buffers ...
-  if (p->h_flag) *p->h_flag = 0ull;  // ... so the host flag of evaluations made before this call must not match again
+  // evaluations that exchange are numbered by a process-wide counter (g_xseq): one exchange buffer serves every plan of
+  // the process, and all ranks make the same sequence of evaluations (SPMD).  The plan's own counter numbers the
+  // evaluations it makes without peers; the host flag of evaluations made before this call must not match again
+  p->x_seq = 0;
+  if (p->h_flag) *p->h_flag = 0ull;
   return 0;
 }
 
 size_t znll_plan_exchange_bytes(const znll_plan* p, int world) {
   if (!p || world < 1) return 0;
-  return 128 + sizeof(double) * 2 * (size_t)world * (size_t)p->total_acc;
+  return 128 + sizeof(double) * 2 * (size_t)world * (size_t)ZNLL_XSTRIDE_HOST;
 }
 
 int znll_plan_n_slots(const znll_plan* p, int ch) { return (p && ch >= 0 && ch < (int)p->ch.size()) ? p->ch[ch].n_slots : -1; }
@@ -1309,6 +1319,7 @@ static int launch_impl(znll_plan* p, const double* slots, uint32_t flags, double
     la.w = c.w;
     la.n = c.n;
     la.log_offset = log_offset;
+    la.log_offset2 = 2.0 * log_offset;
     la.partials = c.d_partials;
     la.ticket = c.d_ticket;
     la.out = p->d_acc + c.acc_off;
@@ -1316,8 +1327,9 @@ static int launch_impl(znll_plan* p, const double* slots, uint32_t flags, double
     if (&c == &p->ch.back() && (p->x_world > 1 || direct)) {
       // the last channel's kernel also performs the cross-GPU exchange and / or the zero-copy hand-off to the host
       la.xc.acc = p->d_acc;
-      la.xc.seq = ++p->x_seq;
+      la.xc.seq = p->pending_seq = (p->x_world > 1) ? ++g_xseq[p->device & 15] : ++p->x_seq;
       la.xc.total = p->total_acc;
+      la.xc.stride = ZNLL_XSTRIDE_HOST;
       if (p->x_world > 1) {
         for (int r = 0; r < p->x_world; ++r) la.xc.buf[r] = p->x_buf[r];
         la.xc.rank = p->x_rank;
@@ -1349,10 +1361,10 @@ int znll_collect(znll_plan* p, uint32_t flags, double* values, double* grad_slot
     p->direct_pending = false;
     volatile unsigned long long* flag = p->h_flag;
     unsigned long long spins = 0;
-    while (*flag != p->x_seq) {
+    while (*flag != p->pending_seq) {
       if ((++spins & 0xfffffull) == 0) {  // every ~1M polls: has the stream failed or finished without publishing?
         cudaError_t q = cudaStreamQuery(st);
-        if (q == cudaSuccess && *flag != p->x_seq) return fail("znll_collect: kernel finished without publishing its result");
+        if (q == cudaSuccess && *flag != p->pending_seq) return fail("znll_collect: kernel finished without publishing its result");
         if (q != cudaSuccess && q != cudaErrorNotReady) return fail("znll_collect: %s", cudaGetErrorString(q));
       }
     }
@@ -1402,6 +1414,8 @@ int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* 
       la.w = c.w;
       la.n = c.n;
       la.log_offset = log_offset;
+      la.log_offset2 = 2.0 * log_offset;
+    la.log_offset2 = 2.0 * log_offset;
       la.partials = d_part;
       la.ticket = c.d_ticket;
       la.out = d_out;
@@ -1468,6 +1482,7 @@ static int pdf_launch(znll_plan* p, int ch, const double* slots, double* d_out, 
   la.w = c.w;
   la.n = c.n;
   la.log_offset = 0.0;
+  la.log_offset2 = 0.0;
   la.partials = d_out;
   la.ticket = c.d_ticket;
   la.out = nullptr;

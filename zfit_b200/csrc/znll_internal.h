@@ -6,7 +6,7 @@ struct ZnllXchg {  // == znll::Xchg
   double* buf[8];
   double* acc;
   unsigned long long seq;
-  int rank, world, total, pad;
+  int rank, world, total, stride;
   double* hout;
   unsigned long long* hflag;
 };
@@ -16,6 +16,7 @@ struct ZnllLaunchArgs {  // == the prefix of znll::KArgs<NC> (the NVRTC path cop
   const double* w;
   long long n;
   double log_offset;
+  double log_offset2;  // 2 * log_offset: the pair loop subtracts it as a constant-bank operand
   double* partials;
   unsigned int* ticket;
   double* out;

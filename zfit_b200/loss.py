@@ -34,10 +34,11 @@ from .exception import (
     ParamNameNotUniqueError,
 )
 from .parameter import OrderedSet, ZfitParameter, set_values
-from .pdf import BasePDF, CrystalBall
+from .pdf import BasePDF, CrystalBall, DoubleCB, GeneralizedCB
 from .space import Space
 
 DEFAULT_FULL_ARG = True  # loss.py:70
+_PIECEWISE = (CrystalBall, DoubleCB, GeneralizedCB)  # leaves whose kernels branch per warp on the event's side of a threshold
 
 
 # ------------------------------------------------------------------------------------------------
@@ -111,8 +112,12 @@ class CudaEngine:
                 try:
                     self._setup_fused_exchange(device)
                     self.reduce_mode = "fused-nvlink"
-                except Exception as exc:  # symmetric memory unavailable: keep the NCCL all-reduce
+                except Exception as exc:  # symmetric memory unavailable: keep the NCCL all-reduce, and say so
                     self.reduce_fallback_reason = repr(exc)
+                    self.plan.set_peers(0, 1, [], 0)
+                    warnings.warn(
+                        "zfit_b200: the fused NVLink exchange is unavailable on this rank, the cross-GPU reduction uses "
+                        f"an NCCL all-reduce per evaluation instead ({exc!r})", RuntimeWarning, stacklevel=2)
             if self.reduce_mode == "nccl":
                 self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
         self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
@@ -180,41 +185,38 @@ class CudaEngine:
         self._lazy_sort_in = self.LAZY_SORT_AFTER if sort_events == "lazy" else None
 
     def _sort_for_coherence(self, model, data, cols, w):
-        """Events are static for the whole fit and the NLL is a sum, so they may be reordered once at bind
-        time: sorting by the CrystalBall observable makes every warp uniformly core or tail."""
-        target = _first_leaf(model, CrystalBall)
+        """Events are static for the whole fit and the NLL is a sum, so they may be reordered once at bind time: a stable
+        partition into 32 buckets of the CrystalBall observable (``znll_partition_events``, csrc/znll_prep.cu) makes
+        every warp uniformly core or tail -- all but those of the one bucket that holds the moving threshold.  Costs
+        about two evaluations' worth of memory traffic (a full ``torch.sort`` cost 25 evaluations' worth of time)."""
+        target = _first_leaf(model, _PIECEWISE)
         if target is None:
             return cols, w
         torch = self.torch
         i = data.obs.index(target.obs[0])
-        if len(cols) == 1 and w is None:
-            return [torch.sort(cols[0]).values], None  # nothing to carry along: no permutation gather needed
-        order = torch.argsort(cols[i])
-        cols = [c[order].contiguous() for c in cols]
-        if w is not None:
-            w = w[order].contiguous()
-        return cols, w
+        lo, hi = data.space.with_obs(target.obs[0]).limit1d if data.space.has_limits else (None, None)
+        if lo is None or not (hi > lo):
+            lo, hi = float(cols[i].min()), float(cols[i].max())
+            if not (hi > lo):
+                return cols, w
+        n = int(cols[0].numel())
+        out = [torch.empty_like(c) for c in cols]
+        wout = None if w is None else torch.empty_like(w)
+        self.Z.partition_events(self.device, [c.data_ptr() for c in cols], [c.data_ptr() for c in out],
+                                0 if w is None else w.data_ptr(), 0 if wout is None else wout.data_ptr(), i, float(lo),
+                                float(hi), n, stream=self._raw_stream_now())
+        return out, wout
+
+    def _raw_stream_now(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def _setup_fused_exchange(self, device):
-        """Peer-mapped exchange buffers through torch's symmetric memory (allocation + handle exchange only); the
-        reduction itself runs inside the NLL kernel (csrc/znll_device.cuh::peer_exchange)."""
-        import torch.distributed as td
-        import torch.distributed._symmetric_memory as symm
-
-        torch = self.torch
-        world, rank = _dist.world_size(), _dist.rank()
-        nbytes = self.plan.exchange_bytes(world)
-        n = (nbytes + 7) // 8
-        buf = symm.empty(n, dtype=torch.float64, device=torch.device("cuda", device))
-        buf.zero_()
-        handle = symm.rendezvous(buf, td.group.WORLD)
-        ptrs = [int(p) for p in handle.buffer_ptrs]
-        if len(ptrs) != world:
-            msg = f"symmetric memory returned {len(ptrs)} peers for world {world}"
-            raise RuntimeError(msg)
-        torch.cuda.synchronize(device)
-        td.barrier()  # every rank has zeroed its flags before anyone publishes
-        self.plan.set_peers(rank, world, ptrs, n * 8, keepalive=(buf, handle))
+        """Peer-mapped exchange buffer through torch's symmetric memory (allocation + handle exchange only); the
+        reduction itself runs inside the NLL kernel (csrc/znll_device.cuh::peer_exchange).  ONE buffer per process and
+        device serves every plan (it is sized for the largest accumulator block the kernels support and the evaluation
+        sequence number is process-wide), so binding a loss costs no rendezvous after the first."""
+        nbytes, ptrs, keep = _exchange_buffer(self.torch, device, self.Z.exchange_bytes_max(_dist.world_size()))
+        self.plan.set_peers(_dist.rank(), _dist.world_size(), ptrs, nbytes, keepalive=keep)
 
     def eval(self, slots, grad=True, log_offset=0.0, kahan=False):
         # kernels go to torch's current stream, so torch ops (NCCL all-reduce, data preparation) order with them
@@ -250,6 +252,45 @@ class CudaEngine:
 
     def close(self):
         self.plan.close()
+
+
+_XCHG = {}  # device -> (nbytes, peer pointers, keepalive) | Exception: the process-wide exchange buffer
+
+
+def _exchange_buffer(torch, device, nbytes):
+    """Symmetric-memory exchange buffer of this process on ``device``, created (collectively) on first use.  Whether the
+    fused path is usable is agreed on by ALL ranks (a MIN all-reduce of a success flag): a rank-local failure must not
+    leave one rank on NCCL while its peers spin in the kernel."""
+    import torch.distributed as td
+
+    if device in _XCHG:
+        got = _XCHG[device]
+        if isinstance(got, Exception):
+            raise got
+        return got
+    err = None
+    try:
+        import torch.distributed._symmetric_memory as symm
+
+        world = _dist.world_size()
+        n = (nbytes + 7) // 8
+        buf = symm.empty(n, dtype=torch.float64, device=torch.device("cuda", device))
+        buf.zero_()
+        handle = symm.rendezvous(buf, td.group.WORLD)
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        if len(ptrs) != world:
+            msg = f"symmetric memory returned {len(ptrs)} peers for world {world}"
+            raise RuntimeError(msg)
+        torch.cuda.synchronize(device)
+    except Exception as exc:
+        err = exc
+    ok = torch.tensor([0.0 if err is not None else 1.0], dtype=torch.float64, device=f"cuda:{device}")
+    td.all_reduce(ok, op=td.ReduceOp.MIN)  # also the barrier: every rank has zeroed its flags before anyone publishes
+    if float(ok.item()) < 1.0:
+        _XCHG[device] = err if err is not None else RuntimeError("a peer rank could not set up the symmetric-memory exchange")
+        raise _XCHG[device]
+    _XCHG[device] = (n * 8, ptrs, (buf, handle))
+    return _XCHG[device]
 
 
 def _first_leaf(model, cls):
