@@ -53,55 +53,91 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    ONE ``nvidia-smi -lms`` child is started when the sampler is created -- before the warm-up steps -- and prints a
+    timestamped row every few milliseconds; ``with sampler:`` only records the wall-clock window of the timed region and
+    the rows inside it are picked afterwards.  (Spawning a process per sample from a thread, as round 1 did, forks this
+    CUDA process inside the timed region: milliseconds of stalled interpreter in an 11 ms measurement.)"""
+
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_ms=10):
         self.index = index
+        self.t_begin = self.t_end = None
         self.rows = []
-        self._stop = threading.Event()
-        self._t = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", str(period_ms)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        import datetime
+
+        self.t_begin = datetime.datetime.now()
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        self._t.join(timeout=6)
+        import datetime
+
+        self.t_end = datetime.datetime.now()
         return False
 
+    def close(self):
+        if self.proc is None:
+            return
+        time.sleep(0.03)  # let the row that covers the end of the window appear
+        try:
+            self.proc.terminate()  # the exact child started above
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+            out = ""
+        self.proc = None
+        import datetime
+
+        for line in out.splitlines():
+            cells = [c.strip() for c in line.split(",")]
+            if len(cells) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(cells[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                continue
+            self.rows.append((ts, cells[1:]))
+
     def summary(self):
-        if not self.rows:
+        self.close()
+        if not self.rows or self.t_begin is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        import datetime
+
+        inside = [r for ts, r in self.rows if self.t_begin <= ts <= self.t_end]
+        window = "inside the timed region"
+        if not inside:  # a region shorter than one sampling period: the rows right around it
+            pad = datetime.timedelta(milliseconds=60)
+            inside = [r for ts, r in self.rows if self.t_begin - pad <= ts <= self.t_end + pad]
+            window = "within 60 ms of the timed region (it is shorter than one sampling period)"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi sample near the timed region"]}
+        sm = sorted(float(r[1]) for r in inside if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             for n, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        pw = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+                "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(inside), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -341,13 +377,14 @@ def measure_config(ctx, cfg, args, headline):
         return loss.value_gradient(params, full=False)
 
     # ---- value: K steps through the loss, inputs resident in HBM, CUDA events on the launch stream ------------
+    sampler = ClockSampler(local)  # its nvidia-smi child starts here, outside the timed region
     with torch.cuda.stream(stream):
         for k in range(args.warmup):
             step(k)
         _barrier(ctx)
         launches0 = plan.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clocks:
+        with sampler as clocks:
             t_wall0 = time.perf_counter()
             e0.record(stream)
             for k in range(args.steps):

@@ -34,7 +34,7 @@ def test_partition_is_the_stable_bucket_order(n, weighted):
         x[7], x[11] = np.nan, hi  # NaN goes to bucket 0, the upper edge to the last bucket
     y = rng.normal(size=n)
     w = rng.normal(1.0, 0.5, n) if weighted else None
-    (px, py), pw = _partition([y, x], w, 1, lo, hi)
+    (py, px), pw = _partition([y, x], w, 1, lo, hi)
     with np.errstate(invalid="ignore"):
         b = np.floor((x - lo) * (32.0 / (hi - lo)))
     b = np.where(np.isnan(b), 0, np.clip(b, 0, 31)).astype(np.int64)

@@ -480,7 +480,7 @@ ZNLL_DEV V exp_core(V x, const Ctx& cx) {  // |x| < 700
   q = zfma(q, r, kExpT[6]);
 #endif
   q = zfma(q, r, 0.5);
-  const V p = zfma(zmul(r, r), q, r);  // e^r - 1
+  const V p = zfma(zmul(r, q), r, r);  // e^r - 1 = r + (r q) r: the DFMA reads two distinct registers, not three
   const V v = zfma(T, p, T);
   return Lanes<V>::make(scale2n_tab(la(v), na), scale2n_tab(lb(v), nb));
 }
@@ -552,7 +552,7 @@ ZNLL_DEV V log_core(V x, const Ctx& cx) {  // x positive, normal, below 2^1022
   for (int j = 3; j >= 0; --j) s = zfma(s, r, kLogC[j]);
 #endif
   const V w = zfma(kd, kMathC[0], logc);
-  return zadd(w, zfma(zmul(r, r), s, r));
+  return zadd(w, zfma(zmul(r, s), r, r));  // log1p(r) = r + (r s) r (two distinct register operands)
 }
 template <class V>
 ZNLL_DEV V fast_log(V x, const Ctx& cx) {

@@ -455,8 +455,12 @@ struct Channel {
   long long n = 0;
   double sumw = 0.0;
   std::vector<void*> owned;
+  void* d_block = nullptr;  // pooled device block: [ticket, 256 B][grid][NACC] partials
+  size_t d_block_bytes = 0;
   double* d_partials = nullptr;
-  double* d_cov = nullptr;  // covariance pass: [grid][NACC] partials followed by [NACC] results, allocated on first use
+  void* d_cov_block = nullptr;  // covariance pass (pooled, on first use): [256 B unused][grid][NACC] partials, [NACC] results
+  size_t d_cov_bytes = 0;
+  double* d_cov = nullptr;
   size_t d_cov_len = 0;
   unsigned int* d_ticket = nullptr;
   // per-call scratch
@@ -467,8 +471,10 @@ struct Channel {
 struct znll_plan {
   int device = 0, sm_count = 148;
   std::vector<Channel> ch;
-  double* d_acc = nullptr;
-  double* h_acc = nullptr;  // pinned
+  double* d_acc = nullptr;      // pooled device block
+  void* h_block = nullptr;      // pooled mapped pinned block: [flag, 64 B][accumulators]
+  size_t acc_cap = 0;           // accumulators the two blocks were sized for
+  double* h_acc = nullptr;
   int total_acc = 0, total_slots = 0;
   long long launches = 0;
   int max_grid = 0;
@@ -482,6 +488,60 @@ struct znll_plan {
   unsigned long long* h_flag_dev = nullptr;
   bool direct_pending = false;
 };
+
+// ------------------------------------------------------------------------------------------------
+// scratch pool.  A plan needs a few small device blocks (block partials + ticket per channel, the accumulators) and one
+// block of mapped pinned host memory (result hand-off).  cudaMalloc / cudaHostAlloc / cudaFree* cost 0.1 - 2 ms each,
+// synchronise the device and showed outliers of 20 - 200 ms on the benchmark box, i.e. more than the whole bind of a
+// loss; so blocks are recycled through a process-wide pool keyed by (device, kind, size class) and only handed back to
+// CUDA at process exit.  Contract of recycled blocks: a device block's first 256 bytes are zero (the kernels' ticket
+// lives there and every launch leaves it zero), everything else is stale.
+// ------------------------------------------------------------------------------------------------
+namespace pool {
+enum Kind { DEVICE = 0, PINNED = 1, DEVICE_ACC = 2 };  // DEVICE: ticketed blocks (zero head); DEVICE_ACC: accumulators
+struct Key {
+  int dev, kind;
+  size_t bytes;
+  bool operator<(const Key& o) const {
+    return dev != o.dev ? dev < o.dev : (kind != o.kind ? kind < o.kind : bytes < o.bytes);
+  }
+};
+static std::mutex mu;
+static std::map<Key, std::vector<void*>> idle;
+static size_t size_class(size_t bytes) {
+  size_t r = 4096;
+  while (r < bytes) r <<= 1;
+  return r;
+}
+static cudaError_t get(int dev, Kind kind, size_t bytes, void** out) {
+  const size_t cls = size_class(bytes);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto& v = idle[Key{dev, (int)kind, cls}];
+    if (!v.empty()) {
+      *out = v.back();
+      v.pop_back();
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e;
+  if (kind != PINNED) {
+    e = cudaMalloc(out, cls);
+    if (e == cudaSuccess) e = cudaMemset(*out, 0, cls);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();  // the zeroes are in place before any stream may use the block
+  } else {
+    e = cudaHostAlloc(out, cls, cudaHostAllocMapped);
+    if (e == cudaSuccess) memset(*out, 0, cls);
+  }
+  return e;
+}
+static void put(int dev, Kind kind, size_t bytes, void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(mu);
+  idle[Key{dev, (int)kind, size_class(bytes)}].push_back(p);
+}
+}  // namespace pool
+#define ZNLL_TICKET_BYTES 256  // head of every per-channel device block: the ticket, then the block partials
 
 #define ZNLL_XSTRIDE_HOST 256  // == ZNLL_XSTRIDE of znll_device.cuh: slots of the exchange buffer per (parity, rank)
 static unsigned long long g_xseq[16] = {0};  // per device: number of exchanging evaluations this process has launched
@@ -1069,9 +1129,19 @@ int znll_plan_create(int device, int n_channels, znll_plan** out) {
   CUDA_OK(cudaSetDevice(device));
   znll_plan* p = new znll_plan();
   p->device = device;
-  cudaDeviceProp prop;
-  CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  p->sm_count = prop.multiProcessorCount;
+  // one attribute, cached per device: cudaGetDeviceProperties queries every property of the board (clocks, PCIe ...) and
+  // was seen to take anything from 2 to 600 ms on the benchmark box -- inside every bind of a loss
+  static int sm_cached[64] = {0};
+  if (device < 0 || device >= 64) {
+    delete p;
+    return fail("znll_plan_create: bad device %d", device);
+  }
+  if (sm_cached[device] == 0) {
+    int sms = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    sm_cached[device] = sms;
+  }
+  p->sm_count = sm_cached[device];
   p->max_grid = p->sm_count * ZNLL_BLOCKS_PER_SM;  // persistent grid: resident CTAs of 256 threads per SM
   p->ch.resize(n_channels);
   *out = p;
@@ -1084,18 +1154,46 @@ static void free_channel_data(Channel& c) {
   c.bound = false;
 }
 
+// accumulators on the device and their mapped pinned twin (+ the hand-off flag), sized for the plan's total
+static void release_plan_buffers(znll_plan* p) {
+  pool::put(p->device, pool::DEVICE_ACC, sizeof(double) * p->acc_cap, p->d_acc);
+  pool::put(p->device, pool::PINNED, 64 + sizeof(double) * p->acc_cap, p->h_block);
+  p->d_acc = nullptr;
+  p->h_block = nullptr;
+  p->h_acc = p->h_acc_dev = nullptr;
+  p->h_flag = p->h_flag_dev = nullptr;
+  p->acc_cap = 0;
+}
+static int ensure_plan_buffers(znll_plan* p) {
+  if (p->d_acc && p->acc_cap >= (size_t)p->total_acc) return 0;
+  release_plan_buffers(p);
+  const size_t cap = (size_t)(p->total_acc > 0 ? p->total_acc : 1);
+  void *d = nullptr, *h = nullptr;
+  CUDA_OK(pool::get(p->device, pool::DEVICE_ACC, sizeof(double) * cap, &d));
+  CUDA_OK(pool::get(p->device, pool::PINNED, 64 + sizeof(double) * cap, &h));
+  p->d_acc = (double*)d;
+  p->h_block = h;
+  p->acc_cap = cap;
+  p->h_flag = (unsigned long long*)h;
+  p->h_acc = (double*)((char*)h + 64);
+  *p->h_flag = 0ull;
+  p->x_seq = 0;
+  void* hd = nullptr;
+  CUDA_OK(cudaHostGetDevicePointer(&hd, h, 0));
+  p->h_flag_dev = (unsigned long long*)hd;
+  p->h_acc_dev = (double*)((char*)hd + 64);
+  return 0;
+}
+
 void znll_plan_destroy(znll_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   for (auto& c : p->ch) {
     free_channel_data(c);
-    if (c.d_partials) cudaFree(c.d_partials);
-    if (c.d_cov) cudaFree(c.d_cov);
-    if (c.d_ticket) cudaFree(c.d_ticket);
+    pool::put(p->device, pool::DEVICE, c.d_block_bytes, c.d_block);
+    pool::put(p->device, pool::DEVICE, c.d_cov_bytes, c.d_cov_block);
   }
-  if (p->d_acc) cudaFree(p->d_acc);
-  if (p->h_acc) cudaFreeHost(p->h_acc);
-  if (p->h_flag) cudaFreeHost(p->h_flag);
+  release_plan_buffers(p);
   delete p;
 }
 
@@ -1122,26 +1220,17 @@ int znll_plan_set_model(znll_plan* p, int ch, const znll_node* nodes, int n_node
     if (rtc::build(name, c.n_slots, &k)) return 1;
   }
   c.kernel = k;
-  if (c.d_partials) cudaFree(c.d_partials), c.d_partials = nullptr;
-  if (c.d_cov) cudaFree(c.d_cov), c.d_cov = nullptr, c.d_cov_len = 0;
-  if (!c.d_ticket) {
-    CUDA_OK(cudaMalloc(&c.d_ticket, sizeof(unsigned int)));
-    CUDA_OK(cudaMemset(c.d_ticket, 0, sizeof(unsigned int)));
-  }
-  CUDA_OK(cudaMalloc(&c.d_partials, sizeof(double) * (size_t)p->max_grid * c.n_acc));
+  pool::put(p->device, pool::DEVICE, c.d_block_bytes, c.d_block);
+  pool::put(p->device, pool::DEVICE, c.d_cov_bytes, c.d_cov_block);
+  c.d_block = c.d_cov_block = nullptr;
+  c.d_cov = nullptr;
+  c.d_cov_len = c.d_cov_bytes = 0;
+  c.d_block_bytes = ZNLL_TICKET_BYTES + sizeof(double) * (size_t)p->max_grid * c.n_acc;
+  CUDA_OK(pool::get(p->device, pool::DEVICE, c.d_block_bytes, &c.d_block));
+  c.d_ticket = (unsigned int*)c.d_block;
+  c.d_partials = (double*)((char*)c.d_block + ZNLL_TICKET_BYTES);
   relayout(p);
-  if (p->d_acc) cudaFree(p->d_acc), p->d_acc = nullptr;
-  if (p->h_acc) cudaFreeHost(p->h_acc), p->h_acc = nullptr;
-  CUDA_OK(cudaMalloc(&p->d_acc, sizeof(double) * p->total_acc));
-  CUDA_OK(cudaMemset(p->d_acc, 0, sizeof(double) * p->total_acc));
-  CUDA_OK(cudaHostAlloc(&p->h_acc, sizeof(double) * p->total_acc, cudaHostAllocMapped));
-  CUDA_OK(cudaHostGetDevicePointer((void**)&p->h_acc_dev, p->h_acc, 0));
-  if (!p->h_flag) {
-    CUDA_OK(cudaHostAlloc(&p->h_flag, sizeof(unsigned long long), cudaHostAllocMapped));
-    *p->h_flag = 0ull;
-    CUDA_OK(cudaHostGetDevicePointer((void**)&p->h_flag_dev, p->h_flag, 0));
-  }
-  return 0;
+  return ensure_plan_buffers(p);
 }
 
 static int grid_for(const znll_plan* p, long long n) {
@@ -1161,17 +1250,18 @@ static int compute_sumw(znll_plan* p, Channel& c) {
     c.sumw = 0.0;
     return 0;
   }
-  double *d_part = nullptr, *d_out = nullptr;
-  CUDA_OK(cudaMalloc(&d_part, sizeof(double) * 2 * p->max_grid));
-  CUDA_OK(cudaMalloc(&d_out, sizeof(double) * 2));
+  void* blk = nullptr;  // [ticket, 256 B][2 results][grid][2] partials
+  const size_t blk_bytes = ZNLL_TICKET_BYTES + sizeof(double) * 2 * ((size_t)p->max_grid + 1);
+  CUDA_OK(pool::get(p->device, pool::DEVICE, blk_bytes, &blk));
+  double* d_out = (double*)((char*)blk + ZNLL_TICKET_BYTES);
+  double* d_part = d_out + 2;
   const int grid = grid_for(p, c.n * 2);
-  cudaError_t e = znll_launch_sumw(c.w, c.n, d_part, c.d_ticket, d_out, grid, 0);
+  cudaError_t e = znll_launch_sumw(c.w, c.n, d_part, (unsigned int*)blk, d_out, grid, 0);
   p->launches++;
   double h[2] = {0, 0};
   if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  cudaFree(d_part);
-  cudaFree(d_out);
+  pool::put(p->device, pool::DEVICE, blk_bytes, blk);
   if (e != cudaSuccess) return fail("sum of weights failed: %s", cudaGetErrorString(e));
   c.sumw = h[0] - h[1];
   return 0;
@@ -1404,8 +1494,13 @@ int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* 
       const int grid = (int)std::min<long long>(p->sm_count, std::max<long long>(1, ((c.n + 1) / 2 + 255) / 256));
       const size_t need = ((size_t)p->sm_count + 1) * NACC;
       if (c.d_cov_len < need) {
-        if (c.d_cov) cudaFree(c.d_cov), c.d_cov = nullptr, c.d_cov_len = 0;
-        CUDA_OK(cudaMalloc(&c.d_cov, sizeof(double) * need));
+        pool::put(p->device, pool::DEVICE, c.d_cov_bytes, c.d_cov_block);
+        c.d_cov_block = nullptr;
+        c.d_cov = nullptr;
+        c.d_cov_len = 0;
+        c.d_cov_bytes = ZNLL_TICKET_BYTES + sizeof(double) * need;
+        CUDA_OK(pool::get(p->device, pool::DEVICE, c.d_cov_bytes, &c.d_cov_block));
+        c.d_cov = (double*)((char*)c.d_cov_block + ZNLL_TICKET_BYTES);
         c.d_cov_len = need;
       }
       double *d_part = c.d_cov, *d_out = c.d_cov + (size_t)p->sm_count * NACC;

@@ -160,8 +160,10 @@ extern "C" int znll_partition_events(int device, int n_cols, const double* const
   }
   if (n == 0) return 0;
   cudaError_t e = cudaSetDevice(device);
-  int sms = 148;
-  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  static int sms_of[64] = {0};
+  if (e == cudaSuccess && device >= 0 && device < 64 && sms_of[device] == 0)
+    e = cudaDeviceGetAttribute(&sms_of[device], cudaDevAttrMultiProcessorCount, device);
+  const int sms = (device >= 0 && device < 64 && sms_of[device] > 0) ? sms_of[device] : 148;
   PrepArgs a;
   a.n_streams = n_cols + (src_w ? 1 : 0);
   for (int i = 0; i < n_cols; ++i) {
@@ -186,16 +188,27 @@ extern "C" int znll_partition_events(int device, int n_cols, const double* const
   a.n_warps = (int)(blocks * ZNLL_PREP_WARPS);
   a.rows_per_warp = (rows + a.n_warps - 1) / a.n_warps;
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned int* counts = nullptr;
+  // the [bucket][warp] counters: one block per device, kept for the life of the process (the stream-ordered allocator
+  // hands memory back at every synchronisation and re-mapping it costs more than the kernels).  Calls on one device
+  // must therefore be ordered by the caller (same stream, or a synchronisation in between); the engine does both.
+  static unsigned int* counts_of[64] = {nullptr};
+  static size_t counts_cap[64] = {0};
   const size_t m = (size_t)ZNLL_PREP_BUCKETS * a.n_warps;
-  if (e == cudaSuccess) e = cudaMallocAsync(&counts, m * sizeof(unsigned int), st);
+  if (e == cudaSuccess && (device < 0 || device >= 64)) e = cudaErrorInvalidDevice;
+  if (e == cudaSuccess && counts_cap[device] < m) {
+    if (counts_of[device]) cudaFree(counts_of[device]);
+    counts_of[device] = nullptr;
+    counts_cap[device] = 0;
+    const size_t cap = (size_t)ZNLL_PREP_BUCKETS * (size_t)sms * 8 * ZNLL_PREP_WARPS;  // the largest grid this function uses
+    e = cudaMalloc(&counts_of[device], (cap > m ? cap : m) * sizeof(unsigned int));
+    if (e == cudaSuccess) counts_cap[device] = cap > m ? cap : m;
+  }
   if (e == cudaSuccess) {
-    a.counts = counts;
+    a.counts = counts_of[device];
     partition_kernel<false><<<(unsigned)blocks, ZNLL_PREP_BLOCK, 0, st>>>(a);
-    scan_kernel<<<1, 1024, 0, st>>>(counts, (int)m);
+    scan_kernel<<<1, 1024, 0, st>>>(a.counts, (int)m);
     partition_kernel<true><<<(unsigned)blocks, ZNLL_PREP_BLOCK, 0, st>>>(a);
     e = cudaGetLastError();
-    cudaFreeAsync(counts, st);
   }
   if (e != cudaSuccess) {
     snprintf(g_prep_err, sizeof g_prep_err, "znll_partition_events: %s", cudaGetErrorString(e));

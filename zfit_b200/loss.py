@@ -64,7 +64,18 @@ class CudaEngine:
         if device is None:
             device = _dist.local_device()
         self.device = device
+        import os as _os
+        import time as _time
+
+        trace = [] if _os.environ.get("ZNLL_BIND_TRACE") else None  # stage times of the bind (tools/bind_breakdown.py)
+
+        def mark(name):
+            if trace is not None:
+                trace.append((name, _time.perf_counter()))
+
+        mark("start")
         self.plan = Z.Plan(len(models), device=device)
+        mark("plan_create")
         self.slot_params: list[ZfitParameter] = []
         self.channel_slots: list[tuple[int, int]] = []
         self._keep = []
@@ -76,19 +87,25 @@ class CudaEngine:
             if rng is not None:
                 data = data.with_obs(rng, guarantee_limits=False)
             nodes, slots = model._lower(data.obs, rng)
+            mark("lower")
             self.plan.set_model(k, nodes)
+            mark("set_model")
             start = len(self.slot_params)
             self.slot_params.extend(slots)
             self.channel_slots.append((start, len(self.slot_params)))
             cols, w = data.device_columns(device)
+            mark("device_columns")
             n = data.num_entries
             if sort_events is True and n > 1:
                 cols, w = self._sort_for_coherence(model, data, cols, w)
             self._keep.append((cols, w))
+            mark("partition(enqueue)")
             # the columns were produced by torch kernels on torch's stream (upload, cut, sort); the plan launches
             # on its own stream, so make them visible first
             torch.cuda.synchronize(device)
+            mark("sync")
             self.plan.bind_device_ptrs(k, [c.data_ptr() for c in cols], 0 if w is None else w.data_ptr(), n)
+            mark("bind+sumw")
             self.n_local.append(n)
         # sort_events="lazy" (experimental, not the default): bind unsorted and sort only once the loss has been evaluated
         # LAZY_SORT_AFTER times -- a bind-time sort of 1e8 events costs about as much as a whole fit's kernel time, so a
@@ -122,6 +139,9 @@ class CudaEngine:
                 self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
         self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
         self._raw_stream = self._pick_stream_getter()
+        mark("rest")
+        if trace is not None:
+            print("bind trace [ms]: " + " | ".join(f"{n} {1e3 * (t - p):.2f}" for (n, t), (_, p) in zip(trace[1:], trace[:-1])), flush=True)
 
     def _pick_stream_getter(self):
         """torch's current stream on this device as a raw ``cudaStream_t``.  ``torch.cuda.current_stream(d).cuda_stream``
