@@ -122,9 +122,9 @@ class ClockSampler:
         inside = [r for ts, r in self.rows if self.t_begin <= ts <= self.t_end]
         window = "inside the timed region"
         if not inside:  # a region shorter than one sampling period: the rows right around it
-            pad = datetime.timedelta(milliseconds=60)
+            pad = datetime.timedelta(milliseconds=150)
             inside = [r for ts, r in self.rows if self.t_begin - pad <= ts <= self.t_end + pad]
-            window = "within 60 ms of the timed region (it is shorter than one sampling period)"
+            window = "within 150 ms of the timed region (it is shorter than one sampling period)"
         if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi sample near the timed region"]}
         sm = sorted(float(r[1]) for r in inside if r[1].replace(".", "").isdigit())
@@ -532,6 +532,28 @@ def measure_config(ctx, cfg, args, headline):
                 "minimizer": "zfit.minimize.Minuit(gradient='zfit'), tol=1e-3",
                 "fitted": {p.name: result.params[p]["value"] for p in result.params},
             }
+        # ---- Hessian at the fit's end point: ONE fused pass per channel (flat trees) against 2P gradient passes -------
+        try:
+            loss.hessian(params)  # first call loads the kernel
+            _barrier(ctx)
+            l0 = plan.launch_count()
+            t0 = time.perf_counter()
+            loss.hessian(params)
+            torch.cuda.synchronize(local)
+            t_one = time.perf_counter() - t0
+            res["hessian"] = {"method": getattr(loss, "last_hessian_method", None), "seconds": t_one,
+                              "launches": int(plan.launch_count() - l0)}
+            if headline:
+                loss.options["hessian"] = "numeric"
+                l0 = plan.launch_count()
+                t0 = time.perf_counter()
+                loss.hessian(params)
+                torch.cuda.synchronize(local)
+                res["hessian"]["gradient_differences"] = {"seconds": time.perf_counter() - t0,
+                                                          "launches": int(plan.launch_count() - l0)}
+                loss.options["hessian"] = "exact"
+        except Exception as exc:
+            res["hessian"] = {"error": repr(exc)}
         for p, v in zip(params, theta0):
             p.assign(v)
 
@@ -614,6 +636,8 @@ def _summary(res):
     }
     if "fit" in res:
         out["fit"] = {k: res["fit"].get(k) for k in ("wall_s", "n_pass", "valid", "edm", "error") if k in res["fit"]}
+    if "hessian" in res:
+        out["hessian"] = res["hessian"]
     if "parity" in res:
         out["parity"] = res["parity"]
     return out
@@ -687,7 +711,7 @@ def run_product(args):
         "gpu_launches": head["gpu_launches"],
         "roofline": head["roofline"],
     }
-    for key in ("cpu_baseline", "fit", "parity"):
+    for key in ("cpu_baseline", "fit", "hessian", "parity"):
         if key in head:
             line[key] = head[key]
     line["configs"] = {f"cfg{c}": _summary(r) for c, r in results.items()}

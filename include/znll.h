@@ -172,6 +172,17 @@ int znll_collect(znll_plan* plan, uint32_t flags, double* values, double* grad_s
 int znll_eval_cov(znll_plan* plan, const double* slots, double log_offset, double* values, double* grad_slots,
                   double* cov, void* stream);
 
+/* Exact Hessian in ONE fused pass.  values[k], d value / d slot and, per channel, the (n_slots)^2
+ * matrix d2 value_k / d slot_a d slot_b (row-major, channels concatenated), value_k = -sum_i (w_i log pdf_k(x_i) - offset)
+ * with the normalisation integrals' dependence on the slots included.  Replaces loss.hessian's second differentiation of
+ * the whole graph (src/zfit/core/loss.py:765-878, src/zfit/z/math.py:288-352; numdifftools over loss.value by default).
+ * Available for flat trees -- a leaf, a SumPDF of leaves, a ProductPDF of leaves of kind Gauss / Exponential /
+ * CrystalBall / the polynomial families -- from the ahead-of-time catalogue (znll_plan_has_hess); for any other tree the
+ * function returns 3 and the caller differences the analytic gradient (2P passes).  A zero fraction yields inf / NaN. */
+int znll_eval_hess(znll_plan* plan, const double* slots, double log_offset, double* values, double* grad_slots,
+                   double* hess, void* stream);
+int znll_plan_has_hess(const znll_plan* plan, int ch);
+
 /* Fused multi-GPU reduction (no reference equivalent; the reference has no multi-device path).  peer_bufs[r] is rank
  * r's exchange buffer of at least znll_plan_exchange_bytes() bytes, zero-initialised, peer-mapped into this process
  * (CUDA IPC / VMM symmetric memory; the host obtains it from torch.distributed._symmetric_memory).  Once set, the last
@@ -234,6 +245,12 @@ int znll_test_prologue(const znll_node* nodes, int n_nodes, const double* slots,
                        int* n_consts, int* n_slots, char* kernel_name, int name_len);
 int znll_test_epilogue(const znll_node* nodes, int n_nodes, const double* slots, const double* acc, double sumw,
                        double* value, double* grad_slots /* nullable */);
+
+/* Test hook, host only: the host half of znll_eval_hess -- raw accumulators of the Hessian pass ([value pair | upper
+ * triangle of sum w [g;1][g;1]^T | the leaves' second-order blocks], n_hess of the latter) -> value, d value / d slot,
+ * d2 value / d slot^2 ((n_slots)^2, row-major). */
+int znll_test_hess_epilogue(const znll_node* nodes, int n_nodes, const double* slots, const double* acc, int n_acc, int n_hess,
+                            double* value, double* grad_slots, double* hess);
 
 /* Test hook, host only (NVRTC compiles without a GPU): obtain the compiled image of a tree outside the catalogue the way
  * znll_plan_set_model does -- from the on-disk cache ($ZNLL_CACHE_DIR, default $XDG_CACHE_HOME/zfit_b200 or

@@ -141,6 +141,43 @@ void run_nll(const double* const* cols, const double* w, long long n, const doub
   }
   delete[] accs;
 }
+// the body of hess_kernel (one thread owns all events): raw accumulators of the exact-Hessian pass
+#ifdef ZNLL_HAS_OPTIMISTIC
+template <class M, bool W>
+int run_hess(const double* const* cols, const double* w, long long n, const double* c, double off, double* out, int* n_hess) {
+  if constexpr (M::HESS) {
+    constexpr int NS = M::NS, NE = NS + 1, NQ = NE * (NE + 1) / 2, NACC = 2 + NQ + M::NH;
+    const Ctx cx = make_ctx();
+    double acc[NACC];
+    for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
+    for (long long i = 0; i < (n >> 1); ++i) {
+      D2 x[ZNLL_MAXCOL], wv;
+      load_pair<M>(cols, i, x);
+      wv.a = wv.b = 1.0;
+      if (W) {
+        wv.a = w[2 * i];
+        wv.b = w[2 * i + 1];
+      }
+      kahan_add(acc, hess_event<M, D2, W>(cx, c, x, wv, 2.0 * off, acc));
+    }
+    if (n & 1) {
+      double xa[ZNLL_MAXCOL];
+      for (int k = 0; k < ZNLL_MAXCOL; ++k)
+        if ((M::COLMASK >> k) & 1) xa[k] = cols[k][n - 1];
+      const double wa = W ? w[n - 1] : 1.0;
+      kahan_add(acc, hess_event<M, double, W>(cx, c, xa, wa, off, acc));
+    }
+    for (int j = 0; j < NACC; ++j) out[j] = acc[j];
+    *n_hess = M::NH;
+    return NACC;
+  } else {
+    return -1;
+  }
+}
+#else
+template <class M, bool W>
+int run_hess(const double* const*, const double*, long long, const double*, double, double*, int*) { return -1; }
+#endif
 // the body of pdf_kernel
 template <class M>
 void run_pdf(const double* const* cols, long long n, const double* c, double* out) {
@@ -161,18 +198,20 @@ void run_pdf(const double* const* cols, long long n, const double* c, double* ou
 }
 typedef void (*nll_fn)(const double* const*, const double*, long long, const double*, double, double*);
 typedef void (*pdf_fn)(const double* const*, long long, const double*, double*);
+typedef int (*hess_fn)(const double* const*, const double*, long long, const double*, double, double*, int*);
 struct Entry {
   const char* name;
   int n_slots, n_consts;
   nll_fn nll[2][2];
   pdf_fn pdf;
+  hess_fn hess[2];
 };
 #define HOSTSIM_ENTRY(...)                                                                                        \
   {                                                                                                               \
     #__VA_ARGS__, __VA_ARGS__::NS, __VA_ARGS__::NC,                                                               \
         {{run_nll<__VA_ARGS__, false, false>, run_nll<__VA_ARGS__, false, true>},                                 \
          {run_nll<__VA_ARGS__, true, false>, run_nll<__VA_ARGS__, true, true>}},                                  \
-        run_pdf<__VA_ARGS__>                                                                                      \
+        run_pdf<__VA_ARGS__>, {run_hess<__VA_ARGS__, false>, run_hess<__VA_ARGS__, true>}                         \
   }
 const Entry kEntries[] = {
 @ENTRIES@
@@ -198,6 +237,13 @@ int hostsim_nll(const char* tree, int weighted, int grad, const double* const* c
   if (!e) return 1;
   e->nll[weighted ? 1 : 0][grad ? 1 : 0](cols, w, n, consts, log_offset, acc_out);
   return 0;
+}
+// -> number of accumulators written (acc_out must hold 512), or -1 when the tree has no one-pass Hessian
+int hostsim_hess(const char* tree, int weighted, const double* const* cols, const double* w, long long n,
+                 const double* consts, double log_offset, double* acc_out, int* n_hess) {
+  const Entry* e = find(tree);
+  if (!e) return -2;
+  return e->hess[weighted ? 1 : 0](cols, w, n, consts, log_offset, acc_out, n_hess);
 }
 int hostsim_pdf(const char* tree, const double* const* cols, long long n, const double* consts, double* out) {
   const Entry* e = find(tree);
@@ -268,6 +314,8 @@ class HostSim:
         self.lib.hostsim_layout.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         self.lib.hostsim_math.argtypes = [C.c_int, C.c_int, C.c_longlong, dp, dp]
         self.lib.hostsim_math.restype = None
+        self.lib.hostsim_hess.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_longlong, dp, C.c_double, dp,
+                                          C.POINTER(C.c_int)]
 
     def layout(self, tree):
         ns, nc = C.c_int(0), C.c_int(0)
@@ -306,6 +354,23 @@ class HostSim:
         sumw = float(len(cols[0])) if weights is None else float(np.sum(np.asarray(weights, dtype=np.float64)))
         value, g = Z.test_epilogue(nodes, slots, acc, sumw, grad=grad)
         return value, g, name
+
+    def hess(self, nodes, slots, cols, weights=None, log_offset=0.0):
+        """What ``znll_eval_hess`` returns for one channel: (value, d value / d slot, d2 value / d slot^2), or None when the
+        tree has no one-pass Hessian.  The accumulators come from the host-compiled ``hess_event``, the assembly from the
+        product library's own host code (``znll_test_hess_epilogue``)."""
+        name, consts = Z.test_prologue(nodes, slots)
+        cols, arr = self._cols(cols)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        acc = np.zeros(512)
+        nh = C.c_int(0)
+        dp = C.POINTER(C.c_double)
+        consts = np.ascontiguousarray(consts, dtype=np.float64)
+        n_acc = self.lib.hostsim_hess(name.encode(), int(w is not None), arr, None if w is None else w.ctypes.data, len(cols[0]),
+                                      consts.ctypes.data_as(dp), float(log_offset), acc.ctypes.data_as(dp), C.byref(nh))
+        if n_acc < 0:
+            return None
+        return Z.test_hess_epilogue(nodes, slots, acc[:n_acc], nh.value)
 
     def pdf(self, nodes, slots, cols):
         name, consts = Z.test_prologue(nodes, slots)
@@ -357,6 +422,18 @@ class HostSimEngine:
             if grad:
                 gs[lo:hi] = g
         return np.asarray(values), (gs if grad else None)
+
+    def eval_hess(self, slots, log_offset=0.0):
+        values, gs, mats = [], np.zeros(len(self.slot_params)), []
+        for (nodes, _, cols, w), (lo, hi) in zip(self.channels, self.channel_slots):
+            got = self.sim.hess(nodes, np.asarray(slots[lo:hi], dtype=np.float64), cols, w, log_offset=log_offset)
+            if got is None:
+                return None
+            v, g, H = got
+            values.append(v)
+            gs[lo:hi] = g
+            mats.append(H)
+        return np.asarray(values), gs, mats
 
     def eval_cov(self, slots):
         """The covariance pass only seeds the MIGRAD metric here: taken from the oracle engine (the kernel's own

@@ -75,6 +75,8 @@ SYMBOLS = {
     "znll_plan_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
     "znll_plan_exchange_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "znll_eval_cov": (C.c_int, [C.c_void_p, _DP, C.c_double, _DP, _DP, _DP, C.c_void_p]),
+    "znll_eval_hess": (C.c_int, [C.c_void_p, _DP, C.c_double, _DP, _DP, _DP, C.c_void_p]),
+    "znll_plan_has_hess": (C.c_int, [C.c_void_p, C.c_int]),
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_pdf_device": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_void_p, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
@@ -82,6 +84,7 @@ SYMBOLS = {
                                     C.c_char_p, C.c_int]),
     "znll_test_rtc_image": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "znll_test_epilogue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_double, _DP, _DP]),
+    "znll_test_hess_epilogue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_int, C.c_int, _DP, _DP, _DP]),
     "znll_migrad": (C.c_int, None),  # callback pointers and structs: see _migrad_native.py
     "znll_test_math": (C.c_int, [C.c_int, C.c_int64, _DP, _DP]),
     "znll_fp64_peak": (C.c_int, [C.c_int, C.c_double, _DP]),
@@ -244,6 +247,27 @@ class Plan:
             off += n * n
         return self._values.copy(), self._grad[: self.total_slots].copy(), mats
 
+    def has_hess(self) -> bool:
+        """True when every channel's tree has the one-pass Hessian kernel (flat tree of supported nodes, catalogue)."""
+        return all(lib().znll_plan_has_hess(self._h, k) for k in range(self.n_channels))
+
+    def eval_hess(self, slots, *, log_offset=0.0, stream=0):
+        """-> (values, grad_slots, [per channel (n_slots, n_slots) d2 value / d slot^2]) in one pass, or None when a
+        tree is unsupported (znll_eval_hess returned 3)."""
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        sizes = [self.n_slots(k) for k in range(self.n_channels)]
+        hess = np.zeros(max(1, sum(n * n for n in sizes)))
+        rc = lib().znll_eval_hess(self._h, _dptr(slots), float(log_offset), _dptr(self._values), _dptr(self._grad),
+                                  _dptr(hess), C.c_void_p(stream))
+        if rc == 3:
+            return None
+        _check(rc)
+        mats, off = [], 0
+        for n in sizes:
+            mats.append(hess[off : off + n * n].reshape(n, n).copy())
+            off += n * n
+        return self._values.copy(), self._grad[: self.total_slots].copy(), mats
+
     def pdf_values(self, ch: int, slots, n: int, stream=0):
         slots = np.ascontiguousarray(slots, dtype=np.float64)
         out = np.empty(n, dtype=np.float64)
@@ -319,6 +343,17 @@ def test_rtc_image(model: str, n_slots: int, use_cache: bool = True):
     size, names, cached = C.c_size_t(0), C.c_int(0), C.c_int(0)
     _check(lib().znll_test_rtc_image(model.encode(), n_slots, int(use_cache), C.byref(size), C.byref(names), C.byref(cached)))
     return size.value, names.value, bool(cached.value)
+
+
+def test_hess_epilogue(nodes, slots, acc, n_hess):
+    """Host only: raw accumulators of the Hessian pass -> (value, d value / d slot, d2 value / d slot^2) -- test hook."""
+    arr = (Node * len(nodes))(*nodes)
+    slots = np.ascontiguousarray(slots, dtype=np.float64)
+    acc = np.ascontiguousarray(acc, dtype=np.float64)
+    ns = slots.size
+    value, g, h = np.zeros(1), np.zeros(max(ns, 1)), np.zeros(max(ns * ns, 1))
+    _check(lib().znll_test_hess_epilogue(arr, len(nodes), _dptr(slots), _dptr(acc), acc.size, int(n_hess), _dptr(value), _dptr(g), _dptr(h)))
+    return float(value[0]), g[:ns].copy(), h[: ns * ns].reshape(ns, ns).copy()
 
 
 def test_epilogue(nodes, slots, acc, sumw, grad=True):

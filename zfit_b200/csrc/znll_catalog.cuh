@@ -59,6 +59,28 @@ cudaError_t launch_cov(const ZnllLaunchArgs& a, const double* consts, int grid, 
   return cudaGetLastError();
 }
 
+template <class M, bool W>
+cudaError_t launch_hess(const ZnllLaunchArgs& a, const double* consts, int grid, cudaStream_t stream) {
+  KArgs<M::NC> k;
+  for (int i = 0; i < ZNLL_MAXCOL; ++i) k.cols[i] = a.cols[i];
+  k.w = a.w;
+  k.n = a.n;
+  k.log_offset = a.log_offset;
+  k.log_offset2 = 2.0 * a.log_offset;
+  k.partials = a.partials;
+  k.ticket = a.ticket;
+  k.out = a.out;
+  memset(&k.xc, 0, sizeof(Xchg));
+  for (int i = 0; i < M::NC; ++i) k.c[i] = consts[i];
+  hess_kernel<M, W><<<grid, ZNLL_BLOCK, 0, stream>>>(k);
+  return cudaGetLastError();
+}
+// the Hessian pass exists for flat trees of nodes that implement Node::second, within the reduction's 256 accumulators
+template <class M>
+constexpr bool has_hess() {
+  return M::HESS && 2 + (M::NS + 1) * (M::NS + 2) / 2 + M::NH <= 256;
+}
+
 template <class M>
 ZnllCatalogEntry make_entry(const char* name) {
   ZnllCatalogEntry e;
@@ -72,6 +94,13 @@ ZnllCatalogEntry make_entry(const char* name) {
   e.pdf = &launch_pdf<M>;
   e.cov[0] = &launch_cov<M, false>;
   e.cov[1] = &launch_cov<M, true>;
+  e.hess[0] = e.hess[1] = nullptr;
+  e.n_hess = 0;
+  if constexpr (has_hess<M>()) {
+    e.hess[0] = &launch_hess<M, false>;
+    e.hess[1] = &launch_hess<M, true>;
+    e.n_hess = M::NH;
+  }
   return e;
 }
 

@@ -691,10 +691,23 @@ struct GaussN {
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
+  // Hessian pass: h += r * (d2 u / d slot_a d slot_b) / u over the upper triangle (mu mu, mu sigma, sigma sigma) of the
+  // leaf's slots, u the leaf's unnormalised density: ((t^2-1), (t^3-3t), (t^4-5t^2+2)) / sigma^2
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__ c, double* h) const {
+    const V t2 = zmul(t, t);
+    const V rs = zmul(r, c[CO + 0] * c[CO + 0]);
+    zacc(h[0], rs, zadd(t2, -1.0));
+    zacc(h[1], rs, zmul(t, zadd(t2, -3.0)));
+    zacc(h[2], rs, zfma(t2, zadd(t2, -5.0), 2.0));
+  }
 };
 template <int COL>
 struct Gauss {
   static constexpr int NS = 2, NC = 3, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = true;  // HESS: the exact one-pass Hessian knows this node
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 3;                     // second-order accumulators: upper triangle over the node's slots
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = false;  // does log-space evaluation look up the exp / log tables?
   template <class V>
@@ -739,6 +752,9 @@ struct TGaussN {
 template <int COL>
 struct TGauss {
   static constexpr int NS = 4, NC = 5, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = false;
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = false;
   template <class V>
@@ -770,10 +786,17 @@ struct ExpoN {
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__, double* h) const {  // u = exp(lambda xs): u'' / u = xs^2
+    zacc(h[0], r, zmul(xs, xs));
+  }
 };
 template <int COL>
 struct Expo {
   static constexpr int NS = 1, NC = 3, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = true;
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 1;
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = false;
   template <class V>
@@ -836,10 +859,66 @@ struct CBallN {
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
   }
+  // Hessian pass: r * (d2 u / da db) / u = r * (d2 ln u + d ln u (x) d ln u) over the upper triangle of (mu, sigma, alpha, n),
+  // row-major: [mm, ms, ma, mn, ss, sa, sn, aa, an, nn].  ln u = phi(t, a, n) with a = |alpha|: -t^2/2 on the core,
+  // n ln(n/a) - a^2/2 - n ln(B - t) on the tail (B = n/a - a); t = (x - mu) sign(alpha) / sigma.  Scalar per lane: this
+  // pass runs once or twice per fit.
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__ c, double* h) const {
+    const double sos = c[CO + 1], is = c[CO + 2], a = c[CO + 3], n = c[CO + 4], sg = c[CO + 12];
+    const double Ba = -c[CO + 11], Bn = c[CO + 9];
+    const double rr[2] = {la(r), lb(r)}, tt[2] = {la(t), lb(t)};
+    bool tl[2] = {false, false};
+    double md[2] = {0.0, 0.0}, lv[2] = {0.0, 0.0};
+    if (any_tail) {
+      tl[0] = la(tail);
+      tl[1] = lb(tail);
+      md[0] = la(mdt);
+      md[1] = lb(mdt);
+      lv[0] = la(lu);
+      lv[1] = lb(lu);
+    }
+#pragma unroll
+    for (int k = 0; k < Lanes<V>::N; ++k) {
+      const double tau = tt[k];
+      double pt, ptt, pta = 0.0, ptn = 0.0, paa = 0.0, pan = 0.0, pnn = 0.0, da = 0.0, dn = 0.0;
+      if (tl[k]) {
+        const double iv = -md[k] / n;  // 1 / (B - t)
+        pt = n * iv;
+        ptt = n * iv * iv;
+        pta = -ptt * Ba;
+        ptn = iv - ptt * Bn;
+        da = c[CO + 10] + pt * c[CO + 11];
+        dn = c[CO + 8] - lv[k] - pt * Bn;
+        paa = n / (a * a) - 1.0 + ptt * Ba * Ba - pt * (2.0 * n / (a * a * a));
+        pan = -1.0 / a - ptn * Ba + pt / (a * a);
+        pnn = 1.0 / n - 2.0 * Bn * iv + ptt * Bn * Bn;
+      } else {
+        pt = -tau;
+        ptt = -1.0;
+      }
+      const double tm = -sos, ts = -tau * is, tms = sos * is, tss = 2.0 * tau * is * is;
+      const double dm = pt * tm, ds = pt * ts;
+      const double w = rr[k];
+      h[0] = fma(w, ptt * tm * tm + dm * dm, h[0]);
+      h[1] = fma(w, ptt * tm * ts + pt * tms + dm * ds, h[1]);
+      h[2] = fma(w, sg * (pta * tm + dm * da), h[2]);
+      h[3] = fma(w, ptn * tm + dm * dn, h[3]);
+      h[4] = fma(w, ptt * ts * ts + pt * tss + ds * ds, h[4]);
+      h[5] = fma(w, sg * (pta * ts + ds * da), h[5]);
+      h[6] = fma(w, ptn * ts + ds * dn, h[6]);
+      h[7] = fma(w, paa + da * da, h[7]);
+      h[8] = fma(w, sg * (pan + da * dn), h[8]);
+      h[9] = fma(w, pnn + dn * dn, h[9]);
+    }
+  }
 };
 template <int COL>
 struct CBall {
   static constexpr int NS = 4, NC = 13, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = true;
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 10;
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = true;
   template <class V>
@@ -882,6 +961,9 @@ struct GETailN {
 template <int COL>
 struct GETail {
   static constexpr int NS = 3, NC = 7, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = false;
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = false;
   template <class V>
@@ -940,6 +1022,9 @@ struct GGETailN {
 template <int COL>
 struct GGETail {
   static constexpr int NS = 5, NC = 12, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = false;
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = false;
   template <class V>
@@ -1033,10 +1118,15 @@ struct PolyN {
   ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     bwd_val<CO, AO>(zmul(g, rP), c, acc);
   }
+  template <int CO>
+  ZNLL_DEV void second(V, const double* __restrict__, double*) const {}  // u is linear in the coefficients: u'' = 0
 };
 template <int COL, int DEG, int KIND>
 struct Poly {
   static constexpr int NS = DEG + 1, NC = 3 + DEG + 1, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = true;
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 0;
   static constexpr bool LOGNAT = false;
   static constexpr bool TABS = true;
   template <class V>
@@ -1129,6 +1219,9 @@ struct GCBallN {
 template <int COL>
 struct GCBall {
   static constexpr int NS = 7, NC = 24, COLMASK = 1 << COL;
+  static constexpr bool LEAF = true, HESS = false;
+  static constexpr int ROOT = 0;
+  static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = true;
   template <class V>
@@ -1142,8 +1235,9 @@ template <class... Cs>
 struct Meta;
 template <>
 struct Meta<> {
-  static constexpr int NS = 0, NC = 0, COLMASK = 0;
+  static constexpr int NS = 0, NC = 0, COLMASK = 0, NH = 0;
   static constexpr bool TABS = false;
+  static constexpr bool FLATHESS = true;  // every child is a leaf the Hessian pass knows
 };
 template <class H, class... T>
 struct Meta<H, T...> {
@@ -1151,6 +1245,8 @@ struct Meta<H, T...> {
   static constexpr int NC = H::NC + Meta<T...>::NC;
   static constexpr int COLMASK = H::COLMASK | Meta<T...>::COLMASK;
   static constexpr bool TABS = H::TABS || Meta<T...>::TABS;
+  static constexpr int NH = H::NH + Meta<T...>::NH;
+  static constexpr bool FLATHESS = H::LEAF && H::HESS && Meta<T...>::FLATHESS;
 };
 
 template <class V, class... Cs>
@@ -1330,8 +1426,13 @@ struct Sum {
   static constexpr int COLMASK = Meta<Cs...>::COLMASK;
   static constexpr bool LOGNAT = AllLog<Cs...>::value;
   static constexpr bool TABS = true;
+  static constexpr bool LEAF = false, HESS = Meta<Cs...>::FLATHESS;  // flat Sum of leaves
+  static constexpr int NH = Meta<Cs...>::NH;
+  static constexpr int ROOT = 1;  // how hess_kernel treats the root: 1 Sum, 2 Prod, 0 leaf
   template <class V>
   using Node = typename SumPick<V, Cs...>::type;
+  template <class V>
+  using HessNode = SumN<V, Cs...>;  // the Hessian pass always uses the value-space Sum (uniform access to the children)
 };
 
 // ProductPDF over disjoint observables: no consts, no slots of its own
@@ -1383,8 +1484,13 @@ struct Prod {
   static constexpr int COLMASK = Meta<Cs...>::COLMASK;
   static constexpr bool LOGNAT = true;
   static constexpr bool TABS = Meta<Cs...>::TABS;
+  static constexpr bool LEAF = false, HESS = Meta<Cs...>::FLATHESS;  // flat Product of leaves
+  static constexpr int NH = Meta<Cs...>::NH;
+  static constexpr int ROOT = 2;
   template <class V>
   using Node = ProdN<V, Cs...>;
+  template <class V>
+  using HessNode = ProdN<V, Cs...>;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -1899,6 +2005,109 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constan
         acc[q] = fma(e[2 + a], e[2 + b], acc[q]);
         ++q;
       }
+  }
+  block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out, nullptr);
+}
+
+// Exact Hessian pass for FLAT trees -- a leaf, a Sum of leaves, a Product of leaves: all five BASELINE configs --
+// (reference: loss.hessian, core/loss.py:765-878, z/math.py:288-352, which differentiates the
+// whole graph twice).  With l = ln P(x; slots), normalisation constants held fixed, one pass accumulates
+//   T  = sum_i w_i [g_i; 1][g_i; 1]^T   (g_i = d l_i / d slot, UNweighted; upper triangle, (NS+1)(NS+2)/2 entries), and
+//   B_k = sum_i r_ik (d2 u_k / da db) / u_k  per leaf k over the leaf's own slots (upper triangle, Node::second), with
+//        r_ik = w_i f_k p_k / P (Sum root: the event's responsibility for leaf k) or w_i (Product / leaf root).
+// Second derivatives of a flat tree are exactly: -g g^T everywhere (Sum) or inside each leaf block (Product), + B_k in
+// leaf blocks, + g_b / f_k between a fraction and its own leaf's slots; the host (znll_eval_hess) assembles these and
+// restores the slots' dependence through the normalisation integrals with their first and second derivatives.
+// out: [0,1] value pair, then T (row-major upper triangle), then the B_k in pre-order.
+template <int CK, int HK, int I, class KD, class RF>
+ZNLL_DEV void second_rec(KD& kd, const RF& rof, const double* __restrict__ c, double* hacc) {
+  if constexpr (KD::N > 0) {
+    kd.h.template second<CK>(rof(I), c, hacc + HK);
+    second_rec<CK + KD::Head::NC, HK + KD::Head::NH, I + 1>(kd.t, rof, c, hacc);
+  }
+}
+template <class M, class V, bool LEAFROOT>
+struct HessRootPick {
+  typedef typename M::template Node<V> type;
+};
+template <class M, class V>
+struct HessRootPick<M, V, false> {
+  typedef typename M::template HessNode<V> type;
+};
+template <class M, class V, bool WEIGHTED>
+ZNLL_DEV double hess_event(const Ctx& cx, const double* __restrict__ c, const V* x, V w, double off, double* acc) {
+  typedef typename Lanes<V>::Mask Mask;
+  constexpr int NS = M::NS, NE = NS + 1, NQ = NE * (NE + 1) / 2;
+  typename HessRootPick<M, V, M::ROOT == 0>::type m;
+  V e[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) e[j] = zbc<V>(0.0);
+  V l;
+  if constexpr (M::ROOT == 1) {
+    const V P = m.template fwd_val<0>(cx, c, x);
+    V g;
+    log_eps_rcp<V, true>(P, cx, l, g);
+    m.template bwd_val<0, 0>(g, c, e);
+  } else {
+    Mask neg = Lanes<V>::mask(false, false);
+    l = m.template fwd_log<0>(cx, c, x, neg);
+    m.template bwd_log<0, 0>(zbc<V>(1.0), c, e);
+  }
+  e[NS] = zbc<V>(1.0);
+  int q = 2;
+#pragma unroll
+  for (int a = 0; a < NE; ++a) {
+    const V wa = zmul(w, e[a]);
+#pragma unroll
+    for (int b = a; b < NE; ++b) {
+      zacc(acc[q], wa, e[b]);
+      ++q;
+    }
+  }
+  double* hacc = acc + 2 + NQ;
+  if constexpr (M::ROOT == 1) {
+    second_rec<M::K, 0, 0>(m.kids, [&](int i) { return zmul(zmul(w, c[i]), e[i]); }, c, hacc);
+  } else if constexpr (M::ROOT == 2) {
+    second_rec<0, 0, 0>(m.kids, [&](int) { return w; }, c, hacc);
+  } else {
+    m.template second<0>(w, c, hacc);
+  }
+  if constexpr (WEIGHTED)
+    return zdot_minus(w, l, off);
+  else
+    return zsum_minus(l, off);
+}
+
+template <class M, bool WEIGHTED>
+__global__ void __launch_bounds__(ZNLL_BLOCK, 1) hess_kernel(const __grid_constant__ KArgs<M::NC> args) {
+  constexpr int NS = M::NS, NE = NS + 1, NQ = NE * (NE + 1) / 2, NACC = 2 + NQ + M::NH;
+  __shared__ MathTabs tabs;
+  init_tabs(tabs);
+  __syncthreads();
+  const Ctx cx = ctx_of(tabs);
+  double acc[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
+  const double* __restrict__ c = args.c;
+  const unsigned nvec = (unsigned)(args.n >> 1);
+  const unsigned stride = gridDim.x * ZNLL_BLOCK;
+  unsigned i = blockIdx.x * ZNLL_BLOCK + threadIdx.x;
+  EventPair<M, WEIGHTED> cur, nxt;
+  if (i < nvec) nxt.load(args, i);
+  while (i < nvec) {
+    cur = nxt;
+    i += stride;
+    if (i < nvec) nxt.load(args, i);
+    kahan_add(acc, hess_event<M, D2, WEIGHTED>(cx, c, cur.x, cur.w, args.log_offset2, acc));
+  }
+  if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event
+    double x[ZNLL_MAXCOL];
+#pragma unroll
+    for (int k = 0; k < ZNLL_MAXCOL; ++k)
+      if ((M::COLMASK >> k) & 1) x[k] = args.cols[k][args.n - 1];
+    double w = 1.0;
+    if constexpr (WEIGHTED) w = args.w[args.n - 1];
+    kahan_add(acc, hess_event<M, double, WEIGHTED>(cx, c, x, w, args.log_offset, acc));
   }
   block_reduce_and_finish<NACC>(acc, args.partials, args.ticket, args.out, nullptr);
 }

@@ -1567,6 +1567,223 @@ int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* 
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// exact Hessian in one fused pass (flat trees)
+// ------------------------------------------------------------------------------------------------
+// d2 ln I / d slot_a d slot_b of one leaf: central differences of the analytic d ln I (leaf_integral) with one Richardson
+// step, O(h^4); the step of every slot is 1e-3 of that slot's natural scale (the width for a location or a width, the
+// inverse range for an exponential slope, ...), so neither truncation nor rounding exceeds ~1e-11 relative.
+static void leaf_step_scales(const znll_node& nd, const double* s, int ns, double* scale) {
+  for (int i = 0; i < ns; ++i) scale[i] = 1.0;
+  switch (nd.kind) {
+    case ZNLL_GAUSS: scale[0] = scale[1] = fabs(s[1]); break;
+    case ZNLL_EXP: scale[0] = 1.0 / std::max(fabs(nd.norm_hi - nd.norm_lo), 1e-300); break;
+    case ZNLL_CB:
+      scale[0] = scale[1] = fabs(s[1]);
+      scale[2] = std::max(fabs(s[2]), 0.1);
+      scale[3] = std::max(fabs(s[3]) * 0.5, 0.1);
+      break;
+    default: break;  // polynomial coefficients: O(1)
+  }
+}
+static void leaf_d2lnI(const znll_node& nd, const double* s, int ns, double* out /* [ns][ns] */) {
+  double scale[32], sp[32], dI[32], I = 0.0;
+  leaf_step_scales(nd, s, ns, scale);
+  std::vector<double> R((size_t)ns * ns, 0.0);
+  for (int a = 0; a < ns; ++a) {
+    double g[2][32];
+    for (int level = 0; level < 2; ++level) {
+      const double h = 1e-3 * scale[a] * (level ? 0.5 : 1.0);
+      double up[32], dn[32];
+      for (int sign = 0; sign < 2; ++sign) {
+        for (int i = 0; i < ns; ++i) sp[i] = s[i];
+        sp[a] += sign ? -h : h;
+        leaf_integral(nd, sp, &I, dI);
+        for (int b = 0; b < ns; ++b) (sign ? dn : up)[b] = dI[b] / I;
+      }
+      for (int b = 0; b < ns; ++b) g[level][b] = (up[b] - dn[b]) / (2.0 * h);
+    }
+    for (int b = 0; b < ns; ++b) R[(size_t)a * ns + b] = (4.0 * g[1][b] - g[0][b]) / 3.0;
+  }
+  for (int a = 0; a < ns; ++a)
+    for (int b = 0; b < ns; ++b) out[(size_t)a * ns + b] = 0.5 * (R[(size_t)a * ns + b] + R[(size_t)b * ns + a]);
+}
+
+// host half of the Hessian pass: raw accumulators [value pair | T | leaf blocks] -> value, d value / d slot (grad_slots,
+// this channel's slots, nullable) and d2 value / d slot^2 (out, NS x NS row-major).  c.slots / c.dlnI are current.
+static int hess_assemble(Channel& c, const std::vector<double>& acc, int NH, double* value, double* grad_slots, double* out) {
+  const int NS = c.n_slots, NE = NS + 1, NQ = NE * (NE + 1) / 2, NACC = 2 + NQ + NH;
+  if ((int)acc.size() != NACC) return fail("znll_eval_hess: %d accumulators given, %d expected", (int)acc.size(), NACC);
+*value = -(acc[0] - acc[1]);
+  // unpack: T = sum w [g;1][g;1]^T, then the leaves' second-order blocks in pre-order
+  std::vector<double> T((size_t)NE * NE);
+  int q = 2;
+  for (int a = 0; a < NE; ++a)
+    for (int b = a; b < NE; ++b) T[(size_t)a * NE + b] = T[(size_t)b * NE + a] = acc[q++];
+  auto Q = [&](int a, int b) { return T[(size_t)a * NE + b]; };
+  auto A = [&](int a) { return T[(size_t)a * NE + NS]; };
+  const double W = T[(size_t)NS * NE + NS];
+  const bool sum_root = c.nodes[0].nd.kind == ZNLL_SUM;
+  struct Leaf {
+    int off, ns, frac;  // first slot, number of slots, fraction slot of the leaf under a Sum root (-1 otherwise)
+    std::vector<double> B, L2;  // sum r U (ns x ns, symmetric) and d2 lambda = -d2 ln I
+  };
+  std::vector<Leaf> leaves;
+  int hq = 2 + NQ;
+  for (auto& ni : c.nodes) {
+    if (ni.nd.kind == ZNLL_SUM || ni.nd.kind == ZNLL_PROD) continue;
+    Leaf lf;
+    lf.off = ni.slot_off;
+    lf.ns = leaf_n_slots(ni.nd);
+    lf.frac = sum_root ? ni.parent_sum_frac_slot : -1;
+    lf.B.assign((size_t)lf.ns * lf.ns, 0.0);
+    const bool has_second = ni.nd.kind == ZNLL_GAUSS || ni.nd.kind == ZNLL_EXP || ni.nd.kind == ZNLL_CB;
+    if (has_second)
+      for (int a = 0; a < lf.ns; ++a)
+        for (int b = a; b < lf.ns; ++b) lf.B[(size_t)a * lf.ns + b] = lf.B[(size_t)b * lf.ns + a] = acc[hq++];
+    lf.L2.assign((size_t)lf.ns * lf.ns, 0.0);
+    leaf_d2lnI(ni.nd, c.slots.data() + lf.off, lf.ns, lf.L2.data());
+    for (auto& v : lf.L2) v = -v;
+    leaves.push_back(lf);
+  }
+  if (hq != NACC) return fail("znll_eval_hess: accumulator layout mismatch (%d vs %d)", hq, NACC);
+  // d lambda_k / d slot_a = -d ln I_k / d slot_a for a in leaf k
+  std::vector<double> H((size_t)NS * NS, 0.0), G(NS, 0.0);
+  auto Hx = [&](int a, int b) -> double& { return H[(size_t)a * NS + b]; };
+  if (sum_root) {
+    for (int a = 0; a < NS; ++a)
+      for (int b = 0; b < NS; ++b) Hx(a, b) = -Q(a, b);
+    for (auto& lf : leaves) {
+      const double fk = c.slots[lf.frac];
+      for (int a = 0; a < lf.ns; ++a) {
+        for (int b = 0; b < lf.ns; ++b) Hx(lf.off + a, lf.off + b) += lf.B[(size_t)a * lf.ns + b];
+        const double cross = A(lf.off + a) / fk;  // (1/P) d2 P / d f_k d slot = g_slot / f_k   (f_k == 0: inf/nan)
+        Hx(lf.frac, lf.off + a) += cross;
+        Hx(lf.off + a, lf.frac) += cross;
+      }
+    }
+    // the slots' route through the normalisation integrals: lambda_k = -ln I_k enters like ln f_k
+    const int NL = (int)leaves.size();
+    std::vector<double> R1(NL);
+    for (int k2 = 0; k2 < NL; ++k2) R1[k2] = c.slots[leaves[k2].frac] * A(leaves[k2].frac);
+    auto group_of = [&](int a) {
+      for (int k2 = 0; k2 < NL; ++k2)
+        if (a == leaves[k2].frac || (a >= leaves[k2].off && a < leaves[k2].off + leaves[k2].ns)) return k2;
+      return -1;
+    };
+    auto C1 = [&](int a, int k2) {  // sum w d rho_k / d a
+      const double fk = c.slots[leaves[k2].frac];
+      return (group_of(a) == k2 ? A(a) : 0.0) - fk * Q(leaves[k2].frac, a);
+    };
+    auto C2 = [&](int k2, int m) {
+      const double fk = c.slots[leaves[k2].frac], fm = c.slots[leaves[m].frac];
+      return (k2 == m ? R1[k2] : 0.0) - fk * fm * Q(leaves[k2].frac, leaves[m].frac);
+    };
+    for (int a = 0; a < NS; ++a) G[a] = A(a);
+    for (int k2 = 0; k2 < NL; ++k2) {
+      const Leaf& lk = leaves[k2];
+      for (int b = 0; b < lk.ns; ++b) {
+        const double l1b = -c.dlnI[lk.off + b];
+        G[lk.off + b] += R1[k2] * l1b;
+        for (int a = 0; a < NS; ++a) {
+          const double t = C1(a, k2) * l1b;
+          Hx(a, lk.off + b) += t;
+          Hx(lk.off + b, a) += t;
+        }
+        for (int b2 = 0; b2 < lk.ns; ++b2) Hx(lk.off + b, lk.off + b2) += R1[k2] * lk.L2[(size_t)b * lk.ns + b2];
+      }
+      for (int m = 0; m < NL; ++m) {
+        const Leaf& lm = leaves[m];
+        const double c2 = C2(k2, m);
+        for (int a = 0; a < lk.ns; ++a)
+          for (int b = 0; b < lm.ns; ++b) Hx(lk.off + a, lm.off + b) += c2 * c.dlnI[lk.off + a] * c.dlnI[lm.off + b];
+      }
+    }
+  } else {  // Product of leaves, or a single leaf: block diagonal
+    for (auto& lf : leaves) {
+      for (int a = 0; a < lf.ns; ++a) {
+        G[lf.off + a] = A(lf.off + a) - W * c.dlnI[lf.off + a];
+        for (int b = 0; b < lf.ns; ++b)
+          Hx(lf.off + a, lf.off + b) = lf.B[(size_t)a * lf.ns + b] - Q(lf.off + a, lf.off + b) + W * lf.L2[(size_t)a * lf.ns + b];
+      }
+    }
+  }
+  // value = -L
+  if (grad_slots)
+    for (int a = 0; a < NS; ++a) grad_slots[a] = -G[a];
+  for (int a = 0; a < NS; ++a)
+    for (int b = 0; b < NS; ++b) out[(size_t)a * NS + b] = -0.5 * (Hx(a, b) + Hx(b, a));
+  return 0;
+}
+
+static bool channel_has_hess(const Channel& c) {
+  return c.kernel.origin == 1 && c.kernel.aot && c.kernel.aot->hess[0] != nullptr;
+}
+
+int znll_plan_has_hess(const znll_plan* p, int ch) {
+  return (p && ch >= 0 && ch < (int)p->ch.size() && channel_has_hess(p->ch[ch])) ? 1 : 0;
+}
+
+// values[k] = -sum_i (w_i l_i - offset), grad_slots = d value / d slot, hess = d2 value / d slot_a d slot_b per channel
+// ((n_slots)^2, row-major, channels concatenated) -- all in ONE pass over the events per channel.  Returns 3 (and leaves
+// the outputs untouched) when a channel's tree is not flat, holds a node without a second-order implementation, or was
+// built at run time through NVRTC: the caller then differences the analytic gradient instead.
+int znll_eval_hess(znll_plan* p, const double* slots, double log_offset, double* values, double* grad_slots,
+                              double* hess, void* stream) {
+  if (!p || !slots || !values || !hess) return fail("znll_eval_hess: bad arguments");
+  for (auto& c : p->ch) {
+    if (c.nodes.empty() || !c.bound) return fail("znll_eval_hess: channel without model or data");
+    if (!channel_has_hess(c)) {
+      fail("znll_eval_hess: no one-pass Hessian for the tree '%s' (not a flat tree of supported nodes)", c.kernel.name.c_str());
+      return 3;
+    }
+  }
+  CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t h_off = 0;
+  for (size_t k = 0; k < p->ch.size(); ++k) {
+    Channel& c = p->ch[k];
+    const int NS = c.n_slots, NE = NS + 1, NQ = NE * (NE + 1) / 2, NH = c.kernel.aot->n_hess, NACC = 2 + NQ + NH;
+    c.slots.assign(slots + c.slot_off, slots + c.slot_off + NS);
+    fill_consts(c, c.slots.data());
+    std::vector<double> acc(NACC, 0.0);
+    if (c.n > 0) {
+      const int grid = (int)std::min<long long>(p->sm_count, std::max<long long>(1, ((c.n + 1) / 2 + 255) / 256));
+      const size_t need = ((size_t)p->sm_count + 1) * NACC;
+      if (c.d_cov_len < need) {
+        pool::put(p->device, pool::DEVICE, c.d_cov_bytes, c.d_cov_block);
+        c.d_cov_block = nullptr;
+        c.d_cov = nullptr;
+        c.d_cov_len = 0;
+        c.d_cov_bytes = ZNLL_TICKET_BYTES + sizeof(double) * need;
+        CUDA_OK(pool::get(p->device, pool::DEVICE, c.d_cov_bytes, &c.d_cov_block));
+        c.d_cov = (double*)((char*)c.d_cov_block + ZNLL_TICKET_BYTES);
+        c.d_cov_len = need;
+      }
+      double *d_part = c.d_cov, *d_out = c.d_cov + (size_t)p->sm_count * NACC;
+      ZnllLaunchArgs la;
+      for (int i = 0; i < ZNLL_MAX_COLS; ++i) la.cols[i] = c.cols[i];
+      la.w = c.w;
+      la.n = c.n;
+      la.log_offset = log_offset;
+      la.log_offset2 = 2.0 * log_offset;
+      la.partials = d_part;
+      la.ticket = c.d_ticket;
+      la.out = d_out;
+      memset(&la.xc, 0, sizeof(la.xc));
+      cudaError_t e = c.kernel.aot->hess[c.w ? 1 : 0](la, c.consts.data(), grid, st);
+      p->launches++;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(acc.data(), d_out, sizeof(double) * NACC, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return fail("znll_eval_hess: %s", cudaGetErrorString(e));
+    }
+    if (hess_assemble(c, acc, NH, &values[k], grad_slots ? grad_slots + c.slot_off : nullptr, hess + h_off)) return 1;
+    h_off += (size_t)NS * NS;
+  }
+  return 0;
+}
+
 // launches pdf_kernel of channel ch into a device buffer of c.n doubles (no synchronisation)
 static int pdf_launch(znll_plan* p, int ch, const double* slots, double* d_out, cudaStream_t st) {
   Channel& c = p->ch[ch];
@@ -1662,6 +1879,15 @@ int znll_test_rtc_image(const char* model, int n_slots, int use_cache, size_t* c
   *cubin_bytes = img.cubin.size();
   *n_names = (int)img.lowered.size();
   return 0;
+}
+
+int znll_test_hess_epilogue(const znll_node* nodes, int n_nodes, const double* slots, const double* acc, int n_acc, int n_hess,
+                            double* value, double* grad_slots, double* hess) {
+  if (!nodes || !slots || !acc || !value || !hess) return fail("znll_test_hess_epilogue: bad arguments");
+  Channel c;
+  if (test_parse(c, nodes, n_nodes, slots, nullptr)) return 1;
+  std::vector<double> a(acc, acc + n_acc);
+  return hess_assemble(c, a, n_hess, value, grad_slots, hess);
 }
 
 int znll_test_epilogue(const znll_node* nodes, int n_nodes, const double* slots, const double* acc, double sumw,

@@ -32,6 +32,8 @@ struct ZnllCatalogEntry {
   znll_launcher_t fn[2][2];  // [weighted][grad]
   znll_launcher_t pdf;       // per-event pdf values into args.partials
   znll_launcher_t cov[2];    // weighted-covariance pass [weighted]
+  znll_launcher_t hess[2];   // exact Hessian pass [weighted]; null when the tree is not flat / a node lacks Node::second
+  int n_hess;                // second-order leaf accumulators of that pass (M::NH)
 };
 
 // each catalogue TU registers its instantiations at static-init time

@@ -267,6 +267,30 @@ class CudaEngine:
             mats = out
         return mats
 
+    def eval_hess(self, slots, log_offset=0.0):
+        """(values[n_channels], d value / d slot, [per channel d2 value / d slot^2]) from ONE fused pass per channel
+        (``znll_eval_hess``), world-summed; ``None`` when a channel's tree has no one-pass Hessian (not flat, an
+        unsupported node, built through NVRTC) -- the loss then differences the analytic gradient."""
+        if not self.plan.has_hess():
+            return None
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        got = self.plan.eval_hess(slots, log_offset=log_offset, stream=stream)
+        if got is None:
+            return None
+        values, gs, mats = got
+        if self.distributed:  # every term of the assembly is linear in the per-rank accumulators and in sum(w)
+            flat = self.torch.from_numpy(np.concatenate([values, gs, *[m.ravel() for m in mats]])).to(f"cuda:{self.device}")
+            _dist.all_reduce_sum_(flat, deterministic=True)
+            flat = flat.cpu().numpy()
+            nv, ng = len(values), len(gs)
+            values, gs = flat[:nv].copy(), flat[nv : nv + ng].copy()
+            out, off = [], nv + ng
+            for m in mats:
+                out.append(flat[off : off + m.size].reshape(m.shape).copy())
+                off += m.size
+            mats = out
+        return values, gs, mats
+
     def launch_count(self):
         return self.plan.launch_count()
 
@@ -751,9 +775,20 @@ class BaseLoss:
             return self._call_hessian(params, hessian, numgrad)
 
     def _call_hessian(self, params, hessian, numgrad):
-        """Central differences of the analytic gradient (2P fused-kernel calls).  The reference's default is a
-        numdifftools Hessian over ``loss.value`` (``numhess=True``, ``loss.py:271-272``, ``z/math.py:104-151``)."""
+        """The exact Hessian from ONE fused pass over the events (``znll_eval_hess``: per-event second derivatives of flat
+        trees accumulated in the kernel, the chain rule through normalisation integrals, composed parameters, the
+        extended term and the constraints on the host) whenever every channel's tree supports it -- all five BASELINE
+        configs do; otherwise, or with ``numgrad=True`` / ``options["hessian"] == "numeric"``, central differences of
+        the analytic gradient (2P fused-kernel calls).  The reference's default is a numdifftools Hessian over
+        ``loss.value`` (``numhess=True``, ``loss.py:271-272``, ``z/math.py:104-151``); its exact route differentiates
+        the whole graph a second time (``z/math.py:288-352``)."""
         log_offset = self._options.get("subtr_const_value", False) or False
+        if not numgrad and self._options.get("hessian", "exact") != "numeric":
+            H = self._exact_hessian(params, log_offset)
+            if H is not None:
+                self.last_hessian_method = "one-pass"
+                return np.diag(H).copy() if hessian == "diag" else H
+        self.last_hessian_method = "gradient-differences"
 
         def grad_fn():
             if numgrad:
@@ -765,6 +800,54 @@ class BaseLoss:
         if hessian == "diag":
             return np.diag(H).copy()
         return H
+
+    def _exact_hessian(self, params, log_offset):
+        """d2 loss / d theta^2 for ``params`` from the one-pass slot Hessian, or None when the engine has none."""
+        eng = self._get_engine(check=False)
+        if not hasattr(eng, "eval_hess"):
+            return None
+        slot_params = eng.slot_params
+        slots = np.array([p.value() for p in slot_params], dtype=np.float64)
+        got = eng.eval_hess(slots, 0.0 if log_offset is False else float(log_offset))
+        if got is None:
+            return None
+        _, gs, mats = got
+        params = list(params)
+        index = {id(p): i for i, p in enumerate(params)}
+        npar = len(params)
+        H = np.zeros((npar, npar))
+        second_cache = {}
+
+        def jac_row(p):  # d p / d theta over `params`
+            row = np.zeros(npar)
+            for leaf, d in (p._partials().items() if not p.independent else [(p, 1.0)]):
+                j = index.get(id(leaf))
+                if j is not None:
+                    row[j] += d
+            return row
+
+        def second(p):  # d2 p / d theta^2 over `params` (zero for independent and constant parameters)
+            if p.independent or not p._leaves():
+                return None
+            if id(p) not in second_cache:
+                second_cache[id(p)] = _second_partials(p, params, index)
+            return second_cache[id(p)]
+
+        for (lo, hi), Hs in zip(self._channel_slot_ranges(eng), mats):
+            J = np.stack([jac_row(sp) for sp in slot_params[lo:hi]]) if hi > lo else np.zeros((0, npar))
+            H += J.T @ Hs @ J
+            for j, sp in enumerate(slot_params[lo:hi]):
+                S = second(sp)
+                if S is not None and gs[lo + j] != 0.0:
+                    H += gs[lo + j] * S
+        H += self._extra_hessian(params, index, jac_row, second)
+        for con in self.constraints:
+            H += _constraint_hessian(con, params, index)
+        return 0.5 * (H + H.T)
+
+    def _extra_hessian(self, params, index, jac_row, second):
+        """Second derivatives of the terms beyond the per-event sum (extended Poisson term); none here."""
+        return np.zeros((len(params), len(params)))
 
     def value_gradient_hessian(self, params=None, *, hessian=None, full=None, numgrad=None, paramvals=None):
         params = self._input_check_params(params)
@@ -944,6 +1027,81 @@ class ExtendedUnbinnedNLL(UnbinnedNLL):
                 for leaf, d in yparam._partials().items():
                     grad[leaf] = grad.get(leaf, 0.0) + dterm * d
         return total, grad
+
+    def _extra_hessian(self, params, index, jac_row, second):
+        """y - T log y per channel: (T / y^2) dy dy^T + (1 - T / y) d2y."""
+        eng = self._get_engine(check=False)
+        n = len(params)
+        H = np.zeros((n, n))
+        for k, mod in enumerate(self.model):
+            t = float(eng.samplesize[k])
+            yparam = mod.get_yield()
+            y = yparam.value()
+            row = jac_row(yparam)
+            H += (t / (y * y)) * np.outer(row, row)
+            S = second(yparam)
+            if S is not None:
+                H += (1.0 - t / y) * S
+        return H
+
+
+def _fd_step(p):
+    v = p.value()
+    h = 1e-4 * max(abs(v), 1e-3)
+    if getattr(p, "has_limits", False):
+        lo = -np.inf if p.lower is None else p.lower
+        up = np.inf if p.upper is None else p.upper
+        room = min(up - v, v - lo)
+        if room > 0:
+            h = min(h, 0.5 * room)
+    return v, h
+
+
+def _second_partials(p, params, index):
+    """d2 p / d theta_i d theta_j of a dependent parameter over ``params``: central differences of its analytic first
+    partials (host scalars only; fractions from yields, user ``ComposedParameter``s)."""
+    n = len(params)
+    S = np.zeros((n, n))
+    for leaf in p._leaves():
+        i = index.get(id(leaf))
+        if i is None:
+            continue
+        v, h = _fd_step(leaf)
+        rows = []
+        for sgn in (1.0, -1.0):
+            leaf.assign(v + sgn * h)
+            row = np.zeros(n)
+            for l2, d in p._partials().items():
+                j = index.get(id(l2))
+                if j is not None:
+                    row[j] += d
+            rows.append(row)
+        leaf.assign(v)
+        S[i, :] = (rows[0] - rows[1]) / (2.0 * h)
+    return 0.5 * (S + S.T)
+
+
+def _constraint_hessian(con, params, index):
+    """d2 constraint / d theta^2 by central differences of its analytic gradient (host scalars only)."""
+    n = len(params)
+    S = np.zeros((n, n))
+    for leaf in con.get_params(floating=None):
+        i = index.get(id(leaf))
+        if i is None:
+            continue
+        v, h = _fd_step(leaf)
+        rows = []
+        for sgn in (1.0, -1.0):
+            leaf.assign(v + sgn * h)
+            row = np.zeros(n)
+            for l2, d in con._partials().items():
+                j = index.get(id(l2))
+                if j is not None:
+                    row[j] += d
+            rows.append(row)
+        leaf.assign(v)
+        S[i, :] = (rows[0] - rows[1]) / (2.0 * h)
+    return 0.5 * (S + S.T)
 
 
 class SimpleLoss(BaseLoss):
