@@ -656,6 +656,11 @@ def run_product(args):
         print(json.dumps({"error": "no CUDA device: zfit_b200 has no CPU fallback"}))
         return 2
     torch.cuda.set_device(ctx.local)
+    ctx.numa = None
+    if ctx.world > 1 and not args.no_numa:
+        from zfit_b200 import distributed as _D
+
+        ctx.numa = _D.bind_to_gpu_numa_node(ctx.local)  # before any pinned allocation of this rank
     if ctx.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
@@ -714,6 +719,8 @@ def run_product(args):
     for key in ("cpu_baseline", "fit", "hessian", "parity"):
         if key in head:
             line[key] = head[key]
+    if ctx.numa is not None:
+        line["config"]["host_placement"] = ctx.numa
     line["configs"] = {f"cfg{c}": _summary(r) for c, r in results.items()}
     for c, e in errors.items():
         line["configs"][f"cfg{c}"] = {"error": e}
@@ -740,6 +747,7 @@ def main():
     ap.add_argument("--no-bind", action="store_true", help="skip the e2e leg that starts from host buffers (e2e then reports the steady state only)")
     ap.add_argument("--nccl", action="store_true", help="multi-GPU: NCCL all-reduce instead of the fused NVLink exchange")
     ap.add_argument("--no-fit", action="store_true", help="skip the end-to-end Minuit fit after the timed region")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not pin each rank to the cores next to its GPU")
     ap.add_argument("--sort", default=None, choices=["1", "0", "lazy"], help="override the loss option sort_events (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -105,3 +105,54 @@ def device_view(ptr: int, n: int, device: int):
     import torch
 
     return torch.as_tensor(_CudaArray(ptr, n), device=f"cuda:{device}")
+
+
+def bind_to_gpu_numa_node(device: int | None = None) -> dict:
+    """Pin this process to the CPU cores that are local to its GPU (``/sys/bus/pci/devices/<bdf>/local_cpulist``).
+
+    With one process per GPU on a multi-socket host, every rank stages its event columns through pinned host memory;
+    Linux places those pages on the NUMA node of the allocating thread, and a rank that runs on the far socket pushes
+    its whole shard across the inter-socket link (and shares it with the ranks that live there).  Binding the process
+    before its first pinned allocation keeps each rank's staging memory, its copy threads and its interpreter next to
+    its own PCIe root.  Returns what was done (for the bench record); a no-op when the topology cannot be read."""
+    info = {"bound": False}
+    try:
+        import torch
+
+        dev = local_device() if device is None else int(device)
+        props = torch.cuda.get_device_properties(dev)
+        bdf = None
+        if hasattr(props, "pci_bus_id"):
+            bdf = f"{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{getattr(props, 'pci_device_id', 0):02x}.0"
+        if bdf is None:  # older torch: ask NVML (CUDA_VISIBLE_DEVICES permitting, NVML indices are the CUDA indices)
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[dev]) if visible and all(t.strip().isdigit() for t in visible.split(",")) else dev
+            raw = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+            raw = raw.decode() if isinstance(raw, bytes) else raw
+            bdf = raw.lower()[-12:]  # "00000000:1b:00.0" -> "0000:1b:00.0"
+        path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+        if not os.path.exists(path):
+            return info
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            info.update({"pci": bdf, "note": "every allowed core is local already"})
+            return info
+        # ranks that share a node split its cores, so that their copy threads do not sit on each other
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        os.sched_setaffinity(0, cpus)
+        numa = f"/sys/bus/pci/devices/{bdf}/numa_node"
+        info.update({"bound": True, "pci": bdf, "cores": len(cpus), "local_world": local_world,
+                     "numa_node": int(open(numa).read().strip()) if os.path.exists(numa) else None})
+    except Exception as exc:  # never fatal: this is a placement hint
+        info["error"] = repr(exc)
+    return info

@@ -442,7 +442,10 @@ class BaseLoss:
                 raise ValueError(msg)
             if mod.space.obs != dat.space.obs:
                 if set(mod.space.obs) <= set(dat.space.obs) and len(mod.space.obs) == len(dat.space.obs):
-                    dat = dat.with_obs(mod.space.obs)
+                    # same observables in another order: keep the caller's Data object (a reordered copy would not see
+                    # SamplerData.resample / update_data on the original); the engine addresses columns by NAME at bind
+                    # time (model._lower(data.obs, ...)), so no reordering is needed
+                    pass
                 else:
                     msg = (
                         f"Model at index {i} has observables {mod.space.obs} but data has "
@@ -568,7 +571,9 @@ class BaseLoss:
         _, direct, composed, slots = self._slot_plan
         for j, p in enumerate(eng.slot_params):
             slots[j] = p.value()
-        kahan = self._options.get("sumtype") == "kahan" and not self.is_extended
+        # the kernels always accumulate with error-free merges of the threads' partial sums; the reference's sumtype
+        # switch (loss.py:138-141) is forwarded for interface parity only
+        kahan = self._options.get("sumtype") == "kahan"
         values, gslots = eng.eval(slots, grad=want_grad, log_offset=0.0 if log_offset is False else float(log_offset), kahan=kahan)
         total = float(values.sum()) if len(values) > 1 else float(values[0])
         grad = {}

@@ -441,13 +441,55 @@ class FitResult:
             out[p] = err
         return out
 
-    def errors(self, params=None, method=None, cl=None, name=None, **_):
-        """Profile-likelihood (MINOS-like) intervals: roots of ``NLL_profiled(theta_i) - NLL_min = errordef * n_sigma^2``
-        (``minimizers/errors.py:50-277``), each profile point being a fit with ``theta_i`` fixed."""
+    def errors(self, params=None, method=None, cl=None, name=None, *, sigma=None, rtol=None, covariance_method=None, **_):
+        """Asymmetric (profile-likelihood) uncertainties (``fitresult.py:1464-1598``).
+
+        ``method``: ``"zfit_errors"`` (default here; alias ``"zfit_error"``) is the reference's iminuit-free route,
+        ``compute_errors`` (``minimizers/errors.py:50-277``, restated in ``zfit_b200/errors.py``): one root search over all
+        parameters per interval end, every function call one fused value+gradient pass; ``"refit"`` brackets the crossing
+        with a fit per profile point instead (each with the parameter fixed).  The reference's default ``minuit_minos``
+        needs iminuit.  Returns ``(errors, new_result)``: ``new_result`` is a fresh ``FitResult`` when the scan met a
+        point below this result's minimum -- this result is then marked invalid, as in the reference."""
+        allp = list(self.params)
+        params = allp if params is None else ([params] if isinstance(params, ZfitParameter) else list(params))
+        method = method or "zfit_errors"
+        if method in ("zfit_error", "zfit_errors"):
+            from .errors import compute_errors
+
+            name = name or "errors"
+            cl_used = 0.68268949 if cl is None and sigma is None else cl
+            with set_values(allp, [self.params[p]["value"] for p in allp]):
+                out, new_result = compute_errors(self, params, cl=cl, rtol=rtol, sigma=sigma, covariance_method=covariance_method)
+            for p in out:
+                out[p]["cl"] = None if cl_used is None else round(cl_used, 3)
+            if new_result is not None:
+                msg = "Invalid, a new minimum was found."
+                for p in params:
+                    self.params[p][name] = msg
+                    if p in new_result.params and p in out:
+                        new_result.params[p][name] = out[p]
+                self._valid = False
+                self.message = msg
+                return {p: self.params[p][name] for p in params}, new_result
+            for p in params:
+                self.params[p][name] = out[p]
+            return {p: self.params[p][name] for p in params}, None
+        if callable(method):
+            out, new_result = method(result=self, params=params, cl=cl)
+            for p in out:
+                self.params[p][name or "errors"] = out[p]
+            return out, new_result
+        if method != "refit":
+            msg = f"The following method is not a valid, implemented method: {method}. Use one of ['zfit_errors', 'refit']"
+            raise KeyError(msg)
+        return self._errors_by_refits(params, cl, name)
+
+    def _errors_by_refits(self, params, cl, name):
+        """Roots of ``NLL_profiled(theta_i) - NLL_min = errordef * n_sigma^2`` by bracketing, each profile point being a
+        fit with ``theta_i`` fixed (what MINOS does; costs a fit per function call)."""
         from scipy import optimize, stats
 
         allp = list(self.params)
-        params = allp if params is None else ([params] if isinstance(params, ZfitParameter) else list(params))
         name = name or "errors"
         cl = 0.68268949 if cl is None else cl
         nsig = stats.norm.ppf(0.5 + cl / 2)
@@ -814,6 +856,14 @@ class ScipyBaseMinimizer(BaseMinimizer):
             hinv = getattr(opt, "hess_inv", None)
             if hinv is not None and not isinstance(hinv, np.ndarray) and hasattr(hinv, "todense"):
                 hinv = hinv.todense()
+            if hinv is not None:  # the minimizer's own metric (minimizers_scipy.py: approx of the temporary and final result)
+                hinv = np.asarray(hinv, dtype=np.float64)
+                if hinv.shape == (len(params), len(params)) and np.all(np.isfinite(hinv)):
+                    inv_hess = hinv
+                    approx = {"inv_hessian": inv_hess}
+                    jac = _dense_vector(getattr(opt, "jac", None), len(params))
+                    if jac is not None:
+                        approx["gradient"] = jac
             tmp = FitResult(loss=loss, params=dict(zip(params, x0)), minimizer=self, valid=True, converged=True,
                             edm=None, fminopt=opt.fun, approx=approx)
             with evaluator.ignore_maxiter():
@@ -826,9 +876,23 @@ class ScipyBaseMinimizer(BaseMinimizer):
             tol_internal *= 0.1
         return FitResult(
             loss=loss, params=dict(zip(params, x0)), minimizer=self.copy(), valid=valid, converged=converged, edm=edm,
-            fminopt=float(opt.fun), message=message, criterion=criterion, approx={"inv_hessian": inv_hess},
+            fminopt=float(opt.fun), message=message, criterion=criterion,
+            approx={"inv_hessian": inv_hess, "gradient": _dense_vector(getattr(opt, "jac", None), len(params))},
             evaluator=evaluator, info={"n_eval": evaluator.niter, "original": opt, "driver": f"scipy:{self._METHOD}"},
         )
+
+
+def _dense_vector(v, n):
+    """scipy's ``OptimizeResult.jac`` as a dense length-n vector, or None (trust-constr may hand back sparse / stacked forms)."""
+    if v is None:
+        return None
+    try:
+        if hasattr(v, "toarray"):
+            v = v.toarray()
+        a = np.asarray(v, dtype=np.float64).reshape(-1)
+    except (TypeError, ValueError):
+        return None
+    return a if a.size == n and np.all(np.isfinite(a)) else None
 
 
 def _scipy(name, method, grad=True, hess=False, bounds=True):

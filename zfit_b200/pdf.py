@@ -672,6 +672,11 @@ class SumPDF(BaseFunctor):
         return self._frac_param_created or self._original_fracs is None
 
     def _emit(self, colmap, ctx, limits, nodes, slots):
+        if ctx == "norm" and limits is None and self.norm is not None and any(p.norm != self.norm.with_obs(p.obs) for p in self.pdfs):
+            # no explicit range requested, but the sum's own norm differs from a daughter's: the reference's _pdf then
+            # raises SpecificFunctionNotImplemented as well (equal_norm_ranges is False, functor.py:199-201) and the
+            # value is _unnormalized_pdf / normalization(self.norm) -- the same branch as below, over self.norm
+            limits = self.norm
         if ctx == "norm" and limits is not None and any(p.norm != limits.with_obs(p.obs) for p in self.pdfs):
             # reference: SpecificFunctionNotImplemented -> _unnormalized_pdf / normalization(norm) (functor.py:189-206):
             #   sum_i f_i pdf_i(x) / sum_j f_j int_norm pdf_j
