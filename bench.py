@@ -64,10 +64,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0, period_ms=10):
+    def __init__(self, index=0, period_ms=20, enabled=True):
         self.index = index
         self.t_begin = self.t_end = None
         self.rows = []
+        self.proc = None
+        if not enabled:  # N > 1: rank 0 samples its GPU; eight pollers on one driver delay every rank's launches
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", str(period_ms)],
@@ -116,7 +119,7 @@ class ClockSampler:
     def summary(self):
         self.close()
         if not self.rows or self.t_begin is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable or not sampled on this rank"]}
         import datetime
 
         inside = [r for ts, r in self.rows if self.t_begin <= ts <= self.t_end]
@@ -377,7 +380,7 @@ def measure_config(ctx, cfg, args, headline):
         return loss.value_gradient(params, full=False)
 
     # ---- value: K steps through the loss, inputs resident in HBM, CUDA events on the launch stream ------------
-    sampler = ClockSampler(local)  # its nvidia-smi child starts here, outside the timed region
+    sampler = ClockSampler(local, enabled=(rank == 0))  # its nvidia-smi child starts here, outside the timed region
     with torch.cuda.stream(stream):
         for k in range(args.warmup):
             step(k)

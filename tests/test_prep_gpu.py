@@ -71,3 +71,39 @@ def test_loss_value_does_not_depend_on_the_partition():
     v0, g0 = out[False]
     assert abs(v1 - v0) <= 1e-12 * abs(v0)
     np.testing.assert_allclose(g1, g0, rtol=1e-10, atol=1e-10 * np.abs(g0).max())
+
+
+def test_streamed_upload_partitions_chunk_by_chunk(monkeypatch):
+    """Pinned host columns take the pipelined path (upload chunk k+1 while chunk k is bucketed): same NLL as the
+    device-born path, every chunk of the resident column is a bucket-ordered permutation of the chunk that was sent."""
+    import torch
+
+    import zfit_b200 as zfit
+    from zfit_b200 import workloads as W
+    from zfit_b200.loss import CudaEngine
+
+    monkeypatch.setattr(CudaEngine, "STREAM_CHUNK", 1 << 16)
+    n = 5 * (1 << 16) + 12_345
+    w = W.build(2, n=n, device="cuda:0")
+    params = list(w["loss"].get_params())
+    ref_v, ref_g = type(w["loss"])(model=w["model"], data=w["data"], options={"subtr_const": False}).value_gradient(params, full=True)
+    dev_x = w["data"][0]._cols[0]
+    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    host.copy_(dev_x)
+    data = zfit.Data({"m": host}, obs=w["data"][0].space, guarantee_limits=True)
+    loss = type(w["loss"])(model=w["model"], data=data, options={"subtr_const": False})
+    v, g = loss.value_gradient(params, full=True)
+    assert data._dev_cache is None  # streamed: the unpartitioned copy never existed on the device
+    assert abs(v - ref_v) <= 1e-12 * abs(ref_v)
+    np.testing.assert_allclose(g, ref_g, rtol=1e-10, atol=1e-10 * np.abs(ref_g).max())
+    resident = loss._get_engine()._keep[0][0][0].cpu().numpy()
+    sent = host.numpy()
+    lo, hi = 5000.0, 5600.0
+    for start in range(0, n, 1 << 16):
+        a, b = sent[start : start + (1 << 16)], resident[start : start + (1 << 16)]
+        bucket = np.clip(np.floor((a - lo) * (32.0 / (hi - lo))), 0, 31).astype(np.int64)
+        np.testing.assert_array_equal(b, a[np.argsort(bucket, kind="stable")])
+    # pageable host memory keeps the two-step path and gives the same numbers
+    data2 = zfit.Data({"m": sent.copy()}, obs=w["data"][0].space, guarantee_limits=True)
+    v2, _ = type(w["loss"])(model=w["model"], data=data2, options={"subtr_const": False}).value_gradient(params, full=True)
+    assert abs(v2 - ref_v) <= 1e-12 * abs(ref_v)

@@ -341,6 +341,24 @@ class Data:
         self._dev_cache = (device, cols, w)
         return cols, w
 
+    def pinned_host_columns(self):
+        """(columns, weights | None) as torch CPU tensors when EVERY column lives in page-locked host memory and no device
+        copy exists yet, else None: the engine then streams them to the GPU in chunks and partitions each chunk while the
+        next one is on the wire (``CudaEngine._stream_and_partition``)."""
+        if self._dev_cache is not None:
+            return None
+        import torch
+
+        out = []
+        for c in [*self._cols, *([] if self._weights is None else [self._weights])]:
+            t = c if _is_torch(c) else torch.from_numpy(np.ascontiguousarray(c))
+            if t.device.type != "cpu" or t.dtype != torch.float64 or not t.is_contiguous() or not _is_pinned(t):
+                return None
+            out.append(t)
+        if self._weights is None:
+            return out, None
+        return out[:-1], out[-1]
+
     def __repr__(self):
         return f"<zfit.Data: {self.name} obs={self.obs} shape=({self.num_entries}, {self.n_obs})>"
 

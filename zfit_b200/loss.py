@@ -93,11 +93,16 @@ class CudaEngine:
             start = len(self.slot_params)
             self.slot_params.extend(slots)
             self.channel_slots.append((start, len(self.slot_params)))
-            cols, w = data.device_columns(device)
-            mark("device_columns")
             n = data.num_entries
-            if sort_events is True and n > 1:
-                cols, w = self._sort_for_coherence(model, data, cols, w)
+            streamed = self._stream_and_partition(model, data) if sort_events is True else None
+            if streamed is not None:
+                cols, w = streamed
+                mark("stream+partition")
+            else:
+                cols, w = data.device_columns(device)
+                mark("device_columns")
+                if sort_events is True and n > 1:
+                    cols, w = self._sort_for_coherence(model, data, cols, w)
             self._keep.append((cols, w))
             mark("partition(enqueue)")
             # the columns were produced by torch kernels on torch's stream (upload, cut, sort); the plan launches
@@ -229,6 +234,60 @@ class CudaEngine:
 
     def _raw_stream_now(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    STREAM_CHUNK = 1 << 23  # events per chunk of the pipelined upload (64 MB per column)
+
+    def _stream_and_partition(self, model, data):
+        """Upload and partition in ONE pipeline when the events still sit in pinned host memory: the columns cross PCIe
+        in chunks of ``STREAM_CHUNK`` events on a copy stream, and every chunk is bucketed
+        (``znll_partition_events``) on the compute stream while the next one is on the wire, straight into its slice of
+        the final columns.  Warp coherence only needs LOCAL order, so the buckets are per chunk; the whole bind then
+        costs the PCIe transfer plus one chunk's partition instead of transfer + a pass over everything, and the
+        unpartitioned copy never exists in HBM.  Returns None when the case does not apply (no piecewise leaf, data
+        already on the device or in pageable memory, a small sample)."""
+        target = _first_leaf(model, _PIECEWISE)
+        n = data.num_entries
+        if target is None or n < 2 * self.STREAM_CHUNK or not data.space.has_limits:
+            return None
+        host = data.pinned_host_columns()
+        if host is None:
+            return None
+        hcols, hw = host
+        torch, dev = self.torch, self.torch.device("cuda", self.device)
+        key = data.obs.index(target.obs[0])
+        lo, hi = data.space.with_obs(target.obs[0]).limit1d
+        if not (hi > lo):
+            return None
+        streams = [*hcols, *([] if hw is None else [hw])]
+        out = [torch.empty(n, dtype=torch.float64, device=dev) for _ in streams]
+        chunk = self.STREAM_CHUNK
+        stage = [[torch.empty(chunk, dtype=torch.float64, device=dev) for _ in streams] for _ in range(2)]
+        compute = torch.cuda.current_stream(self.device)
+        copy = torch.cuda.Stream(device=self.device)
+        free = [None, None]
+        copy.wait_stream(compute)
+        nc = len(hcols)
+        for k, start in enumerate(range(0, n, chunk)):
+            m = min(chunk, n - start)
+            b = k & 1
+            with torch.cuda.stream(copy):
+                if free[b] is not None:
+                    copy.wait_event(free[b])  # the partition that read this staging buffer two chunks ago is done
+                for s, h in zip(stage[b], streams):
+                    s[:m].copy_(h[start : start + m], non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(copy)
+            compute.wait_event(arrived)
+            self.Z.partition_events(self.device, [s.data_ptr() for s in stage[b][:nc]],
+                                    [o.data_ptr() + 8 * start for o in out[:nc]],
+                                    0 if hw is None else stage[b][nc].data_ptr(),
+                                    0 if hw is None else out[nc].data_ptr() + 8 * start, key, float(lo), float(hi), m,
+                                    stream=compute.cuda_stream)
+            free[b] = torch.cuda.Event()
+            free[b].record(compute)
+        for s in stage[0] + stage[1]:
+            s.record_stream(compute)
+        return out[:nc], (None if hw is None else out[nc])
 
     def _setup_fused_exchange(self, device):
         """Peer-mapped exchange buffer through torch's symmetric memory (allocation + handle exchange only); the
