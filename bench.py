@@ -69,6 +69,7 @@ class ClockSampler:
         self.t_begin = self.t_end = None
         self.rows = []
         self.proc = None
+        self._lines = []
         if not enabled:  # N > 1: rank 0 samples its GPU; eight pollers on one driver delay every rank's launches
             return
         try:
@@ -77,6 +78,19 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+        self._reader = threading.Thread(target=self._read, daemon=True)
+        self._reader.start()
+        t0 = time.perf_counter()
+        while not self._lines and time.perf_counter() - t0 < 3.0:  # NVML start-up (0.1 - 0.3 s) must not fall into the timed region
+            time.sleep(0.01)
+
+    def _read(self):
+        try:
+            for line in self.proc.stdout:
+                self._lines.append(line)
+        except Exception:
+            pass
 
     def __enter__(self):
         import datetime
@@ -93,20 +107,20 @@ class ClockSampler:
     def close(self):
         if self.proc is None:
             return
-        time.sleep(0.03)  # let the row that covers the end of the window appear
+        time.sleep(0.05)  # let the row that covers the end of the window appear
         try:
             self.proc.terminate()  # the exact child started above
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             try:
                 self.proc.kill()
             except Exception:
                 pass
-            out = ""
+        self._reader.join(timeout=2)
         self.proc = None
         import datetime
 
-        for line in out.splitlines():
+        for line in list(self._lines):
             cells = [c.strip() for c in line.split(",")]
             if len(cells) < 10:
                 continue

@@ -20,14 +20,16 @@ S = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(S)
 
 # kernel (demangled, no spaces) -> (DP instructions, modelled issue cycles) of one trip through the event loop.
-# cfg 4 reads three columns and runs the loop body twice per trip (two register buffers): its numbers are for two pairs.
+# (round 1's cfg 4 ran the loop body twice per trip -- two register buffers --; its old numbers were for two pairs.)
 BUDGET = {
     # round 2 (optimistic sweep with one rare-path test per pair, fixed-reference log-sum-exp, plain per-thread sums,
     # 32-bit pair index, table addresses in registers); round 1 had (94, 311), (109, 325), (111, 341), (170, 513)
-    "nll_kernel<znll::Sum<znll::CBall<0>,znll::Expo<0>>,false,true>": (86, 267),  # cfg 2, pair on the Gaussian core
-    "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,false,true>": (105, 302),  # cfg 3
+    # (every tree now streams its columns through a cp.async ring whose loop body exists once: a few more address
+    # instructions per pair than the register prefetch, paid back several times over by the hidden HBM latency)
+    "nll_kernel<znll::Sum<znll::CBall<0>,znll::Expo<0>>,false,true>": (86, 270),  # cfg 2, pair on the Gaussian core
+    "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,false,true>": (105, 305),  # cfg 3
     "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,true,true>": (107, 315),  # cfg 5 (weighted)
-    "nll_kernel<znll::Prod<znll::Gauss<0>,znll::Expo<1>,znll::Poly<2,4,0>>,false,true>": (162, 478),  # cfg 4, two pairs
+    "nll_kernel<znll::Prod<znll::Gauss<0>,znll::Expo<1>,znll::Poly<2,4,0>>,false,true>": (81, 239),  # cfg 4, ONE pair
 }
 
 

@@ -1816,13 +1816,18 @@ ZNLL_DEV void cp_async16(void* smem, const void* gmem) {  // LDGSTS, L2 only
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 ZNLL_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-ZNLL_DEV void cp_async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 ZNLL_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <class M, bool WEIGHTED>
+template <int N>
+ZNLL_DEV void cp_async_wait_all_but() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// STAGES-deep cp.async ring: STAGES pairs per thread are in flight while one is computed.  The stage index is a run-time
+// value (one multiply-add per access), so the loop body exists ONCE whatever the depth.
+template <class M, bool WEIGHTED, int STAGES>
 struct Ring {
   static constexpr int NSTREAM = zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0);
-  double2 slot[2][NSTREAM][ZNLL_BLOCK];  // [stage][stream][thread]
+  double2 slot[STAGES][NSTREAM][ZNLL_BLOCK];  // [stage][stream][thread]
   template <int NC>
   ZNLL_DEV void issue(int stage, const KArgs<NC>& args, unsigned i) {
     int s = 0;
@@ -1848,6 +1853,21 @@ struct Ring {
     }
   }
 };
+// depth of the ring by the number of 8-byte streams a tree reads (0: register prefetch of one pair instead).  One pair per
+// thread in flight is 148 SMs x 512 threads x 16 B x streams = 1.2 MB x streams on the wire; at ~0.8 us of HBM latency
+// that caps a one-stream tree at ~1.5 TB/s and a two-stream tree at ~3 TB/s -- BELOW what cfg 2 / 3 (8 B per event in
+// 0.46 - 0.49 ms) and cfg 5 (16 B in 0.55 ms) ask for, so once their instruction streams had been cut they became
+// memory-LATENCY bound (ncu: long-scoreboard stalls 0.4 - 1.3 per issue).  Deeper prefetch is the cure, and shared
+// memory is where it costs no registers.
+#ifndef ZNLL_RING_STAGES_SMALL
+#define ZNLL_RING_STAGES_SMALL 3  // trees with one or two streams
+#endif
+#ifndef ZNLL_RING_STAGES_WIDE
+#define ZNLL_RING_STAGES_WIDE 2   // three or four streams (48 KB of static shared memory hold the tables + 2 x 4 x 4 KB)
+#endif
+__host__ __device__ constexpr int ring_stages(int nstream) {
+  return (ZNLL_RING == 0 || nstream > 4) ? 0 : (nstream <= 2 ? ZNLL_RING_STAGES_SMALL : ZNLL_RING_STAGES_WIDE);
+}
 
 // The pair loop.  Per thread the value is accumulated with plain fp64 adds (a thread sees a few hundred pairs, each term
 // is O(1) after the per-event offset: the rounding error of a thread's partial sum is below 1e-13 of it), and the partial
@@ -1872,32 +1892,31 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
   const unsigned stride = gridDim.x * ZNLL_BLOCK;
   unsigned i = blockIdx.x * ZNLL_BLOCK + threadIdx.x;
   constexpr int NSTREAM = zpopc((unsigned)M::COLMASK) + (WEIGHTED ? 1 : 0);
+  constexpr int STAGES = ring_stages(NSTREAM);
   // the ring, the tables and the reduction scratch must fit the 48 KB of static shared memory
-  constexpr bool RING_FITS = 2 * NSTREAM * ZNLL_BLOCK * 16 + sizeof(MathTabs) + (ZNLL_BLOCK / 32) * NACC * 8 + 256 <= 48 * 1024;
-  if constexpr ((ZNLL_RING != 0) && (NSTREAM == 3 || NSTREAM == 4) && RING_FITS) {
-    // three or four 8-byte streams per event (cfg 4): a two-deep cp.async ring in shared memory keeps TWO pairs per
-    // thread in flight -- measured on the B200: 0.474 -> 0.393 ms per launch of cfg 4, i.e. 5.07 -> 6.10 TB/s
-    __shared__ Ring<M, WEIGHTED> ring;
+  constexpr bool RING_FITS = STAGES * NSTREAM * ZNLL_BLOCK * 16 + sizeof(MathTabs) + (ZNLL_BLOCK / 32) * NACC * 8 + 256 <= 48 * 1024;
+  if constexpr (STAGES > 0 && RING_FITS) {
+    __shared__ Ring<M, WEIGHTED, (STAGES > 0 ? STAGES : 1)> ring;
     EventPair<M, WEIGHTED> p;
-    // groups are committed unconditionally (an empty group is legal), so "all but the newest" is always the stage read next
-    if (i < nvec) ring.issue(0, args, i);
-    cp_async_commit();
-    if (i + stride < nvec) ring.issue(1, args, i + stride);
-    cp_async_commit();
+    // groups are committed unconditionally (an empty group is legal), so "all but the newest STAGES - 1" is always the
+    // stage read next; a stage is refilled by the thread that has just read it (program order)
+    unsigned pre = i;
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      if (pre < nvec) ring.issue(s, args, pre);
+      cp_async_commit();
+      pre += stride;
+    }
+    int stage = 0;
     while (i < nvec) {
-      cp_async_wait_all_but_one();
-      ring.fetch(0, p);
-      if (i + 2 * stride < nvec) ring.issue(0, args, i + 2 * stride);  // refill the stage just read (same thread: program order)
+      cp_async_wait_all_but<(STAGES > 0 ? STAGES - 1 : 0)>();
+      ring.fetch(stage, p);
+      if (pre < nvec) ring.issue(stage, args, pre);
       cp_async_commit();
+      pre += stride;
       acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, args.log_offset2, acc);
       i += stride;
-      if (i >= nvec) break;
-      cp_async_wait_all_but_one();
-      ring.fetch(1, p);
-      if (i + 2 * stride < nvec) ring.issue(1, args, i + 2 * stride);
-      cp_async_commit();
-      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, args.log_offset2, acc);
-      i += stride;
+      stage = (stage + 1 == STAGES) ? 0 : stage + 1;
     }
     cp_async_wait_all();
   } else if constexpr ((ZNLL_PINGPONG != 0) && (NSTREAM >= 3)) {
