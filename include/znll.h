@@ -183,6 +183,35 @@ int znll_eval_hess(znll_plan* plan, const double* slots, double log_offset, doub
                    double* hess, void* stream);
 int znll_plan_has_hess(const znll_plan* plan, int ch);
 
+/* ---- theta-space evaluation: the host chain rule of loss.value_gradient behind the C ABI -------------------------------
+ * Replaces, for the built-in parameter kinds, what BaseLoss.value_gradient does around the per-event sum on every call:
+ * Parameter.value with its clip (core/parameter.py:548-557), the fractions a SumPDF derives from yields and the
+ * remaining fraction (models/basefunctor.py:189-205, 228-244), the reverse sweep through them (z/math.py:236-261), and
+ * ExtendedUnbinnedNLL's Poisson term per channel (core/loss.py:1301-1317).  theta is the vector of ALL independent
+ * parameters the loss depends on (floating or not), in an order the caller fixes once; every slot is one rule over refs. */
+typedef struct znll_ref {
+  int32_t kind;  /* 0: the constant `value`;  1: theta[index] (clipped to its limits, identity gradient) */
+  int32_t index;
+  double value;
+} znll_ref;
+enum znll_rule_kind {
+  ZNLL_RULE_VALUE = 0,     /* slot = ref[first]                                   (Parameter, ConstantParameter)      */
+  ZNLL_RULE_FRACTION = 1,  /* slot = ref[first] / sum(ref[first+1 .. first+n-1])  (frac_i = yield_i / sum(yields))    */
+  ZNLL_RULE_REMAINDER = 2, /* slot = 1 - sum(ref[first .. first+n-1])             (the last fraction of a SumPDF)     */
+  ZNLL_RULE_SUM = 3        /* slot = sum(ref[first .. first+n-1])                 (the yield of an automatic extended sum) */
+};
+typedef struct znll_rule {
+  int32_t kind, first, n, pad;
+} znll_rule;
+#define ZNLL_FULL 4u /* flag of znll_eval_theta: full=True, i.e. log_offset is False (no offset, Stirling term kept) */
+/* lower / upper: clip bounds of theta (+-inf = none; either may be NULL).  slot_rules: one per slot of the plan, channel
+ * major.  yield_rules: one per channel for an extended loss (the channel's yield), NULL otherwise. */
+int znll_plan_set_theta_map(znll_plan* plan, int n_theta, const double* lower, const double* upper, const znll_ref* refs,
+                            int n_refs, const znll_rule* slot_rules, const znll_rule* yield_rules);
+/* value = sum_k value_k (+ the extended terms), grad_theta[n_theta] = d value / d theta (NULL without ZNLL_WANT_GRAD).
+ * One fused pass per channel; with peers set the result is world-reduced like znll_eval's. */
+int znll_eval_theta(znll_plan* plan, const double* theta, uint32_t flags, double log_offset, double* value,
+                    double* grad_theta, void* stream);
 /* Fused multi-GPU reduction (no reference equivalent; the reference has no multi-device path).  peer_bufs[r] is rank
  * r's exchange buffer of at least znll_plan_exchange_bytes() bytes, zero-initialised, peer-mapped into this process
  * (CUDA IPC / VMM symmetric memory; the host obtains it from torch.distributed._symmetric_memory).  Once set, the last
@@ -230,6 +259,15 @@ typedef struct znll_migrad_result {
 int znll_migrad(znll_fcn_t fcn, znll_info_t info, void* user, int n, const double* x0, const double* steps,
                 const double* lower, const double* upper, const znll_migrad_options* options, double* x_out,
                 double* cov_out, double* grad_out, znll_migrad_result* result);
+
+/* A whole MIGRAD minimisation without leaving native code: znll_migrad driven by znll_eval_theta over the n_fit entries
+ * fit_index[] of theta (the others stay at theta0), metric seeded from the information matrix of znll_eval_cov when
+ * use_information != 0.  Outputs as znll_migrad's; theta_out[n_theta] holds the final point.  Returns 2 when an
+ * evaluation produced a non-finite value (the caller falls back to the evaluator path and its NaN strategy). */
+int znll_migrad_theta(znll_plan* plan, int n_fit, const int32_t* fit_index, const double* theta0, const double* steps,
+                      const double* lower, const double* upper, const znll_migrad_options* options, uint32_t flags,
+                      double log_offset, int use_information, double* theta_out, double* cov_out, double* grad_out,
+                      znll_migrad_result* result, void* stream);
 
 /* Host-only helpers (no GPU needed): normalisation integral of one leaf and d I / d slot, exactly
  * as the per-call prologue computes them.  Replaces the registered analytic integrals

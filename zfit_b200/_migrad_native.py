@@ -107,3 +107,45 @@ def minimize(value, gradient, x0, steps, lower, upper, *, edm_goal, maxfcn=10000
     res.nfcn, res.ngrad, res.niter = out.nfcn, out.ngrad, out.niter
     res.message = out.message.decode(errors="replace")
     return res
+
+
+def minimize_theta(plan, fit_index, theta0, steps, lower, upper, *, edm_goal, maxfcn=10000, hesse=True, full=False,
+                   log_offset=0.0, use_information=True, stream=0):
+    """A whole MIGRAD minimisation inside ``libznll.so`` (``znll_migrad_theta``): the driver calls ``znll_eval_theta``
+    directly, so no Python runs between the first and the last fused pass.  ``plan``: a ``_znll.Plan`` with a theta map;
+    ``fit_index``: positions of the fitted parameters in its theta vector, ``theta0`` the full start vector.
+    -> (MigradResult | None, theta_out): None when an evaluation was not finite (the caller then takes the evaluator
+    route with its NaN strategy)."""
+    lib = Z.lib()
+    fn = lib.znll_migrad_theta
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), _DP, _DP, _DP, _DP, C.POINTER(Options), C.c_uint32, C.c_double,
+                   C.c_int, _DP, _DP, _DP, C.POINTER(Result), C.c_void_p]
+    n = len(fit_index)
+    idx = (C.c_int32 * n)(*[int(i) for i in fit_index])
+    theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+    steps = np.ascontiguousarray(steps, dtype=np.float64)
+    lo = np.array([_bound(v, -np.inf) for v in lower], dtype=np.float64)
+    up = np.array([_bound(v, np.inf) for v in upper], dtype=np.float64)
+    opts = Options(float(edm_goal), int(min(maxfcn, 2**31 - 1)), int(bool(hesse)), 1, 1)
+    out = Result()
+    theta_out = np.zeros_like(theta0)
+    cov = np.zeros((n, n))
+    grad = np.zeros(n)
+    rc = fn(plan._h, n, idx, theta0.ctypes.data_as(_DP), steps.ctypes.data_as(_DP), lo.ctypes.data_as(_DP),
+            up.ctypes.data_as(_DP), C.byref(opts), Z.FULL if full else 0, float(log_offset), int(bool(use_information)),
+            theta_out.ctypes.data_as(_DP), cov.ctypes.data_as(_DP), grad.ctypes.data_as(_DP), C.byref(out),
+            C.c_void_p(stream or 0))
+    if rc == 2:
+        return None, theta_out
+    if rc:
+        msg = f"znll_migrad_theta failed (rc={rc}): {Z.lib().znll_last_error().decode(errors='replace')} {out.message.decode(errors='replace')}"
+        raise RuntimeError(msg)
+    res = MigradResult()
+    res.x = theta_out[np.asarray(fit_index, dtype=np.int64)]
+    res.fval, res.edm = out.fval, out.edm
+    res.covariance, res.grad = cov, grad
+    res.valid, res.converged = bool(out.valid), bool(out.converged)
+    res.nfcn, res.ngrad, res.niter = out.nfcn, out.ngrad, out.niter
+    res.message = out.message.decode(errors="replace")
+    return res, theta_out

@@ -38,6 +38,22 @@ class Node(C.Structure):
     ]
 
 
+class Ref(C.Structure):
+    """Mirror of ``znll_ref``: kind 0 = the constant ``value``, 1 = ``theta[index]``."""
+
+    _fields_ = [("kind", C.c_int32), ("index", C.c_int32), ("value", C.c_double)]
+
+
+class Rule(C.Structure):
+    """Mirror of ``znll_rule``: how one slot (or a channel's yield) follows from refs ``first .. first + n - 1``."""
+
+    _fields_ = [("kind", C.c_int32), ("first", C.c_int32), ("n", C.c_int32), ("pad", C.c_int32)]
+
+
+RULE_VALUE, RULE_FRACTION, RULE_REMAINDER, RULE_SUM = 0, 1, 2, 3
+FULL = 4
+
+
 class ZnllError(RuntimeError):
     pass
 
@@ -77,6 +93,9 @@ SYMBOLS = {
     "znll_eval_cov": (C.c_int, [C.c_void_p, _DP, C.c_double, _DP, _DP, _DP, C.c_void_p]),
     "znll_eval_hess": (C.c_int, [C.c_void_p, _DP, C.c_double, _DP, _DP, _DP, C.c_void_p]),
     "znll_plan_has_hess": (C.c_int, [C.c_void_p, C.c_int]),
+    "znll_plan_set_theta_map": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.POINTER(Ref), C.c_int, C.POINTER(Rule), C.POINTER(Rule)]),
+    "znll_eval_theta": (C.c_int, [C.c_void_p, _DP, C.c_uint32, C.c_double, _DP, _DP, C.c_void_p]),
+    "znll_migrad_theta": (C.c_int, None),  # structs of _migrad_native.py: argtypes are set there
     "znll_pdf": (C.c_int, [C.c_void_p, C.c_int, _DP, _DP, C.c_void_p]),
     "znll_pdf_device": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_void_p, C.c_void_p]),
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
@@ -246,6 +265,31 @@ class Plan:
             mats.append(cov[off : off + n * n].reshape(n, n).copy())
             off += n * n
         return self._values.copy(), self._grad[: self.total_slots].copy(), mats
+
+    def set_theta_map(self, n_theta, lower, upper, refs, slot_rules, yield_rules=None):
+        """``refs``: [(kind, index, value)], ``slot_rules`` / ``yield_rules``: [(kind, first, n)] (include/znll.h)."""
+        lo = np.ascontiguousarray(lower, dtype=np.float64)
+        up = np.ascontiguousarray(upper, dtype=np.float64)
+        r = (Ref * max(len(refs), 1))(*[Ref(int(k), int(i), float(v)) for k, i, v in refs])
+        sr = (Rule * max(len(slot_rules), 1))(*[Rule(int(k), int(f), int(n), 0) for k, f, n in slot_rules])
+        yr = None if yield_rules is None else (Rule * len(yield_rules))(*[Rule(int(k), int(f), int(n), 0) for k, f, n in yield_rules])
+        _check(lib().znll_plan_set_theta_map(self._h, int(n_theta), _dptr(lo), _dptr(up), r, len(refs), sr, yr))
+        self.n_theta = int(n_theta)
+        self._theta = np.zeros(max(self.n_theta, 1))
+        self._gtheta = np.zeros(max(self.n_theta, 1))
+        self._tvalue = np.zeros(1)
+        self._p_theta, self._p_gtheta, self._p_tvalue = _dptr(self._theta), _dptr(self._gtheta), _dptr(self._tvalue)
+        self._f_eval_theta = lib().znll_eval_theta
+
+    def eval_theta(self, theta, *, grad=True, full=False, log_offset=0.0, stream=0):
+        """-> (value, d value / d theta | None): slots from theta, the fused pass, the chain rule and the extended term
+        behind the C ABI (``znll_eval_theta``)."""
+        self._theta[: self.n_theta] = theta
+        flags = (WANT_GRAD if grad else 0) | (FULL if full else 0)
+        if self._f_eval_theta(self._h, self._p_theta, flags, log_offset, self._p_tvalue, self._p_gtheta if grad else None,
+                              stream or None):
+            _check(1)
+        return float(self._tvalue[0]), (self._gtheta[: self.n_theta].copy() if grad else None)
 
     def has_hess(self) -> bool:
         """True when every channel's tree has the one-pass Hessian kernel (flat tree of supported nodes, catalogue)."""

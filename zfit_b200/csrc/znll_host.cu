@@ -487,6 +487,12 @@ struct znll_plan {
   unsigned long long* h_flag = nullptr;
   unsigned long long* h_flag_dev = nullptr;
   bool direct_pending = false;
+  // theta-space map (znll_plan_set_theta_map): empty until set
+  int n_theta = 0;
+  std::vector<double> th_lo, th_hi;
+  std::vector<znll_ref> refs;
+  std::vector<znll_rule> slot_rules, yield_rules;
+  std::vector<double> th_clip, th_slots, th_values, th_gslots;  // per-call scratch
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1782,6 +1788,244 @@ int znll_eval_hess(znll_plan* p, const double* slots, double log_offset, double*
     h_off += (size_t)NS * NS;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// theta-space evaluation (include/znll.h): slots from theta, the fused pass, the chain rule back, the extended term
+// ------------------------------------------------------------------------------------------------
+static inline double ref_value(const znll_plan* p, const znll_ref& r, const double* th) {
+  return r.kind == 1 ? th[r.index] : r.value;
+}
+static double rule_value(const znll_plan* p, const znll_rule& ru, const double* th) {
+  const znll_ref* r = p->refs.data() + ru.first;
+  switch (ru.kind) {
+    case ZNLL_RULE_VALUE: return ref_value(p, r[0], th);
+    case ZNLL_RULE_FRACTION: {
+      double tot = 0.0;
+      for (int k = 1; k < ru.n; ++k) tot += ref_value(p, r[k], th);
+      return ref_value(p, r[0], th) / tot;
+    }
+    case ZNLL_RULE_REMAINDER: {
+      double v = 1.0;
+      for (int k = 0; k < ru.n; ++k) v -= ref_value(p, r[k], th);
+      return v;
+    }
+    default: {  // ZNLL_RULE_SUM
+      double v = 0.0;
+      for (int k = 0; k < ru.n; ++k) v += ref_value(p, r[k], th);
+      return v;
+    }
+  }
+}
+// grad[i] += g * d rule / d theta_i
+static void rule_backward(const znll_plan* p, const znll_rule& ru, const double* th, double g, double* grad) {
+  const znll_ref* r = p->refs.data() + ru.first;
+  auto add = [&](const znll_ref& rf, double d) {
+    if (rf.kind == 1) grad[rf.index] += g * d;
+  };
+  switch (ru.kind) {
+    case ZNLL_RULE_VALUE: add(r[0], 1.0); break;
+    case ZNLL_RULE_FRACTION: {
+      double tot = 0.0;
+      for (int k = 1; k < ru.n; ++k) tot += ref_value(p, r[k], th);
+      const double a = ref_value(p, r[0], th);
+      add(r[0], 1.0 / tot);
+      for (int k = 1; k < ru.n; ++k) add(r[k], -a / (tot * tot));
+      break;
+    }
+    case ZNLL_RULE_REMAINDER:
+      for (int k = 0; k < ru.n; ++k) add(r[k], -1.0);
+      break;
+    default:
+      for (int k = 0; k < ru.n; ++k) add(r[k], 1.0);
+      break;
+  }
+}
+
+int znll_plan_set_theta_map(znll_plan* p, int n_theta, const double* lower, const double* upper, const znll_ref* refs,
+                            int n_refs, const znll_rule* slot_rules, const znll_rule* yield_rules) {
+  if (!p || n_theta < 0 || n_refs < 0 || (n_refs > 0 && !refs) || !slot_rules) return fail("znll_plan_set_theta_map: bad arguments");
+  auto check = [&](const znll_rule& ru) {
+    if (ru.kind < 0 || ru.kind > ZNLL_RULE_SUM || ru.first < 0 || ru.n < 1 || ru.first + ru.n > n_refs) return false;
+    if (ru.kind == ZNLL_RULE_FRACTION && ru.n < 2) return false;
+    for (int k = 0; k < ru.n; ++k) {
+      const znll_ref& r = refs[ru.first + k];
+      if (r.kind != 0 && r.kind != 1) return false;
+      if (r.kind == 1 && (r.index < 0 || r.index >= n_theta)) return false;
+    }
+    return true;
+  };
+  for (int j = 0; j < p->total_slots; ++j)
+    if (!check(slot_rules[j])) return fail("znll_plan_set_theta_map: malformed rule of slot %d", j);
+  if (yield_rules)
+    for (size_t k = 0; k < p->ch.size(); ++k)
+      if (!check(yield_rules[k])) return fail("znll_plan_set_theta_map: malformed yield rule of channel %d", (int)k);
+  p->n_theta = n_theta;
+  p->th_lo.assign(n_theta, -INFINITY);
+  p->th_hi.assign(n_theta, INFINITY);
+  for (int i = 0; i < n_theta; ++i) {
+    if (lower && lower[i] == lower[i]) p->th_lo[i] = lower[i];
+    if (upper && upper[i] == upper[i]) p->th_hi[i] = upper[i];
+  }
+  p->refs.assign(refs, refs + n_refs);
+  p->slot_rules.assign(slot_rules, slot_rules + p->total_slots);
+  p->yield_rules.clear();
+  if (yield_rules) p->yield_rules.assign(yield_rules, yield_rules + p->ch.size());
+  p->th_clip.assign(n_theta, 0.0);
+  p->th_slots.assign(p->total_slots, 0.0);
+  p->th_values.assign(p->ch.size(), 0.0);
+  p->th_gslots.assign(p->total_slots, 0.0);
+  return 0;
+}
+
+int znll_eval_theta(znll_plan* p, const double* theta, uint32_t flags, double log_offset, double* value,
+                    double* grad_theta, void* stream) {
+  if (!p || !theta || !value) return fail("znll_eval_theta: bad arguments");
+  if ((int)p->slot_rules.size() != p->total_slots || p->total_slots == 0) return fail("znll_eval_theta: no theta map set");
+  const bool want_grad = (flags & ZNLL_WANT_GRAD) && grad_theta;
+  const bool full = (flags & ZNLL_FULL) != 0;
+  double* th = p->th_clip.data();
+  for (int i = 0; i < p->n_theta; ++i) th[i] = std::min(std::max(theta[i], p->th_lo[i]), p->th_hi[i]);  // NaN passes through
+  for (int j = 0; j < p->total_slots; ++j) p->th_slots[j] = rule_value(p, p->slot_rules[j], th);
+  const uint32_t f = want_grad ? ZNLL_WANT_GRAD : 0u;
+  if (launch_impl(p, p->th_slots.data(), f, full ? 0.0 : log_offset, stream, true)) return 1;
+  if (znll_collect(p, f, p->th_values.data(), want_grad ? p->th_gslots.data() : nullptr, stream)) return 1;
+  double total = 0.0;
+  for (double v : p->th_values) total += v;
+  if (want_grad) {
+    for (int i = 0; i < p->n_theta; ++i) grad_theta[i] = 0.0;
+    for (int j = 0; j < p->total_slots; ++j) rule_backward(p, p->slot_rules[j], th, p->th_gslots[j], grad_theta);
+  }
+  // tf.nn.log_poisson_loss(samplesize, log(yield), compute_full_loss = full) per channel, + log_offset when an offset
+  // is in use (core/loss.py:1301-1317)
+  for (size_t k = 0; k < p->yield_rules.size(); ++k) {
+    const double t = p->ch[k].sumw;
+    const double y = rule_value(p, p->yield_rules[k], th);
+    const double log_y = y > 0 ? log(y) : (y == 0 ? -INFINITY : NAN);
+    double term = exp(log_y) - log_y * t;
+    if (full) {
+      if (!(t >= 0.0 && t <= 1.0)) term += t * log(t) - t + 0.5 * log(2.0 * M_PI * t);
+    } else {
+      term += log_offset;
+    }
+    total += term;
+    if (want_grad) rule_backward(p, p->yield_rules[k], th, y != 0 ? 1.0 - t / y : NAN, grad_theta);
+  }
+  *value = total;
+  return 0;
+}
+
+// information matrix in theta space (the MIGRAD metric seed): sum over channels of B^T E B with E from znll_eval_cov
+// (rescaled by sum w / sum w^2 for weighted channels) and B = d [slots; log yield] / d theta -- loss.information_matrix
+static int theta_information(znll_plan* p, const double* theta, double* info /* n_theta^2 */, void* stream) {
+  const int n = p->n_theta;
+  double* th = p->th_clip.data();
+  for (int i = 0; i < n; ++i) th[i] = std::min(std::max(theta[i], p->th_lo[i]), p->th_hi[i]);
+  for (int j = 0; j < p->total_slots; ++j) p->th_slots[j] = rule_value(p, p->slot_rules[j], th);
+  size_t cov_len = 0;
+  for (auto& c : p->ch) cov_len += (size_t)(c.n_slots + 1) * (c.n_slots + 1);
+  std::vector<double> cov(cov_len), vals(p->ch.size()), gs(p->total_slots);
+  if (znll_eval_cov(p, p->th_slots.data(), 0.0, vals.data(), gs.data(), cov.data(), stream)) return 1;
+  for (int i = 0; i < n * n; ++i) info[i] = 0.0;
+  size_t off = 0;
+  for (size_t k = 0; k < p->ch.size(); ++k) {
+    const Channel& c = p->ch[k];
+    const int ns = c.n_slots, ne = ns + 1;
+    std::vector<double> B((size_t)ne * n, 0.0);
+    for (int j = 0; j < ns; ++j) rule_backward(p, p->slot_rules[c.slot_off + j], th, 1.0, B.data() + (size_t)j * n);
+    if (!p->yield_rules.empty()) {
+      const double y = rule_value(p, p->yield_rules[k], th);
+      rule_backward(p, p->yield_rules[k], th, 1.0 / y, B.data() + (size_t)ns * n);
+    }
+    const double* E = cov.data() + off;
+    double scale = 1.0;
+    if (c.w && E[(size_t)ns * ne + ns] > 0) scale = c.sumw / E[(size_t)ns * ne + ns];
+    std::vector<double> EB((size_t)ne * n, 0.0);
+    for (int a = 0; a < ne; ++a)
+      for (int b = 0; b < ne; ++b) {
+        const double e = E[(size_t)a * ne + b] * scale;
+        if (e == 0.0) continue;
+        for (int i = 0; i < n; ++i) EB[(size_t)a * n + i] += e * B[(size_t)b * n + i];
+      }
+    for (int a = 0; a < ne; ++a)
+      for (int i = 0; i < n; ++i) {
+        const double bi = B[(size_t)a * n + i];
+        if (bi == 0.0) continue;
+        for (int j = 0; j < n; ++j) info[(size_t)i * n + j] += bi * EB[(size_t)a * n + j];
+      }
+    off += (size_t)ne * ne;
+  }
+  return 0;
+}
+
+struct ThetaFit {
+  znll_plan* plan;
+  std::vector<double> theta;      // full vector; the fitted entries are overwritten per call
+  std::vector<double> grad_full, info_full;
+  std::vector<int32_t> index;     // fit parameter -> theta entry
+  uint32_t flags;
+  double log_offset;
+  void* stream;
+  bool nonfinite = false;
+};
+static int theta_fcn(void* user, const double* x, int what, double* value, double* grad) {
+  ThetaFit* f = (ThetaFit*)user;
+  for (size_t i = 0; i < f->index.size(); ++i) f->theta[f->index[i]] = x[i];
+  double v = 0.0;
+  const bool g = (what & ZNLL_FCN_GRADIENT) != 0;
+  if (znll_eval_theta(f->plan, f->theta.data(), f->flags | (g ? ZNLL_WANT_GRAD : 0u), f->log_offset, &v,
+                      g ? f->grad_full.data() : nullptr, f->stream))
+    return 1;
+  if (!(v == v) || v == INFINITY || v == -INFINITY) {
+    f->nonfinite = true;
+    return 1;
+  }
+  if (what & ZNLL_FCN_VALUE) *value = v;
+  if (g)
+    for (size_t i = 0; i < f->index.size(); ++i) grad[i] = f->grad_full[f->index[i]];
+  return 0;
+}
+static int theta_info(void* user, const double* x, double* info) {
+  ThetaFit* f = (ThetaFit*)user;
+  for (size_t i = 0; i < f->index.size(); ++i) f->theta[f->index[i]] = x[i];
+  if (theta_information(f->plan, f->theta.data(), f->info_full.data(), f->stream)) return 1;
+  const int n = (int)f->index.size(), nt = f->plan->n_theta;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      const double v = f->info_full[(size_t)f->index[i] * nt + f->index[j]];
+      if (!(v == v)) return 1;
+      info[(size_t)i * n + j] = v;
+    }
+  return 0;
+}
+
+int znll_migrad_theta(znll_plan* p, int n_fit, const int32_t* fit_index, const double* theta0, const double* steps,
+                      const double* lower, const double* upper, const znll_migrad_options* options, uint32_t flags,
+                      double log_offset, int use_information, double* theta_out, double* cov_out, double* grad_out,
+                      znll_migrad_result* result, void* stream) {
+  if (!p || n_fit < 1 || !fit_index || !theta0 || !steps || !options || !result) return fail("znll_migrad_theta: bad arguments");
+  if ((int)p->slot_rules.size() != p->total_slots || p->total_slots == 0) return fail("znll_migrad_theta: no theta map set");
+  ThetaFit f;
+  f.plan = p;
+  f.theta.assign(theta0, theta0 + p->n_theta);
+  f.grad_full.assign(p->n_theta, 0.0);
+  f.info_full.assign((size_t)p->n_theta * p->n_theta, 0.0);
+  f.index.assign(fit_index, fit_index + n_fit);
+  for (int i = 0; i < n_fit; ++i)
+    if (fit_index[i] < 0 || fit_index[i] >= p->n_theta) return fail("znll_migrad_theta: fit index %d out of range", fit_index[i]);
+  f.flags = flags & ZNLL_FULL;
+  f.log_offset = log_offset;
+  f.stream = stream;
+  std::vector<double> x0(n_fit), x(n_fit);
+  for (int i = 0; i < n_fit; ++i) x0[i] = theta0[fit_index[i]];
+  const int rc = znll_migrad(theta_fcn, use_information ? theta_info : nullptr, &f, n_fit, x0.data(), steps, lower, upper,
+                             options, x.data(), cov_out, grad_out, result);
+  if (theta_out) {
+    for (int i = 0; i < p->n_theta; ++i) theta_out[i] = theta0[i];
+    for (int i = 0; i < n_fit; ++i) theta_out[fit_index[i]] = x[i];
+  }
+  if (rc && f.nonfinite) return 2;
+  return rc;
 }
 
 // launches pdf_kernel of channel ch into a device buffer of c.n doubles (no synchronisation)

@@ -396,6 +396,87 @@ def _exchange_buffer(torch, device, nbytes):
     return _XCHG[device]
 
 
+class ThetaPath:
+    """The loss in theta space behind the C ABI (``znll_plan_set_theta_map`` / ``znll_eval_theta``): ``indep`` are the
+    independent parameters the loss depends on, in the order of the C side's theta vector."""
+
+    def __init__(self, indep, extended):
+        self.indep = indep
+        self.extended = extended
+        self._index_cache = {}
+
+    def index_of(self, params):
+        key = tuple(id(p) for p in params)
+        got = self._index_cache.get(key)
+        if got is None:
+            pos = {id(p): i for i, p in enumerate(self.indep)}
+            got = np.array([pos.get(id(p), -1) for p in params], dtype=np.int64)
+            self._index_cache[key] = got
+        return got
+
+
+def _build_theta_path(loss, eng):
+    """Describe every slot (and, for an extended loss, every channel's yield) as a rule over the independent parameters
+    -- a plain value, ``yield_i / sum(yields)``, ``1 - sum(fracs)``, a sum of yields -- and hand the map to the plan.
+    Returns None when a slot depends on anything else (a user ``ComposedParameter``, renormalised fractions): the loss
+    then keeps the Python chain rule."""
+    from . import _znll as Z
+    from .parameter import ConstantParameter, FractionOfSum, OneMinusSum, SumOfParameters
+
+    indep, refs = [], []
+
+    def ref_of(p):
+        if p.independent:
+            for i, q in enumerate(indep):
+                if q is p:
+                    return (1, i, 0.0)
+            indep.append(p)
+            return (1, len(indep) - 1, 0.0)
+        if isinstance(p, ConstantParameter) or not p._leaves():
+            return (0, 0, float(p.value()))
+        return None
+
+    def rule_of(p):
+        if p.independent or isinstance(p, ConstantParameter) or not p._leaves():
+            terms, kind = [p], Z.RULE_VALUE
+        elif isinstance(p, FractionOfSum) and p._plain:
+            terms, kind = [p._term, *p._total._terms], Z.RULE_FRACTION
+        elif isinstance(p, OneMinusSum) and p._plain:
+            terms, kind = list(p._terms), Z.RULE_REMAINDER
+        elif isinstance(p, SumOfParameters) and p._plain:
+            terms, kind = list(p._terms), Z.RULE_SUM
+        else:
+            return None
+        first = len(refs)
+        for t in terms:
+            r = ref_of(t)
+            if r is None:
+                return None
+            refs.append(r)
+        return (kind, first, len(terms))
+
+    slot_rules = []
+    for sp in eng.slot_params:
+        ru = rule_of(sp)
+        if ru is None:
+            return None
+        slot_rules.append(ru)
+    yield_rules = None
+    if loss.is_extended:
+        yield_rules = []
+        for mod in loss.model:
+            if not mod.is_extended:
+                return None
+            ru = rule_of(mod.get_yield())
+            if ru is None:
+                return None
+            yield_rules.append(ru)
+    n = len(indep)
+    # theta arrives clipped (Parameter.value): no bounds on the C side, so a limit changed later cannot go stale there
+    eng.plan.set_theta_map(n, np.full(n, -np.inf), np.full(n, np.inf), refs, slot_rules, yield_rules)
+    return ThetaPath(indep, yield_rules is not None)
+
+
 def _first_leaf(model, cls):
     if isinstance(model, cls):
         return model
@@ -650,7 +731,42 @@ class BaseLoss:
         """Terms beyond the per-event sum (extended Poisson term); overridden by ExtendedUnbinnedNLL."""
         return 0.0, {}
 
+    def _theta_path(self, eng):
+        """The C-level theta path for this engine (built once), or None: only the CUDA engine has one, a sharded loss only
+        with the fused exchange (the NCCL route reduces between launch and collect), and only while every slot follows a
+        built-in rule; ``options={"theta_path": False}`` keeps the Python chain rule (the parity tests compare the two)."""
+        cached = getattr(self, "_theta_cache", None)
+        if cached is not None and cached[0] is eng:
+            return cached[1]
+        path = None
+        if (isinstance(eng, CudaEngine) and self._options.get("theta_path", True)
+                and (not eng.distributed or eng.reduce_mode == "fused-nvlink")):
+            path = _build_theta_path(self, eng)
+        self._theta_cache = (eng, path)
+        return path
+
     def _evaluate(self, params, want_grad, log_offset):
+        eng = self._get_engine(check=False)
+        path = self._theta_path(eng)
+        if path is not None and eng._lazy_sort_in is None:
+            # slots from theta, the fused pass, the chain rule and the extended term in ONE native call
+            full = log_offset is False
+            theta = [p.value() for p in path.indep]
+            value, g = eng.plan.eval_theta(theta, grad=want_grad, full=full, log_offset=0.0 if full else float(log_offset),
+                                           stream=eng._raw_stream())
+            grad = None
+            if want_grad:
+                idx = path.index_of(params)
+                grad = np.where(idx >= 0, g[np.maximum(idx, 0)], 0.0) if len(idx) else np.zeros(0)
+            for c in self.constraints:
+                value += float(c.value())
+                if want_grad:
+                    pos = {id(p): i for i, p in enumerate(params)}
+                    for k, v in c._partials().items():
+                        i = pos.get(id(k))
+                        if i is not None:
+                            grad[i] += v
+            return value, grad
         value, grad = self._nll_channels(want_grad, log_offset)
         extra, egrad = self._extra_terms(want_grad, log_offset)
         value += extra

@@ -779,6 +779,9 @@ class Minuit(BaseMinimizer):
 
         return information
 
+    def _minimize_in_native_code(self, loss, params, steps, evaluator, criterion):
+        return _native_loop_fit(self, loss, params, steps, evaluator, criterion)
+
     def _minimize_native(self, loss, params, init):
         evaluator = self.create_evaluator(loss, params, numpy_converter=np.array)
         criterion = self.create_criterion(loss, params)
@@ -789,6 +792,10 @@ class Minuit(BaseMinimizer):
                 steps[i] = min(steps[i], 0.1 * (p.upper - p.lower))
         # the C++ driver runs unless the Python statement of the same algorithm is asked for (or its per-iteration trace)
         use_python = self.minimizer_options.get("driver") == "python" or self.verbosity > 6
+        if not use_python and not self.minuit_grad and self.minimizer_options.get("native_loop", True):
+            res = self._minimize_in_native_code(loss, params, steps, evaluator, criterion)
+            if res is not None:
+                return res
         driver = _migrad if use_python else _migrad_native
         res = driver.minimize(
             evaluator.value, grad, [p.value() for p in params], steps, [p.lower for p in params],
@@ -806,6 +813,59 @@ class Minuit(BaseMinimizer):
                   "n_pass": evaluator.npass, "n_iter": res.niter,
                   "driver": ("python-migrad" if driver is _migrad else "native-migrad (C++)") + " (iminuit not installed)"},
         )
+
+
+def _native_loop_fit(minimizer, loss, params, steps, evaluator, criterion):
+    """The whole MIGRAD minimisation inside ``libznll.so`` (``znll_migrad_theta``) when the loss has the C-level theta
+    path (built-in parameter kinds, no constraints, CUDA engine) and the minimizer's strategy is the default one: the
+    driver, the slot map, the chain rule and the extended term are all native, so no interpreter runs between the
+    fit's first and last fused pass.  Returns None when that does not apply or an evaluation was not finite -- the
+    evaluator route with its NaN strategy then runs from the same start values."""
+    from .loss import CudaEngine
+
+    if type(minimizer.strategy) is not DefaultStrategy or getattr(loss, "constraints", None) or not hasattr(loss, "_theta_path"):
+        return None
+    if evaluator.do_print:
+        return None
+    try:
+        loss.check_precompile()
+        eng = loss._get_engine()
+    except Exception:
+        return None
+    if not isinstance(eng, CudaEngine) or eng._lazy_sort_in is not None:
+        return None
+    if eng.distributed:  # the metric seed (information matrix) is all-reduced by the Python route; the native loop's is rank-local
+        return None
+    path = loss._theta_path(eng)
+    if path is None:
+        return None
+    idx = path.index_of(params)
+    if np.any(idx < 0):
+        return None
+    log_offset = loss.options.get("subtr_const_value", False)
+    full = log_offset is False or log_offset is None
+    theta0 = np.array([p.value() for p in path.indep], dtype=np.float64)
+    start = theta0[idx].copy()
+    launches0 = eng.launch_count()
+    res, theta = _migrad_native.minimize_theta(
+        eng.plan, idx, theta0, steps, [p.lower for p in params], [p.upper for p in params], edm_goal=minimizer.tol,
+        maxfcn=evaluator.maxiter or 100000, hesse=minimizer.mode >= 1, full=full, log_offset=0.0 if full else float(log_offset),
+        use_information=True, stream=eng._raw_stream())
+    if res is None:
+        assign_values(params, start)
+        return None
+    assign_values(params, res.x)
+    criterion.last_value = res.edm
+    npass = (eng.launch_count() - launches0) // max(1, len(loss.model))
+    evaluator._nfunc_eval, evaluator._ngrad_eval, evaluator.npass = int(res.nfcn), int(res.ngrad), int(npass)
+    return FitResult(
+        loss=loss, params=dict(zip(params, res.x)), minimizer=minimizer.copy(), valid=res.valid, converged=res.converged,
+        edm=res.edm, fminopt=res.fval, message=res.message, criterion=criterion,
+        approx={"inv_hessian": res.covariance * (2.0 * loss.errordef), "gradient": res.grad}, evaluator=evaluator,
+        info={"n_eval": max(int(res.nfcn), int(res.ngrad)), "n_value": int(res.nfcn), "n_gradient": int(res.ngrad),
+              "n_pass": int(npass), "n_iter": res.niter,
+              "driver": "native-migrad (C++), whole fit in native code (iminuit not installed)"},
+    )
 
 
 class ScipyBaseMinimizer(BaseMinimizer):
