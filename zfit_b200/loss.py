@@ -52,6 +52,8 @@ class CudaEngine:
     of the raw ``sum(1 + n_slots)`` fp64 accumulators per call, issued on the launch stream).
     """
 
+    is_cuda_engine = True  # (test doubles with the same interface lack it: no C-level theta path, no native fit loop)
+
     def __init__(self, models, datas, fit_ranges, *, device=None, sort_events=True, deterministic_reduce=False,
                  distributed=None, fused_reduce=True):
         from . import _znll as Z
@@ -739,7 +741,7 @@ class BaseLoss:
         if cached is not None and cached[0] is eng:
             return cached[1]
         path = None
-        if (isinstance(eng, CudaEngine) and self._options.get("theta_path", True)
+        if (getattr(eng, "is_cuda_engine", False) and self._options.get("theta_path", True)
                 and (not eng.distributed or eng.reduce_mode == "fused-nvlink")):
             path = _build_theta_path(self, eng)
         self._theta_cache = (eng, path)
@@ -748,7 +750,7 @@ class BaseLoss:
     def _evaluate(self, params, want_grad, log_offset):
         eng = self._get_engine(check=False)
         path = self._theta_path(eng)
-        if path is not None and eng._lazy_sort_in is None:
+        if path is not None and getattr(eng, "_lazy_sort_in", None) is None:
             # slots from theta, the fused pass, the chain rule and the extended term in ONE native call
             full = log_offset is False
             theta = [p.value() for p in path.indep]

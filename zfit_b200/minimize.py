@@ -821,8 +821,6 @@ def _native_loop_fit(minimizer, loss, params, steps, evaluator, criterion):
     driver, the slot map, the chain rule and the extended term are all native, so no interpreter runs between the
     fit's first and last fused pass.  Returns None when that does not apply or an evaluation was not finite -- the
     evaluator route with its NaN strategy then runs from the same start values."""
-    from .loss import CudaEngine
-
     if type(minimizer.strategy) is not DefaultStrategy or getattr(loss, "constraints", None) or not hasattr(loss, "_theta_path"):
         return None
     if evaluator.do_print:
@@ -832,7 +830,7 @@ def _native_loop_fit(minimizer, loss, params, steps, evaluator, criterion):
         eng = loss._get_engine()
     except Exception:
         return None
-    if not isinstance(eng, CudaEngine) or eng._lazy_sort_in is not None:
+    if not getattr(eng, "is_cuda_engine", False) or eng._lazy_sort_in is not None:
         return None
     if eng.distributed:  # the metric seed (information matrix) is all-reduced by the Python route; the native loop's is rank-local
         return None
