@@ -112,6 +112,8 @@ void run_nll(const double* const* cols, const double* w, long long n, const doub
 #endif
   const long long nthreads = nvec < T ? (nvec > 0 ? nvec : 1) : T;
   double* accs = new double[nthreads * NACC]();
+  double* prods = new double[nthreads];
+  for (long long t = 0; t < nthreads; ++t) prods[t] = 1.0;
   for (long long i = 0; i < nvec; ++i) {
     double* acc = accs + (i % nthreads) * NACC;
     D2 x[ZNLL_MAXCOL], wv;
@@ -121,8 +123,20 @@ void run_nll(const double* const* cols, const double* w, long long n, const doub
       wv.a = w[2 * i];
       wv.b = w[2 * i + 1];
     }
+#ifdef ZNLL_HAS_SPLIT
+    if constexpr (M::HAS_MULT && !W) {  // the running-product form of nll_kernel's pair loop (event_split)
+      double& prod = prods[i % nthreads];
+      acc[0] += event_split<M, D2, G>(HOSTSIM_PAIR_CTX(cx), c, x, HOSTSIM_PAIR_OFFSET(off), acc, prod);
+      if (!prod_in_range(prod)) fold_product(acc, prod);
+      continue;
+    }
+#endif
     HOSTSIM_PAIR_ADD(acc, pair_term(event<M, D2, W, G>(HOSTSIM_PAIR_CTX(cx), c, x, wv, HOSTSIM_PAIR_OFFSET(off), acc)));
   }
+#ifdef ZNLL_HAS_SPLIT
+  if constexpr (M::HAS_MULT && !W)
+    for (long long t = 0; t < nthreads; ++t) fold_product(accs + t * NACC, prods[t]);
+#endif
   if (n & 1) {  // thread 0 of block 0
     double xa[ZNLL_MAXCOL];
     for (int k = 0; k < ZNLL_MAXCOL; ++k)
@@ -140,6 +154,7 @@ void run_nll(const double* const* cols, const double* w, long long n, const doub
     out[j] = v;
   }
   delete[] accs;
+  delete[] prods;
 }
 // the body of hess_kernel (one thread owns all events): raw accumulators of the exact-Hessian pass
 #ifdef ZNLL_HAS_OPTIMISTIC

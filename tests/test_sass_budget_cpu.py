@@ -26,10 +26,12 @@ BUDGET = {
     # 32-bit pair index, table addresses in registers); round 1 had (94, 311), (109, 325), (111, 341), (170, 513)
     # (every tree now streams its columns through a cp.async ring whose loop body exists once: a few more address
     # instructions per pair than the register prefetch, paid back several times over by the hidden HBM latency)
-    "nll_kernel<znll::Sum<znll::CBall<0>,znll::Expo<0>>,false,true>": (86, 270),  # cfg 2, pair on the Gaussian core
-    "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,false,true>": (105, 305),  # cfg 3
+    # (unweighted trees: split evaluation -- the root log's arguments go into a running product per thread, one log per
+    # few hundred pairs instead of one per event; before it cfg 2 / 3 / 4 stood at (86, 270), (105, 305), (81, 239))
+    "nll_kernel<znll::Sum<znll::CBall<0>,znll::Expo<0>>,false,true>": (68, 215),  # cfg 2, pair on the Gaussian core
+    "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,false,true>": (88, 250),  # cfg 3
     "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,true,true>": (107, 315),  # cfg 5 (weighted)
-    "nll_kernel<znll::Prod<znll::Gauss<0>,znll::Expo<1>,znll::Poly<2,4,0>>,false,true>": (81, 239),  # cfg 4, ONE pair
+    "nll_kernel<znll::Prod<znll::Gauss<0>,znll::Expo<1>,znll::Poly<2,4,0>>,false,true>": (63, 187),  # cfg 4, ONE pair
 }
 
 
@@ -58,7 +60,7 @@ def test_event_loop_stays_within_its_instruction_budget(kernels, name):
         if cycles is None or cycles > 50_000:  # loops whose every path holds a rare-path marker (table fill)
             continue
         dp = sum(1 for _, op, _ in path if op.split(".")[0] in S.DP_OPS)
-        if dp >= 60 and (best is None or dp > best[0]):  # the event loop is the one long DP-heavy loop
+        if dp >= 50 and (best is None or dp > best[0]):  # the event loop is the one long DP-heavy loop
             best = (dp, cycles, len(path))
     assert best is not None, "event loop not found"
     dp, cycles, n = best

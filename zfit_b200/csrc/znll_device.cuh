@@ -163,6 +163,8 @@ template <class M, class V>
 ZNLL_DEV V zsel(M m, V x, V y) {
   return Lanes<V>::make(la(m) ? la(x) : la(y), lb(m) ? lb(x) : lb(y));
 }
+ZNLL_DEV double zlaneprod(double x) { return x; }
+ZNLL_DEV double zlaneprod(D2 x) { return x.a * x.b; }
 // a value the compiler must treat as new (blocks common-subexpression hoisting across a branch)
 ZNLL_DEV double opaque(double x) {
 #if defined(__CUDA_ARCH__)
@@ -400,6 +402,7 @@ struct MathTabs {
   double exp2[ZNLL_TAB_N];  // 2^(j/ZNLL_TAB_N)
 };
 #define ZNLL_HAS_OPTIMISTIC 1  // (tests/hostsim keys on this to drive the pair loop the way nll_kernel does)
+#define ZNLL_HAS_SPLIT 1       // (... and on this for the running-product form of the pair loop)
 // Evaluation context of one thread: where the tables are, and HOW out-of-range arguments are handled.
 //   careful = true : every elementary function tests its argument and answers an out-of-range one (|x| >= 700 for exp;
 //                    non-positive, subnormal, huge, inf or NaN for log / reciprocal) through libdevice on the spot --
@@ -617,6 +620,12 @@ ZNLL_DEV void log_eps_rcp(V p, const Ctx& cx, V& lg, V& rc) {
   if (WANT_RCP) rc = rcp_core(p);
 }
 
+// a factor of the running product of the split evaluation: positive, within [2^-200, 2^200)
+ZNLL_DEV bool mult_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x33700000) < 0x19000000u; }
+// the running product itself: positive, within [2^-512, 2^512) -- one more factor pair (each within 2^+-400) cannot overflow it
+ZNLL_DEV bool prod_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x1FF00000) < 0x40000000u; }
+ZNLL_DEV bool below_m600(double x) { return (unsigned)__double2hiint(x) > 0xC082C000u; }  // x < -600 (incl. -inf, negative NaN)
+
 // every thread fills its share of the tables, then __syncthreads() by the caller
 ZNLL_DEV void init_tabs(MathTabs& tabs) {
   for (int j = threadIdx.x; j < ZNLL_TAB_N; j += ZNLL_BLOCK) {
@@ -675,6 +684,12 @@ struct GaussN {
     t = zfma(x[COL], c[CO + 0], c[CO + 1]);  // x/sigma - mu/sigma (tfp Normal._log_prob)
     return zfma(zmul(t, -0.5), t, c[CO + 2]);
   }
+  // split evaluation (ln P = add + ln mult): a log-native leaf only adds
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V&) {
+    Mask neg;
+    return fwd_log<CO>(cx, c, x, neg);
+  }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
@@ -709,6 +724,7 @@ struct Gauss {
   static constexpr int ROOT = 0;
   static constexpr int NH = 3;                     // second-order accumulators: upper triangle over the node's slots
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;  // does log-space evaluation look up the exp / log tables?
   template <class V>
   using Node = GaussN<COL, V>;
@@ -731,6 +747,12 @@ struct TGaussN {
     out = Lanes<V>::mask(la(x[COL]) < low || la(x[COL]) > high, lb(x[COL]) < low || lb(x[COL]) > high);
     // a huge negative log stands for "probability zero": exp() gives 0, sums and differences stay finite
     return zsel(out, zbc<V>(-1e300), zfma(zmul(t, -0.5), t, c[CO + 2]));
+  }
+  // split evaluation (ln P = add + ln mult): a log-native leaf only adds
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V&) {
+    Mask neg;
+    return fwd_log<CO>(cx, c, x, neg);
   }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
@@ -756,6 +778,7 @@ struct TGauss {
   static constexpr int ROOT = 0;
   static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;
   template <class V>
   using Node = TGaussN<COL, V>;
@@ -771,6 +794,12 @@ struct ExpoN {
   ZNLL_DEV V fwd_log(const Ctx&, const double* __restrict__ c, const V* x, Mask&) {
     xs = zsub(x[COL], c[CO + 1]);
     return zfma(xs, c[CO + 0], c[CO + 2]);
+  }
+  // split evaluation (ln P = add + ln mult): a log-native leaf only adds
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V&) {
+    Mask neg;
+    return fwd_log<CO>(cx, c, x, neg);
   }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
@@ -798,6 +827,7 @@ struct Expo {
   static constexpr int ROOT = 0;
   static constexpr int NH = 1;
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;
   template <class V>
   using Node = ExpoN<COL, V>;
@@ -832,6 +862,12 @@ struct CBallN {
     const V lp_tail = zfma(lu, -c[CO + 4], c[CO + 6]);
     mdt = zsel(tail, mdtt, t);
     return zsel(tail, lp_tail, lp_core);
+  }
+  // split evaluation (ln P = add + ln mult): a log-native leaf only adds
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V&) {
+    Mask neg;
+    return fwd_log<CO>(cx, c, x, neg);
   }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
@@ -920,6 +956,7 @@ struct CBall {
   static constexpr int ROOT = 0;
   static constexpr int NH = 10;
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = true;
   template <class V>
   using Node = CBallN<COL, V>;
@@ -939,6 +976,12 @@ struct GETailN {
     tail = zlt(t, -c[CO + 3]);
     dt = zsel(tail, zbc<V>(c[CO + 3]), zneg(t));  // d ln v / d t
     return zsel(tail, zfma(t, c[CO + 3], c[CO + 4]), zfma(zmul(t, -0.5), t, c[CO + 5]));
+  }
+  // split evaluation (ln P = add + ln mult): a log-native leaf only adds
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V&) {
+    Mask neg;
+    return fwd_log<CO>(cx, c, x, neg);
   }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
@@ -965,6 +1008,7 @@ struct GETail {
   static constexpr int ROOT = 0;
   static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;
   template <class V>
   using Node = GETailN<COL, V>;
@@ -994,6 +1038,12 @@ struct GGETailN {
     tail = Lanes<V>::mask(la(t) < -la(a), lb(t) < -lb(a));
     dt = zsel(tail, a, zneg(t));
     return zsel(tail, zfma(t, a, side<3>(cc)), zfma(zmul(t, -0.5), t, cc[1]));
+  }
+  // split evaluation (ln P = add + ln mult): a log-native leaf only adds
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V&) {
+    Mask neg;
+    return fwd_log<CO>(cx, c, x, neg);
   }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
@@ -1026,6 +1076,7 @@ struct GGETail {
   static constexpr int ROOT = 0;
   static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;
   template <class V>
   using Node = GGETailN<COL, V>;
@@ -1104,6 +1155,14 @@ struct PolyN {
     neg = mxor(neg, ng);
     return lg;
   }
+  // split evaluation (optimistic sweep only): the value goes into the pair's running product instead of through a log
+  template <int CO>
+  ZNLL_DEV void fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V& mult) {
+    const V p = fwd_val<CO>(cx, c, x);
+    flag_unless(cx, mult_in_range(la(p)) && mult_in_range(lb(p)));
+    rP = rcp_core(p);
+    mult = zmul(mult, p);
+  }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     const V ai = zmul(a, c[CO + 2]);
@@ -1128,6 +1187,7 @@ struct Poly {
   static constexpr int ROOT = 0;
   static constexpr int NH = 0;
   static constexpr bool LOGNAT = false;
+  static constexpr bool HAS_ADD = false, HAS_MULT = true;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = true;
   template <class V>
   using Node = PolyN<COL, DEG, KIND, V>;
@@ -1186,6 +1246,12 @@ struct GCBallN {
     dt = zsel(tail, dtt, zneg(t));
     return zsel(tail, lp_tail, lp_core);
   }
+  // split evaluation (ln P = add + ln mult): a log-native leaf only adds
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V&) {
+    Mask neg;
+    return fwd_log<CO>(cx, c, x, neg);
+  }
   template <int CO>
   ZNLL_DEV V fwd_val(const Ctx& cx, const double* __restrict__ c, const V* x) {
     Mask neg;
@@ -1223,6 +1289,7 @@ struct GCBall {
   static constexpr int ROOT = 0;
   static constexpr int NH = 0;
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = true;
   template <class V>
   using Node = GCBallN<COL, V>;
@@ -1238,6 +1305,7 @@ struct Meta<> {
   static constexpr int NS = 0, NC = 0, COLMASK = 0, NH = 0;
   static constexpr bool TABS = false;
   static constexpr bool FLATHESS = true;  // every child is a leaf the Hessian pass knows
+  static constexpr bool ANY_ADD = false, ANY_MULT = false;
 };
 template <class H, class... T>
 struct Meta<H, T...> {
@@ -1247,6 +1315,7 @@ struct Meta<H, T...> {
   static constexpr bool TABS = H::TABS || Meta<T...>::TABS;
   static constexpr int NH = H::NH + Meta<T...>::NH;
   static constexpr bool FLATHESS = H::LEAF && H::HESS && Meta<T...>::FLATHESS;
+  static constexpr bool ANY_ADD = H::HAS_ADD || Meta<T...>::ANY_ADD, ANY_MULT = H::HAS_MULT || Meta<T...>::ANY_MULT;
 };
 
 template <class V, class... Cs>
@@ -1303,6 +1372,13 @@ struct SumN {
     fast_logabs_rcp(v, cx, lg, rP, ng);
     neg = mxor(neg, ng);
     return lg;
+  }
+  template <int CO>
+  ZNLL_DEV void fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V& mult) {
+    const V v = fwd_val<CO>(cx, c, x);
+    flag_unless(cx, mult_in_range(la(v)) && mult_in_range(lb(v)));
+    rP = rcp_core(v);
+    mult = zmul(mult, v);
   }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
@@ -1380,6 +1456,23 @@ struct SumLseN {
     P = zsel(neg, zneg(e), e);
     return P;
   }
+  // split evaluation (optimistic sweep only): ln P = l1 + ln S with S handed to the pair's running product -- no log
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V& mult) {
+    Mask n0 = Lanes<V>::mask(false, false), n1 = n0;  // (a negative factor inside a child has flagged the pair already)
+    const V l0 = k0.template fwd_log<CO + 2>(cx, c, x, n0);
+    const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
+    const V d = zsub(l0, l1);
+    flag_unless(cx, lse_in_range(la(d)) && lse_in_range(lb(d)));
+    const V e = exp_core(d, cx);
+    const V S = zfma(e, c[CO + 0], c[CO + 1]);
+    flag_unless(cx, mult_in_range(la(S)) && mult_in_range(lb(S)));
+    const V rS = rcp_core(S);
+    q0 = zmul(e, rS);
+    q1 = rS;
+    mult = zmul(mult, S);
+    return l1;
+  }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_log(V g, const double* __restrict__ c, A* acc) {
     const V g0 = zmul(g, q0), g1 = zmul(g, q1);
@@ -1425,6 +1518,7 @@ struct Sum {
   static constexpr int NS = K + Meta<Cs...>::NS, NC = K + Meta<Cs...>::NC;
   static constexpr int COLMASK = Meta<Cs...>::COLMASK;
   static constexpr bool LOGNAT = AllLog<Cs...>::value;
+  static constexpr bool HAS_ADD = AllLog<Cs...>::value, HAS_MULT = true;  // log-sum-exp: l1 + ln S; value-space sum: ln P
   static constexpr bool TABS = true;
   static constexpr bool LEAF = false, HESS = Meta<Cs...>::FLATHESS;  // flat Sum of leaves
   static constexpr int NH = Meta<Cs...>::NH;
@@ -1456,6 +1550,29 @@ struct ProdN {
       bwd_rec<CK + KD::Head::NC, AK + KD::Head::NS>(kd.t, g, c, acc);
     }
   }
+  // split evaluation: log-native factors add, value-space factors (polynomials, value-space sums) multiply
+  template <int CK, bool STARTED, class KD>
+  ZNLL_DEV void split_rec(KD& kd, const Ctx& cx, const double* __restrict__ c, const V* x, V& add, V& mult) {
+    if constexpr (KD::N > 0) {
+      if constexpr (KD::Head::HAS_ADD) {
+        const V a = kd.h.template fwd_split<CK>(cx, c, x, mult);
+        if constexpr (STARTED)
+          add = zadd(add, a);
+        else
+          add = a;
+        split_rec<CK + KD::Head::NC, true>(kd.t, cx, c, x, add, mult);
+      } else {
+        kd.h.template fwd_split<CK>(cx, c, x, mult);
+        split_rec<CK + KD::Head::NC, STARTED>(kd.t, cx, c, x, add, mult);
+      }
+    }
+  }
+  template <int CO>
+  ZNLL_DEV V fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V& mult) {
+    V add = zbc<V>(0.0);  // overwritten by the first adding factor (HAS_ADD says whether there is one)
+    split_rec<CO, false>(kids, cx, c, x, add, mult);
+    return add;
+  }
   template <int CO>
   ZNLL_DEV V fwd_log(const Ctx& cx, const double* __restrict__ c, const V* x, Mask& neg) {
     V tot = kids.h.template fwd_log<CO>(cx, c, x, neg);  // at least one factor
@@ -1483,6 +1600,7 @@ struct Prod {
   static constexpr int NS = Meta<Cs...>::NS, NC = Meta<Cs...>::NC;
   static constexpr int COLMASK = Meta<Cs...>::COLMASK;
   static constexpr bool LOGNAT = true;
+  static constexpr bool HAS_ADD = Meta<Cs...>::ANY_ADD, HAS_MULT = Meta<Cs...>::ANY_MULT;
   static constexpr bool TABS = Meta<Cs...>::TABS;
   static constexpr bool LEAF = false, HESS = Meta<Cs...>::FLATHESS;  // flat Product of leaves
   static constexpr int NH = Meta<Cs...>::NH;
@@ -1672,6 +1790,41 @@ ZNLL_DEV double event(const Ctx& cx0, const double* __restrict__ c, const V* x, 
     term = term_of(l);
   }
   return term;
+}
+
+// Split evaluation of an unweighted pair in the optimistic sweep (round 2): ln P = add + ln(mult), where `mult` -- the
+// argument of the root's logarithm: S of a log-sum-exp, P of a value-space sum, the polynomial factors of a product -- is
+// NOT put through a log per event but multiplied into the thread's running product `prod`; the thread takes ONE log of
+// that product when its exponent drifts out of [2^-512, 2^512) and at the end of its loop (sum of logs = log of the
+// product; the rounding error of n factors, ~sqrt(n) 1.1e-16 relative, is that of n rounded logs).  This removes the
+// per-event log (11 DP + ~12 integer instructions per lane) from every unweighted tree with a Sum or a polynomial in it;
+// the gradient still needs 1/mult per event (rcp_core).  Weighted data needs w_i ln(mult_i) and keeps the per-event log.
+// Every factor must be positive and within [2^-200, 2^200), every add above -600 (so that ln P > -690 and the +1e-307 of
+// loss.py:117 is invisible); anything else flags the pair, which is then evaluated carefully, event by event, through
+// event<>() -- `prod` untouched.  Returns the pair's additive term (sum over lanes of add, minus `off`).
+template <class M, class V, bool GRAD, class A>
+ZNLL_DEV double event_split(const Ctx& cx0, const double* __restrict__ c, const V* x, double off, A* acc, double& prod) {
+  typename M::template Node<V> m;
+  cx0.bad = 0u;
+  V mult = zbc<V>(1.0);
+  double term;
+  if constexpr (M::HAS_ADD) {
+    const V add = m.template fwd_split<0>(cx0, c, x, mult);
+    flag_unless(cx0, !(below_m600(la(add)) | below_m600(lb(add))));
+    term = zsum_minus(add, off);
+  } else {
+    m.template fwd_split<0>(cx0, c, x, mult);
+    term = -off;
+  }
+  if (cx0.bad != 0u) return event<M, V, false, GRAD>(with_mode(cx0, true), c, x, zbc<V>(1.0), off, acc);  // rare
+  if constexpr (GRAD) m.template bwd_log<0, 2>(zbc<V>(1.0), c, acc);
+  prod *= zlaneprod(mult);
+  return term;
+}
+// fold the running product into the value accumulator (rare inside the loop, once at its end)
+ZNLL_DEV void fold_product(double* acc, double& prod) {
+  acc[0] += log(prod);
+  prod = 1.0;
 }
 
 ZNLL_DEV void kahan_add(double* acc, double term) {
@@ -1888,6 +2041,18 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
   const double* __restrict__ c = args.c;
+  // unweighted trees whose root takes a log (a Sum, a polynomial factor): the log's arguments go into a running product
+  // per thread instead (event_split)
+  constexpr bool SPLIT = M::HAS_MULT && !WEIGHTED;
+  double prod = 1.0;
+  auto do_pair = [&](const EventPair<M, WEIGHTED>& p) {
+    if constexpr (SPLIT) {
+      acc[0] += event_split<M, D2, GRAD>(cx, c, p.x, args.log_offset2, acc, prod);
+      if (!prod_in_range(prod)) fold_product(acc, prod);  // rare: every few hundred pairs at most
+    } else {
+      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, args.log_offset2, acc);
+    }
+  };
   const unsigned nvec = (unsigned)(args.n >> 1);
   const unsigned stride = gridDim.x * ZNLL_BLOCK;
   unsigned i = blockIdx.x * ZNLL_BLOCK + threadIdx.x;
@@ -1914,7 +2079,7 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
       if (pre < nvec) ring.issue(stage, args, pre);
       cp_async_commit();
       pre += stride;
-      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, p.x, p.w, args.log_offset2, acc);
+      do_pair(p);
       i += stride;
       stage = (stage + 1 == STAGES) ? 0 : stage + 1;
     }
@@ -1927,11 +2092,11 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
     while (i < nvec) {
       i += stride;
       if (i < nvec) b1.load(args, i);
-      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, b0.x, b0.w, args.log_offset2, acc);
+      do_pair(b0);
       if (i >= nvec) break;
       i += stride;
       if (i < nvec) b0.load(args, i);
-      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, b1.x, b1.w, args.log_offset2, acc);
+      do_pair(b1);
     }
   } else {
     EventPair<M, WEIGHTED> cur, nxt;
@@ -1942,9 +2107,10 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const 
       i += stride;
       more = i < nvec;
       if (more) nxt.load(args, i);  // software prefetch: the next pair is in flight while this one computes
-      acc[0] += event<M, D2, WEIGHTED, GRAD>(cx, c, cur.x, cur.w, args.log_offset2, acc);
+      do_pair(cur);
     }
   }
+  if constexpr (SPLIT) fold_product(acc, prod);
   if ((args.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail event: scalar, careful instantiation
     double xa[ZNLL_MAXCOL];
 #pragma unroll
