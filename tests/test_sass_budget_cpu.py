@@ -27,11 +27,12 @@ BUDGET = {
     # (every tree now streams its columns through a cp.async ring whose loop body exists once: a few more address
     # instructions per pair than the register prefetch, paid back several times over by the hidden HBM latency)
     # (unweighted trees: split evaluation -- the root log's arguments go into a running product per thread, one log per
-    # few hundred pairs instead of one per event; before it cfg 2 / 3 / 4 stood at (86, 270), (105, 305), (81, 239))
-    "nll_kernel<znll::Sum<znll::CBall<0>,znll::Expo<0>>,false,true>": (68, 215),  # cfg 2, pair on the Gaussian core
-    "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,false,true>": (88, 250),  # cfg 3
+    # few hundred pairs instead of one per event --, pair reciprocals from one rcp, range tests as running maxima;
+    # before these cfg 2 / 3 / 4 stood at (86, 270), (105, 305), (81, 239))
+    "nll_kernel<znll::Sum<znll::CBall<0>,znll::Expo<0>>,false,true>": (66, 205),  # cfg 2, pair on the Gaussian core
+    "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,false,true>": (86, 244),  # cfg 3
     "nll_kernel<znll::Sum<znll::Gauss<0>,znll::Poly<0,4,0>>,true,true>": (107, 315),  # cfg 5 (weighted)
-    "nll_kernel<znll::Prod<znll::Gauss<0>,znll::Expo<1>,znll::Poly<2,4,0>>,false,true>": (63, 187),  # cfg 4, ONE pair
+    "nll_kernel<znll::Prod<znll::Gauss<0>,znll::Expo<1>,znll::Poly<2,4,0>>,false,true>": (61, 181),  # cfg 4, ONE pair
 }
 
 

@@ -422,7 +422,12 @@ struct Ctx {
   const double* exptab;
 #endif
   bool careful;
-  mutable unsigned bad;
+  // optimistic sweep: running maxima of the range-test operands, one per KIND of test; any_flag() compares each with its
+  // bound once per pair.  (An accumulated 0/1 flag cost a compare, a select and an OR per call site.)
+  mutable unsigned chk_abs;   // |x| < 600        : high word with the sign cleared            (exp arguments, l0 - l1)
+  mutable unsigned chk_mult;  // 2^-200 <= x < 2^200 : high word - 0x33700000 (factors of the running product)
+  mutable unsigned chk_pos;   // 2^-958 <= x < 2^1022: high word - 0x04100000 (arguments of log / reciprocal)
+  mutable unsigned chk_add;   // x >= -600         : high word as it is                         (log-density terms)
 };
 ZNLL_DEV double tab_exp2(const Ctx& cx, int n) {  // 2^((n mod N)/N)
 #if defined(__CUDA_ARCH__)
@@ -442,8 +447,30 @@ ZNLL_DEV double2 tab_log(const Ctx& cx, int j) {  // (1/c_j, log c_j), j already
   return cx.logtab[j];
 #endif
 }
-ZNLL_DEV void flag_unless(const Ctx& cx, bool ok) { cx.bad |= ok ? 0u : 1u; }
+ZNLL_DEV unsigned umax2(unsigned a, unsigned b) { return a > b ? a : b; }
+ZNLL_DEV unsigned umax3(unsigned a, unsigned b, unsigned c) { return umax2(a, umax2(b, c)); }
+ZNLL_DEV unsigned hi_of(double x) { return (unsigned)__double2hiint(x); }
+ZNLL_DEV void reset_flags(const Ctx& cx) { cx.chk_abs = cx.chk_mult = cx.chk_pos = cx.chk_add = 0u; }
+ZNLL_DEV bool any_flag(const Ctx& cx) {
+  return (cx.chk_abs >= 0x4082C000u) | (cx.chk_mult >= 0x19000000u) | (cx.chk_pos >= 0x7bc00000u) | (cx.chk_add > 0xC082C000u);
+}
 
+template <class V>
+ZNLL_DEV void flag_abs600(const Ctx& cx, V x) {
+  cx.chk_abs = umax3(cx.chk_abs, hi_of(la(x)) & 0x7fffffffu, hi_of(lb(x)) & 0x7fffffffu);
+}
+template <class V>
+ZNLL_DEV void flag_mult(const Ctx& cx, V x) {
+  cx.chk_mult = umax3(cx.chk_mult, hi_of(la(x)) - 0x33700000u, hi_of(lb(x)) - 0x33700000u);
+}
+template <class V>
+ZNLL_DEV void flag_pos(const Ctx& cx, V x) {
+  cx.chk_pos = umax3(cx.chk_pos, hi_of(la(x)) - 0x04100000u, hi_of(lb(x)) - 0x04100000u);
+}
+template <class V>
+ZNLL_DEV void flag_add(const Ctx& cx, V x) {
+  cx.chk_add = umax3(cx.chk_add, hi_of(la(x)), hi_of(lb(x)));
+}
 ZNLL_DEV bool exp_in_range(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x4085E000; }  // |x| < 700
 ZNLL_DEV bool log_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fc00000u; }  // normal, < 2^1022
 // x < -690 read off the high word (the sign bit set and the magnitude above 690; -inf and negative NaNs included)
@@ -489,10 +516,9 @@ ZNLL_DEV V exp_core(V x, const Ctx& cx) {  // |x| < 700
 }
 template <class V>
 ZNLL_DEV V fast_exp(V x, const Ctx& cx) {
-  const bool ok = exp_in_range(la(x)) && exp_in_range(lb(x));
   if (!cx.careful)
-    flag_unless(cx, ok);
-  else if (!ok)
+    flag_abs600(cx, x);
+  else if (!(exp_in_range(la(x)) && exp_in_range(lb(x))))
     return Lanes<V>::make(exp(la(x)), exp(lb(x)));  // rare
   return exp_core(x, cx);
 }
@@ -500,10 +526,9 @@ ZNLL_DEV V fast_exp(V x, const Ctx& cx) {
 // through their operand modifiers)
 template <class V>
 ZNLL_DEV V fast_exp_negabs(V d, const Ctx& cx) {
-  const bool ok = exp_in_range(la(d)) && exp_in_range(lb(d));
   if (!cx.careful)
-    flag_unless(cx, ok);
-  else if (!ok)
+    flag_abs600(cx, d);
+  else if (!(exp_in_range(la(d)) && exp_in_range(lb(d))))
     return Lanes<V>::make(exp(-fabs(la(d))), exp(-fabs(lb(d))));  // rare
   return exp_core(zneg(zabs(d)), cx);
 }
@@ -570,10 +595,9 @@ ZNLL_DEV V log_core(V x, const Ctx& cx) {  // x positive, normal, below 2^1022
 }
 template <class V>
 ZNLL_DEV V fast_log(V x, const Ctx& cx) {
-  const bool ok = log_in_range(la(x)) && log_in_range(lb(x));
   if (!cx.careful)
-    flag_unless(cx, ok);
-  else if (!ok)
+    flag_pos(cx, x);
+  else if (!(log_in_range(la(x)) && log_in_range(lb(x))))
     return Lanes<V>::make(log(la(x)), log(lb(x)));  // rare
   return log_core(x, cx);
 }
@@ -584,10 +608,9 @@ ZNLL_DEV V fast_log(V x, const Ctx& cx) {
 ZNLL_DEV bool pos_normal(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fc00000u; }  // [2^-1022, 2^1022)
 template <class V>
 ZNLL_DEV void fast_log_rcp(V x, const Ctx& cx, V& lg, V& rc) {
-  const bool ok = pos_normal(la(x)) && pos_normal(lb(x));
   if (!cx.careful) {
-    flag_unless(cx, ok);
-  } else if (!ok) {  // rare
+    flag_pos(cx, x);
+  } else if (!(pos_normal(la(x)) && pos_normal(lb(x)))) {  // rare
     lg = Lanes<V>::make(log(la(x)), log(lb(x)));
     rc = Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));
     return;
@@ -599,10 +622,9 @@ ZNLL_DEV void fast_log_rcp(V x, const Ctx& cx, V& lg, V& rc) {
 // fractions times pdfs) but whose sign must be tracked when they are not
 template <class V>
 ZNLL_DEV void fast_logabs_rcp(V x, const Ctx& cx, V& lg, V& rc, typename Lanes<V>::Mask& neg) {
-  const bool ok = pos_normal(la(x)) && pos_normal(lb(x));
   if (!cx.careful) {
-    flag_unless(cx, ok);  // a negative x is flagged as well: the optimistic sweep never sees a sign
-  } else if (!ok) {  // rare
+    flag_pos(cx, x);  // a negative x is flagged as well: the optimistic sweep never sees a sign
+  } else if (!(pos_normal(la(x)) && pos_normal(lb(x)))) {  // rare
     lg = Lanes<V>::make(log(fabs(la(x))), log(fabs(lb(x))));
     rc = Lanes<V>::make(1.0 / la(x), 1.0 / lb(x));
     neg = zlt(x, 0.0);
@@ -618,10 +640,9 @@ ZNLL_DEV void fast_logabs_rcp(V x, const Ctx& cx, V& lg, V& rc, typename Lanes<V
 ZNLL_DEV bool pos_not_tiny(double x) { return (unsigned)(__double2hiint(x) - 0x04100000) < 0x7bc00000u; }  // [2^-958, 2^1022)
 template <class V, bool WANT_RCP>
 ZNLL_DEV void log_eps_rcp(V p, const Ctx& cx, V& lg, V& rc) {
-  const bool ok = pos_not_tiny(la(p)) && pos_not_tiny(lb(p));
   if (!cx.careful) {
-    flag_unless(cx, ok);
-  } else if (!ok) {  // rare
+    flag_pos(cx, p);
+  } else if (!(pos_not_tiny(la(p)) && pos_not_tiny(lb(p)))) {  // rare
     const double pa = la(p) + ZNLL_LOG_EPS, pb = lb(p) + ZNLL_LOG_EPS;
     lg = Lanes<V>::make(log(pa), log(pb));
     rc = Lanes<V>::make(1.0 / pa, 1.0 / pb);
@@ -662,13 +683,13 @@ ZNLL_DEV Ctx ctx_of(const MathTabs& tabs, bool careful = true) {
   cx.exptab = tabs.exp2;
 #endif
   cx.careful = careful;
-  cx.bad = 0u;
+  reset_flags(cx);
   return cx;
 }
 ZNLL_DEV Ctx with_mode(const Ctx& cx, bool careful) {
   Ctx r = cx;
   r.careful = careful;
-  r.bad = 0u;
+  reset_flags(r);
   return r;
 }
 // A tree that is evaluated in log space from leaves that need neither exp nor log (a Gauss, an Exponential, products of
@@ -1170,7 +1191,7 @@ struct PolyN {
   template <int CO>
   ZNLL_DEV void fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V& mult) {
     const V p = fwd_val<CO>(cx, c, x);
-    flag_unless(cx, mult_in_range(la(p)) && mult_in_range(lb(p)));
+    flag_mult(cx, p);
     rP = rcp_lanes(p, zlaneprod(p));
     mult = zmul(mult, p);
   }
@@ -1387,7 +1408,7 @@ struct SumN {
   template <int CO>
   ZNLL_DEV void fwd_split(const Ctx& cx, const double* __restrict__ c, const V* x, V& mult) {
     const V v = fwd_val<CO>(cx, c, x);
-    flag_unless(cx, mult_in_range(la(v)) && mult_in_range(lb(v)));
+    flag_mult(cx, v);
     rP = rcp_lanes(v, zlaneprod(v));
     mult = zmul(mult, v);
   }
@@ -1422,11 +1443,10 @@ struct SumLseN {
     const V l0 = k0.template fwd_log<CO + 2>(cx, c, x, n0);
     const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
     const V d = zsub(l0, l1);
-    const bool ok = lse_in_range(la(d)) && lse_in_range(lb(d));
     const V one = zbc<V>(1.0);
     if (!cx.careful) {
-      flag_unless(cx, ok);
-    } else if (!ok) {  // rare: max-based form, exp through libdevice (0 for a huge |d|, NaN stays NaN)
+      flag_abs600(cx, d);
+    } else if (!(lse_in_range(la(d)) && lse_in_range(lb(d)))) {  // rare: max-based form, exp through libdevice (0 for a huge |d|, NaN stays NaN)
       const Mask lt = zsignbit(d);
       const V e = Lanes<V>::make(exp(-fabs(la(d))), exp(-fabs(lb(d))));
       V e0 = zsel(lt, e, one), e1 = zsel(lt, one, e);
@@ -1474,10 +1494,10 @@ struct SumLseN {
     const V l0 = k0.template fwd_log<CO + 2>(cx, c, x, n0);
     const V l1 = k1.template fwd_log<CO + 2 + C0::NC>(cx, c, x, n1);
     const V d = zsub(l0, l1);
-    flag_unless(cx, lse_in_range(la(d)) && lse_in_range(lb(d)));
+    flag_abs600(cx, d);
     const V e = exp_core(d, cx);
     const V S = zfma(e, c[CO + 0], c[CO + 1]);
-    flag_unless(cx, mult_in_range(la(S)) && mult_in_range(lb(S)));
+    flag_mult(cx, S);
     const V rS = rcp_lanes(S, zlaneprod(S));
     q0 = zmul(e, rS);
     q1 = rS;
@@ -1710,7 +1730,7 @@ struct KArgs {
 // the number of lanes, prepared by the caller.
 //
 // With an optimistic context (cx0.careful == false, the step kernels' pair loop) the forward sweep runs the fast cores
-// unconditionally and every range test only sets cx0.bad; ONE test after the sweep decides whether the pair is evaluated
+// unconditionally and every range test only feeds a running maximum; ONE test after the sweep (any_flag) decides whether the pair is evaluated
 // again carefully (out-of-range argument of an exp / log / reciprocal, a negative factor, ln P < -690 where the
 // p + 1e-307 of loss.py:117 matters).  With a careful context only the careful evaluation is instantiated.
 template <class M, class V, bool WEIGHTED, bool GRAD, class A>
@@ -1728,12 +1748,13 @@ ZNLL_DEV double event(const Ctx& cx0, const double* __restrict__ c, const V* x, 
   double term = 0.0;
   bool redo = cx0.careful;
   if (!cx0.careful) {
-    cx0.bad = 0u;
+    reset_flags(cx0);
     V l;
     if constexpr (M::LOGNAT) {
       Mask neg = Lanes<V>::mask(false, false);
       l = m.template fwd_log<0>(cx0, c, x, neg);
-      redo = (cx0.bad != 0u) | below_m690(la(l)) | below_m690(lb(l));
+      flag_add(cx0, l);  // ln P < -600: the careful evaluation decides whether the +1e-307 matters
+      redo = any_flag(cx0);
       if (!redo) {
         term = term_of(l);
         if constexpr (GRAD) {
@@ -1748,7 +1769,7 @@ ZNLL_DEV double event(const Ctx& cx0, const double* __restrict__ c, const V* x, 
       const V P = m.template fwd_val<0>(cx0, c, x);
       V g;
       log_eps_rcp<V, GRAD>(P, cx0, l, g);  // l = log P, g = 1/P: for P >= 2^-958 the sum P + 1e-307 IS P, bit for bit
-      redo = cx0.bad != 0u;
+      redo = any_flag(cx0);
       if (!redo) {
         term = term_of(l);
         if constexpr (GRAD) {
@@ -1816,18 +1837,18 @@ ZNLL_DEV double event(const Ctx& cx0, const double* __restrict__ c, const V* x, 
 template <class M, class V, bool GRAD, class A>
 ZNLL_DEV double event_split(const Ctx& cx0, const double* __restrict__ c, const V* x, double off, A* acc, double& prod) {
   typename M::template Node<V> m;
-  cx0.bad = 0u;
+  reset_flags(cx0);
   V mult = zbc<V>(1.0);
   double term;
   if constexpr (M::HAS_ADD) {
     const V add = m.template fwd_split<0>(cx0, c, x, mult);
-    flag_unless(cx0, !(below_m600(la(add)) | below_m600(lb(add))));
+    flag_add(cx0, add);
     term = zsum_minus(add, off);
   } else {
     m.template fwd_split<0>(cx0, c, x, mult);
     term = -off;
   }
-  if (cx0.bad != 0u) return event<M, V, false, GRAD>(with_mode(cx0, true), c, x, zbc<V>(1.0), off, acc);  // rare
+  if (any_flag(cx0)) return event<M, V, false, GRAD>(with_mode(cx0, true), c, x, zbc<V>(1.0), off, acc);  // rare
   if constexpr (GRAD) m.template bwd_log<0, 2>(zbc<V>(1.0), c, acc);
   prod *= zlaneprod(mult);
   return term;
