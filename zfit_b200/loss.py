@@ -412,9 +412,18 @@ class ThetaPath:
         got = self._index_cache.get(key)
         if got is None:
             pos = {id(p): i for i, p in enumerate(self.indep)}
-            got = np.array([pos.get(id(p), -1) for p in params], dtype=np.int64)
+            idx = np.array([pos.get(id(p), -1) for p in params], dtype=np.int64)
+            got = (idx, bool(np.all(idx >= 0)))
             self._index_cache[key] = got
-        return got
+        return got[0]
+
+    def gather(self, g, params):
+        """d value / d params from the gradient over ``indep`` (0 for a parameter the loss does not depend on)."""
+        self.index_of(params)
+        idx, complete = self._index_cache[tuple(id(p) for p in params)]
+        if complete:
+            return g[idx]
+        return np.where(idx >= 0, g[np.maximum(idx, 0)], 0.0) if len(idx) else np.zeros(0)
 
 
 def _build_theta_path(loss, eng):
@@ -758,8 +767,7 @@ class BaseLoss:
                                            stream=eng._raw_stream())
             grad = None
             if want_grad:
-                idx = path.index_of(params)
-                grad = np.where(idx >= 0, g[np.maximum(idx, 0)], 0.0) if len(idx) else np.zeros(0)
+                grad = path.gather(g, params)
             for c in self.constraints:
                 value += float(c.value())
                 if want_grad:
