@@ -401,14 +401,21 @@ def measure_config(ctx, cfg, args, headline):
         _barrier(ctx)
         launches0 = plan.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with sampler as clocks:
-            t_wall0 = time.perf_counter()
-            e0.record(stream)
-            for k in range(args.steps):
-                step(k)
-            e1.record(stream)
-            _barrier(ctx)
-            t_wall = time.perf_counter() - t_wall0
+        import gc
+
+        gc.collect()
+        gc.disable()  # a collection pause inside an 8 ms timed region is a 10 % outlier; re-enabled right after
+        try:
+            with sampler as clocks:
+                t_wall0 = time.perf_counter()
+                e0.record(stream)
+                for k in range(args.steps):
+                    step(k)
+                e1.record(stream)
+                _barrier(ctx)
+                t_wall = time.perf_counter() - t_wall0
+        finally:
+            gc.enable()
         dev_ms = e0.elapsed_time(e1)
         launches = plan.launch_count() - launches0
     dev_ms, wall_ms = _max_over_ranks(ctx, [dev_ms, t_wall * 1e3])
