@@ -44,6 +44,12 @@ def main():
         sv, sg = single.value_gradient(params, full=True)
         assert abs(v - sv) <= 1e-12 * abs(sv), (v, sv)
         assert np.all(np.abs(g - sg) <= 1e-10 * np.abs(sg).max()), (g, sg)
+        # the one-pass Hessian all-reduces its per-rank results: same matrix as the single-GPU loss on the whole sample
+        H, Hs = nll.hessian(params), single.hessian(params)
+        assert nll.last_hessian_method == "one-pass" and single.last_hessian_method == "one-pass"
+        assert np.all(np.abs(H - Hs) <= 1e-9 * np.sqrt(np.abs(np.outer(np.diag(Hs), np.diag(Hs))))), (H, Hs)
+        # the C-level theta path is active exactly where the reduction is fused into the kernel
+        assert (nll._theta_path(nll._get_engine()) is not None) == (mode == "fused")
         result = zfit.minimize.Minuit(gradient="zfit").minimize(nll)
         fitted = torch.tensor([result.params[p]["value"] for p in result.params], dtype=torch.float64, device=f"cuda:{local_rank}")
         gathered = [torch.empty_like(fitted) for _ in range(world)]
