@@ -82,3 +82,36 @@ def test_native_loop_hands_over_on_a_non_finite_start():
     [p for p in params if p.name.startswith("c2")][0].set_value(-0.999)  # a polynomial that goes negative: NaN events
     res = zfit.minimize.Minuit(gradient="zfit").minimize(loss)
     assert "whole fit" not in res.info.get("driver", "")
+
+
+def test_theta_path_extended_weighted_two_channels_with_constraint():
+    """Every term the native call owns at once: two channels, weights, yields -> fractions, the Poisson terms with sum(w) as
+    the observed count, a constant slot, a shared parameter -- plus a Gaussian constraint added on the Python side."""
+    rng = np.random.default_rng(8)
+    mu = zfit.Parameter("mu_tx", 0.4, -2, 2)
+    sg = zfit.Parameter("sg_tx", 1.2, 0.3, 4)
+    models, datas = [], []
+    for ch in range(2):
+        obs = zfit.Space(f"x{ch}", -6, 6)
+        ns = zfit.Parameter(f"ns_tx{ch}", 3000.0 + 500 * ch, 0, 1e5)
+        nb = zfit.Parameter(f"nb_tx{ch}", 6000.0, 0, 1e5)
+        lam = zfit.Parameter(f"lam_tx{ch}", -0.1 - 0.05 * ch, -2, 2)
+        g = zfit.pdf.Gauss(mu, sg if ch == 0 else 1.5, obs, extended=ns)  # channel 1: a constant width slot
+        e = zfit.pdf.Exponential(lam, obs, extended=nb)
+        models.append(zfit.pdf.SumPDF([g, e]))
+        x = np.concatenate([rng.normal(0.5, 1.3, 3000), rng.uniform(-6, 6, 6000)]).clip(-6, 6)
+        datas.append(zfit.Data(x, obs=obs, weights=rng.normal(1.0, 0.4, x.size)))
+    con = zfit.constraint.GaussianConstraint(mu, 0.45, sigma=0.2)
+    fast = zfit.loss.ExtendedUnbinnedNLL(models, datas, constraints=con)
+    slow = zfit.loss.ExtendedUnbinnedNLL(models, datas, constraints=con, options={"theta_path": False})
+    params = list(fast.get_params())
+    for full in (True, False):
+        v1, g1 = fast.value_gradient(params, full=full)
+        slow.options["subtr_const_value"] = fast.options["subtr_const_value"]
+        v2, g2 = slow.value_gradient(params, full=full)
+        assert fast._theta_path(fast._get_engine()) is not None and slow._theta_path(slow._get_engine()) is None
+        assert abs(v1 - v2) <= 1e-13 * max(abs(v2), 1.0)
+        np.testing.assert_allclose(g1, g2, rtol=1e-12, atol=1e-12 * np.abs(g2).max())
+    # constraints keep the evaluator route for fits (they live in Python); the result must not depend on the route
+    r = zfit.minimize.Minuit(gradient="zfit").minimize(fast)
+    assert r.valid and "whole fit" not in r.info["driver"]
