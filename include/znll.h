@@ -294,7 +294,8 @@ int znll_test_hess_epilogue(const znll_node* nodes, int n_nodes, const double* s
  * znll_plan_set_model does -- from the on-disk cache ($ZNLL_CACHE_DIR, default $XDG_CACHE_HOME/zfit_b200 or
  * ~/.cache/zfit_b200; "" / "off" disables) when use_cache != 0 and a valid file exists, else through NVRTC (and store it).
  * model: instantiation name, e.g. "Sum<Gauss<0>,Gauss<0>,Cheb<0,2>>".  Loading the image needs the driver and is not done. */
-int znll_test_rtc_image(const char* model, int n_slots, int use_cache, size_t* cubin_bytes, int* n_names, int* from_cache);
+int znll_test_rtc_image(const char* model, int n_slots, int hess_nh, int use_cache, size_t* cubin_bytes, int* n_names,
+                        int* from_cache);
 
 /* Test hook: out[i] = f(in[i]) on the device for the kernel's own fp64 elementary functions
  * (kind 0: exp, 1: log, 2: reciprocal), so their accuracy can be checked against libm. */

@@ -40,6 +40,13 @@ CASES = {
     "gauss_cheb": lambda: CS.gauss_cheb_case(n=6001),
     "gauss_cheb_weighted": lambda: CS.gauss_cheb_case(n=6000, weighted=True),
     "product": lambda: CS.product_case(n=6001),
+    "gcb_exp": lambda: CS.gcb_exp_case(n=6001),
+    "get_exp": lambda: CS.get_exp_case(False, n=6001),
+    "gget_exp": lambda: CS.get_exp_case(True, n=6000),
+    "tgauss": lambda: CS.tgauss_case(n=6001),
+    "legendre": lambda: CS.poly_case("legendre", n=4000),
+    "bernstein": lambda: CS.bernstein_case(n=4000),
+    "three_leaves_outside_catalogue": lambda: CS.rtc_case(n=6001),  # on the GPU this tree is built by NVRTC
 }
 
 

@@ -107,6 +107,23 @@ def test_compiled_images_are_cached_on_disk(tmp_path, monkeypatch):
     assert Z.test_rtc_image(tree, n_slots)[1:] == (names, False)
 
 
+def test_flat_trees_outside_the_catalogue_get_the_hessian_kernels(tmp_path, monkeypatch):
+    """A flat tree built at run time carries the two ``hess_kernel`` instantiations too (``znll_plan_set_model`` passes the
+    tree's count of second-order accumulators); the count is part of the cache key, and a tree that needs more than the
+    reduction's 256 accumulators is built without them."""
+    _nvrtc()
+    monkeypatch.setenv("ZNLL_CACHE_DIR", str(tmp_path))
+    tree, n_slots = "Sum<Gauss<0>,Gauss<0>,Cheb<0,2>>", 3 + 2 + 2 + 3
+    size, names, cached = Z.test_rtc_image(tree, n_slots, hess_nh=6)
+    assert names == 9 and not cached
+    plain = Z.test_rtc_image(tree, n_slots)
+    assert plain[1:] == (7, False) and plain[0] < size
+    assert Z.test_rtc_image(tree, n_slots, hess_nh=6) == (size, 9, True)
+    # 2 + (21 + 1)(21 + 2)/2 + 3 = 258 accumulators: neither Hessian nor covariance kernels, the step kernels only
+    wide = "Sum<Gauss<0>,Cheb<0,16>>"
+    assert Z.test_rtc_image(wide, 2 + 2 + 17, hess_nh=3)[1] == 5
+
+
 def test_built_step_kernels_fit_two_blocks_per_sm_without_spills():
     """Resource usage of every kernel in the built ``libznll.so`` (``cuobjdump --dump-resource-usage``, no GPU needed): the
     step kernels are tuned for two resident 256-thread blocks per SM, i.e. at most 128 registers,

@@ -101,7 +101,7 @@ SYMBOLS = {
     "znll_leaf_integral": (C.c_int, [C.POINTER(Node), _DP, _DP, _DP]),
     "znll_test_prologue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.c_char_p, C.c_int]),
-    "znll_test_rtc_image": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "znll_test_rtc_image": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "znll_test_epilogue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_double, _DP, _DP]),
     "znll_test_hess_epilogue": (C.c_int, [C.POINTER(Node), C.c_int, _DP, _DP, C.c_int, C.c_int, _DP, _DP, _DP]),
     "znll_migrad": (C.c_int, None),  # callback pointers and structs: see _migrad_native.py
@@ -382,10 +382,12 @@ def test_prologue(nodes, slots):
     return name.value.decode(), consts[: nc.value].copy()
 
 
-def test_rtc_image(model: str, n_slots: int, use_cache: bool = True):
-    """Host only: (cubin bytes, number of kernels, came from the on-disk cache) for a tree outside the catalogue -- test hook."""
+def test_rtc_image(model: str, n_slots: int, use_cache: bool = True, hess_nh: int = -1):
+    """Host only: (cubin bytes, number of kernels, came from the on-disk cache) for a tree outside the catalogue -- test hook.
+    ``hess_nh`` >= 0: also build the one-pass Hessian kernels of a flat tree with that many second-order accumulators."""
     size, names, cached = C.c_size_t(0), C.c_int(0), C.c_int(0)
-    _check(lib().znll_test_rtc_image(model.encode(), n_slots, int(use_cache), C.byref(size), C.byref(names), C.byref(cached)))
+    _check(lib().znll_test_rtc_image(model.encode(), n_slots, int(hess_nh), int(use_cache), C.byref(size), C.byref(names),
+                                     C.byref(cached)))
     return size.value, names.value, bool(cached.value)
 
 

@@ -163,6 +163,8 @@ template <class M, class V>
 ZNLL_DEV V zsel(M m, V x, V y) {
   return Lanes<V>::make(la(m) ? la(x) : la(y), lb(m) ? lb(x) : lb(y));
 }
+// index of (a, b), a <= b, in the row-major upper triangle of an n x n symmetric matrix
+__host__ __device__ constexpr int tri_index(int a, int b, int n) { return a * n - a * (a - 1) / 2 + (b - a); }
 ZNLL_DEV double zlaneprod(double x) { return x; }
 ZNLL_DEV double zlaneprod(D2 x) { return x.a * x.b; }
 // a value the compiler must treat as new (blocks common-subexpression hoisting across a branch)
@@ -798,6 +800,16 @@ struct TGaussN {
     zacc(acc[AO + 0], gi, t);
     zacc(acc[AO + 1], gi, zfma(t, t, -1.0));
   }
+  // Hessian pass: the Gauss block on (mu, sigma) for events inside [low, high]; low / high only move the normalisation.
+  // h: upper triangle over the four slots.
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__ c, double* h) const {
+    const V t2 = zmul(t, t);
+    const V rs = zsel(out, zbc<V>(0.0), zmul(r, c[CO + 0] * c[CO + 0]));
+    zacc(h[tri_index(0, 0, 4)], rs, zadd(t2, -1.0));
+    zacc(h[tri_index(0, 1, 4)], rs, zmul(t, zadd(t2, -3.0)));
+    zacc(h[tri_index(1, 1, 4)], rs, zfma(t2, zadd(t2, -5.0), 2.0));
+  }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
@@ -806,9 +818,9 @@ struct TGaussN {
 template <int COL>
 struct TGauss {
   static constexpr int NS = 4, NC = 5, COLMASK = 1 << COL;
-  static constexpr bool LEAF = true, HESS = false;
+  static constexpr bool LEAF = true, HESS = true;
   static constexpr int ROOT = 0;
-  static constexpr int NH = 0;
+  static constexpr int NH = 10;
   static constexpr bool LOGNAT = true;
   static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;
@@ -994,6 +1006,51 @@ struct CBall {
   using Node = CBallN<COL, V>;
 };
 
+// Second-order leaf primitive of the piecewise "Gaussian core + tail" shapes, one lane: with ln u = phi(t, a[, n]),
+// t = (x - mu) s / sigma, returns U_xy = d2 ln u / dx dy + (d ln u / dx)(d ln u / dy) over (mu, sigma, a[, n]) as
+// [mm, ms, ma, mn, ss, sa, sn, aa, an, nn] (n entries zero for the exponential tail).  sos = s / sigma, is = 1 / sigma.
+struct TailDerivs {
+  double pt, ptt, pta, ptn, paa, pan, pnn, da, dn;  // partial derivatives of phi; da, dn = d phi / da, d phi / dn
+};
+ZNLL_DEV void tail_block(const TailDerivs& d, double tau, double sos, double is, double* U) {
+  const double tm = -sos, ts = -tau * is, tms = sos * is, tss = 2.0 * tau * is * is;
+  const double dm = d.pt * tm, ds = d.pt * ts;
+  U[0] = d.ptt * tm * tm + dm * dm;
+  U[1] = d.ptt * tm * ts + d.pt * tms + dm * ds;
+  U[2] = d.pta * tm + dm * d.da;
+  U[3] = d.ptn * tm + dm * d.dn;
+  U[4] = d.ptt * ts * ts + d.pt * tss + ds * ds;
+  U[5] = d.pta * ts + ds * d.da;
+  U[6] = d.ptn * ts + ds * d.dn;
+  U[7] = d.paa + d.da * d.da;
+  U[8] = d.pan + d.da * d.dn;
+  U[9] = d.pnn + d.dn * d.dn;
+}
+// power-law tail of the CrystalBall family: phi = n ln(n/a) - a^2/2 - n ln(B - t), B = n/a - a; iv = 1/(B - t), lv = ln(B - t)
+ZNLL_DEV TailDerivs cb_tail_derivs(double a, double n, double iv, double lv) {
+  TailDerivs d;
+  const double Ba = -(n / (a * a) + 1.0), Bn = 1.0 / a;
+  d.pt = n * iv;
+  d.ptt = n * iv * iv;
+  d.pta = -d.ptt * Ba;
+  d.ptn = iv - d.ptt * Bn;
+  d.da = -n / a - a - d.pt * Ba;
+  d.dn = log(n / a) + 1.0 - lv - d.pt * Bn;
+  d.paa = n / (a * a) - 1.0 + d.ptt * Ba * Ba - d.pt * (2.0 * n / (a * a * a));
+  d.pan = -1.0 / a - d.ptn * Ba + d.pt / (a * a);
+  d.pnn = 1.0 / n - 2.0 * Bn * iv + d.ptt * Bn * Bn;
+  return d;
+}
+ZNLL_DEV TailDerivs core_derivs(double tau) {
+  TailDerivs d = {-tau, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  return d;
+}
+// exponential tail of the GaussExpTail family: phi = a^2/2 + a t
+ZNLL_DEV TailDerivs exp_tail_derivs(double a, double tau) {
+  TailDerivs d = {a, 0.0, 1.0, 0.0, 1.0, 0.0, 0.0, a + tau, 0.0};
+  return d;
+}
+
 // GaussExpTail (models/physics.py:608-623, 727-805): Gaussian core, exponential tail  exp(a^2/2 + a t)  for t < -|alpha|.
 // slots [mu, sigma, alpha];  consts [0 mu, 1 sign(alpha)/sigma, 2 1/sigma, 3 |alpha|, 4 a^2/2 - ln I, 5 -ln I, 6 sign(alpha)]
 template <int COL, class V>
@@ -1028,6 +1085,24 @@ struct GETailN {
     zacc(acc[AO + 1], zmul(gd, t), c[CO + 2]);
     zacc(acc[AO + 2], zsel(tail, g, zbc<V>(0.0)), zmul(zadd(t, c[CO + 3]), c[CO + 6]));  // d ln v/d|alpha| = a + t
   }
+  // Hessian pass: upper triangle over (mu, sigma, alpha)
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__ c, double* h) const {
+    const double rr[2] = {la(r), lb(r)}, tt[2] = {la(t), lb(t)};
+    const bool tl[2] = {la(tail), lb(tail)};
+    const double sg = c[CO + 6];
+#pragma unroll
+    for (int k = 0; k < Lanes<V>::N; ++k) {
+      double U[10];
+      tail_block(tl[k] ? exp_tail_derivs(c[CO + 3], tt[k]) : core_derivs(tt[k]), tt[k], c[CO + 1], c[CO + 2], U);
+      h[tri_index(0, 0, 3)] = fma(rr[k], U[0], h[tri_index(0, 0, 3)]);
+      h[tri_index(0, 1, 3)] = fma(rr[k], U[1], h[tri_index(0, 1, 3)]);
+      h[tri_index(0, 2, 3)] = fma(rr[k], sg * U[2], h[tri_index(0, 2, 3)]);
+      h[tri_index(1, 1, 3)] = fma(rr[k], U[4], h[tri_index(1, 1, 3)]);
+      h[tri_index(1, 2, 3)] = fma(rr[k], sg * U[5], h[tri_index(1, 2, 3)]);
+      h[tri_index(2, 2, 3)] = fma(rr[k], U[7], h[tri_index(2, 2, 3)]);
+    }
+  }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
@@ -1036,9 +1111,9 @@ struct GETailN {
 template <int COL>
 struct GETail {
   static constexpr int NS = 3, NC = 7, COLMASK = 1 << COL;
-  static constexpr bool LEAF = true, HESS = false;
+  static constexpr bool LEAF = true, HESS = true;
   static constexpr int ROOT = 0;
-  static constexpr int NH = 0;
+  static constexpr int NH = 6;
   static constexpr bool LOGNAT = true;
   static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;
@@ -1096,6 +1171,32 @@ struct GGETailN {
     zacc1(acc[AO + 2], zsel(left, ga, zero));
     zacc1(acc[AO + 4], zsel(left, zero, ga));
   }
+  // Hessian pass: upper triangle over (mu, sigmal, alphal, sigmar, alphar); an event touches mu and its own side's slots
+  template <int IS, int IA>
+  ZNLL_DEV static void scatter3(double w, double sg, const double* U, double* h) {
+    h[tri_index(0, 0, 5)] = fma(w, U[0], h[tri_index(0, 0, 5)]);
+    h[tri_index(0, IS, 5)] = fma(w, U[1], h[tri_index(0, IS, 5)]);
+    h[tri_index(0, IA, 5)] = fma(w, sg * U[2], h[tri_index(0, IA, 5)]);
+    h[tri_index(IS, IS, 5)] = fma(w, U[4], h[tri_index(IS, IS, 5)]);
+    h[tri_index(IS, IA, 5)] = fma(w, sg * U[5], h[tri_index(IS, IA, 5)]);
+    h[tri_index(IA, IA, 5)] = fma(w, U[7], h[tri_index(IA, IA, 5)]);
+  }
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__ c, double* h) const {
+    const double* cc = c + CO;
+    const double rr[2] = {la(r), lb(r)}, tt[2] = {la(t), lb(t)};
+    const bool tl[2] = {la(tail), lb(tail)}, lf[2] = {la(left), lb(left)};
+#pragma unroll
+    for (int k = 0; k < Lanes<V>::N; ++k) {
+      const double* q = cc + (lf[k] ? 2 : 7);
+      double U[10];
+      tail_block(tl[k] ? exp_tail_derivs(q[2], tt[k]) : core_derivs(tt[k]), tt[k], q[0], q[1], U);
+      if (lf[k])
+        scatter3<1, 2>(rr[k], q[4], U, h);
+      else
+        scatter3<3, 4>(rr[k], q[4], U, h);
+    }
+  }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
@@ -1104,9 +1205,9 @@ struct GGETailN {
 template <int COL>
 struct GGETail {
   static constexpr int NS = 5, NC = 12, COLMASK = 1 << COL;
-  static constexpr bool LEAF = true, HESS = false;
+  static constexpr bool LEAF = true, HESS = true;
   static constexpr int ROOT = 0;
-  static constexpr int NH = 0;
+  static constexpr int NH = 15;
   static constexpr bool LOGNAT = true;
   static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = false;
@@ -1309,6 +1410,46 @@ struct GCBallN {
       zacc1(acc[AO + 6], zsel(left, zero, gn));
     }
   }
+  // Hessian pass: upper triangle over (mu, sigmal, alphal, nl, sigmar, alphar, nr); an event touches mu and its side's slots
+  template <int IS, int IA, int IN>
+  ZNLL_DEV static void scatter4(double w, double sg, const double* U, double* h) {
+    h[tri_index(0, 0, 7)] = fma(w, U[0], h[tri_index(0, 0, 7)]);
+    h[tri_index(0, IS, 7)] = fma(w, U[1], h[tri_index(0, IS, 7)]);
+    h[tri_index(0, IA, 7)] = fma(w, sg * U[2], h[tri_index(0, IA, 7)]);
+    h[tri_index(0, IN, 7)] = fma(w, U[3], h[tri_index(0, IN, 7)]);
+    h[tri_index(IS, IS, 7)] = fma(w, U[4], h[tri_index(IS, IS, 7)]);
+    h[tri_index(IS, IA, 7)] = fma(w, sg * U[5], h[tri_index(IS, IA, 7)]);
+    h[tri_index(IS, IN, 7)] = fma(w, U[6], h[tri_index(IS, IN, 7)]);
+    h[tri_index(IA, IA, 7)] = fma(w, U[7], h[tri_index(IA, IA, 7)]);
+    h[tri_index(IA, IN, 7)] = fma(w, sg * U[8], h[tri_index(IA, IN, 7)]);
+    h[tri_index(IN, IN, 7)] = fma(w, U[9], h[tri_index(IN, IN, 7)]);
+  }
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__ c, double* h) const {
+    const double* cc = c + CO;
+    const double rr[2] = {la(r), lb(r)}, tt[2] = {la(t), lb(t)};
+    const bool lf[2] = {la(left), lb(left)};
+    bool tl[2] = {false, false};
+    double dd[2] = {0.0, 0.0}, lv[2] = {0.0, 0.0};
+    if (any_tail) {
+      tl[0] = la(tail);
+      tl[1] = lb(tail);
+      dd[0] = la(dt);
+      dd[1] = lb(dt);
+      lv[0] = la(lu);
+      lv[1] = lb(lu);
+    }
+#pragma unroll
+    for (int k = 0; k < Lanes<V>::N; ++k) {
+      const double* q = cc + (lf[k] ? 2 : 13);
+      double U[10];
+      tail_block(tl[k] ? cb_tail_derivs(q[2], q[3], dd[k] / q[3], lv[k]) : core_derivs(tt[k]), tt[k], q[0], q[1], U);
+      if (lf[k])
+        scatter4<1, 2, 3>(rr[k], q[10], U, h);
+      else
+        scatter4<4, 5, 6>(rr[k], q[10], U, h);
+    }
+  }
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
@@ -1317,9 +1458,9 @@ struct GCBallN {
 template <int COL>
 struct GCBall {
   static constexpr int NS = 7, NC = 24, COLMASK = 1 << COL;
-  static constexpr bool LEAF = true, HESS = false;
+  static constexpr bool LEAF = true, HESS = true;
   static constexpr int ROOT = 0;
-  static constexpr int NH = 0;
+  static constexpr int NH = 28;
   static constexpr bool LOGNAT = true;
   static constexpr bool HAS_ADD = true, HAS_MULT = false;  // split evaluation: ln P = add + ln(mult)
   static constexpr bool TABS = true;

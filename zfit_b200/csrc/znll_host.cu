@@ -442,6 +442,8 @@ struct Kernel {
   void* cufunc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // CUfunction, NVRTC path
   void* cufunc_pdf = nullptr;
   void* cufunc_cov[2] = {nullptr, nullptr};
+  void* cufunc_hess[2] = {nullptr, nullptr};  // NVRTC path: the one-pass Hessian kernels of a flat tree, else null
+  int n_hess = -1;                            // their second-order leaf accumulators (M::NH)
 };
 
 struct Channel {
@@ -867,7 +869,7 @@ static const char* const kOpts[] = {"--gpu-architecture=sm_100a", "--std=c++17",
 // compile nll_kernel<Model, W, G> for the four (W, G) variants, pdf_kernel<Model> and -- n_slots permitting -- cov_kernel:
 // with 2 + NS + (NS+1)(NS+2)/2 > 256 accumulators the covariance pass would not fit the reduction's shared memory
 // (znll_eval_cov refuses such trees), and must not break the build.
-static int compile_image(const std::string& model, int n_slots, Image* img) {
+static int compile_image(const std::string& model, int n_slots, int hess_nh, Image* img) {
   Api& a = api();
   if (!a.nvrtc_ok) return fail("model '%s' is not in the ahead-of-time catalogue and NVRTC is unavailable (%s)",
                                model.c_str(), a.why.c_str());
@@ -899,6 +901,11 @@ static int compile_image(const std::string& model, int n_slots, Image* img) {
   if (2 + n_slots + (n_slots + 1) * (n_slots + 2) / 2 <= 256) {
     exprs.push_back("znll::cov_kernel<" + q + ",false>");
     exprs.push_back("znll::cov_kernel<" + q + ",true>");
+  }
+  // the one-pass Hessian of a flat tree of supported nodes (hess_nh >= 0: the host's count of M::NH), accumulators permitting
+  if (hess_nh >= 0 && 2 + (n_slots + 1) * (n_slots + 2) / 2 + hess_nh <= 256) {
+    exprs.push_back("znll::hess_kernel<" + q + ",false>");
+    exprs.push_back("znll::hess_kernel<" + q + ",true>");
   }
   for (auto& e : exprs) a.addname(prog, e.c_str());
   const int rc = a.compile(prog, (int)(sizeof(kOpts) / sizeof(kOpts[0])), kOpts);
@@ -947,14 +954,14 @@ static std::string cache_dir() {
   return std::string();
 }
 
-static uint64_t image_key(const std::string& model, int n_slots) {
+static uint64_t image_key(const std::string& model, int n_slots, int hess_nh) {
   int major = 0, minor = 0;
   Api& a = api();
   if (a.nvrtc_ok) a.version(&major, &minor);
   uint64_t h = fnv1a(znll_device_src, strlen(znll_device_src));
   h = fnv1a(model.data(), model.size(), h);
   for (auto o : kOpts) h = fnv1a(o, strlen(o) + 1, h);
-  const int tail[4] = {n_slots, major, minor, 1 /* file format */};
+  const int tail[5] = {n_slots, major, minor, 2 /* file format */, hess_nh};
   return fnv1a(tail, sizeof(tail), h);
 }
 
@@ -991,7 +998,7 @@ static bool cache_load(const std::string& path, uint64_t key, Image* img) {
     return true;
   };
   uint32_t n_names = 0;
-  if (!take(&n_names, 4) || (n_names != 5 && n_names != 7)) return false;
+  if (!take(&n_names, 4) || n_names < 5 || n_names > 9) return false;
   img->lowered.clear();
   for (uint32_t i = 0; i < n_names; ++i) {
     uint32_t l = 0;
@@ -1038,15 +1045,15 @@ static void cache_store(const std::string& path, uint64_t key, const Image& img)
 }
 
 // from_cache (nullable): 1 when the image came from disk
-static int obtain_image(const std::string& model, int n_slots, Image* img, int* from_cache, bool use_cache = true) {
-  const uint64_t key = image_key(model, n_slots);
+static int obtain_image(const std::string& model, int n_slots, int hess_nh, Image* img, int* from_cache, bool use_cache = true) {
+  const uint64_t key = image_key(model, n_slots, hess_nh);
   const std::string path = use_cache ? cache_file(key) : std::string();
   if (from_cache) *from_cache = 0;
   if (cache_load(path, key, img)) {
     if (from_cache) *from_cache = 1;
     return 0;
   }
-  if (compile_image(model, n_slots, img)) return 1;
+  if (compile_image(model, n_slots, hess_nh, img)) return 1;
   cache_store(path, key, *img);
   return 0;
 }
@@ -1058,14 +1065,25 @@ static int load_image(const Image& img, const std::string& model, Kernel* k) {
   if (a.modload(&mod, img.cubin.data())) return fail("cuModuleLoadData failed for '%s'", model.c_str());
   k->name = model;
   k->origin = 2;
-  void** dst[7] = {&k->cufunc[0][0], &k->cufunc[0][1], &k->cufunc[1][0], &k->cufunc[1][1], &k->cufunc_pdf,
-                   &k->cufunc_cov[0], &k->cufunc_cov[1]};
-  for (size_t i = 0; i < img.lowered.size() && i < 7; ++i)
-    if (a.getfn(dst[i], mod, img.lowered[i].c_str())) return fail("cuModuleGetFunction failed for '%s'", img.lowered[i].c_str());
+  // the lowered names are classified by the kernel they instantiate (Itanium mangling: <length><identifier>); within one
+  // kernel they keep compile_image's order (nll: weighted x gradient; cov and hess: unweighted, weighted)
+  void** nll[4] = {&k->cufunc[0][0], &k->cufunc[0][1], &k->cufunc[1][0], &k->cufunc[1][1]};
+  int n_nll = 0, n_pdf = 0, n_cov = 0, n_hess = 0;
+  for (auto& name : img.lowered) {
+    void** dst = nullptr;
+    if (name.find("10nll_kernel") != std::string::npos && n_nll < 4) dst = nll[n_nll++];
+    else if (name.find("10pdf_kernel") != std::string::npos && n_pdf < 1) dst = (++n_pdf, &k->cufunc_pdf);
+    else if (name.find("10cov_kernel") != std::string::npos && n_cov < 2) dst = &k->cufunc_cov[n_cov++];
+    else if (name.find("11hess_kernel") != std::string::npos && n_hess < 2) dst = &k->cufunc_hess[n_hess++];
+    else return fail("unexpected kernel '%s' in the image of '%s'", name.c_str(), model.c_str());
+    if (a.getfn(dst, mod, name.c_str())) return fail("cuModuleGetFunction failed for '%s'", name.c_str());
+  }
+  if (n_nll != 4 || n_pdf != 1 || (n_cov != 0 && n_cov != 2) || (n_hess != 0 && n_hess != 2))
+    return fail("incomplete image for '%s' (%d/%d/%d/%d kernels)", model.c_str(), n_nll, n_pdf, n_cov, n_hess);
   return 0;
 }
 
-static int build(const std::string& model, int n_slots, Kernel* out) {
+static int build(const std::string& model, int n_slots, int hess_nh, Kernel* out) {
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_cache.find(model);
   if (it != g_cache.end()) {
@@ -1077,16 +1095,18 @@ static int build(const std::string& model, int n_slots, Kernel* out) {
                          model.c_str(), a.why.c_str());
   Image img;
   int from_cache = 0;
-  if (obtain_image(model, n_slots, &img, &from_cache)) return 1;
+  if (obtain_image(model, n_slots, hess_nh, &img, &from_cache)) return 1;
   Kernel k;
   if (load_image(img, model, &k)) {
     if (!from_cache) return 1;
     // a cached image the driver refuses (e.g. written by another toolkit): drop it and compile
-    remove(cache_file(image_key(model, n_slots)).c_str());
+    const uint64_t key = image_key(model, n_slots, hess_nh);
+    remove(cache_file(key).c_str());
     k = Kernel();
-    if (obtain_image(model, n_slots, &img, nullptr, /*use_cache=*/false) || load_image(img, model, &k)) return 1;
-    cache_store(cache_file(image_key(model, n_slots)), image_key(model, n_slots), img);
+    if (obtain_image(model, n_slots, hess_nh, &img, nullptr, /*use_cache=*/false) || load_image(img, model, &k)) return 1;
+    cache_store(cache_file(key), key, img);
   }
+  k.n_hess = k.cufunc_hess[0] ? hess_nh : -1;
   g_cache[model] = k;
   *out = k;
   return 0;
@@ -1203,6 +1223,36 @@ void znll_plan_destroy(znll_plan* p) {
   delete p;
 }
 
+// M::NH of the tree as the device header counts it (upper triangles of the leaves with a curved log-density), or -1 when
+// the tree is not flat (a leaf, or one Sum / Product of leaves): only then does hess_kernel exist for it
+static int leaf_hess_acc(const znll_node& nd) {
+  switch (nd.kind) {
+    case ZNLL_GAUSS:
+    case ZNLL_EXP:
+    case ZNLL_CB:
+    case ZNLL_TGAUSS:
+    case ZNLL_GET:
+    case ZNLL_GGET:
+    case ZNLL_GCB: {
+      const int ns = leaf_n_slots(nd);
+      return ns * (ns + 1) / 2;
+    }
+    default: return 0;  // the polynomial families are linear in their coefficients
+  }
+}
+static int tree_hess_nh(const Channel& c) {
+  if (c.nodes.empty()) return -1;
+  const znll_node& root = c.nodes[0].nd;
+  const bool composite = root.kind == ZNLL_SUM || root.kind == ZNLL_PROD;
+  if (composite ? (int)c.nodes.size() != 1 + root.n_children : c.nodes.size() != 1) return -1;
+  int nh = 0;
+  for (size_t i = composite ? 1 : 0; i < c.nodes.size(); ++i) {
+    if (c.nodes[i].nd.kind == ZNLL_SUM || c.nodes[i].nd.kind == ZNLL_PROD) return -1;
+    nh += leaf_hess_acc(c.nodes[i].nd);
+  }
+  return nh;
+}
+
 int znll_plan_set_model(znll_plan* p, int ch, const znll_node* nodes, int n_nodes) {
   if (!p || ch < 0 || ch >= (int)p->ch.size() || !nodes || n_nodes < 1) return fail("znll_plan_set_model: bad arguments");
   CUDA_OK(cudaSetDevice(p->device));
@@ -1223,7 +1273,7 @@ int znll_plan_set_model(znll_plan* p, int ch, const znll_node* nodes, int n_node
     k.origin = 1;
     k.aot = e;
   } else {
-    if (rtc::build(name, c.n_slots, &k)) return 1;
+    if (rtc::build(name, c.n_slots, tree_hess_nh(c), &k)) return 1;
   }
   c.kernel = k;
   pool::put(p->device, pool::DEVICE, c.d_block_bytes, c.d_block);
@@ -1590,6 +1640,29 @@ static void leaf_step_scales(const znll_node& nd, const double* s, int ns, doubl
       scale[2] = std::max(fabs(s[2]), 0.1);
       scale[3] = std::max(fabs(s[3]) * 0.5, 0.1);
       break;
+    case ZNLL_TGAUSS:
+      scale[0] = scale[1] = scale[2] = scale[3] = fabs(s[1]);
+      break;
+    case ZNLL_GET:
+      scale[0] = scale[1] = fabs(s[1]);
+      scale[2] = std::max(fabs(s[2]), 0.1);
+      break;
+    case ZNLL_GGET:
+      scale[0] = std::min(fabs(s[1]), fabs(s[3]));
+      scale[1] = fabs(s[1]);
+      scale[3] = fabs(s[3]);
+      scale[2] = std::max(fabs(s[2]), 0.1);
+      scale[4] = std::max(fabs(s[4]), 0.1);
+      break;
+    case ZNLL_GCB:
+      scale[0] = std::min(fabs(s[1]), fabs(s[4]));
+      scale[1] = fabs(s[1]);
+      scale[4] = fabs(s[4]);
+      scale[2] = std::max(fabs(s[2]), 0.1);
+      scale[5] = std::max(fabs(s[5]), 0.1);
+      scale[3] = std::max(fabs(s[3]) * 0.5, 0.1);
+      scale[6] = std::max(fabs(s[6]) * 0.5, 0.1);
+      break;
     default: break;  // polynomial coefficients: O(1)
   }
 }
@@ -1644,7 +1717,8 @@ static int hess_assemble(Channel& c, const std::vector<double>& acc, int NH, dou
     lf.ns = leaf_n_slots(ni.nd);
     lf.frac = sum_root ? ni.parent_sum_frac_slot : -1;
     lf.B.assign((size_t)lf.ns * lf.ns, 0.0);
-    const bool has_second = ni.nd.kind == ZNLL_GAUSS || ni.nd.kind == ZNLL_EXP || ni.nd.kind == ZNLL_CB;
+    // every leaf but the polynomial families (linear in their coefficients) carries the full upper triangle over its slots
+    const bool has_second = leaf_hess_acc(ni.nd) > 0;
     if (has_second)
       for (int a = 0; a < lf.ns; ++a)
         for (int b = a; b < lf.ns; ++b) lf.B[(size_t)a * lf.ns + b] = lf.B[(size_t)b * lf.ns + a] = acc[hq++];
@@ -1724,7 +1798,8 @@ static int hess_assemble(Channel& c, const std::vector<double>& acc, int NH, dou
 }
 
 static bool channel_has_hess(const Channel& c) {
-  return c.kernel.origin == 1 && c.kernel.aot && c.kernel.aot->hess[0] != nullptr;
+  if (c.kernel.origin == 1) return c.kernel.aot && c.kernel.aot->hess[0] != nullptr;
+  return c.kernel.origin == 2 && c.kernel.cufunc_hess[0] != nullptr && c.kernel.n_hess >= 0;
 }
 
 int znll_plan_has_hess(const znll_plan* p, int ch) {
@@ -1733,8 +1808,8 @@ int znll_plan_has_hess(const znll_plan* p, int ch) {
 
 // values[k] = -sum_i (w_i l_i - offset), grad_slots = d value / d slot, hess = d2 value / d slot_a d slot_b per channel
 // ((n_slots)^2, row-major, channels concatenated) -- all in ONE pass over the events per channel.  Returns 3 (and leaves
-// the outputs untouched) when a channel's tree is not flat, holds a node without a second-order implementation, or was
-// built at run time through NVRTC: the caller then differences the analytic gradient instead.
+// the outputs untouched) when a channel's tree is not flat or needs more than the reduction's 256 accumulators: the
+// caller then differences the analytic gradient instead.  Catalogue and NVRTC-built trees alike.
 int znll_eval_hess(znll_plan* p, const double* slots, double log_offset, double* values, double* grad_slots,
                               double* hess, void* stream) {
   if (!p || !slots || !values || !hess) return fail("znll_eval_hess: bad arguments");
@@ -1750,7 +1825,8 @@ int znll_eval_hess(znll_plan* p, const double* slots, double log_offset, double*
   size_t h_off = 0;
   for (size_t k = 0; k < p->ch.size(); ++k) {
     Channel& c = p->ch[k];
-    const int NS = c.n_slots, NE = NS + 1, NQ = NE * (NE + 1) / 2, NH = c.kernel.aot->n_hess, NACC = 2 + NQ + NH;
+    const int NS = c.n_slots, NE = NS + 1, NQ = NE * (NE + 1) / 2, NH = c.kernel.origin == 1 ? c.kernel.aot->n_hess : c.kernel.n_hess,
+              NACC = 2 + NQ + NH;
     c.slots.assign(slots + c.slot_off, slots + c.slot_off + NS);
     fill_consts(c, c.slots.data());
     std::vector<double> acc(NACC, 0.0);
@@ -1778,7 +1854,10 @@ int znll_eval_hess(znll_plan* p, const double* slots, double log_offset, double*
       la.ticket = c.d_ticket;
       la.out = d_out;
       memset(&la.xc, 0, sizeof(la.xc));
-      cudaError_t e = c.kernel.aot->hess[c.w ? 1 : 0](la, c.consts.data(), grid, st);
+      cudaError_t e = cudaSuccess;
+      if (c.kernel.origin == 1) e = c.kernel.aot->hess[c.w ? 1 : 0](la, c.consts.data(), grid, st);
+      else if (rtc::launch_fn(c.kernel.cufunc_hess[c.w ? 1 : 0], c.kernel.name.c_str(), la, c.consts.data(), c.n_consts, grid, st))
+        return 1;
       p->launches++;
       if (e == cudaSuccess) e = cudaMemcpyAsync(acc.data(), d_out, sizeof(double) * NACC, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -2116,10 +2195,11 @@ int znll_test_prologue(const znll_node* nodes, int n_nodes, const double* slots,
   return 0;
 }
 
-int znll_test_rtc_image(const char* model, int n_slots, int use_cache, size_t* cubin_bytes, int* n_names, int* from_cache) {
+int znll_test_rtc_image(const char* model, int n_slots, int hess_nh, int use_cache, size_t* cubin_bytes, int* n_names,
+                        int* from_cache) {
   if (!model || !*model || n_slots < 0 || !cubin_bytes || !n_names || !from_cache) return fail("znll_test_rtc_image: bad arguments");
   rtc::Image img;
-  if (rtc::obtain_image(model, n_slots, &img, from_cache, use_cache != 0)) return 1;
+  if (rtc::obtain_image(model, n_slots, hess_nh, &img, from_cache, use_cache != 0)) return 1;
   *cubin_bytes = img.cubin.size();
   *n_names = (int)img.lowered.size();
   return 0;
