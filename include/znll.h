@@ -125,6 +125,17 @@ int znll_plan_bind_host(znll_plan* plan, int ch, int n_cols, const double* const
 int znll_partition_events(int device, int n_cols, const double* const* src_cols, double* const* dst_cols,
                           const double* src_w, double* dst_w, int key_col, double lo, double hi, int64_t n,
                           void* stream);
+
+/* The one-time inclusive cut of the events to the observable space, on the device, with a STABLE compaction (kept events
+ * stay in their original order).  Replaces check_cut_data_weights / the boolean mask of Data (core/data.py:1203-1244:
+ * `lower <= x <= upper` on every observable, weights cut alongside) for columns that already live in HBM.  An event is
+ * kept iff lower[c] <= src_cols[c][i] <= upper[c] for every column c (NaN fails) and, when the optional pair is given,
+ * less_a[i] < less_b[i] -- the accept step of accept-reject sampling (u < pdf, core/sample.py:440-505) compacts with the
+ * same pass.  dst columns (and dst_w) need room for n events; *n_kept receives the survivor count.  lower / upper are
+ * HOST arrays of n_cols doubles.  Synchronises `stream` before returning (the count is needed on the host). */
+int znll_cut_events(int device, int n_cols, const double* const* src_cols, double* const* dst_cols, const double* src_w,
+                    double* dst_w, const double* lower, const double* upper, const double* less_a /* nullable */,
+                    const double* less_b /* nullable */, int64_t n, int64_t* n_kept, void* stream);
 const char* znll_prep_last_error(void);
 
 /* Sum of weights (or N) of the bound shard, computed on the device at bind time with the same

@@ -107,3 +107,86 @@ def test_streamed_upload_partitions_chunk_by_chunk(monkeypatch):
     data2 = zfit.Data({"m": sent.copy()}, obs=w["data"][0].space, guarantee_limits=True)
     v2, _ = type(w["loss"])(model=w["model"], data=data2, options={"subtr_const": False}).value_gradient(params, full=True)
     assert abs(v2 - ref_v) <= 1e-12 * abs(ref_v)
+
+
+def _cut(cols, w, lo, hi, less=None):
+    import torch
+
+    from zfit_b200 import _znll as Z
+
+    dev = torch.device("cuda", 0)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    src = [up(c) for c in cols]
+    sw = None if w is None else up(w)
+    dst = [torch.full_like(c, -777.0) for c in src]
+    dw = None if sw is None else torch.full_like(sw, -777.0)
+    la, lb = (0, 0) if less is None else (up(less[0]), up(less[1]))
+    kept = Z.cut_events(0, [c.data_ptr() for c in src], [c.data_ptr() for c in dst], 0 if sw is None else sw.data_ptr(),
+                        0 if dw is None else dw.data_ptr(), lo, hi, src[0].numel(),
+                        less_a=0 if less is None else la.data_ptr(), less_b=0 if less is None else lb.data_ptr(),
+                        stream=torch.cuda.current_stream(0).cuda_stream)
+    return kept, [c.cpu().numpy() for c in dst], None if dw is None else dw.cpu().numpy()
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 65_537, 3_000_001])
+@pytest.mark.parametrize("n_cols,weighted", [(1, False), (1, True), (3, True), (4, False)])
+def test_cut_is_the_inclusive_stable_mask(n, n_cols, weighted):
+    """``check_cut_data_weights`` (core/data.py:1203-1244): ``lower <= x <= upper`` on every observable, weights alongside;
+    the kept events keep their order, the rest of the destination is not touched."""
+    rng = np.random.default_rng(100 * n_cols + n)
+    lo = np.array([-1.0, 0.0, 2.0, -5.0][:n_cols])
+    hi = np.array([1.5, 4.0, 2.5, 5.0][:n_cols])
+    cols = [rng.uniform(lo[c] - 0.2 * (hi[c] - lo[c]), hi[c] + 0.2 * (hi[c] - lo[c]), n) for c in range(n_cols)]
+    if n > 40:
+        cols[0][3], cols[0][5], cols[0][9] = lo[0], hi[0], np.nan  # the edges are inside (inclusive), NaN is outside
+        cols[-1][17] = np.inf
+    w = rng.normal(1.0, 0.5, n) if weighted else None
+    mask = np.ones(n, dtype=bool)
+    for c in range(n_cols):
+        with np.errstate(invalid="ignore"):
+            mask &= (cols[c] >= lo[c]) & (cols[c] <= hi[c])
+    kept, out, ow = _cut(cols, w, lo, hi)
+    assert kept == int(mask.sum())
+    for c in range(n_cols):
+        np.testing.assert_array_equal(out[c][:kept], cols[c][mask])
+        assert np.all(out[c][kept:] == -777.0)
+    if weighted:
+        np.testing.assert_array_equal(ow[:kept], w[mask])
+
+
+def test_cut_keeps_all_none_and_takes_the_accept_predicate():
+    from zfit_b200 import _znll as Z
+
+    rng = np.random.default_rng(8)
+    x = rng.uniform(0, 1, 100_001)
+    kept, out, _ = _cut([x], None, [0.0], [1.0])
+    assert kept == x.size and np.array_equal(out[0], x)
+    kept, out, _ = _cut([x], None, [2.0], [3.0])
+    assert kept == 0 and np.all(out[0] == -777.0)
+    u, p = rng.uniform(0, 1, x.size), rng.uniform(0, 1, x.size)
+    kept, out, _ = _cut([x], None, [0.25], [1.0], less=(u, p))
+    mask = (x >= 0.25) & (u < p)
+    assert kept == int(mask.sum()) and np.array_equal(out[0][:kept], x[mask])
+    assert Z.cut_events(0, [8], [16], 0, 0, [0.0], [1.0], 0) == 0  # no events: nothing is read
+    with pytest.raises(Z.ZnllError):
+        Z.cut_events(0, [8], [8], 0, 0, [0.0], [1.0], 10)  # aliased
+
+
+def test_data_on_the_device_is_cut_by_the_library():
+    """``zfit.Data`` built from CUDA tensors: the cut to the Space runs in HBM and matches the host cut event by event."""
+    import torch
+
+    import zfit_b200 as zfit
+
+    rng = np.random.default_rng(9)
+    raw = np.stack([rng.normal(0.5, 2.0, 300_007), rng.uniform(-1, 6, 300_007)], axis=1)
+    w = rng.normal(1.0, 0.3, raw.shape[0])
+    obs = zfit.Space("x", -2, 3) * zfit.Space("y", 0, 5)
+    host = zfit.Data(raw, obs=obs, weights=w)
+    dev = zfit.Data(torch.from_numpy(raw).to("cuda:0"), obs=obs, weights=torch.from_numpy(w).to("cuda:0"))
+    assert dev.num_entries == host.num_entries < raw.shape[0]
+    assert dev.on_device
+    np.testing.assert_array_equal(np.asarray(dev.value()), np.asarray(host.value()))
+    np.testing.assert_array_equal(np.asarray(dev.weights), np.asarray(host.weights))
+    inside = zfit.Data(torch.from_numpy(np.asarray(host.value())).to("cuda:0"), obs=obs)
+    assert inside.num_entries == host.num_entries  # nothing to cut: the caller's tensors are kept

@@ -74,6 +74,8 @@ SYMBOLS = {
     "znll_plan_bind_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]),
     "znll_partition_events": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
+    "znll_cut_events": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, _DP, _DP,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "znll_prep_last_error": (C.c_char_p, []),
     "znll_plan_get_sumw": (C.c_int, [C.c_void_p, C.c_int, _DP]),
     "znll_plan_set_sumw": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
@@ -352,6 +354,25 @@ def partition_events(device: int, src_ptrs, dst_ptrs, src_w: int, dst_w: int, ke
     if L.znll_partition_events(device, len(src_ptrs), src, dst, C.c_void_p(src_w or 0), C.c_void_p(dst_w or 0), key_col,
                                float(lo), float(hi), int(n), C.c_void_p(stream or 0)):
         raise ZnllError(L.znll_prep_last_error().decode(errors="replace"))
+
+
+def cut_events(device: int, src_ptrs, dst_ptrs, src_w: int, dst_w: int, lower, upper, n: int, *, less_a: int = 0, less_b: int = 0,
+               stream=0) -> int:
+    """Inclusive cut ``lower <= x <= upper`` on every column (and ``less_a < less_b`` when given) with a stable compaction of
+    resident columns (device pointers); returns the number of kept events (synchronises ``stream``)."""
+    src = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+    dst = (C.c_void_p * len(dst_ptrs))(*dst_ptrs)
+    lo = np.ascontiguousarray(lower, dtype=np.float64)
+    hi = np.ascontiguousarray(upper, dtype=np.float64)
+    if lo.size != len(src_ptrs) or hi.size != len(src_ptrs):
+        msg = "one lower and one upper limit per column"
+        raise ValueError(msg)
+    kept = C.c_int64(0)
+    L = lib()
+    if L.znll_cut_events(device, len(src_ptrs), src, dst, C.c_void_p(src_w or 0), C.c_void_p(dst_w or 0), _dptr(lo), _dptr(hi),
+                         C.c_void_p(less_a or 0), C.c_void_p(less_b or 0), int(n), C.byref(kept), C.c_void_p(stream or 0)):
+        raise ZnllError(L.znll_prep_last_error().decode(errors="replace"))
+    return int(kept.value)
 
 
 def fp64_peak(device: int = 0, ms: float = 200.0) -> float:

@@ -469,8 +469,38 @@ def _to_numpy(c):
     return c
 
 
+def _cut_on_device(cols, weights, lo, up):
+    """Columns that already live in HBM are cut there: one predicate + stable compaction pass of libznll
+    (``znll_cut_events``, csrc/znll_prep.cu); only the survivor count comes back to the host."""
+    import torch
+
+    from . import _znll as Z
+
+    n = int(cols[0].shape[0])
+    if n == 0:
+        return cols, weights
+    dev = cols[0].device
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    cols = [c.contiguous() for c in cols]
+    w = None if weights is None else weights.to(dev).contiguous()
+    with torch.cuda.device(index):
+        out = [torch.empty_like(c) for c in cols]
+        out_w = None if w is None else torch.empty_like(w)
+        stream = torch.cuda.current_stream(index).cuda_stream
+        kept = Z.cut_events(index, [c.data_ptr() for c in cols], [c.data_ptr() for c in out], 0 if w is None else w.data_ptr(),
+                            0 if out_w is None else out_w.data_ptr(), [float(v) for v in lo], [float(v) for v in up], n,
+                            stream=stream)
+    if kept == n:
+        return cols, weights
+    # a view of the compacted buffer; when most events went, give the memory back
+    shrink = (lambda t: t[:kept].clone()) if kept < n // 2 else (lambda t: t[:kept])
+    return [shrink(c) for c in out], (None if out_w is None else shrink(out_w))
+
+
 def _cut(cols, weights, space: Space):
     lo, up = space._lower, space._upper
+    if _is_torch(cols[0]) and cols[0].is_cuda:
+        return _cut_on_device(cols, weights, lo, up)
     if _is_torch(cols[0]):
         inside = None
         for i, c in enumerate(cols):

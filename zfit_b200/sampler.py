@@ -4,7 +4,8 @@
 
 Accept-reject with uniform proposals, entirely on the GPU: torch's generator fills a fixed proposal buffer per observable,
 the model tree's ``pdf_kernel`` (the same compiled tree the likelihood uses) writes the densities into a device buffer
-(``znll_pdf_device``), and the accepted events are compacted with a boolean mask.  The only host traffic per batch is the
+(``znll_pdf_device``), and the accepted events are compacted by the library's cut pass (``znll_cut_events`` with the
+``u < p`` predicate).  The only host traffic per batch is the
 accepted count.  The envelope starts at 1.2 x the largest density seen and is raised -- and the sample restarted -- if a
 proposal ever exceeds it, so the result is an unbiased sample (the reference re-weights instead, ``sample.py:440-505``).
 """
@@ -80,10 +81,14 @@ class DeviceSampler:
                     pmax, restart = 1.2 * batch_max, True
                     break
                 self.unif.uniform_(0.0, pmax, generator=self.generator)
-                mask = self.unif < self.pvals
-                for k, c in enumerate(self.cols):
-                    kept[k].append(c[mask])
-                have += int(mask.sum())
+                # accept u < p and compact the accepted proposals in one pass (znll_cut_events; only the count comes back)
+                out = [torch.empty_like(c) for c in self.cols]
+                n_acc = Z.cut_events(self.device, [c.data_ptr() for c in self.cols], [c.data_ptr() for c in out], 0, 0,
+                                     self.lower, self.upper, self.batch, less_a=self.unif.data_ptr(),
+                                     less_b=self.pvals.data_ptr(), stream=stream)
+                for k, c in enumerate(out):
+                    kept[k].append(c[:n_acc])
+                have += n_acc
             if not restart:
                 break
         self.pmax = pmax
