@@ -144,6 +144,14 @@ const char* znll_prep_last_error(void);
 int znll_plan_get_sumw(znll_plan* plan, int ch, double* sumw);
 int znll_plan_set_sumw(znll_plan* plan, int ch, double sumw);
 
+/* Multi-GPU, one process per GPU: how the library sums a small HOST buffer over the ranks (in place, identical result on
+ * every rank; returns 0 on success).  Only the passes that are not reduced inside the kernel need it -- today the
+ * information matrix that seeds znll_migrad_theta's metric (znll_eval itself exchanges its accumulators over NVLink inside
+ * the kernel, znll_plan_set_peers).  The host layer installs an all-gather + fixed-order sum over its communicator
+ * (zfit_b200/distributed.py::all_reduce_sum_); NULL removes the hook. */
+typedef int (*znll_reduce_t)(void* user, double* buf, int n);
+int znll_plan_set_reduce_hook(znll_plan* plan, znll_reduce_t fn, void* user);
+
 int znll_plan_n_slots(const znll_plan* plan, int ch);   /* slots of channel ch        */
 int znll_plan_n_acc(const znll_plan* plan, int ch);     /* accumulators of channel ch */
 int znll_plan_total_slots(const znll_plan* plan);       /* sum over channels          */

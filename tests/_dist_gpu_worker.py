@@ -50,11 +50,24 @@ def main():
         assert np.all(np.abs(H - Hs) <= 1e-9 * np.sqrt(np.abs(np.outer(np.diag(Hs), np.diag(Hs))))), (H, Hs)
         # the C-level theta path is active exactly where the reduction is fused into the kernel
         assert (nll._theta_path(nll._get_engine()) is not None) == (mode == "fused")
+        start = [float(p.value()) for p in params]
         result = zfit.minimize.Minuit(gradient="zfit").minimize(nll)
         fitted = torch.tensor([result.params[p]["value"] for p in result.params], dtype=torch.float64, device=f"cuda:{local_rank}")
         gathered = [torch.empty_like(fitted) for _ in range(world)]
         td.all_gather(gathered, fitted)
         assert all(torch.equal(gathered[0], t) for t in gathered)
+        # with the fused exchange every rank runs the whole fit in native code (metric seed all-reduced through the hook);
+        # it ends at the minimum the single-GPU fit of the whole sample finds
+        native = "whole fit in native code" in result.info["driver"]
+        assert native == (mode == "fused"), result.info["driver"]
+        if mode == "fused":
+            for p, val in zip(params, start):
+                p.assign(val)
+            alone = zfit.minimize.Minuit(gradient="zfit").minimize(single)
+            a = np.array([result.params[p]["value"] for p in params])
+            b = np.array([alone.params[p]["value"] for p in params])
+            errs = np.sqrt(np.diag(np.linalg.inv(Hs)))
+            assert np.all(np.abs(a - b) <= 1e-3 * errs), (a, b, errs)
         eng = nll._get_engine()
         res[mode] = {"value": v, "single": sv, "valid": bool(result.valid), "n_eval": int(result.info["n_eval"]),
                      "kernel": eng.kernel_names, "reduce_mode": eng.reduce_mode,

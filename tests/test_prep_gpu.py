@@ -190,3 +190,29 @@ def test_data_on_the_device_is_cut_by_the_library():
     np.testing.assert_array_equal(np.asarray(dev.weights), np.asarray(host.weights))
     inside = zfit.Data(torch.from_numpy(np.asarray(host.value())).to("cuda:0"), obs=obs)
     assert inside.num_entries == host.num_entries  # nothing to cut: the caller's tensors are kept
+
+
+def test_large_host_arrays_are_cut_in_hbm(monkeypatch):
+    """Host arrays above ``settings.options.device_cut_min_events`` that still need their cut are uploaded and cut on the
+    device (the Data is then resident); the events and their order equal the host cut's, and a loss built on it agrees."""
+    import zfit_b200 as zfit
+
+    rng = np.random.default_rng(10)
+    n = 600_011
+    raw = rng.normal(0.3, 1.5, n)
+    w = rng.normal(1.0, 0.3, n)
+    obs = zfit.Space("x", -2, 3)
+    host = zfit.Data(raw, obs=obs, weights=w)
+    assert not host.on_device
+    monkeypatch.setitem(zfit.settings.options, "device_cut_min_events", 100_000)
+    dev = zfit.Data(raw, obs=obs, weights=w)
+    assert dev.on_device and dev.num_entries == host.num_entries < n
+    np.testing.assert_array_equal(np.asarray(dev.value())[:, 0], np.asarray(host.value())[:, 0])
+    np.testing.assert_array_equal(np.asarray(dev.weights), np.asarray(host.weights))
+    mu, sg = zfit.Parameter("mu_dc", 0.2, -1, 1), zfit.Parameter("sg_dc", 1.4, 0.5, 3)
+    model = zfit.pdf.Gauss(mu, sg, obs)
+    a = zfit.loss.UnbinnedNLL(model, host).value_gradient([mu, sg])
+    b = zfit.loss.UnbinnedNLL(model, dev).value_gradient([mu, sg])
+    assert float(a[0]) == float(b[0]) and np.array_equal(np.asarray(a[1]), np.asarray(b[1]))
+    monkeypatch.setitem(zfit.settings.options, "device_cut_min_events", None)
+    assert not zfit.Data(raw, obs=obs).on_device

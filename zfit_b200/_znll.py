@@ -61,6 +61,7 @@ class ZnllError(RuntimeError):
 _lib = None
 
 _DP = C.POINTER(C.c_double)
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int)
 
 # every symbol include/znll.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -79,6 +80,7 @@ SYMBOLS = {
     "znll_prep_last_error": (C.c_char_p, []),
     "znll_plan_get_sumw": (C.c_int, [C.c_void_p, C.c_int, _DP]),
     "znll_plan_set_sumw": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "znll_plan_set_reduce_hook": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "znll_plan_n_slots": (C.c_int, [C.c_void_p, C.c_int]),
     "znll_plan_n_acc": (C.c_int, [C.c_void_p, C.c_int]),
     "znll_plan_total_slots": (C.c_int, [C.c_void_p]),
@@ -220,6 +222,26 @@ class Plan:
 
     def set_sumw(self, ch: int, v: float):
         _check(lib().znll_plan_set_sumw(self._h, ch, float(v)))
+
+    def set_reduce_hook(self, fn):
+        """``fn(array)``: sum a 1-D float64 numpy array over the ranks in place (identical on every rank); None removes it."""
+        if fn is None:
+            _check(lib().znll_plan_set_reduce_hook(self._h, None, None))
+            self._reduce_cb = None
+            return
+
+        def trampoline(_user, buf, n):
+            try:
+                fn(np.ctypeslib.as_array(buf, shape=(n,)))
+            except Exception:  # an exception must not cross the C frames
+                import traceback
+
+                traceback.print_exc()
+                return 1
+            return 0
+
+        self._reduce_cb = REDUCE_FN(trampoline)  # kept alive with the plan
+        _check(lib().znll_plan_set_reduce_hook(self._h, C.cast(self._reduce_cb, C.c_void_p), None))
 
     def exchange_bytes(self, world: int) -> int:
         return int(lib().znll_plan_exchange_bytes(self._h, world))

@@ -495,6 +495,9 @@ struct znll_plan {
   std::vector<znll_ref> refs;
   std::vector<znll_rule> slot_rules, yield_rules;
   std::vector<double> th_clip, th_slots, th_values, th_gslots;  // per-call scratch
+  // sums a host buffer over the ranks of a multi-GPU job (znll_plan_set_reduce_hook); null: single GPU
+  znll_reduce_t reduce_fn = nullptr;
+  void* reduce_user = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1389,6 +1392,12 @@ int znll_plan_get_sumw(znll_plan* p, int ch, double* sumw) {
   *sumw = p->ch[ch].sumw;
   return 0;
 }
+int znll_plan_set_reduce_hook(znll_plan* p, znll_reduce_t fn, void* user) {
+  if (!p) return fail("znll_plan_set_reduce_hook: bad arguments");
+  p->reduce_fn = fn;
+  p->reduce_user = user;
+  return 0;
+}
 int znll_plan_set_sumw(znll_plan* p, int ch, double sumw) {
   if (!p || ch < 0 || ch >= (int)p->ch.size()) return fail("znll_plan_set_sumw: bad arguments");
   p->ch[ch].sumw = sumw;
@@ -2005,6 +2014,8 @@ static int theta_information(znll_plan* p, const double* theta, double* info /* 
   for (auto& c : p->ch) cov_len += (size_t)(c.n_slots + 1) * (c.n_slots + 1);
   std::vector<double> cov(cov_len), vals(p->ch.size()), gs(p->total_slots);
   if (znll_eval_cov(p, p->th_slots.data(), 0.0, vals.data(), gs.data(), cov.data(), stream)) return 1;
+  // one process per GPU: the pass saw this rank's shard; the matrix is linear in the events
+  if (p->reduce_fn && p->reduce_fn(p->reduce_user, cov.data(), (int)cov.size())) return fail("theta_information: the reduce hook failed");
   for (int i = 0; i < n * n; ++i) info[i] = 0.0;
   size_t off = 0;
   for (size_t k = 0; k < p->ch.size(); ++k) {

@@ -144,11 +144,19 @@ class CudaEngine:
                         f"an NCCL all-reduce per evaluation instead ({exc!r})", RuntimeWarning, stacklevel=2)
             if self.reduce_mode == "nccl":
                 self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
+            self.plan.set_reduce_hook(self._sum_over_ranks)  # the passes the kernel does not reduce itself (information matrix)
         self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
         self._raw_stream = self._pick_stream_getter()
         mark("rest")
         if trace is not None:
             print("bind trace [ms]: " + " | ".join(f"{n} {1e3 * (t - p):.2f}" for (n, t), (_, p) in zip(trace[1:], trace[:-1])), flush=True)
+
+    def _sum_over_ranks(self, buf):
+        """In-place world sum of a small host float64 array through the communicator (all-gather + fixed-order sum:
+        identical on every rank) -- what ``libznll`` calls for its rank-local passes (``znll_plan_set_reduce_hook``)."""
+        t = self.torch.from_numpy(buf).to(f"cuda:{self.device}")
+        _dist.all_reduce_sum_(t, deterministic=True)
+        buf[:] = t.cpu().numpy()
 
     def _pick_stream_getter(self):
         """torch's current stream on this device as a raw ``cudaStream_t``.  ``torch.cuda.current_stream(d).cuda_stream``

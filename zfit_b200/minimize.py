@@ -832,8 +832,8 @@ def _native_loop_fit(minimizer, loss, params, steps, evaluator, criterion):
         return None
     if not getattr(eng, "is_cuda_engine", False) or eng._lazy_sort_in is not None:
         return None
-    if eng.distributed:  # the metric seed (information matrix) is all-reduced by the Python route; the native loop's is rank-local
-        return None
+    if eng.distributed and eng.reduce_mode != "fused-nvlink":  # every rank runs the same native loop on the numbers the
+        return None                                             # kernel reduced over NVLink; the NCCL route is driven from Python
     path = loss._theta_path(eng)
     if path is None:
         return None

@@ -12,7 +12,9 @@ class _Options(dict):
     __setattr__ = dict.__setitem__
 
 
-options = _Options(numerical_grad=False, auto_update_params=True, epsilon=1e-8)
+# device_cut_min_events: host arrays with at least this many events that still have to be cut to their Space are
+# uploaded first and cut in HBM (zfit_b200/data.py::_cut); None keeps every cut on the host
+options = _Options(numerical_grad=False, auto_update_params=True, epsilon=1e-8, device_cut_min_events=1 << 22)
 
 
 class _ZTypes:
