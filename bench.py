@@ -394,7 +394,7 @@ def measure_config(ctx, cfg, args, headline):
         return loss.value_gradient(params, full=False)
 
     # ---- value: K steps through the loss, inputs resident in HBM, CUDA events on the launch stream ------------
-    sampler = ClockSampler(local, enabled=(rank == 0))  # its nvidia-smi child starts here, outside the timed region
+    sampler = ClockSampler(local, period_ms=max(1, args.clock_period_ms), enabled=(rank == 0 and args.clock_period_ms > 0))  # its nvidia-smi child starts here, outside the timed region
     with torch.cuda.stream(stream):
         for k in range(args.warmup):
             step(k)
@@ -772,6 +772,7 @@ def main():
     ap.add_argument("--nccl", action="store_true", help="multi-GPU: NCCL all-reduce instead of the fused NVLink exchange")
     ap.add_argument("--no-fit", action="store_true", help="skip the end-to-end Minuit fit after the timed region")
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not pin each rank to the cores next to its GPU")
+    ap.add_argument("--clock-period-ms", type=int, default=20, help="nvidia-smi sampling period during the timed region; 0: no sampler (A/B runs only)")
     ap.add_argument("--sort", default=None, choices=["1", "0", "lazy"], help="override the loss option sort_events (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
