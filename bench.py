@@ -157,6 +157,67 @@ class ClockSampler:
                 "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(inside), "window": window}
 
 
+class NvmlSampler(ClockSampler):
+    """The same record taken in-process through NVML (the library ``nvidia-smi`` is a front end of): a thread reads SM
+    clock, power and the clock-event reasons every ``period_ms``.  ``--clock-source nvml``; for A/B runs of how much the
+    external ``nvidia-smi -lms`` child perturbs the launches."""
+
+    def __init__(self, index=0, period_ms=20, enabled=True):
+        self.index = index
+        self.t_begin = self.t_end = None
+        self.rows = []
+        self.proc = None
+        self._stop = threading.Event()
+        self._thread = None
+        if not enabled:
+            return
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(index)
+            try:
+                bdf = f"{getattr(props, 'pci_domain_id', 0):08x}:{props.pci_bus_id:02x}:{getattr(props, 'pci_device_id', 0):02x}.0"
+                self._h = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nv = pynvml
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return
+        self._period = period_ms * 1e-3
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < 3.0:
+            time.sleep(0.01)
+
+    def _loop(self):
+        import datetime
+
+        nv, h = self._nv, self._h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                mask = int(get_reasons(h))
+                flags = ["Active" if mask & bits[n] else "Not Active" for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append((datetime.datetime.now(), [str(self.index), f"{sm:.0f}", f"{self._max:.0f}", f"{pw:.2f}", hex(mask), *flags]))
+            except Exception:
+                pass
+            self._stop.wait(self._period)
+
+    def close(self):
+        if self._thread is not None:
+            time.sleep(0.03)
+            self._stop.set()
+            self._thread.join(timeout=2)
+            self._thread = None
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU oracle port (cpu_baseline leg and --impl reference): the checker, timed -- never the product
 # ------------------------------------------------------------------------------------------------
@@ -394,7 +455,8 @@ def measure_config(ctx, cfg, args, headline):
         return loss.value_gradient(params, full=False)
 
     # ---- value: K steps through the loss, inputs resident in HBM, CUDA events on the launch stream ------------
-    sampler = ClockSampler(local, period_ms=max(1, args.clock_period_ms), enabled=(rank == 0 and args.clock_period_ms > 0))  # its nvidia-smi child starts here, outside the timed region
+    sampler = (NvmlSampler if args.clock_source == "nvml" else ClockSampler)(
+        local, period_ms=max(1, args.clock_period_ms), enabled=(rank == 0 and args.clock_period_ms > 0))  # its nvidia-smi child starts here, outside the timed region
     with torch.cuda.stream(stream):
         for k in range(args.warmup):
             step(k)
@@ -773,6 +835,7 @@ def main():
     ap.add_argument("--no-fit", action="store_true", help="skip the end-to-end Minuit fit after the timed region")
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not pin each rank to the cores next to its GPU")
     ap.add_argument("--clock-period-ms", type=int, default=20, help="nvidia-smi sampling period during the timed region; 0: no sampler (A/B runs only)")
+    ap.add_argument("--clock-source", default="smi", choices=["smi", "nvml"], help="clock record: the nvidia-smi -lms child (recipe) or in-process NVML")
     ap.add_argument("--sort", default=None, choices=["1", "0", "lazy"], help="override the loss option sort_events (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
