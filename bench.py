@@ -157,6 +157,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None, "samples": len(inside), "window": window}
 
 
+def _step_spread(marks):
+    """Spread of this rank's per-step wall times inside the timed region (a step returns when its result is on the host):
+    a mean well above the median means a few stalled steps (an interrupted rank stalls all its peers in the exchange)."""
+    d = sorted((b - a) * 1e6 for a, b in zip(marks[:-1], marks[1:]))
+    if not d:
+        return None
+    return {"median": d[len(d) // 2], "p90": d[min(len(d) - 1, (9 * len(d)) // 10)], "max": d[-1], "mean": sum(d) / len(d)}
+
+
 class NvmlSampler(ClockSampler):
     """The same record taken in-process through NVML (the library ``nvidia-smi`` is a front end of): a thread reads SM
     clock, power and the clock-event reasons every ``period_ms``.  ``--clock-source nvml``; for A/B runs of how much the
@@ -469,10 +478,12 @@ def measure_config(ctx, cfg, args, headline):
         gc.disable()  # a collection pause inside an 8 ms timed region is a 10 % outlier; re-enabled right after
         try:
             with sampler as clocks:
-                t_wall0 = time.perf_counter()
+                marks = [0.0] * (args.steps + 1)
+                t_wall0 = marks[0] = time.perf_counter()
                 e0.record(stream)
                 for k in range(args.steps):
                     step(k)
+                    marks[k + 1] = time.perf_counter()
                 e1.record(stream)
                 _barrier(ctx)
                 t_wall = time.perf_counter() - t_wall0
@@ -488,6 +499,7 @@ def measure_config(ctx, cfg, args, headline):
         "units_per_step": units,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
+        "step_wall_us": _step_spread(marks),
         "l2": "inputs (%.0f MB per GPU) are larger than the 126 MB L2; no flush needed" % (n_events * w["bytes_per_event"] / 1e6)
               if n_events * w["bytes_per_event"] > 130e6 else
               "inputs (%.2f MB) fit the L2: this config is launch-latency-bound by design (report us per call)" % (n_events * w["bytes_per_event"] / 1e6),
