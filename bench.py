@@ -731,6 +731,7 @@ def _summary(res):
                 "steady_state": res["e2e"]["steady_state"]["value"]},
         "clocks": res["clocks"],
         "gpu_launches": res["gpu_launches"],
+        "step_wall_us": res.get("step_wall_us"),
     }
     if "fit" in res:
         out["fit"] = {k: res["fit"].get(k) for k in ("wall_s", "n_pass", "valid", "edm", "error") if k in res["fit"]}
@@ -814,7 +815,7 @@ def run_product(args):
         "gpu_launches": head["gpu_launches"],
         "roofline": head["roofline"],
     }
-    for key in ("cpu_baseline", "fit", "hessian", "parity"):
+    for key in ("cpu_baseline", "fit", "hessian", "parity", "step_wall_us"):
         if key in head:
             line[key] = head[key]
     if ctx.numa is not None:
