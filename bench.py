@@ -469,7 +469,6 @@ def measure_config(ctx, cfg, args, headline):
     with torch.cuda.stream(stream):
         for k in range(args.warmup):
             step(k)
-        _barrier(ctx)
         launches0 = plan.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         import gc
@@ -479,6 +478,10 @@ def measure_config(ctx, cfg, args, headline):
         try:
             with sampler as clocks:
                 marks = [0.0] * (args.steps + 1)
+                # nothing rank-dependent between the barrier and the first step: with the reduction inside the kernel a
+                # rank that starts late (the collection above takes milliseconds and differs per rank) makes every peer
+                # wait in its first launch, and their event pair would time that wait
+                _barrier(ctx)
                 t_wall0 = marks[0] = time.perf_counter()
                 e0.record(stream)
                 for k in range(args.steps):
