@@ -639,7 +639,7 @@ def measure_config(ctx, cfg, args, headline):
             _barrier(ctx)
             l0 = plan.launch_count()
             t0 = time.perf_counter()
-            loss.hessian(params)
+            H_one = np.asarray(loss.hessian(params), dtype=np.float64)
             torch.cuda.synchronize(local)
             t_one = time.perf_counter() - t0
             res["hessian"] = {"method": getattr(loss, "last_hessian_method", None), "seconds": t_one,
@@ -648,10 +648,15 @@ def measure_config(ctx, cfg, args, headline):
                 loss.options["hessian"] = "numeric"
                 l0 = plan.launch_count()
                 t0 = time.perf_counter()
-                loss.hessian(params)
+                H_num = np.asarray(loss.hessian(params), dtype=np.float64)
                 torch.cuda.synchronize(local)
                 res["hessian"]["gradient_differences"] = {"seconds": time.perf_counter() - t0,
                                                           "launches": int(plan.launch_count() - l0)}
+                # full-size agreement of the two routes, in units of sqrt(H_aa H_bb) (the differences carry O(h^2) error)
+                scale = np.sqrt(np.abs(np.outer(np.diag(H_num), np.diag(H_num))))
+                res["hessian"]["max_scaled_difference"] = float(np.max(np.abs(H_one - H_num) / np.where(scale > 0, scale, 1.0)))
+                eig = np.linalg.eigvalsh(0.5 * (H_one + H_one.T))
+                res["hessian"]["positive_definite"] = bool(eig[0] > 0)
                 loss.options["hessian"] = "exact"
         except Exception as exc:
             res["hessian"] = {"error": repr(exc)}
