@@ -195,9 +195,10 @@ int znll_eval_cov(znll_plan* plan, const double* slots, double log_offset, doubl
  * matrix d2 value_k / d slot_a d slot_b (row-major, channels concatenated), value_k = -sum_i (w_i log pdf_k(x_i) - offset)
  * with the normalisation integrals' dependence on the slots included.  Replaces loss.hessian's second differentiation of
  * the whole graph (src/zfit/core/loss.py:765-878, src/zfit/z/math.py:288-352; numdifftools over loss.value by default).
- * Available for flat trees -- a leaf, a SumPDF of leaves, a ProductPDF of leaves of kind Gauss / Exponential /
- * CrystalBall / the polynomial families -- from the ahead-of-time catalogue (znll_plan_has_hess); for any other tree the
- * function returns 3 and the caller differences the analytic gradient (2P passes).  A zero fraction yields inf / NaN. */
+ * Available (znll_plan_has_hess) for a leaf, a ProductPDF of leaves, a SumPDF of leaves and of ProductPDFs of leaves, every
+ * leaf kind, from the ahead-of-time catalogue or built through NVRTC, as long as 2 + (n+1)(n+2)/2 + the leaves'
+ * second-order blocks fit the reduction's 256 accumulators (n = n_slots, about 20); for any other tree the function
+ * returns 3 and the caller differences the analytic gradient (2P passes).  A zero fraction yields inf / NaN. */
 int znll_eval_hess(znll_plan* plan, const double* slots, double log_offset, double* values, double* grad_slots,
                    double* hess, void* stream);
 int znll_plan_has_hess(const znll_plan* plan, int ch);

@@ -47,6 +47,7 @@ CASES = {
     "legendre": lambda: CS.poly_case("legendre", n=4000),
     "bernstein": lambda: CS.bernstein_case(n=4000),
     "three_leaves_outside_catalogue": lambda: CS.rtc_case(n=6001),  # on the GPU this tree is built by NVRTC
+    "sum_of_products": lambda: CS.nested_case(n=6001),  # signal(x) signal(y) + background(x) background(y)
 }
 
 
@@ -67,19 +68,18 @@ def test_one_pass_hessian_matches_double_backward(name):
 
 
 def test_unsupported_tree_reports_none():
-    """A nested tree (Sum of a Product) has no one-pass Hessian: the caller falls back to gradient differences."""
+    """A Product whose factor is itself a Sum has no one-pass Hessian (the pass knows a leaf, a Product of leaves, and a Sum
+    of leaves and of Products of leaves): the caller falls back to gradient differences."""
     from zfit_b200 import _znll as Z
 
     nodes = [
+        Z.Node(Z.PROD, 2, 0, 0, 0, 0, 0, 0, 0),
         Z.Node(Z.SUM, 2, 0, 0, 0, 0, 0, 0, 0),
-        Z.Node(Z.PROD, 2, 0, 0, 0, 0, 0, 0, 0),
         Z.Node(Z.GAUSS, 0, 0, 0, -5, 5, 0, 0, 0),
-        Z.Node(Z.EXP, 0, 1, 0, 0, 4, 0, 0, 0),
-        Z.Node(Z.PROD, 2, 0, 0, 0, 0, 0, 0, 0),
         Z.Node(Z.GAUSS, 0, 0, 0, -5, 5, 0, 0, 0),
         Z.Node(Z.EXP, 0, 1, 0, 0, 4, 0, 0, 0),
     ]
-    slots = [0.4, 0.6, 0.1, 1.0, -0.5, -0.2, 1.5, -0.8]
+    slots = [0.4, 0.6, 0.1, 1.0, -0.2, 1.5, -0.8]
     name, _ = Z.test_prologue(nodes, slots)
     sim = HostSim([name])
     rng = np.random.default_rng(0)

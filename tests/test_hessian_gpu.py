@@ -58,19 +58,38 @@ def test_loss_hessian_one_pass(cfg, n):
     assert np.all(np.linalg.eigvalsh(cov) > 0)
 
 
-def test_nested_tree_falls_back_to_gradient_differences():
+def _two_dim_parts(tag):
     import zfit_b200 as zfit
 
     rng = np.random.default_rng(3)
     ox, oy = zfit.Space("x", -5, 5), zfit.Space("y", 0, 4)
-    mu, sg = zfit.Parameter("mu_nh", 0.1, -1, 1), zfit.Parameter("sg_nh", 1.1, 0.3, 3)
-    l1, l2 = zfit.Parameter("l1_nh", -0.5, -3, -0.01), zfit.Parameter("l2_nh", -1.0, -3, -0.01)
-    fr = zfit.Parameter("fr_nh", 0.4, 0, 1)
+    mu, sg = zfit.Parameter(f"mu_{tag}", 0.1, -1, 1), zfit.Parameter(f"sg_{tag}", 1.1, 0.3, 3)
+    l1, l2 = zfit.Parameter(f"l1_{tag}", -0.5, -3, -0.01), zfit.Parameter(f"l2_{tag}", -1.0, -3, -0.01)
+    fr = zfit.Parameter(f"fr_{tag}", 0.4, 0, 1)
+    data = zfit.Data(np.stack([rng.normal(0, 1.3, 5000).clip(-5, 5), rng.uniform(0, 4, 5000)], axis=1), obs=ox * oy)
+    return zfit, ox, oy, mu, sg, l1, l2, fr, data
+
+
+def test_sum_of_products_has_the_one_pass_hessian():
+    """signal(x) signal(y) + background(x) background(y): every branch of the Sum is a Product of leaves, which the
+    Hessian pass treats as one generalised leaf (leaf blocks + outer products of the leaves' scores)."""
+    zfit, ox, oy, mu, sg, l1, l2, fr, data = _two_dim_parts("sp")
     a = zfit.pdf.ProductPDF([zfit.pdf.Gauss(mu, sg, ox), zfit.pdf.Exponential(l1, oy)])
     b = zfit.pdf.ProductPDF([zfit.pdf.Gauss(mu, 2.0, ox), zfit.pdf.Exponential(l2, oy)])
-    model = zfit.pdf.SumPDF([a, b], fracs=fr)
-    data = zfit.Data(np.stack([rng.normal(0, 1.3, 5000).clip(-5, 5), rng.uniform(0, 4, 5000)], axis=1), obs=ox * oy)
-    loss = zfit.loss.UnbinnedNLL(model, data)
+    loss = zfit.loss.UnbinnedNLL(zfit.pdf.SumPDF([a, b], fracs=fr), data)
+    H = loss.hessian()
+    assert loss.last_hessian_method == "one-pass"
+    loss.options["hessian"] = "numeric"
+    Hn = loss.hessian()
+    scale = np.sqrt(np.abs(np.outer(np.diag(Hn), np.diag(Hn))))
+    assert np.all(np.abs(H - Hn) <= 2e-5 * scale + 1e-7 * np.abs(Hn).max()), np.abs(H - Hn).max()
+
+
+def test_deeper_tree_falls_back_to_gradient_differences():
+    """A Product with a Sum among its factors is outside the shapes of the Hessian pass."""
+    zfit, ox, oy, mu, sg, l1, l2, fr, data = _two_dim_parts("dp")
+    sx = zfit.pdf.SumPDF([zfit.pdf.Gauss(mu, sg, ox), zfit.pdf.Gauss(mu, 2.0, ox)], fracs=fr)
+    loss = zfit.loss.UnbinnedNLL(zfit.pdf.ProductPDF([sx, zfit.pdf.Exponential(l1, oy)]), data)
     H = loss.hessian()
     assert loss.last_hessian_method == "gradient-differences"
     assert np.all(np.isfinite(H)) and np.allclose(H, H.T)

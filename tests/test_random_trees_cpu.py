@@ -64,3 +64,38 @@ def test_hermite_laguerre_through_the_api(name):
         shape = lambda x: np.polynomial.laguerre.lagval(z(x), c)
     num = si.quad(shape, -2.0, 5.0)[0] / si.quad(shape, -6.0, 8.0)[0]
     assert abs(float(poly.integrate((-2.0, 5.0))[0]) - num) <= 1e-12
+
+
+@pytest.mark.parametrize("seed", [102, 104, 106, 111, 112, 113, 115, 116])
+def test_random_tree_one_pass_hessian_matches_double_backward(seed):
+    """The random trees whose shape the Hessian pass knows (a leaf, a Product of leaves, a Sum of leaves and of Products of
+    leaves -- seed 104 and 115 are sums of products): ``eval_hess`` at slot level (host-compiled ``hess_event`` + the
+    library's assembly) against torch's double backward over the oracle graph.  (Differences of the analytic gradient are
+    NOT a valid check here: a TruncatedGauss bound or a CrystalBall junction moves events across a kink.)"""
+    import torch
+
+    from oracle import nll as ON
+    from oracle.backend import TorchBackend
+
+    b, loss = build_case(seed, 3_001)
+    ref = loss.create_new()
+    ref._set_engine_factory(OracleEngine)
+    loss._set_engine_factory(HostSimEngine)
+    eng, oeng = loss._get_engine(), ref._get_engine()
+    slots = np.array([p.value() for p in eng.slot_params], dtype=np.float64)
+    got = eng.eval_hess(slots)
+    assert got is not None, eng.kernel_names
+    H = got[2][0]
+    tree, cols, w, off, ns = oeng.channels[0]
+    B = TorchBackend()
+    names = [f"s{k}" for k in range(ns)]
+    data = [{k: B.asarray(v) for k, v in cols.items()}]
+
+    ww = None if w is None else [B.asarray(w)]
+
+    def f(th):
+        return ON.unbinned_nll([tree], data, {n: th[i] for i, n in enumerate(names)}, weights=ww, B=B)
+
+    oH = torch.autograd.functional.hessian(f, torch.tensor(slots, dtype=torch.float64)).numpy()
+    scale = np.sqrt(np.abs(np.outer(np.diag(oH), np.diag(oH))))
+    assert np.all(np.abs(H - oH) <= 1e-7 * scale + 1e-9 * np.abs(oH).max()), (eng.kernel_names, np.abs(H - oH).max())

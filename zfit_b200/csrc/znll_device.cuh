@@ -1684,6 +1684,48 @@ struct AllLog<C0, C1> {
   static constexpr bool value = C0::LOGNAT && C1::LOGNAT;
 };
 
+// The Hessian pass (hess_kernel, below) knows a Sum root whose branches are leaves or Products of leaves.  Seen from the
+// root a branch is one generalised leaf u_k: it contributes r_k * (d2 u_k / u_k) over ALL of its slots -- for a Product
+// of leaves over disjoint observables the leaves' own blocks plus, between two leaves, the outer product of their scores.
+template <class... Cs>
+struct Prod;
+template <class... Cs>
+struct CrossCount {  // sum over pairs of children i < j of NS_i * NS_j
+  static constexpr int value = 0;
+};
+template <class H, class... T>
+struct CrossCount<H, T...> {
+  static constexpr int value = H::NS * Meta<T...>::NS + CrossCount<T...>::value;
+};
+template <class T>
+struct Branch {  // a leaf
+  static constexpr bool OK = T::LEAF && T::HESS;
+  static constexpr int NH = T::NH;
+};
+template <class... Cs>
+struct Branch<Prod<Cs...>> {
+  static constexpr bool OK = Meta<Cs...>::FLATHESS;
+  static constexpr int NH = Meta<Cs...>::NH + CrossCount<Cs...>::value;
+};
+template <class... Cs>
+struct BranchMeta {
+  static constexpr bool OK = true;
+  static constexpr int NH = 0;
+};
+template <class H, class... T>
+struct BranchMeta<H, T...> {
+  static constexpr bool OK = Branch<H>::OK && BranchMeta<T...>::OK;
+  static constexpr int NH = Branch<H>::NH + BranchMeta<T...>::NH;
+};
+// the children's second-order blocks, one after the other (HK advances by each child's Branch<>::NH)
+template <int CK, int HK, int I, class KD, class RF>
+ZNLL_DEV void second_rec(KD& kd, const RF& rof, const double* __restrict__ c, double* hacc) {
+  if constexpr (KD::N > 0) {
+    kd.h.template second<CK>(rof(I), c, hacc + HK);
+    second_rec<CK + KD::Head::NC, HK + Branch<typename KD::Head>::NH, I + 1>(kd.t, rof, c, hacc);
+  }
+}
+
 template <class... Cs>
 struct Sum {
   static constexpr int K = sizeof...(Cs);
@@ -1692,8 +1734,8 @@ struct Sum {
   static constexpr bool LOGNAT = AllLog<Cs...>::value;
   static constexpr bool HAS_ADD = AllLog<Cs...>::value, HAS_MULT = true;  // log-sum-exp: l1 + ln S; value-space sum: ln P
   static constexpr bool TABS = true;
-  static constexpr bool LEAF = false, HESS = Meta<Cs...>::FLATHESS;  // flat Sum of leaves
-  static constexpr int NH = Meta<Cs...>::NH;
+  static constexpr bool LEAF = false, HESS = BranchMeta<Cs...>::OK;  // Sum of leaves and of Products of leaves
+  static constexpr int NH = BranchMeta<Cs...>::NH;
   static constexpr int ROOT = 1;  // how hess_kernel treats the root: 1 Sum, 2 Prod, 0 leaf
   template <class V>
   using Node = typename SumPick<V, Cs...>::type;
@@ -1765,6 +1807,39 @@ struct ProdN {
   template <int CO, int AO, class A>
   ZNLL_DEV void bwd_val(V a, const double* __restrict__ c, A* acc) {
     bwd_log<CO, AO>(zmul(a, P), c, acc);
+  }
+  // As a branch of a Sum root (Hessian pass): r * (d2 u / u) over all of the branch's slots.  Layout: the leaves' own
+  // triangles in pre-order (their `second`), then for every pair of leaves i < j the full NS_i x NS_j block
+  // r * s_a * s_b of their scores s = d ln p / d slot (row-major).
+  template <int CO>
+  ZNLL_DEV void second(V r, const double* __restrict__ c, double* h) {
+    constexpr int K = sizeof...(Cs);
+    constexpr int ns[K] = {Cs::NS...};
+    constexpr int NSB = Meta<Cs...>::NS;
+    second_rec<CO, 0, 0>(kids, [&](int) { return r; }, c, h);
+    V sc[NSB > 0 ? NSB : 1];
+#pragma unroll
+    for (int a = 0; a < NSB; ++a) sc[a] = zbc<V>(0.0);
+    bwd_rec<CO, 0>(kids, zbc<V>(1.0), c, sc);
+    int q = Meta<Cs...>::NH, oi = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      int oj = oi + ns[i];
+#pragma unroll
+      for (int j = i + 1; j < K; ++j) {
+#pragma unroll
+        for (int a = 0; a < ns[i]; ++a) {
+          const V ra = zmul(r, sc[oi + a]);
+#pragma unroll
+          for (int b = 0; b < ns[j]; ++b) {
+            zacc(h[q], ra, sc[oj + b]);
+            ++q;
+          }
+        }
+        oj += ns[j];
+      }
+      oi += ns[i];
+    }
   }
 };
 template <class... Cs>
@@ -2377,13 +2452,6 @@ __global__ void __launch_bounds__(ZNLL_BLOCK, 1) cov_kernel(const __grid_constan
 // leaf blocks, + g_b / f_k between a fraction and its own leaf's slots; the host (znll_eval_hess) assembles these and
 // restores the slots' dependence through the normalisation integrals with their first and second derivatives.
 // out: [0,1] value pair, then T (row-major upper triangle), then the B_k in pre-order.
-template <int CK, int HK, int I, class KD, class RF>
-ZNLL_DEV void second_rec(KD& kd, const RF& rof, const double* __restrict__ c, double* hacc) {
-  if constexpr (KD::N > 0) {
-    kd.h.template second<CK>(rof(I), c, hacc + HK);
-    second_rec<CK + KD::Head::NC, HK + KD::Head::NH, I + 1>(kd.t, rof, c, hacc);
-  }
-}
 template <class M, class V, bool LEAFROOT>
 struct HessRootPick {
   typedef typename M::template Node<V> type;

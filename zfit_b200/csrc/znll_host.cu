@@ -442,7 +442,7 @@ struct Kernel {
   void* cufunc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // CUfunction, NVRTC path
   void* cufunc_pdf = nullptr;
   void* cufunc_cov[2] = {nullptr, nullptr};
-  void* cufunc_hess[2] = {nullptr, nullptr};  // NVRTC path: the one-pass Hessian kernels of a flat tree, else null
+  void* cufunc_hess[2] = {nullptr, nullptr};  // NVRTC path: the one-pass Hessian kernels when the tree has them, else null
   int n_hess = -1;                            // their second-order leaf accumulators (M::NH)
 };
 
@@ -905,7 +905,7 @@ static int compile_image(const std::string& model, int n_slots, int hess_nh, Ima
     exprs.push_back("znll::cov_kernel<" + q + ",false>");
     exprs.push_back("znll::cov_kernel<" + q + ",true>");
   }
-  // the one-pass Hessian of a flat tree of supported nodes (hess_nh >= 0: the host's count of M::NH), accumulators permitting
+  // the one-pass Hessian of a tree the pass knows (hess_nh >= 0: the host's count of M::NH, hess_branches), accumulators permitting
   if (hess_nh >= 0 && 2 + (n_slots + 1) * (n_slots + 2) / 2 + hess_nh <= 256) {
     exprs.push_back("znll::hess_kernel<" + q + ",false>");
     exprs.push_back("znll::hess_kernel<" + q + ",true>");
@@ -1243,16 +1243,61 @@ static int leaf_hess_acc(const znll_node& nd) {
     default: return 0;  // the polynomial families are linear in their coefficients
   }
 }
-static int tree_hess_nh(const Channel& c) {
-  if (c.nodes.empty()) return -1;
+// A branch of the root as the Hessian pass sees it: one leaf, or (under a Sum root) a Product of leaves.
+struct HessBranch {
+  std::vector<int> leaves;  // node indices
+  int off = 0, ns = 0;      // first slot, number of slots (contiguous in pre-order)
+  int nh = 0;               // device accumulators: the leaves' triangles, then the cross blocks of leaf pairs i < j
+};
+// Splits the tree into the root's branches; false when the Hessian pass does not know the shape (Znll's device traits
+// Sum::HESS / Prod::HESS say the same at compile time): a leaf, a Product of leaves, or a Sum of leaves and of Products
+// of leaves.
+static bool hess_branches(const Channel& c, std::vector<HessBranch>* out) {
+  out->clear();
+  if (c.nodes.empty()) return false;
   const znll_node& root = c.nodes[0].nd;
-  const bool composite = root.kind == ZNLL_SUM || root.kind == ZNLL_PROD;
-  if (composite ? (int)c.nodes.size() != 1 + root.n_children : c.nodes.size() != 1) return -1;
-  int nh = 0;
-  for (size_t i = composite ? 1 : 0; i < c.nodes.size(); ++i) {
-    if (c.nodes[i].nd.kind == ZNLL_SUM || c.nodes[i].nd.kind == ZNLL_PROD) return -1;
-    nh += leaf_hess_acc(c.nodes[i].nd);
+  auto is_leaf = [&](size_t i) { return c.nodes[i].nd.kind != ZNLL_SUM && c.nodes[i].nd.kind != ZNLL_PROD; };
+  auto add_leaf = [&](HessBranch& b, size_t i) {
+    if (b.leaves.empty()) b.off = c.nodes[i].slot_off;
+    b.leaves.push_back((int)i);
+    b.ns += leaf_n_slots(c.nodes[i].nd);
+    b.nh += leaf_hess_acc(c.nodes[i].nd);
+  };
+  if (is_leaf(0)) {
+    if (c.nodes.size() != 1) return false;
+    HessBranch b;
+    add_leaf(b, 0);
+    out->push_back(b);
+    return true;
   }
+  size_t i = 1;
+  for (int k = 0; k < root.n_children; ++k) {
+    if (i >= c.nodes.size()) return false;
+    HessBranch b;
+    if (is_leaf(i)) {
+      add_leaf(b, i++);
+    } else if (root.kind == ZNLL_SUM && c.nodes[i].nd.kind == ZNLL_PROD) {
+      const int m = c.nodes[i].nd.n_children;
+      ++i;
+      for (int j = 0; j < m; ++j) {
+        if (i >= c.nodes.size() || !is_leaf(i)) return false;
+        add_leaf(b, i++);
+      }
+      for (size_t a = 0; a < b.leaves.size(); ++a)
+        for (size_t d = a + 1; d < b.leaves.size(); ++d)
+          b.nh += leaf_n_slots(c.nodes[b.leaves[a]].nd) * leaf_n_slots(c.nodes[b.leaves[d]].nd);
+    } else {
+      return false;
+    }
+    out->push_back(b);
+  }
+  return i == c.nodes.size();
+}
+static int tree_hess_nh(const Channel& c) {
+  std::vector<HessBranch> br;
+  if (!hess_branches(c, &br)) return -1;
+  int nh = 0;
+  for (auto& b : br) nh += b.nh;
   return nh;
 }
 
@@ -1634,7 +1679,7 @@ int znll_eval_cov(znll_plan* p, const double* slots, double log_offset, double* 
 
 
 // ------------------------------------------------------------------------------------------------
-// exact Hessian in one fused pass (flat trees)
+// exact Hessian in one fused pass (a leaf, a Product of leaves, a Sum of leaves and of Products of leaves)
 // ------------------------------------------------------------------------------------------------
 // d2 ln I / d slot_a d slot_b of one leaf: central differences of the analytic d ln I (leaf_integral) with one Richardson
 // step, O(h^4); the step of every slot is 1e-3 of that slot's natural scale (the width for a location or a width, the
@@ -1713,27 +1758,42 @@ static int hess_assemble(Channel& c, const std::vector<double>& acc, int NH, dou
   auto A = [&](int a) { return T[(size_t)a * NE + NS]; };
   const double W = T[(size_t)NS * NE + NS];
   const bool sum_root = c.nodes[0].nd.kind == ZNLL_SUM;
-  struct Leaf {
-    int off, ns, frac;  // first slot, number of slots, fraction slot of the leaf under a Sum root (-1 otherwise)
-    std::vector<double> B, L2;  // sum r U (ns x ns, symmetric) and d2 lambda = -d2 ln I
+  struct Leaf {  // a branch of the root: one leaf, or a Product of leaves under a Sum root (one generalised leaf)
+    int off, ns, frac;  // first slot, number of slots, fraction slot of the branch under a Sum root (-1 otherwise)
+    std::vector<double> B, L2;  // sum r (d2 u / u) (ns x ns, symmetric) and d2 lambda = -d2 ln I (block diagonal per leaf)
   };
+  std::vector<HessBranch> branches;
+  if (!hess_branches(c, &branches)) return fail("znll_eval_hess: the tree has no one-pass Hessian");
   std::vector<Leaf> leaves;
   int hq = 2 + NQ;
-  for (auto& ni : c.nodes) {
-    if (ni.nd.kind == ZNLL_SUM || ni.nd.kind == ZNLL_PROD) continue;
+  for (auto& br : branches) {
     Leaf lf;
-    lf.off = ni.slot_off;
-    lf.ns = leaf_n_slots(ni.nd);
-    lf.frac = sum_root ? ni.parent_sum_frac_slot : -1;
+    lf.off = br.off;
+    lf.ns = br.ns;
+    lf.frac = sum_root ? c.nodes[br.leaves[0]].parent_sum_frac_slot : -1;
     lf.B.assign((size_t)lf.ns * lf.ns, 0.0);
-    // every leaf but the polynomial families (linear in their coefficients) carries the full upper triangle over its slots
-    const bool has_second = leaf_hess_acc(ni.nd) > 0;
-    if (has_second)
-      for (int a = 0; a < lf.ns; ++a)
-        for (int b = a; b < lf.ns; ++b) lf.B[(size_t)a * lf.ns + b] = lf.B[(size_t)b * lf.ns + a] = acc[hq++];
     lf.L2.assign((size_t)lf.ns * lf.ns, 0.0);
-    leaf_d2lnI(ni.nd, c.slots.data() + lf.off, lf.ns, lf.L2.data());
-    for (auto& v : lf.L2) v = -v;
+    auto Bx = [&](int a, int b) -> double& { return lf.B[(size_t)a * lf.ns + b]; };
+    // the leaves' own triangles (every leaf but the polynomial families, which are linear in their coefficients) ...
+    for (int li : br.leaves) {
+      const NodeInfo& ni = c.nodes[li];
+      const int o = ni.slot_off - br.off, n1 = leaf_n_slots(ni.nd);
+      if (leaf_hess_acc(ni.nd) > 0)
+        for (int a = 0; a < n1; ++a)
+          for (int b = a; b < n1; ++b) Bx(o + a, o + b) = Bx(o + b, o + a) = acc[hq++];
+      std::vector<double> l2((size_t)n1 * n1, 0.0);
+      leaf_d2lnI(ni.nd, c.slots.data() + ni.slot_off, n1, l2.data());
+      for (int a = 0; a < n1; ++a)
+        for (int b = 0; b < n1; ++b) lf.L2[(size_t)(o + a) * lf.ns + o + b] = -l2[(size_t)a * n1 + b];
+    }
+    // ... then the cross blocks of a Product branch: sum r s_a s_b for leaves i < j, row-major
+    for (size_t i = 0; i < br.leaves.size(); ++i)
+      for (size_t j = i + 1; j < br.leaves.size(); ++j) {
+        const NodeInfo &ni = c.nodes[br.leaves[i]], &nj = c.nodes[br.leaves[j]];
+        const int oi = ni.slot_off - br.off, oj = nj.slot_off - br.off;
+        for (int a = 0; a < leaf_n_slots(ni.nd); ++a)
+          for (int b = 0; b < leaf_n_slots(nj.nd); ++b) Bx(oi + a, oj + b) = Bx(oj + b, oi + a) = acc[hq++];
+      }
     leaves.push_back(lf);
   }
   if (hq != NACC) return fail("znll_eval_hess: accumulator layout mismatch (%d vs %d)", hq, NACC);
@@ -1825,7 +1885,7 @@ int znll_eval_hess(znll_plan* p, const double* slots, double log_offset, double*
   for (auto& c : p->ch) {
     if (c.nodes.empty() || !c.bound) return fail("znll_eval_hess: channel without model or data");
     if (!channel_has_hess(c)) {
-      fail("znll_eval_hess: no one-pass Hessian for the tree '%s' (not a flat tree of supported nodes)", c.kernel.name.c_str());
+      fail("znll_eval_hess: no one-pass Hessian for the tree '%s' (deeper than a Sum of Products of leaves, or too many accumulators)", c.kernel.name.c_str());
       return 3;
     }
   }
