@@ -29,7 +29,9 @@
 #pragma once
 
 #define ZNLL_MAXCOL 8
-#define ZNLL_BLOCK 256
+#ifndef ZNLL_BLOCK
+#define ZNLL_BLOCK 256  // threads per CTA (tuning experiments: -DZNLL_BLOCK=192 with three resident CTAs)
+#endif
 #ifndef ZNLL_MIN_BLOCKS
 #define ZNLL_MIN_BLOCKS 2  // resident CTAs per SM the register allocation is tuned for
 #endif
@@ -2276,8 +2278,13 @@ __host__ __device__ constexpr int ring_stages(int nstream) {
 // a compensated sum at the granularity that matters for 1e8..1e9 events, and the per-pair Kahan step (4 dependent DADDs
 // on the FP64 pipe that bounds these kernels) is gone.  Event pairs are indexed with 32 bits (the host refuses more
 // than 8e9 events per channel and GPU): one IADD, one ISETP and one IMAD.WIDE per pair for the whole loop control.
+#ifdef ZNLL_MAXNREG  // tuning experiments: an explicit register cap instead of the one ptxas derives from the CTA count
+#define ZNLL_STEP_BOUNDS __maxnreg__(ZNLL_MAXNREG)
+#else
+#define ZNLL_STEP_BOUNDS __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS)
+#endif
 template <class M, bool WEIGHTED, bool GRAD>
-__global__ void __launch_bounds__(ZNLL_BLOCK, ZNLL_MIN_BLOCKS) nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
+__global__ void ZNLL_STEP_BOUNDS nll_kernel(const __grid_constant__ KArgs<M::NC> args) {
   constexpr int NACC = 2 + M::NS;
   __shared__ MathTabs tabs;
   if constexpr (NeedTabs<M>::value) {
