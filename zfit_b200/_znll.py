@@ -173,6 +173,7 @@ class Plan:
         if getattr(self, "_h", None) and self._h.value:
             lib().znll_plan_destroy(self._h)
             self._h = C.c_void_p()
+            self._reduce_cb = None
 
     def __del__(self):
         try:

@@ -144,7 +144,12 @@ class CudaEngine:
                         f"an NCCL all-reduce per evaluation instead ({exc!r})", RuntimeWarning, stacklevel=2)
             if self.reduce_mode == "nccl":
                 self._acc = _dist.device_view(self.plan.acc_device_ptr(), self.plan.total_acc(), device)
-            self.plan.set_reduce_hook(self._sum_over_ranks)  # the passes the kernel does not reduce itself (information matrix)
+            # the passes the kernel does not reduce itself (information matrix); a weak reference: the plan must not keep
+            # its engine alive through the callback
+            import weakref
+
+            me = weakref.ref(self)
+            self.plan.set_reduce_hook(lambda buf: me()._sum_over_ranks(buf))
         self.kernel_names = [self.plan.kernel_name(k) for k in range(len(models))]
         self._raw_stream = self._pick_stream_getter()
         mark("rest")
