@@ -216,3 +216,35 @@ def test_large_host_arrays_are_cut_in_hbm(monkeypatch):
     assert float(a[0]) == float(b[0]) and np.array_equal(np.asarray(a[1]), np.asarray(b[1]))
     monkeypatch.setitem(zfit.settings.options, "device_cut_min_events", None)
     assert not zfit.Data(raw, obs=obs).on_device
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 511, 513, 8_191, 100_003])
+def test_prep_kernels_stay_inside_their_destination(n):
+    """Guard bands around every destination (and the sources read back unchanged): the staged move of the partition and
+    the compaction of the cut write exactly their n (resp. kept) elements."""
+    import torch
+
+    from zfit_b200 import _znll as Z
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(n)
+    G = 64  # guard elements on both sides
+    srcs = [torch.from_numpy(rng.uniform(-1.3, 1.3, n)).to(dev) for _ in range(3)]
+    keep_src = [s.clone() for s in srcs]
+    bufs = [torch.full((n + 2 * G,), 12345.0, dtype=torch.float64, device=dev) for _ in range(3)]
+    dsts = [b[G : G + n] for b in bufs]
+    stream = torch.cuda.current_stream(0).cuda_stream
+    sp, dp = [s.data_ptr() for s in srcs], [d.data_ptr() for d in dsts]
+    Z.partition_events(0, sp[:2], dp[:2], sp[2], dp[2], 1, -1.0, 1.0, n, stream=stream)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.all(b[:G] == 12345.0) and torch.all(b[G + n :] == 12345.0)
+        assert not torch.any(b[G : G + n] == 12345.0)
+    for b in bufs:
+        b.fill_(12345.0)
+    kept = Z.cut_events(0, sp[:2], dp[:2], sp[2], dp[2], [-1.0, -1.0], [1.0, 1.0], n, stream=stream)
+    for b in bufs:
+        assert torch.all(b[:G] == 12345.0) and torch.all(b[G + kept :] == 12345.0)
+        assert not torch.any(b[G : G + kept] == 12345.0)
+    for s, k in zip(srcs, keep_src):
+        assert torch.equal(s, k)
