@@ -655,8 +655,13 @@ def measure_config(ctx, cfg, args, headline):
                 # full-size agreement of the two routes, in units of sqrt(H_aa H_bb) (the differences carry O(h^2) error)
                 scale = np.sqrt(np.abs(np.outer(np.diag(H_num), np.diag(H_num))))
                 res["hessian"]["max_scaled_difference"] = float(np.max(np.abs(H_one - H_num) / np.where(scale > 0, scale, 1.0)))
-                eig = np.linalg.eigvalsh(0.5 * (H_one + H_one.T))
+                # positive definiteness in correlation units: yields of 1e7 next to shape parameters of O(1) make the
+                # raw matrix's smallest eigenvalue a rounding artefact
+                dg = np.sqrt(np.abs(np.diag(H_one)))
+                dg = np.where(dg > 0, dg, 1.0)
+                eig = np.linalg.eigvalsh(0.5 * (H_one + H_one.T) / np.outer(dg, dg))
                 res["hessian"]["positive_definite"] = bool(eig[0] > 0)
+                res["hessian"]["min_eigenvalue_scaled"] = float(eig[0])
                 loss.options["hessian"] = "exact"
         except Exception as exc:
             res["hessian"] = {"error": repr(exc)}
