@@ -18,7 +18,10 @@ from . import _znll as Z
 
 
 class DeviceSampler:
-    def __init__(self, pdf, limits, *, device=None, batch=1 << 20):
+    MIN_PROPOSALS = 1 << 14
+    MAX_PROPOSALS = 1 << 26  # 512 MB per buffer
+
+    def __init__(self, pdf, limits, *, device=None, batch=None):
         import torch
 
         from . import distributed as _dist
@@ -27,21 +30,18 @@ class DeviceSampler:
         self.pdf = pdf
         self.limits = limits
         self.device = _dist.local_device() if device is None else device
-        self.batch = int(batch)
-        dev = torch.device("cuda", self.device)
+        self.fixed_batch = None if batch is None else int(batch)  # a caller-chosen proposal count (tests); else adaptive
         self.lower = [float(v) for v in np.atleast_1d(limits._lower).ravel()]
         self.upper = [float(v) for v in np.atleast_1d(limits._upper).ravel()]
         nodes, self.slot_params = pdf._lower(limits.obs, None)
         self.plan = Z.Plan(1, device=self.device)
         self.plan.set_model(0, nodes)
-        self.cols = [torch.empty(self.batch, dtype=torch.float64, device=dev) for _ in limits.obs]
-        self.pvals = torch.empty(self.batch, dtype=torch.float64, device=dev)
-        self.unif = torch.empty(self.batch, dtype=torch.float64, device=dev)
-        torch.cuda.synchronize(self.device)
-        self.plan.bind_device_ptrs(0, [c.data_ptr() for c in self.cols], 0, self.batch, keepalive=self.cols)
-        self.generator = torch.Generator(device=dev)
+        self.batch = 0  # proposals per pass = size of the buffers below
+        self.cols, self.pvals, self.unif = [], None, None
+        self.generator = torch.Generator(device=torch.device("cuda", self.device))
         self.generator.manual_seed(int(np.random.randint(0, 2**31 - 1)))
         self.pmax = None
+        self.accept_rate = None  # accepted / proposed of the last draw
 
     def seed(self, seed):
         self.generator.manual_seed(int(seed))
@@ -51,6 +51,27 @@ class DeviceSampler:
 
         with _maybe_set(dict(values), self.pdf):
             return np.array([p.value() for p in self.slot_params], dtype=np.float64)
+
+    def _size_buffers(self, n):
+        """Proposal buffers for draws of about n events: one pass should be enough (n / acceptance, +15 %), so that a toy
+        costs a handful of launches whatever its size; buffers only grow, in powers of two."""
+        torch = self.torch
+        if self.fixed_batch is not None:
+            want = self.fixed_batch
+        else:
+            rate = self.accept_rate if self.accept_rate else 0.25
+            want = int(min(self.MAX_PROPOSALS, max(self.MIN_PROPOSALS, 1.15 * n / max(rate, 1e-3) + 1024)))
+            want = 1 << (want - 1).bit_length()
+        if want <= self.batch:
+            return
+        dev = torch.device("cuda", self.device)
+        self.batch = want
+        self.cols = [torch.empty(want, dtype=torch.float64, device=dev) for _ in self.limits.obs]
+        self.pvals = torch.empty(want, dtype=torch.float64, device=dev)
+        self.unif = torch.empty(want, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(self.device)
+        self.plan._keep.clear()  # the previous, smaller buffers
+        self.plan.bind_device_ptrs(0, [c.data_ptr() for c in self.cols], 0, want, keepalive=self.cols)
 
     def draw(self, n, values):
         """-> dict obs -> device column with exactly n events drawn at the parameter values ``values``."""
@@ -64,12 +85,13 @@ class DeviceSampler:
             with _maybe_set(dict(values), self.pdf):
                 n = int(np.random.poisson(self.pdf.get_yield().value()))
         n = int(n)
+        self._size_buffers(n)
         slots = self._slots(values)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         pmax = self.pmax
         while True:  # restarted only if the envelope turned out too low
             kept = [[] for _ in self.cols]
-            have, restart = 0, False
+            have, proposed, restart = 0, 0, False
             while have < n:
                 for c, lo, up in zip(self.cols, self.lower, self.upper):
                     c.uniform_(lo, up, generator=self.generator)
@@ -89,9 +111,18 @@ class DeviceSampler:
                 for k, c in enumerate(out):
                     kept[k].append(c[:n_acc])
                 have += n_acc
+                proposed += self.batch
             if not restart:
                 break
         self.pmax = pmax
+        if proposed:
+            self.accept_rate = max(have / proposed, 1e-6)
+        if not kept[0]:  # n == 0
+            dev = torch.device("cuda", self.device)
+            return {o: torch.empty(0, dtype=torch.float64, device=dev) for o in self.limits.obs}
+        if len(kept[0]) == 1:  # the usual case: one pass was enough -- its compacted buffer (copied when much larger than n)
+            take = (lambda t: t[:n].clone()) if self.batch > 2 * n else (lambda t: t[:n])
+            return {o: take(parts[0]) for o, parts in zip(self.limits.obs, kept)}
         return {o: torch.cat(parts)[:n].contiguous() for o, parts in zip(self.limits.obs, kept)}
 
     def close(self):
