@@ -54,14 +54,15 @@ class DeviceSampler:
 
     def _size_buffers(self, n):
         """Proposal buffers for draws of about n events: one pass should be enough (n / acceptance, +15 %), so that a toy
-        costs a handful of launches whatever its size; buffers only grow, in powers of two."""
+        costs a handful of launches whatever its size; buffers only grow."""
         torch = self.torch
         if self.fixed_batch is not None:
             want = self.fixed_batch
         else:
             rate = self.accept_rate if self.accept_rate else 0.25
             want = int(min(self.MAX_PROPOSALS, max(self.MIN_PROPOSALS, 1.15 * n / max(rate, 1e-3) + 1024)))
-            want = 1 << (want - 1).bit_length()
+            step = 1 << max(14, want.bit_length() - 4)  # sixteenths of the next power of two: regrowth stays rare
+            want = -(-want // step) * step
         if want <= self.batch:
             return
         dev = torch.device("cuda", self.device)
