@@ -72,17 +72,17 @@ __global__ void __launch_bounds__(ZNLL_PREP_BLOCK) count_kernel(const __grid_con
   const long long r_end = min(rows, r + a.rows_per_warp);
   const double* __restrict__ keycol = a.src[a.key];
   unsigned int cnt = 0;
-  for (; r < r_end; r += 4) {  // four key loads in flight per lane
-    double x[4];
-    bool live[4];
+  for (; r < r_end; r += 8) {  // eight key loads in flight per lane (the pass shares the move's two CTAs per SM)
+    double x[8];
+    bool live[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const long long i = ((r + k) << 5) + lane;
       live[k] = (r + k) < r_end && i < a.n;
       x[k] = live[k] ? __ldg(keycol + i) : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       unsigned bit[5];
       bucket_ballots(bit, bucket_of(x[k], a.lo, a.scale));
       cnt += __popc(lanes_in_bucket(bit, __ballot_sync(0xffffffffu, live[k]), lane));
