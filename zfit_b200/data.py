@@ -479,7 +479,10 @@ def _upload_for_cut(cols, weights):
     from . import settings
 
     threshold = settings.options.get("device_cut_min_events")
-    if threshold is None or int(cols[0].shape[0]) < int(threshold) or _dist.is_distributed():
+    import os
+
+    multi = _dist.is_distributed() or int(os.environ.get("WORLD_SIZE", "1") or 1) > 1  # torchrun, group not up yet
+    if threshold is None or int(cols[0].shape[0]) < int(threshold) or multi:
         return None
     try:
         import torch
