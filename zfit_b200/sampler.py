@@ -97,18 +97,18 @@ class DeviceSampler:
                 for c, lo, up in zip(self.cols, self.lower, self.upper):
                     c.uniform_(lo, up, generator=self.generator)
                 self.plan.pdf_values_device(0, slots, self.pvals.data_ptr(), stream=stream)
-                batch_max = float(self.pvals.max())
+                top = self.pvals.max()  # stays on the device; read after the compaction's own synchronisation
                 if pmax is None:
-                    pmax = 1.2 * batch_max
-                elif batch_max > pmax:
-                    pmax, restart = 1.2 * batch_max, True
-                    break
+                    pmax, top = 1.2 * float(top), None
                 self.unif.uniform_(0.0, pmax, generator=self.generator)
                 # accept u < p and compact the accepted proposals in one pass (znll_cut_events; only the count comes back)
                 out = [torch.empty_like(c) for c in self.cols]
                 n_acc = Z.cut_events(self.device, [c.data_ptr() for c in self.cols], [c.data_ptr() for c in out], 0, 0,
                                      self.lower, self.upper, self.batch, less_a=self.unif.data_ptr(),
                                      less_b=self.pvals.data_ptr(), stream=stream)
+                if top is not None and float(top) > pmax:  # a proposal above the envelope: raise it and start over
+                    pmax, restart = 1.2 * float(top), True
+                    break
                 for k, c in enumerate(out):
                     kept[k].append(c[:n_acc])
                 have += n_acc
