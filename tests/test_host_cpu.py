@@ -842,3 +842,27 @@ def test_lazy_sort_countdown_of_the_engine():
             if not calls:
                 assert mode is None or eng._lazy_sort_in >= 0
         assert len(calls) == expect and eng._lazy_sort_in is None
+
+
+def test_large_host_cut_stays_on_the_host_without_a_gpu_or_under_a_launcher(monkeypatch):
+    """``data._upload_for_cut``: the HBM route for the cut of large host arrays needs a CUDA device, a single-process job and
+    the ``device_cut_min_events`` option; otherwise the inclusive cut runs on the host exactly as for small arrays."""
+    import zfit_b200 as zfit
+    from zfit_b200 import data as D
+
+    rng = np.random.default_rng(4)
+    cols = [rng.normal(size=1000)]
+    monkeypatch.setitem(zfit.settings.options, "device_cut_min_events", 100)
+    monkeypatch.setenv("WORLD_SIZE", "2")  # torchrun before init_process_group: every rank would upload everything
+    assert D._upload_for_cut(cols, None) is None
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setitem(zfit.settings.options, "device_cut_min_events", None)
+    assert D._upload_for_cut(cols, None) is None
+    monkeypatch.setitem(zfit.settings.options, "device_cut_min_events", 100)
+    import torch
+
+    if not torch.cuda.is_available():
+        assert D._upload_for_cut(cols, None) is None
+    d = zfit.Data(cols[0], obs=zfit.Space("x", -1, 1)) if not torch.cuda.is_available() else None
+    if d is not None:
+        assert not d.on_device and d.num_entries == int(((cols[0] >= -1) & (cols[0] <= 1)).sum())
