@@ -847,9 +847,11 @@ def test_lazy_sort_countdown_of_the_engine():
 def test_large_host_cut_stays_on_the_host_without_a_gpu_or_under_a_launcher(monkeypatch):
     """``data._upload_for_cut``: the HBM route for the cut of large host arrays needs a CUDA device, a single-process job and
     the ``device_cut_min_events`` option; otherwise the inclusive cut runs on the host exactly as for small arrays."""
-    import zfit_b200 as zfit
-    from zfit_b200 import data as D
+    import importlib
 
+    import zfit_b200 as zfit
+
+    D = importlib.import_module("zfit_b200.data")  # (the package attribute `zfit.data` is the public namespace)
     rng = np.random.default_rng(4)
     cols = [rng.normal(size=1000)]
     monkeypatch.setitem(zfit.settings.options, "device_cut_min_events", 100)
